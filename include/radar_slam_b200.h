@@ -1,0 +1,139 @@
+/*
+ * radar_slam_b200.h -- C ABI of libradarslam_b200.so (sm_100a).
+ *
+ * Drop-in boundary for radar-slam's per-frame signal-processing hot path.  The reference has
+ * no FFI: its boundary is four Python classes.  The Python modules under
+ * src/ keep those classes and call the entry points below through ctypes with raw device
+ * pointers (torch is only the allocator / stream owner).  INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host
+ *   - complex64 = interleaved (re, im) float; complex128 = interleaved double
+ *   - all entry points enqueue on `stream` (a cudaStream_t passed as void*) and return
+ *     immediately; they never allocate, never synchronise and never throw
+ *   - return value: RS_OK or a negative RS_E* code; rs_last_error() gives the message
+ *   - re-entrant across streams; outputs are caller-allocated
+ *
+ * Device data layout (one batch of F independent frames)
+ *   cube   complex64 [F][A][C][S]   raw frame, reference layout frame_signals[A, C, S]
+ *                                   (dechirp.py:168-181)
+ *   mid    complex64 [F][S][A][C]   range spectrum, range axis already fftshift-ed (private)
+ *   rds    complex64 [F][S][C][A]   range-Doppler spectrum, both axes fftshift-ed, CELL-MAJOR:
+ *                                   the A-channel snapshot of a cell (the "spatial signature",
+ *                                   angle_estimation.py:83) is contiguous.  The reference's
+ *                                   rds[a, r, d] (dechirp.py:193-213) is rds_dev[r][d][a].
+ *   detections: per (frame, tile) segments of `seg_cap` slots, `det_count[F*ntiles]` valid each
+ *       det_key    uint32  (antenna << 24) | (range_bin << 12) | doppler_bin; ascending key order
+ *                          is the reference's output order antenna -> range -> doppler
+ *                          (dechirp.py:246-258)
+ *       det_power  float   |X|^2 of the cell on that antenna
+ *       det_flags  uint8   RS_FLAG_* bits
+ *       det_aidx   int32   argmax index into the azimuth grid (-1 for ESPRIT)
+ *       det_adeg   float   azimuth in degrees
+ *       det_phase  float   angle(s[1] conj(s[0]))            (velocity_solver.py:136)
+ *   vel    double [F][8]    v_x v_y v_z w_x w_y w_z success n_targets
+ */
+#ifndef RADAR_SLAM_B200_H
+#define RADAR_SLAM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RS_OK            0
+#define RS_EINVAL       -1   /* bad argument / unsupported size */
+#define RS_ECUDA        -2   /* CUDA runtime error (message in rs_last_error) */
+#define RS_ECAPACITY    -3   /* configuration needs more shared memory than one SM has */
+
+#define RS_METHOD_MUSIC        0   /* angle_estimation.py:109-176 */
+#define RS_METHOD_BEAMFORMING  1   /* angle_estimation.py:227-251, robust_angle_estimation.py:237-245 */
+#define RS_METHOD_ESPRIT       2   /* angle_estimation.py:178-225 */
+
+#define RS_FLAG_TIE        1   /* top-2 grid values closer than tie_eps: argmax not trustworthy in fp32 */
+#define RS_FLAG_NEARMAX    2   /* cell within det_eps of a neighbour or of the threshold */
+#define RS_FLAG_GUARD      4   /* MUSIC denominator inside the 1e-12 guard zone (angle_estimation.py:149) */
+#define RS_FLAG_FIXED      8   /* decision re-evaluated in fp64 by rs_recheck_f64 */
+#define RS_FLAG_DROPPED   16   /* fp64 recheck says this is not a detection; consumers skip it */
+
+#define RS_MAX_RANGE_BINS   4096
+#define RS_MAX_DOPPLER_BINS 4096
+#define RS_MAX_ANTENNAS     256
+
+int rs_version(void);
+const char* rs_last_error(void);
+
+/* Number of detection tiles per frame and the tile shape rs_detect will use for [R, D, A]. */
+int rs_detect_tiling(int R, int D, int A, int* tile_r, int* tile_d, int* ntiles);
+
+/* (a1)  replaces SignalPreprocessor.process_chirp + the range half of fft2/fftshift
+ *       (dechirp.py:143-166, 196-211).  x * table, FFT over fast time, bin 0 zeroed when
+ *       dc_removal (== subtracting the mean, dechirp.py:120), range fftshift, stored transposed.
+ *       table     complex64 [S]  conj(reference_chirp) * window, built in fp64 by the host
+ *       twiddle_s complex64 [S]  exp(-2 pi i k / S), built in fp64 by the host
+ *       chirp0, C_used: chirp_subset (dechirp.py:184-187); `cube` holds C_total chirps, `mid` C_used. */
+int rs_range_fft(const void* cube, const void* table, const void* twiddle_s, void* mid,
+                 int F, int A, int C_total, int chirp0, int C_used, int S, int dc_removal, void* stream);
+
+/* (a2)  the Doppler half of fft2/fftshift (dechirp.py:208-211): FFT over slow time, Doppler
+ *       fftshift, antenna-innermost store.   twiddle_c complex64 [C] */
+int rs_doppler_fft(const void* mid, const void* twiddle_c, void* rds, int F, int A, int C, int S, void* stream);
+
+/* (b)   replaces extract_range_doppler_peaks (dechirp.py:215-278): |X|^2, 3x3 local maximum per
+ *       antenna plane (scipy maximum_filter 'reflect' == ignore out-of-range neighbours, ties
+ *       count), strict threshold, range gate, per-tile compaction by ballot/prefix sums.
+ *       thr_power   p > thr_power  <=>  10 log10(p + 1e-12) > threshold_db  (host computes in fp64)
+ *       range_gate  uint8 [R], 1 where min_range <= range_bins_m[i] <= max_range
+ *       det_eps     relative guard band for RS_FLAG_NEARMAX
+ *       det_overflow int32 [F], set to 1 when a tile had more than seg_cap detections */
+int rs_detect(const void* rds, const uint8_t* range_gate, float thr_power, float det_eps,
+              uint32_t* det_key, float* det_power, uint8_t* det_flags, int32_t* det_count, int32_t* det_overflow,
+              int seg_cap, int F, int R, int D, int A, void* stream);
+
+/* (c)   replaces AngleEstimator.process_targets (angle_estimation.py:253-309) for every detection:
+ *       snapshot gather, (rank-1) MUSIC / beamforming scan over the azimuth grid with first-index
+ *       argmax, or the ESPRIT closed form; also the inter-antenna phase the solver uses.
+ *       scan_table  float [G][scan_stride]  (cos k phi_g, sin k phi_g), k = 1..A-1, fp64-built;
+ *                   scan_stride = 2 * (A_pad - 1) rounded up to 4        (A <= 16 path)
+ *       steer       complex64 [A][G] exp(+i m phi_g)                      (A > 16 path; may be NULL otherwise)
+ *       grid_deg    float [G]
+ *       esprit_scale  lambda / (2 pi d)   (angle_estimation.py:218) */
+int rs_angles(const void* rds, const float* scan_table, int scan_stride, const void* steer, const float* grid_deg, int G,
+              int method, float tie_eps, double esprit_scale,
+              const uint32_t* det_key, const int32_t* det_count, uint8_t* det_flags,
+              int32_t* det_aidx, float* det_adeg, float* det_phase,
+              int seg_cap, int nseg_per_frame, int F, int R, int D, int A, void* stream);
+
+/* (d)   replaces VelocitySolver.solve_velocity / two_step_optimization (velocity_solver.py:178-355):
+ *       fp64 normal equations of  y = k (v_x cos az + v_y sin az),  k = 4 pi dt / lambda, solved under
+ *       the reference's box |v_x|,|v_y| <= bound; success = (n >= 3).  v_z and omega are unobservable
+ *       in the reference model and are returned as 0.  irls_iters > 0 adds Huber reweighting.
+ *       grid_cs  double [G][2] (cos, sin) of radians(grid_deg), fp64-built; NULL => use det_adeg. */
+int rs_velocity_ls(const int32_t* det_aidx, const float* det_adeg, const float* det_phase, const uint8_t* det_flags,
+                   const int32_t* det_count, const double* grid_cs, double k_phase, double bound,
+                   int irls_iters, double huber_delta,
+                   double* vel, int seg_cap, int nseg_per_frame, int F, void* stream);
+
+/* helpers for the legacy (list-of-dict) adapters ---------------------------------------------- */
+
+/* rds [F][S][C][A] -> reference layout [F][A][S][C] (complex64) */
+int rs_rds_to_reference_layout(const void* rds, void* out, int F, int A, int C, int S, void* stream);
+
+/* reference layout [F][A][S][C] complex64 -> cell-major [F][S][C][A] */
+int rs_rds_from_reference_layout(const void* rds_ref, void* out, int F, int A, int C, int S, void* stream);
+
+/* unit-energy snapshots (angle_estimation.py:83-88) of n cells: keys as in det_key, frame index per key.
+ * out complex128 [n][A]. */
+int rs_signatures_f64(const void* rds, const uint32_t* keys, const int32_t* frames, int n,
+                      void* out, int F, int R, int D, int A, void* stream);
+
+/* fp64 pseudo-spectra for n unit-energy snapshots: method MUSIC -> 1/(M - |a^H s|^2) with the 1e-12
+ * guard, BEAMFORMING -> |a^H s|^2.   steer128 complex128 [A][G];  out double [n][G];  aidx int32 [n]. */
+int rs_spectra_f64(const void* sig128, const void* steer128, int method, int n, int A, int G,
+                   double* out, int32_t* aidx, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

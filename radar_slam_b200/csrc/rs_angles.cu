@@ -1,0 +1,403 @@
+// Per-detection angle estimation on the cell-major RDS.
+//
+// Replaces AngleEstimator.extract_spatial_signature / music_spectrum / estimate_angle_* /
+// process_targets (angle_estimation.py:67-309).
+//
+// MUSIC in the reference is single-snapshot: R = s s^H (angle_estimation.py:127), eigh, noise
+// subspace = all but the top eigenvector, so a^H E_n E_n^H a = M - |a^H s|^2 / |s|^2 exactly and
+// argmax(1/den) == argmax |a^H s|^2 except inside the den <= 1e-12 guard (:149), which fp32
+// cannot resolve: those detections get RS_FLAG_GUARD and are re-evaluated in fp64 by the caller.
+// The scan uses the lag form  |a^H s|^2 = R_0 + 2 sum_k Re(R_k e^{-ik phi}),  R_k = sum_n s[n+k] conj(s[n]),
+// which halves the multiply-adds per grid point; cos/sin(k phi_g) come from an fp64-built table.
+//
+// ESPRIT (angle_estimation.py:195-221) reduces, for one snapshot, to the principal eigenvector of a
+// 2x2 Hermitian matrix; it is evaluated in fp64 from the fp32 snapshot.
+#include "rs_common.cuh"
+
+namespace {
+
+constexpr int ANG_THREADS = 128;
+
+struct AngleArgs {
+    const float2* rds;
+    const float* scan_table;
+    int scan_stride;
+    const float2* steer;
+    const float* grid_deg;
+    int G;
+    int method;
+    float tie_eps;
+    double esprit_scale;
+    const uint32_t* det_key;
+    const int32_t* det_count;
+    uint8_t* det_flags;
+    int32_t* det_aidx;
+    float* det_adeg;
+    float* det_phase;
+    int seg_cap, nseg_per_frame, R, D, A;
+};
+
+// ESPRIT closed form from a snapshot held in registers (s[0..M-1]); returns degrees.
+template <int AP>
+__device__ __forceinline__ float esprit_deg(const float2 (&s)[AP], int M, double scale) {
+    double alpha = 0, gamma = 0, br = 0, bi = 0;
+#pragma unroll
+    for (int i = 0; i < AP - 1; ++i) {
+        if (i < M - 1) {
+            const double xr = s[i].x, xi = s[i].y, yr = s[i + 1].x, yi = s[i + 1].y;
+            alpha += xr * xr + xi * xi;
+            gamma += yr * yr + yi * yi;
+            br += xr * yr + xi * yi;     // conj(x) * y
+            bi += xr * yi - xi * yr;
+        }
+    }
+    const double half = 0.5 * (alpha - gamma);
+    const double lam = 0.5 * (alpha + gamma) + sqrt(half * half + br * br + bi * bi);
+    // eigenvector of [[alpha, beta],[conj(beta), gamma]] for lam: take the better conditioned row
+    double v0r, v0i, v1r, v1i;
+    const double na = br * br + bi * bi + (lam - alpha) * (lam - alpha);
+    const double nb = (lam - gamma) * (lam - gamma) + br * br + bi * bi;
+    if (na >= nb) { v0r = br; v0i = bi; v1r = lam - alpha; v1i = 0; }
+    else          { v0r = lam - gamma; v0i = 0; v1r = br; v1i = -bi; }
+    // u_i = v0 s_i + v1 s_{i+1};  num = sum_{i<M-2} conj(u_i) u_{i+1}
+    double nr = 0, ni = 0, pr = 0, pi = 0;
+#pragma unroll
+    for (int i = 0; i < AP - 1; ++i) {
+        if (i < M - 1) {
+            const double xr = s[i].x, xi = s[i].y, yr = s[i + 1].x, yi = s[i + 1].y;
+            const double ur = v0r * xr - v0i * xi + v1r * yr - v1i * yi;
+            const double ui = v0r * xi + v0i * xr + v1r * yi + v1i * yr;
+            if (i > 0) {
+                nr += pr * ur + pi * ui;
+                ni += pr * ui - pi * ur;
+            }
+            pr = ur; pi = ui;
+        }
+    }
+    const double phase = atan2(ni, nr);
+    return (float)(asin(phase * scale) * (180.0 / 3.14159265358979323846));
+}
+
+// thread-per-detection kernel for A <= AP (AP in {2,4,8,16})
+template <int AP>
+__global__ void __launch_bounds__(ANG_THREADS) angles_small_kernel(AngleArgs p) {
+    extern __shared__ float tab[];   // [G][scan_stride]
+    const int seg = blockIdx.x;
+    const int n = p.det_count[seg];
+    if (n == 0) return;
+    const bool scan = p.method != RS_METHOD_ESPRIT;
+    if (scan) {
+        const int nt = p.G * p.scan_stride;
+        for (int i = threadIdx.x; i < nt; i += blockDim.x) tab[i] = p.scan_table[i];
+        __syncthreads();
+    }
+    const int f = seg / p.nseg_per_frame;
+    const float2* frame = p.rds + (size_t)f * p.R * p.D * p.A;
+    const int M = p.A;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const size_t o = (size_t)seg * p.seg_cap + i;
+        int a, r, d;
+        rs_split_key(p.det_key[o], a, r, d);
+        const float2* cell = frame + ((size_t)r * p.D + d) * M;
+        float2 s[AP];
+#pragma unroll
+        for (int m = 0; m < AP; ++m) s[m] = (m < M) ? __ldg(cell + m) : make_float2(0.f, 0.f);
+
+        // inter-antenna phase angle(s[1] conj(s[0]))  (velocity_solver.py:136)
+        const float pr = s[1].x * s[0].x + s[1].y * s[0].y;
+        const float pi = s[1].y * s[0].x - s[1].x * s[0].y;
+        p.det_phase[o] = atan2f(pi, pr);
+
+        uint8_t flags = p.det_flags[o];
+        if (!scan) {
+            p.det_adeg[o] = esprit_deg<AP>(s, M, p.esprit_scale);
+            p.det_aidx[o] = -1;
+            continue;
+        }
+        // lags R_k, k = 0..AP-1
+        float rr[AP], ri[AP];
+#pragma unroll
+        for (int k = 0; k < AP; ++k) {
+            float xr = 0.f, xi = 0.f;
+#pragma unroll
+            for (int m = 0; m + k < AP; ++m) {
+                xr = fmaf(s[m + k].x, s[m].x, xr);
+                xr = fmaf(s[m + k].y, s[m].y, xr);
+                xi = fmaf(s[m + k].y, s[m].x, xi);
+                xi = fmaf(-s[m + k].x, s[m].y, xi);
+            }
+            rr[k] = xr;
+            ri[k] = xi;
+        }
+        float best = -3.0e38f, second = -3.0e38f;
+        int bi = 0;
+        const float* t = tab;
+        for (int g = 0; g < p.G; ++g, t += p.scan_stride) {
+            float acc = 0.f;
+#pragma unroll
+            for (int k = 1; k < AP; ++k) {
+                acc = fmaf(rr[k], t[2 * (k - 1)], acc);
+                acc = fmaf(ri[k], t[2 * (k - 1) + 1], acc);
+            }
+            if (acc > best) { second = best; best = acc; bi = g; }
+            else if (acc > second) second = acc;
+        }
+        const float pbest = rr[0] + 2.f * best;
+        if (2.f * (best - second) <= p.tie_eps * fabsf(pbest)) flags |= RS_FLAG_TIE;
+        if (p.method == RS_METHOD_MUSIC) {
+            const float full = (float)M * rr[0];
+            if (full - pbest <= 1e-4f * full) flags |= RS_FLAG_GUARD;
+        }
+        p.det_aidx[o] = bi;
+        p.det_adeg[o] = p.grid_deg[bi];
+        p.det_flags[o] = flags;
+    }
+}
+
+// warp-per-detection kernel for any A (used for A > 16): lanes scan the grid, snapshot in smem
+__global__ void __launch_bounds__(ANG_THREADS) angles_large_kernel(AngleArgs p) {
+    extern __shared__ float2 snap[];   // [warps][A]
+    const int seg = blockIdx.x;
+    const int n = p.det_count[seg];
+    if (n == 0) return;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int f = seg / p.nseg_per_frame;
+    const int M = p.A;
+    const float2* frame = p.rds + (size_t)f * p.R * p.D * M;
+    float2* s = snap + wid * M;
+    for (int i = wid; i < n; i += nw) {
+        const size_t o = (size_t)seg * p.seg_cap + i;
+        int a, r, d;
+        rs_split_key(p.det_key[o], a, r, d);
+        const float2* cell = frame + ((size_t)r * p.D + d) * M;
+        __syncwarp();
+        float e = 0.f;
+        for (int m = lane; m < M; m += 32) {
+            const float2 x = __ldg(cell + m);
+            s[m] = x;
+            e = fmaf(x.x, x.x, fmaf(x.y, x.y, e));
+        }
+#pragma unroll
+        for (int off = 16; off; off >>= 1) e += __shfl_xor_sync(0xffffffffu, e, off);
+        __syncwarp();
+        uint8_t flags = p.det_flags[o];
+        if (lane == 0) {
+            const float pr = s[1].x * s[0].x + s[1].y * s[0].y;
+            const float pi = s[1].y * s[0].x - s[1].x * s[0].y;
+            p.det_phase[o] = atan2f(pi, pr);
+        }
+        if (p.method == RS_METHOD_ESPRIT) {
+            // warp-cooperative sums in fp64
+            double alpha = 0, gamma = 0, br = 0, bi = 0;
+            for (int m = lane; m < M - 1; m += 32) {
+                const double xr = s[m].x, xi = s[m].y, yr = s[m + 1].x, yi = s[m + 1].y;
+                alpha += xr * xr + xi * xi; gamma += yr * yr + yi * yi;
+                br += xr * yr + xi * yi;    bi += xr * yi - xi * yr;
+            }
+#pragma unroll
+            for (int off = 16; off; off >>= 1) {
+                alpha += __shfl_xor_sync(0xffffffffu, alpha, off); gamma += __shfl_xor_sync(0xffffffffu, gamma, off);
+                br += __shfl_xor_sync(0xffffffffu, br, off);       bi += __shfl_xor_sync(0xffffffffu, bi, off);
+            }
+            const double half = 0.5 * (alpha - gamma);
+            const double lam = 0.5 * (alpha + gamma) + sqrt(half * half + br * br + bi * bi);
+            double v0r, v0i, v1r, v1i;
+            const double na = br * br + bi * bi + (lam - alpha) * (lam - alpha);
+            const double nb = (lam - gamma) * (lam - gamma) + br * br + bi * bi;
+            if (na >= nb) { v0r = br; v0i = bi; v1r = lam - alpha; v1i = 0; }
+            else          { v0r = lam - gamma; v0i = 0; v1r = br; v1i = -bi; }
+            double nr = 0, ni = 0;
+            for (int m = lane; m < M - 2; m += 32) {
+                const double x0r = s[m].x, x0i = s[m].y, x1r = s[m + 1].x, x1i = s[m + 1].y, x2r = s[m + 2].x, x2i = s[m + 2].y;
+                const double ur = v0r * x0r - v0i * x0i + v1r * x1r - v1i * x1i;
+                const double ui = v0r * x0i + v0i * x0r + v1r * x1i + v1i * x1r;
+                const double wr = v0r * x1r - v0i * x1i + v1r * x2r - v1i * x2i;
+                const double wi = v0r * x1i + v0i * x1r + v1r * x2i + v1i * x2r;
+                nr += ur * wr + ui * wi;
+                ni += ur * wi - ui * wr;
+            }
+#pragma unroll
+            for (int off = 16; off; off >>= 1) {
+                nr += __shfl_xor_sync(0xffffffffu, nr, off);
+                ni += __shfl_xor_sync(0xffffffffu, ni, off);
+            }
+            if (lane == 0) {
+                p.det_adeg[o] = (float)(asin(atan2(ni, nr) * p.esprit_scale) * (180.0 / 3.14159265358979323846));
+                p.det_aidx[o] = -1;
+            }
+            continue;
+        }
+        float best = -1.f, second = -1.f;
+        int bi = 0x7fffffff;
+        for (int g = lane; g < p.G; g += 32) {
+            float ar = 0.f, ai = 0.f;
+            const float2* st = p.steer + g;
+            for (int m = 0; m < M; ++m) {
+                const float2 w = __ldg(st + (size_t)m * p.G);     // a_g[m]; accumulate conj(a) * s
+                const float2 x = s[m];
+                ar = fmaf(w.x, x.x, fmaf(w.y, x.y, ar));
+                ai = fmaf(w.x, x.y, fmaf(-w.y, x.x, ai));
+            }
+            const float v = fmaf(ar, ar, ai * ai);
+            if (v > best) { second = best; best = v; bi = g; }
+            else if (v > second) second = v;
+        }
+        // warp arg-max with first-index tie break; second = best of the rest
+#pragma unroll
+        for (int off = 16; off; off >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, off);
+            const float os = __shfl_xor_sync(0xffffffffu, second, off);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+            if (ob > best || (ob == best && oi < bi)) { second = fmaxf(best, os); best = ob; bi = oi; }
+            else second = fmaxf(second, ob);
+        }
+        if (lane == 0) {
+            if ((best - second) <= p.tie_eps * best) flags |= RS_FLAG_TIE;
+            if (p.method == RS_METHOD_MUSIC) {
+                const float full = (float)M * e;
+                if (full - best <= 1e-4f * full) flags |= RS_FLAG_GUARD;
+            }
+            p.det_aidx[o] = bi;
+            p.det_adeg[o] = p.grid_deg[bi];
+            p.det_flags[o] = flags;
+        }
+    }
+}
+
+// ---- fp64 helpers for the legacy adapters -----------------------------------------------------
+__global__ void signatures_f64_kernel(const float2* __restrict__ rds, const uint32_t* __restrict__ keys,
+                                      const int32_t* __restrict__ frames, int n, double2* __restrict__ out, int R, int D,
+                                      int A) {
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= n) return;
+    int a, r, d;
+    rs_split_key(keys[i], a, r, d);
+    const float2* cell = rds + (((size_t)frames[i] * R + r) * D + d) * A;
+    double e = 0;
+    for (int m = lane; m < A; m += 32) {
+        const float2 x = cell[m];
+        e += (double)x.x * x.x + (double)x.y * x.y;
+    }
+#pragma unroll
+    for (int off = 16; off; off >>= 1) e += __shfl_xor_sync(0xffffffffu, e, off);
+    // angle_estimation.py:86-88: divide by sqrt(power) only when power > 0
+    const double sc = e > 0 ? sqrt(e) : 1.0;
+    for (int m = lane; m < A; m += 32) {
+        const float2 x = cell[m];
+        out[(size_t)i * A + m] = make_double2((double)x.x / sc, (double)x.y / sc);
+    }
+}
+
+__global__ void spectra_f64_kernel(const double2* __restrict__ sig, const double2* __restrict__ steer, int method, int A,
+                                   int G, double* __restrict__ out, int32_t* __restrict__ aidx) {
+    extern __shared__ double2 sm_s[];   // [A]
+    __shared__ double red_v[256];
+    __shared__ int red_i[256];
+    const int i = blockIdx.x;
+    for (int m = threadIdx.x; m < A; m += blockDim.x) sm_s[m] = sig[(size_t)i * A + m];
+    __syncthreads();
+    double best = -1.0;
+    int bi = 0x7fffffff;
+    for (int g = threadIdx.x; g < G; g += blockDim.x) {
+        double ar = 0, ai = 0;
+        for (int m = 0; m < A; ++m) {
+            const double2 w = steer[(size_t)m * G + g];
+            const double2 x = sm_s[m];
+            ar += w.x * x.x + w.y * x.y;
+            ai += w.x * x.y - w.y * x.x;
+        }
+        double v = ar * ar + ai * ai;
+        if (method == RS_METHOD_MUSIC) {
+            // a^H E_n E_n^H a = M - |a^H s|^2 for a unit-energy snapshot; guard at angle_estimation.py:149
+            const double den = fabs((double)A - v);
+            v = den > 1e-12 ? 1.0 / den : 0.0;
+        }
+        out[(size_t)i * G + g] = v;
+        if (v > best) { best = v; bi = g; }
+    }
+    red_v[threadIdx.x] = best;
+    red_i[threadIdx.x] = bi;
+    __syncthreads();
+    for (int s = blockDim.x >> 1; s; s >>= 1) {
+        if (threadIdx.x < s) {
+            const double ov = red_v[threadIdx.x + s];
+            const int oi = red_i[threadIdx.x + s];
+            if (ov > red_v[threadIdx.x] || (ov == red_v[threadIdx.x] && oi < red_i[threadIdx.x])) {
+                red_v[threadIdx.x] = ov;
+                red_i[threadIdx.x] = oi;
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) aidx[i] = red_i[0];
+}
+
+}  // namespace
+
+extern "C" int rs_angles(const void* rds, const float* scan_table, int scan_stride, const void* steer,
+                         const float* grid_deg, int G, int method, float tie_eps, double esprit_scale,
+                         const uint32_t* det_key, const int32_t* det_count, uint8_t* det_flags, int32_t* det_aidx,
+                         float* det_adeg, float* det_phase, int seg_cap, int nseg_per_frame, int F, int R, int D, int A,
+                         void* stream) {
+    RS_CHECK_ARG(rds && det_key && det_count && det_flags && det_aidx && det_adeg && det_phase, "rs_angles: null pointer");
+    RS_CHECK_ARG(method >= 0 && method <= 2, "rs_angles: unknown method %d", method);
+    RS_CHECK_ARG(A >= 2 && A <= RS_MAX_ANTENNAS, "rs_angles: need 2 <= A <= %d", RS_MAX_ANTENNAS);
+    RS_CHECK_ARG(F > 0 && R > 0 && D > 0 && seg_cap > 0 && nseg_per_frame > 0, "rs_angles: bad dims");
+    const bool scan = method != RS_METHOD_ESPRIT;
+    RS_CHECK_ARG(!scan || (G > 0 && grid_deg), "rs_angles: grid required");
+    AngleArgs p{(const float2*)rds, scan_table, scan_stride, (const float2*)steer, grid_deg, G, method, tie_eps,
+                esprit_scale, det_key, det_count, det_flags, det_aidx, det_adeg, det_phase, seg_cap, nseg_per_frame,
+                R, D, A};
+    const long long blocks = (long long)F * nseg_per_frame;
+    RS_CHECK_ARG(blocks < (1ll << 31), "rs_angles: too many segments");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (A <= 16) {
+        RS_CHECK_ARG(!scan || scan_table, "rs_angles: scan_table required for A <= 16");
+        const int ap = A <= 2 ? 2 : A <= 4 ? 4 : A <= 8 ? 8 : 16;
+        int need_stride = 2 * (ap - 1);
+        need_stride = (need_stride + 3) & ~3;
+        RS_CHECK_ARG(!scan || scan_stride == need_stride, "rs_angles: scan_stride must be %d for A=%d", need_stride, A);
+        const size_t smem = scan ? (size_t)G * scan_stride * sizeof(float) : 0;
+        if (smem > (size_t)rs_smem_optin_limit()) {
+            rs_set_error("rs_angles: grid table needs %zu B of shared memory", smem);
+            return RS_ECAPACITY;
+        }
+#define LAUNCH_SMALL(AP)                                                                                     \
+    cudaFuncSetAttribute(angles_small_kernel<AP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
+    angles_small_kernel<AP><<<(unsigned)blocks, ANG_THREADS, smem, st>>>(p)
+        if (ap == 2) { LAUNCH_SMALL(2); }
+        else if (ap == 4) { LAUNCH_SMALL(4); }
+        else if (ap == 8) { LAUNCH_SMALL(8); }
+        else { LAUNCH_SMALL(16); }
+#undef LAUNCH_SMALL
+    } else {
+        RS_CHECK_ARG(!scan || steer, "rs_angles: steer table required for A > 16");
+        const size_t smem = (size_t)(ANG_THREADS / 32) * A * sizeof(float2);
+        angles_large_kernel<<<(unsigned)blocks, ANG_THREADS, smem, st>>>(p);
+    }
+    RS_CHECK_LAUNCH("rs_angles");
+    return RS_OK;
+}
+
+extern "C" int rs_signatures_f64(const void* rds, const uint32_t* keys, const int32_t* frames, int n, void* out, int F,
+                                 int R, int D, int A, void* stream) {
+    RS_CHECK_ARG(rds && keys && frames && out && n >= 0 && F > 0, "rs_signatures_f64: bad args");
+    if (n == 0) return RS_OK;
+    const int wpb = 8;
+    signatures_f64_kernel<<<(n + wpb - 1) / wpb, wpb * 32, 0, (cudaStream_t)stream>>>(
+        (const float2*)rds, keys, frames, n, (double2*)out, R, D, A);
+    RS_CHECK_LAUNCH("rs_signatures_f64");
+    return RS_OK;
+}
+
+extern "C" int rs_spectra_f64(const void* sig128, const void* steer128, int method, int n, int A, int G, double* out,
+                              int32_t* aidx, void* stream) {
+    RS_CHECK_ARG(sig128 && steer128 && out && aidx && n >= 0 && A > 0 && G > 0, "rs_spectra_f64: bad args");
+    RS_CHECK_ARG(method == RS_METHOD_MUSIC || method == RS_METHOD_BEAMFORMING, "rs_spectra_f64: bad method");
+    if (n == 0) return RS_OK;
+    spectra_f64_kernel<<<n, 256, (size_t)A * sizeof(double2), (cudaStream_t)stream>>>(
+        (const double2*)sig128, (const double2*)steer128, method, A, G, out, aidx);
+    RS_CHECK_LAUNCH("rs_spectra_f64");
+    return RS_OK;
+}

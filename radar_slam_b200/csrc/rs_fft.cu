@@ -1,0 +1,321 @@
+// Range and Doppler FFT stages.
+//
+//   rs_range_fft   : cube[F][A][C][S] * table[S] -> FFT over S -> zero bin 0 (DC removal) ->
+//                    range fftshift -> mid[F][S][A][C]           (dechirp.py:139,108,120,205,208,211)
+//   rs_doppler_fft : mid[F][S][A][C] -> FFT over C -> Doppler fftshift -> rds[F][S][C][A]
+//
+// Both are shared-memory Stockham autosort kernels: a CTA stages a block of rows, runs the radix
+// passes out of a host-built fp64-accurate twiddle table, and stores with the transpose fused so
+// that the next stage reads contiguous memory.  Any length whose prime factors are <= 13 is
+// supported (the reference's defaults are S=400, C=64; BASELINE configs are powers of two).
+#include "rs_common.cuh"
+
+namespace {
+
+struct FftPlan {
+    int n;
+    int npass;
+    int radix[16];
+};
+
+static bool make_plan(int n, FftPlan* p) {
+    p->n = n;
+    p->npass = 0;
+    int m = n;
+    // powers of two: as many radix-8 as possible, the remainder as 4 or 2
+    while (m % 8 == 0 && p->npass < 16) { p->radix[p->npass++] = 8; m /= 8; }
+    while (m % 4 == 0 && p->npass < 16) { p->radix[p->npass++] = 4; m /= 4; }
+    while (m % 2 == 0 && p->npass < 16) { p->radix[p->npass++] = 2; m /= 2; }
+    const int odd[] = {3, 5, 7, 11, 13};
+    for (int q : odd)
+        while (m % q == 0 && p->npass < 16) { p->radix[p->npass++] = q; m /= q; }
+    return m == 1;
+}
+
+template <int R>
+__device__ __forceinline__ void dft_small(float2 (&v)[R], const float2* tw, int tw_n) {
+    if constexpr (R == 2) {
+        float2 a = v[0], b = v[1];
+        v[0] = cadd(a, b);
+        v[1] = csub(a, b);
+    } else if constexpr (R == 4) {
+        float2 t0 = cadd(v[0], v[2]), t1 = csub(v[0], v[2]);
+        float2 t2 = cadd(v[1], v[3]), t3 = cmul_mi(csub(v[1], v[3]));
+        v[0] = cadd(t0, t2);
+        v[1] = cadd(t1, t3);
+        v[2] = csub(t0, t2);
+        v[3] = csub(t1, t3);
+    } else if constexpr (R == 8) {
+        // two radix-4 on even / odd inputs, then the radix-2 combine with w8^k
+        float2 e[4] = {v[0], v[2], v[4], v[6]};
+        float2 o[4] = {v[1], v[3], v[5], v[7]};
+        dft_small<4>(e, tw, tw_n);
+        dft_small<4>(o, tw, tw_n);
+        const float h = 0.70710678118654752440f;
+        o[1] = make_float2(h * (o[1].x + o[1].y), h * (o[1].y - o[1].x));      // * w8^1 = (1 - i)/sqrt2
+        o[2] = cmul_mi(o[2]);                                                    // * w8^2 = -i
+        o[3] = make_float2(h * (o[3].y - o[3].x), -h * (o[3].x + o[3].y));     // * w8^3 = (-1 - i)/sqrt2
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            v[k] = cadd(e[k], o[k]);
+            v[k + 4] = csub(e[k], o[k]);
+        }
+    } else {
+        // odd prime radix: direct O(R^2) DFT out of the length-n twiddle table (w_R^q = tw[q * n / R])
+        float2 x[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) x[r] = v[r];
+        const int step = tw_n / R;
+#pragma unroll
+        for (int q = 0; q < R; ++q) {
+            float2 acc = x[0];
+#pragma unroll
+            for (int r = 1; r < R; ++r) acc = cadd(acc, cmul(x[r], tw[((r * q) % R) * step]));
+            v[q] = acc;
+        }
+    }
+}
+
+// One Stockham pass over `nrows` rows held in shared memory.  Ns = product of the radices of the
+// passes already done.  in/out are distinct buffers with row strides ldi/ldo.
+template <int R>
+__device__ __forceinline__ void stockham_pass(const float2* __restrict__ in, int ldi, float2* __restrict__ out, int ldo,
+                                              int nrows, int n, int Ns, const float2* __restrict__ tw) {
+    const int per_row = n / R;
+    const int tstep = n / (Ns * R);
+    const int total = nrows * per_row;
+    for (int w = threadIdx.x; w < total; w += blockDim.x) {
+        const int b = w / per_row;
+        const int j = w - b * per_row;
+        const int k = j % Ns;
+        float2 v[R];
+        const float2* src = in + (size_t)b * ldi + j;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            float2 x = src[r * per_row];
+            if (r > 0 && Ns > 1) x = cmul(x, tw[k * r * tstep]);
+            v[r] = x;
+        }
+        dft_small<R>(v, tw, n);
+        float2* dst = out + (size_t)b * ldo + (j - k) * R + k;
+#pragma unroll
+        for (int r = 0; r < R; ++r) dst[r * Ns] = v[r];
+    }
+}
+
+// Runs every pass of `plan`; returns the buffer that holds the result.
+__device__ float2* run_plan(const FftPlan& plan, float2* a, float2* b, int ld, int nrows, const float2* tw) {
+    int Ns = 1;
+    float2* in = a;
+    float2* out = b;
+    for (int p = 0; p < plan.npass; ++p) {
+        const int R = plan.radix[p];
+        switch (R) {
+            case 8: stockham_pass<8>(in, ld, out, ld, nrows, plan.n, Ns, tw); break;
+            case 4: stockham_pass<4>(in, ld, out, ld, nrows, plan.n, Ns, tw); break;
+            case 2: stockham_pass<2>(in, ld, out, ld, nrows, plan.n, Ns, tw); break;
+            case 3: stockham_pass<3>(in, ld, out, ld, nrows, plan.n, Ns, tw); break;
+            case 5: stockham_pass<5>(in, ld, out, ld, nrows, plan.n, Ns, tw); break;
+            case 7: stockham_pass<7>(in, ld, out, ld, nrows, plan.n, Ns, tw); break;
+            case 11: stockham_pass<11>(in, ld, out, ld, nrows, plan.n, Ns, tw); break;
+            default: stockham_pass<13>(in, ld, out, ld, nrows, plan.n, Ns, tw); break;
+        }
+        Ns *= R;
+        __syncthreads();
+        float2* t = in; in = out; out = t;
+    }
+    return in;
+}
+
+// ---------------------------------------------------------------------------------------------
+// range stage: one CTA = CB consecutive chirps of one (frame, antenna)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+range_fft_kernel(const float2* __restrict__ cube, const float2* __restrict__ table, const float2* __restrict__ tw_g,
+                 float2* __restrict__ mid, FftPlan plan, int A, int C_total, int chirp0, int C_used, int S, int CB,
+                 int dc_removal) {
+    extern __shared__ float2 smem[];
+    const int ld = S + 1;
+    float2* tw = smem;                 // [S]
+    float2* bufA = tw + S;             // [CB][ld]
+    float2* bufB = bufA + CB * ld;     // [CB][ld]
+
+    const int blocks_per_fa = C_used / CB;
+    const int fa = blockIdx.x / blocks_per_fa;                 // f * A + a
+    const int c0 = (blockIdx.x - fa * blocks_per_fa) * CB;     // first chirp (within the subset)
+    const int f = fa / A, a = fa - f * A;
+
+    for (int i = threadIdx.x; i < S; i += blockDim.x) tw[i] = tw_g[i];
+    const float2* src = cube + ((size_t)fa * C_total + chirp0 + c0) * S;
+    for (int i = threadIdx.x; i < CB * S; i += blockDim.x) {
+        const int row = i / S, s = i - row * S;
+        bufA[row * ld + s] = cmul(src[i], __ldg(table + s));
+    }
+    __syncthreads();
+    float2* res = run_plan(plan, bufA, bufB, ld, CB, tw);
+
+    // transposed store with the range fftshift (np.fft.fftshift moves bin k to (k + S/2) mod S)
+    const int half = S / 2;
+    float2* dst = mid + (size_t)f * S * A * C_used + (size_t)a * C_used + c0;
+    for (int i = threadIdx.x; i < CB * S; i += blockDim.x) {
+        const int k = i / CB, row = i - k * CB;
+        float2 v = res[row * ld + k];
+        if (dc_removal && k == 0) v = make_float2(0.f, 0.f);
+        int p = k + half;
+        if (p >= S) p -= S;
+        dst[(size_t)p * A * C_used + row] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Doppler stage: rows of mid are (f, s, a) flattened, each C contiguous; one CTA = NB rows
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+doppler_fft_kernel(const float2* __restrict__ mid, const float2* __restrict__ tw_g, float2* __restrict__ rds,
+                   FftPlan plan, int A, int C, int NB, long long nrows_total) {
+    extern __shared__ float2 smem[];
+    const int ld = C + 1;
+    float2* tw = smem;
+    float2* bufA = tw + C;
+    float2* bufB = bufA + NB * ld;
+
+    const long long row0 = (long long)blockIdx.x * NB;
+    const int nb = (int)min((long long)NB, nrows_total - row0);
+    for (int i = threadIdx.x; i < C; i += blockDim.x) tw[i] = tw_g[i];
+    const float2* src = mid + row0 * C;
+    for (int i = threadIdx.x; i < nb * C; i += blockDim.x) {
+        const int b = i / C, c = i - b * C;
+        bufA[b * ld + c] = src[i];
+    }
+    __syncthreads();
+    float2* res = run_plan(plan, bufA, bufB, ld, nb, tw);
+
+    const int half = C / 2;
+    for (int i = threadIdx.x; i < nb * C; i += blockDim.x) {
+        const int k = i / nb, b = i - k * nb;
+        const long long gr = row0 + b;
+        const long long fs = gr / A;
+        const int a = (int)(gr - fs * A);
+        int p = k + half;
+        if (p >= C) p -= C;
+        rds[(fs * C + p) * A + a] = res[b * ld + k];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// layout converters for the legacy adapters
+// ---------------------------------------------------------------------------------------------
+__global__ void cell_to_ref_kernel(const float2* __restrict__ rds, float2* __restrict__ out, int A, long long cells) {
+    // rds [F][cells][A] -> out [F][A][cells]; tile transpose through shared memory
+    __shared__ float2 tile[32][33];
+    const long long f = blockIdx.z;
+    const long long cell0 = (long long)blockIdx.x * 32;
+    const int a0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        long long cell = cell0 + i;
+        int a = a0 + threadIdx.x;
+        if (cell < cells && a < A) tile[i][threadIdx.x] = rds[(f * cells + cell) * A + a];
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int a = a0 + i;
+        long long cell = cell0 + threadIdx.x;
+        if (cell < cells && a < A) out[(f * A + a) * cells + cell] = tile[threadIdx.x][i];
+    }
+}
+
+__global__ void ref_to_cell_kernel(const float2* __restrict__ in, float2* __restrict__ rds, int A, long long cells) {
+    __shared__ float2 tile[32][33];
+    const long long f = blockIdx.z;
+    const long long cell0 = (long long)blockIdx.x * 32;
+    const int a0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int a = a0 + i;
+        long long cell = cell0 + threadIdx.x;
+        if (cell < cells && a < A) tile[i][threadIdx.x] = in[(f * A + a) * cells + cell];
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        long long cell = cell0 + i;
+        int a = a0 + threadIdx.x;
+        if (cell < cells && a < A) rds[(f * cells + cell) * A + a] = tile[threadIdx.x][i];
+    }
+}
+
+static int largest_divisor_le(int n, int cap) {
+    int best = 1;
+    for (int d = 1; d <= cap && d <= n; ++d)
+        if (n % d == 0) best = d;
+    return best;
+}
+
+}  // namespace
+
+extern "C" int rs_range_fft(const void* cube, const void* table, const void* twiddle_s, void* mid, int F, int A,
+                            int C_total, int chirp0, int C_used, int S, int dc_removal, void* stream) {
+    RS_CHECK_ARG(cube && table && twiddle_s && mid, "rs_range_fft: null pointer");
+    RS_CHECK_ARG(F > 0 && A > 0 && A <= RS_MAX_ANTENNAS && S > 0 && S <= RS_MAX_RANGE_BINS, "rs_range_fft: bad F/A/S");
+    RS_CHECK_ARG(C_used > 0 && chirp0 >= 0 && chirp0 + C_used <= C_total && C_used <= RS_MAX_DOPPLER_BINS,
+                 "rs_range_fft: bad chirp subset");
+    FftPlan plan;
+    RS_CHECK_ARG(make_plan(S, &plan), "rs_range_fft: S=%d has a prime factor > 13", S);
+    const int limit = rs_smem_optin_limit();
+    int CB = largest_divisor_le(C_used, 16);
+    auto need = [&](int cb) { return (size_t)(S + 2 * cb * (S + 1)) * sizeof(float2); };
+    while (CB > 1 && need(CB) > (size_t)limit / 2) CB = largest_divisor_le(C_used, CB - 1);
+    if (need(CB) > (size_t)limit) {
+        rs_set_error("rs_range_fft: S=%d needs %zu B of shared memory", S, need(CB));
+        return RS_ECAPACITY;
+    }
+    cudaFuncSetAttribute(range_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need(CB));
+    const long long blocks = (long long)F * A * (C_used / CB);
+    RS_CHECK_ARG(blocks < (1ll << 31), "rs_range_fft: too many blocks");
+    range_fft_kernel<<<(unsigned)blocks, 256, need(CB), (cudaStream_t)stream>>>(
+        (const float2*)cube, (const float2*)table, (const float2*)twiddle_s, (float2*)mid, plan, A, C_total, chirp0,
+        C_used, S, CB, dc_removal);
+    RS_CHECK_LAUNCH("rs_range_fft");
+    return RS_OK;
+}
+
+extern "C" int rs_doppler_fft(const void* mid, const void* twiddle_c, void* rds, int F, int A, int C, int S,
+                              void* stream) {
+    RS_CHECK_ARG(mid && twiddle_c && rds, "rs_doppler_fft: null pointer");
+    RS_CHECK_ARG(F > 0 && A > 0 && A <= RS_MAX_ANTENNAS && S > 0 && C > 0 && C <= RS_MAX_DOPPLER_BINS,
+                 "rs_doppler_fft: bad dims");
+    FftPlan plan;
+    RS_CHECK_ARG(make_plan(C, &plan), "rs_doppler_fft: C=%d has a prime factor > 13", C);
+    const int limit = rs_smem_optin_limit();
+    int NB = (A <= 16) ? A * (16 / A) : largest_divisor_le(A, 16);
+    auto need = [&](int nb) { return (size_t)(C + 2 * nb * (C + 1)) * sizeof(float2); };
+    while (NB > 1 && need(NB) > (size_t)limit / 2) NB = (NB % 2 == 0) ? NB / 2 : NB - 1;
+    if (need(NB) > (size_t)limit) {
+        rs_set_error("rs_doppler_fft: C=%d needs %zu B of shared memory", C, need(NB));
+        return RS_ECAPACITY;
+    }
+    cudaFuncSetAttribute(doppler_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need(NB));
+    const long long nrows = (long long)F * S * A;
+    const long long blocks = (nrows + NB - 1) / NB;
+    RS_CHECK_ARG(blocks < (1ll << 31), "rs_doppler_fft: too many blocks");
+    doppler_fft_kernel<<<(unsigned)blocks, 256, need(NB), (cudaStream_t)stream>>>(
+        (const float2*)mid, (const float2*)twiddle_c, (float2*)rds, plan, A, C, NB, nrows);
+    RS_CHECK_LAUNCH("rs_doppler_fft");
+    return RS_OK;
+}
+
+extern "C" int rs_rds_to_reference_layout(const void* rds, void* out, int F, int A, int C, int S, void* stream) {
+    RS_CHECK_ARG(rds && out && F > 0 && A > 0 && C > 0 && S > 0, "rs_rds_to_reference_layout: bad args");
+    const long long cells = (long long)S * C;
+    dim3 grid((unsigned)((cells + 31) / 32), (unsigned)((A + 31) / 32), (unsigned)F);
+    cell_to_ref_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>((const float2*)rds, (float2*)out, A, cells);
+    RS_CHECK_LAUNCH("rs_rds_to_reference_layout");
+    return RS_OK;
+}
+
+extern "C" int rs_rds_from_reference_layout(const void* rds_ref, void* out, int F, int A, int C, int S, void* stream) {
+    RS_CHECK_ARG(rds_ref && out && F > 0 && A > 0 && C > 0 && S > 0, "rs_rds_from_reference_layout: bad args");
+    const long long cells = (long long)S * C;
+    dim3 grid((unsigned)((cells + 31) / 32), (unsigned)((A + 31) / 32), (unsigned)F);
+    ref_to_cell_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>((const float2*)rds_ref, (float2*)out, A, cells);
+    RS_CHECK_LAUNCH("rs_rds_from_reference_layout");
+    return RS_OK;
+}

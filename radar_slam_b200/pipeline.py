@@ -1,0 +1,295 @@
+"""Batched device API of the B200 hot path: cube[F,A,C,S] -> RDS -> detections -> angles -> ego-velocity.
+
+This is the layer the drop-in classes under ``src/`` and ``bench.py`` call.  torch owns memory and
+streams; all arithmetic runs in libradarslam_b200.so (hand-written sm_100a CUDA).  There is no CPU
+fallback: constructing a pipeline without a CUDA device or without the library raises.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib, tables
+
+
+@dataclass
+class RadarConfig:
+    """Union of the constructor arguments of the reference's hot-path classes."""
+    fc: float = 77e9
+    bandwidth: float = 1e9
+    chirp_duration: float = 40e-6
+    pri: float = 100e-6
+    num_chirps: int = 64
+    sampling_rate: float = 10e6
+    window_type: str = "hann"
+    dc_removal: bool = True
+    num_antennas: int = 8
+    antenna_spacing: Optional[float] = None
+    search_range: Tuple[float, float] = (-90, 90)
+    search_resolution: float = 0.5
+    method: str = "music"
+    threshold_db: float = -20.0
+    min_range: float = 1.0
+    max_range: float = 200.0
+    lambda_c_solver: Optional[float] = None      # VelocitySolver(lambda_c=...)
+    dt: float = 0.1
+    velocity_bound: float = 50.0                 # velocity_solver.py:216
+    irls_iters: int = 0                          # robust reweighting (off: the reference has none)
+    huber_delta: float = 1.0
+    det_eps: float = 2e-6                        # guard bands for decisions fp32 cannot settle
+    tie_eps: float = 4e-6
+
+    @property
+    def lambda_c(self) -> float:
+        return tables.C0 / self.fc
+
+    @property
+    def samples_per_chirp(self) -> int:
+        return int(self.chirp_duration * self.sampling_rate)
+
+    @property
+    def chirp_rate(self) -> float:
+        return self.bandwidth / self.chirp_duration
+
+    @property
+    def range_resolution(self) -> float:
+        return tables.C0 / (2 * self.bandwidth)
+
+    @property
+    def spacing(self) -> float:
+        return self.antenna_spacing or (self.lambda_c / 2)
+
+
+@dataclass
+class Detections:
+    """Per-(frame, tile) segments written by rs_detect / rs_angles (layout in radar_slam_b200.h)."""
+    key: torch.Tensor
+    power: torch.Tensor
+    flags: torch.Tensor
+    aidx: torch.Tensor
+    adeg: torch.Tensor
+    phase: torch.Tensor
+    count: torch.Tensor
+    overflow: torch.Tensor
+    seg_cap: int
+    ntiles: int
+    F: int
+    R: int
+    D: int
+    A: int
+
+    def valid_mask(self) -> torch.Tensor:
+        n = self.F * self.ntiles
+        slot = torch.arange(self.seg_cap, device=self.key.device, dtype=torch.int32)
+        m = slot[None, :] < self.count[:n, None]
+        m &= (self.flags[: n * self.seg_cap].view(n, self.seg_cap) & _lib.RS_FLAG_DROPPED) == 0
+        return m
+
+    def per_frame_counts(self) -> torch.Tensor:
+        return self.valid_mask().view(self.F, -1).sum(dim=1)
+
+    def frame(self, f: int) -> Dict[str, np.ndarray]:
+        """Host copy of frame f's detections in the reference's order (antenna, range, doppler)."""
+        lo, hi = f * self.ntiles, (f + 1) * self.ntiles
+        m = self.valid_mask()[lo:hi].reshape(-1)
+        sl = slice(lo * self.seg_cap, hi * self.seg_cap)
+        key = self.key[sl][m].to(torch.int64) & 0xFFFFFFFF
+        order = torch.argsort(key)
+        key = key[order]
+        out = {"key": key.cpu().numpy().astype(np.uint32)}
+        for name in ("power", "flags", "aidx", "adeg", "phase"):
+            out[name] = getattr(self, name)[sl][m][order].cpu().numpy()
+        k = out["key"]
+        out["antenna"] = (k >> 24).astype(np.int64)
+        out["range_bin"] = ((k >> 12) & 0xFFF).astype(np.int64)
+        out["doppler_bin"] = (k & 0xFFF).astype(np.int64)
+        return out
+
+
+class FramePipeline:
+    def __init__(self, cfg: RadarConfig, device: Optional[str] = None, seg_cap: Optional[int] = None):
+        if not torch.cuda.is_available():
+            raise _lib.RadarSlamError("radar_slam_b200 needs a CUDA device (no CPU fallback)")
+        self.lib = _lib.load()
+        self.cfg = cfg
+        self.device = torch.device(device or f"cuda:{torch.cuda.current_device()}")
+        if cfg.method not in _lib.METHODS:
+            raise ValueError(f"Unknown method: {cfg.method}")
+        self.seg_cap_override = seg_cap
+        self._tab: Dict = {}
+        self._ws: Dict = {}
+        self.launches = 0          # kernels of libradarslam_b200 launched since the last reset
+
+    # ------------------------------------------------------------------ host tables (cached)
+    def _dev(self, arr: np.ndarray) -> torch.Tensor:
+        return torch.from_numpy(np.ascontiguousarray(arr)).to(self.device)
+
+    def _fft_tables(self, S: int, C: int):
+        key = ("fft", S, C)
+        if key not in self._tab:
+            c = self.cfg
+            tab = tables.dechirp_table(c.fc, c.chirp_rate, c.chirp_duration, S, c.window_type)
+            self._tab[key] = (self._dev(tab.astype(np.complex64)), self._dev(tables.twiddles(S)),
+                              self._dev(tables.twiddles(C)), self._dev(tab))
+        return self._tab[key]
+
+    def _angle_tables(self, A: int):
+        key = ("ang", A)
+        if key not in self._tab:
+            c = self.cfg
+            grid = tables.azimuth_grid(c.search_range, c.search_resolution)
+            scan, stride = tables.scan_table(grid, c.spacing, c.lambda_c, A)
+            pos = np.arange(A) * c.spacing
+            steer = tables.steering(grid, pos, c.lambda_c)
+            self._tab[key] = {
+                "grid": grid, "G": len(grid), "stride": stride,
+                "scan": self._dev(scan), "grid_f32": self._dev(grid.astype(np.float32)),
+                "steer64": self._dev(steer.astype(np.complex64)) if A > 16 else None,
+                "steer128": self._dev(steer), "grid_cs": self._dev(tables.grid_cos_sin(grid)),
+            }
+        return self._tab[key]
+
+    def _gate(self, R: int, min_range: float, max_range: float) -> torch.Tensor:
+        key = ("gate", R, float(min_range), float(max_range))
+        if key not in self._tab:
+            self._tab[key] = self._dev(tables.range_gate(self.cfg.range_resolution, R, min_range, max_range))
+        return self._tab[key]
+
+    def _buf(self, name: str, shape, dtype) -> torch.Tensor:
+        n = int(np.prod(shape))
+        cur = self._ws.get(name)
+        if cur is None or cur.dtype != dtype or cur.numel() < n:
+            cur = torch.empty(n, dtype=dtype, device=self.device)
+            self._ws[name] = cur
+        return cur[:n].view(*shape)
+
+    @property
+    def stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    # ------------------------------------------------------------------ stages
+    def range_doppler(self, cube: torch.Tensor, chirp_subset: Optional[Tuple[int, int]] = None,
+                      out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """cube complex64 [F, A, C, S] on the device -> cell-major RDS complex64 [F, S, C', A]."""
+        assert cube.is_cuda and cube.dtype == torch.complex64 and cube.dim() == 4 and cube.is_contiguous()
+        F, A, C, S = cube.shape
+        c0, c1 = (0, C) if chirp_subset is None else chirp_subset
+        c0, c1 = max(0, min(C, int(c0))), max(0, min(C, int(c1)))
+        Cu = c1 - c0
+        if Cu <= 0:
+            raise ValueError("empty chirp subset")
+        tab, tw_s, tw_c, _ = self._fft_tables(S, Cu)
+        mid = self._buf("mid", (F, S, A, Cu), torch.complex64)
+        rds = out if out is not None else torch.empty((F, S, Cu, A), dtype=torch.complex64, device=self.device)
+        st = self.stream
+        _lib.check(self.lib.rs_range_fft(cube.data_ptr(), tab.data_ptr(), tw_s.data_ptr(), mid.data_ptr(),
+                                         F, A, C, c0, Cu, S, int(self.cfg.dc_removal), st), "rs_range_fft")
+        _lib.check(self.lib.rs_doppler_fft(mid.data_ptr(), tw_c.data_ptr(), rds.data_ptr(), F, A, Cu, S, st),
+                   "rs_doppler_fft")
+        return rds
+
+    def seg_cap_for(self, R: int, D: int, A: int) -> Tuple[int, int]:
+        tr, td, ntiles = _lib.detect_tiling(R, D, A)
+        cap = self.seg_cap_override or max(32, (tr * td * min(A, 8) + 3) // 4)
+        return cap, ntiles
+
+    def detect(self, rds: torch.Tensor, threshold_db: Optional[float] = None, min_range: Optional[float] = None,
+               max_range: Optional[float] = None, workspace: bool = False) -> Detections:
+        assert rds.is_cuda and rds.dtype == torch.complex64 and rds.dim() == 4 and rds.is_contiguous()
+        F, R, D, A = rds.shape
+        c = self.cfg
+        thr = tables.power_threshold(c.threshold_db if threshold_db is None else threshold_db)
+        gate = self._gate(R, c.min_range if min_range is None else min_range, c.max_range if max_range is None else max_range)
+        cap, ntiles = self.seg_cap_for(R, D, A)
+        n = F * ntiles * cap
+        alloc = (lambda nm, shp, dt: self._buf(nm, shp, dt)) if workspace else \
+            (lambda nm, shp, dt: torch.empty(shp, dtype=dt, device=self.device))
+        det = Detections(
+            key=alloc("det_key", (n,), torch.int32), power=alloc("det_power", (n,), torch.float32),
+            flags=alloc("det_flags", (n,), torch.uint8), aidx=alloc("det_aidx", (n,), torch.int32),
+            adeg=alloc("det_adeg", (n,), torch.float32), phase=alloc("det_phase", (n,), torch.float32),
+            count=alloc("det_count", (F * ntiles,), torch.int32), overflow=alloc("det_overflow", (F,), torch.int32),
+            seg_cap=cap, ntiles=ntiles, F=F, R=R, D=D, A=A)
+        _lib.check(self.lib.rs_detect(rds.data_ptr(), gate.data_ptr(), thr, c.det_eps, det.key.data_ptr(),
+                                      det.power.data_ptr(), det.flags.data_ptr(), det.count.data_ptr(),
+                                      det.overflow.data_ptr(), cap, F, R, D, A, self.stream), "rs_detect")
+        return det
+
+    def angles(self, rds: torch.Tensor, det: Detections, method: Optional[str] = None) -> Detections:
+        c = self.cfg
+        method = method or c.method
+        if method not in _lib.METHODS:
+            raise ValueError(f"Unknown method: {method}")
+        t = self._angle_tables(det.A)
+        esprit_scale = c.lambda_c / (2 * np.pi * c.spacing)                       # angle_estimation.py:218
+        _lib.check(self.lib.rs_angles(
+            rds.data_ptr(), t["scan"].data_ptr(), t["stride"], _lib.ptr(t["steer64"]), t["grid_f32"].data_ptr(), t["G"],
+            _lib.METHODS[method], c.tie_eps, esprit_scale, det.key.data_ptr(), det.count.data_ptr(),
+            det.flags.data_ptr(), det.aidx.data_ptr(), det.adeg.data_ptr(), det.phase.data_ptr(),
+            det.seg_cap, det.ntiles, det.F, det.R, det.D, det.A, self.stream), "rs_angles")
+        return det
+
+    def velocity(self, det: Detections, out: Optional[torch.Tensor] = None, lambda_c: Optional[float] = None,
+                 dt: Optional[float] = None, use_grid: bool = True) -> torch.Tensor:
+        """-> float64 [F, 8] = v_x v_y v_z w_x w_y w_z success n_targets."""
+        c = self.cfg
+        lam = lambda_c or c.lambda_c_solver or c.lambda_c
+        k = 4 * np.pi * (c.dt if dt is None else dt) / lam                        # velocity_solver.py:109
+        t = self._angle_tables(det.A)
+        vel = out if out is not None else torch.empty((det.F, 8), dtype=torch.float64, device=self.device)
+        assert vel.is_contiguous() and vel.dtype == torch.float64
+        _lib.check(self.lib.rs_velocity_ls(
+            det.aidx.data_ptr(), det.adeg.data_ptr(), det.phase.data_ptr(), det.flags.data_ptr(), det.count.data_ptr(),
+            t["grid_cs"].data_ptr() if use_grid else 0, k, c.velocity_bound, c.irls_iters, c.huber_delta,
+            vel.data_ptr(), det.seg_cap, det.ntiles, det.F, self.stream), "rs_velocity_ls")
+        return vel
+
+    # ------------------------------------------------------------------ whole path
+    def process(self, cube: torch.Tensor, chunk_frames: int = 64, vel_out: Optional[torch.Tensor] = None,
+                keep: bool = False):
+        """Device-resident batch: returns vel float64 [F, 8] (and the last chunk's RDS / detections when
+        keep=True and the batch is a single chunk)."""
+        F = cube.shape[0]
+        vel = vel_out if vel_out is not None else torch.empty((F, 8), dtype=torch.float64, device=self.device)
+        last = None
+        for lo in range(0, F, chunk_frames):
+            hi = min(F, lo + chunk_frames)
+            n = hi - lo
+            _, A, C, S = cube.shape
+            rds = self.range_doppler(cube[lo:hi], out=None if keep else self._buf("rds", (n, S, C, A), torch.complex64))
+            det = self.detect(rds, workspace=not keep)
+            self.angles(rds, det)
+            self.velocity(det, out=vel[lo:hi])
+            self.launches += 5
+            last = (rds, det)
+        return (vel, last[0], last[1]) if keep else vel
+
+    def process_host(self, cube_host: torch.Tensor, chunk_frames: int = 64) -> torch.Tensor:
+        """End-to-end with HOST buffers: pinned cube[F,A,C,S] -> pinned vel[F,8]; H2D and D2H copies run on
+        a second stream and overlap the kernels of the neighbouring chunk."""
+        assert not cube_host.is_cuda and cube_host.dtype == torch.complex64
+        F, A, C, S = cube_host.shape
+        vel_dev = torch.empty((F, 8), dtype=torch.float64, device=self.device)
+        vel_host = torch.empty((F, 8), dtype=torch.float64, pin_memory=True)
+        copy_stream = self._ws.setdefault("copy_stream", torch.cuda.Stream(self.device))
+        main = torch.cuda.current_stream(self.device)
+        stage = [self._buf(f"stage{i}", (chunk_frames, A, C, S), torch.complex64) for i in range(2)]
+        ev_h2d = [torch.cuda.Event() for _ in range(2)]
+        ev_free = [torch.cuda.Event() for _ in range(2)]
+        for ci, lo in enumerate(range(0, F, chunk_frames)):
+            hi = min(F, lo + chunk_frames)
+            b = ci & 1
+            with torch.cuda.stream(copy_stream):
+                if ci >= 2:
+                    copy_stream.wait_event(ev_free[b])
+                stage[b][: hi - lo].copy_(cube_host[lo:hi], non_blocking=True)
+                ev_h2d[b].record(copy_stream)
+            main.wait_event(ev_h2d[b])
+            self.process(stage[b][: hi - lo], chunk_frames=chunk_frames, vel_out=vel_dev[lo:hi])
+            ev_free[b].record(main)
+        vel_host.copy_(vel_dev, non_blocking=True)
+        main.synchronize()
+        return vel_host

@@ -1,0 +1,95 @@
+"""Host-side constant tables for the CUDA path, evaluated in fp64 with the reference's own
+expressions and rounded once (the chirp phase reaches ~2e6 cycles and cannot be
+evaluated in fp32 on the device).  Pure numpy; no oracle import."""
+from __future__ import annotations
+
+from typing import Tuple
+
+import numpy as np
+from scipy.signal import windows as _windows
+
+C0 = 3e8
+
+
+def window(window_type: str, n: int) -> np.ndarray:
+    """Symmetric scipy windows, ValueError on unknown names (dechirp.py:96-106)."""
+    if window_type == "hann":
+        return _windows.hann(n)
+    if window_type == "hamming":
+        return _windows.hamming(n)
+    if window_type == "blackman":
+        return _windows.blackman(n)
+    raise ValueError(f"Unknown window type: {window_type}")
+
+
+def reference_chirp(fc: float, chirp_rate: float, chirp_duration: float, n: int) -> np.ndarray:
+    """dechirp.py:74-83."""
+    t = np.linspace(0, chirp_duration, n)
+    phase = 2 * np.pi * (fc * t + 0.5 * chirp_rate * t ** 2)
+    return np.exp(1j * phase)
+
+
+def dechirp_table(fc, chirp_rate, chirp_duration, n, window_type) -> np.ndarray:
+    """conj(ref) * window, the whole per-sample factor of process_chirp (dechirp.py:139,108). c128[n]."""
+    return np.conj(reference_chirp(fc, chirp_rate, chirp_duration, n)) * window(window_type, n)
+
+
+def twiddles(n: int) -> np.ndarray:
+    """exp(-2 pi i k / n), k < n, complex64 rounded from fp64."""
+    k = np.arange(n)
+    return np.exp(-2j * np.pi * k / n).astype(np.complex64)
+
+
+def azimuth_grid(search_range: Tuple[float, float], search_resolution: float) -> np.ndarray:
+    """angle_estimation.py:59."""
+    return np.arange(search_range[0], search_range[1] + search_resolution, search_resolution)
+
+
+def steering(grid_deg: np.ndarray, positions: np.ndarray, lambda_c: float) -> np.ndarray:
+    """exp(i 2 pi pos sin(az) / lambda) for every (antenna, grid angle): c128 [A][G]
+    (angle_estimation.py:102-107, transposed so a grid scan reads contiguous memory)."""
+    az = np.radians(grid_deg)
+    phases = 2 * np.pi * positions[:, None] * np.sin(az)[None, :] / lambda_c
+    return np.exp(1j * phases)
+
+
+def padded_antennas(A: int) -> int:
+    return 2 if A <= 2 else 4 if A <= 4 else 8 if A <= 8 else 16
+
+
+def scan_table(grid_deg: np.ndarray, spacing: float, lambda_c: float, A: int) -> Tuple[np.ndarray, int]:
+    """(cos k phi_g, sin k phi_g), k = 1..A_pad-1, float32 [G][stride] for the lag-form scan; a ULA
+    with positions m*d has steering phase m*phi_g, phi_g = 2 pi d sin(az_g) / lambda."""
+    ap = padded_antennas(A)
+    stride = (2 * (ap - 1) + 3) & ~3
+    az = np.radians(grid_deg)
+    tab = np.zeros((len(grid_deg), stride), dtype=np.float64)
+    for k in range(1, ap):
+        ph = 2 * np.pi * (k * spacing) * np.sin(az) / lambda_c
+        tab[:, 2 * (k - 1)] = np.cos(ph)
+        tab[:, 2 * (k - 1) + 1] = np.sin(ph)
+    return tab.astype(np.float32), stride
+
+
+def grid_cos_sin(grid_deg: np.ndarray) -> np.ndarray:
+    """(cos, sin) of np.radians(grid) -- what velocity_solver.py:94-97 evaluates per target. f64 [G][2]."""
+    az = np.radians(grid_deg)
+    return np.stack([np.cos(az), np.sin(az)], axis=1)
+
+
+def power_threshold(threshold_db: float) -> float:
+    """p > thr  <=>  10 log10(p + 1e-12) > threshold_db   (dechirp.py:238, 252)."""
+    return float(10.0 ** (threshold_db / 10.0) - 1e-12)
+
+
+def range_axis(range_resolution: float, range_bins: int) -> np.ndarray:
+    return np.linspace(0, range_resolution * range_bins, range_bins)          # dechirp.py:241
+
+
+def doppler_axis(sampling_rate: float, doppler_bins: int) -> np.ndarray:
+    return np.linspace(-sampling_rate / 2, sampling_rate / 2, doppler_bins)   # dechirp.py:242
+
+
+def range_gate(range_resolution: float, range_bins: int, min_range: float, max_range: float) -> np.ndarray:
+    r = range_axis(range_resolution, range_bins)
+    return ((r >= min_range) & (r <= max_range)).astype(np.uint8)              # dechirp.py:263

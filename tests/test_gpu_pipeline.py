@@ -1,0 +1,190 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle and the committed reference
+outputs.  Tolerances are BASELINE.json's: detection bin indices bit-exact, range-Doppler
+magnitudes within 1e-4 relative, angles within 0.05 deg, ego-velocity within 1e-3 m/s.
+
+Two decisions are not decidable from complex64 inputs in fp32 arithmetic and are tested the
+way DESIGN.md states them: a cell whose power is within the guard band of a neighbour / the
+threshold, and a grid argmax whose top-2 values are closer than the tie band.  The CUDA path
+must FLAG those (RS_FLAG_NEARMAX / RS_FLAG_TIE); any unflagged disagreement fails the test.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import radar_oracle as orc
+from golden_util import CASE_NAMES, load_case, params_of, make_input
+
+pytestmark = pytest.mark.gpu
+
+FLAG_TIE, FLAG_NEARMAX, FLAG_GUARD = 1, 2, 4
+
+
+def _pipeline(cfg, p, method="music", **kw):
+    from radar_slam_b200 import RadarConfig, FramePipeline
+    rc = RadarConfig(fc=p.fc, bandwidth=p.bandwidth, chirp_duration=p.chirp_duration, pri=p.pri,
+                     num_chirps=p.num_chirps, sampling_rate=p.sampling_rate, window_type=p.window_type,
+                     dc_removal=p.dc_removal, num_antennas=p.num_antennas, search_resolution=cfg["res"],
+                     method=method, threshold_db=cfg["thr"], **kw)
+    return FramePipeline(rc)
+
+
+@pytest.fixture(scope="module", params=CASE_NAMES)
+def case(request):
+    g, cfg = load_case(request.param)
+    p = params_of(cfg)
+    cube = make_input(cfg)
+    rds_ref = orc.range_doppler_spectrum(cube.astype(np.complex128), p)
+    pk = orc.extract_peaks(rds_ref, p, threshold_db=cfg["thr"])
+    pipe = _pipeline(cfg, p)
+    dev = torch.from_numpy(cube[None]).cuda()
+    rds = pipe.range_doppler(dev)
+    det = pipe.detect(rds)
+    pipe.angles(rds, det)
+    vel = pipe.velocity(det)
+    torch.cuda.synchronize()
+    return dict(g=g, cfg=cfg, p=p, cube=cube, rds_ref=rds_ref, pk=pk, pipe=pipe, rds=rds, det=det, vel=vel)
+
+
+def test_rds_magnitudes(case):
+    rds = case["rds"][0].permute(2, 0, 1).cpu().numpy().astype(np.complex128)     # [S,C,A] -> [A,S,C]
+    ref = case["rds_ref"]
+    assert rds.shape == ref.shape
+    mx = np.abs(ref).max()
+    assert np.abs(rds - ref).max() <= 2e-6 * mx
+    big = np.abs(ref) > 1e-3 * mx
+    rel = np.abs(np.abs(rds[big]) - np.abs(ref[big])) / np.abs(ref[big])
+    assert rel.max() < 1e-4
+    # committed reference sample
+    g = case["g"]
+    got = rds.reshape(-1)[g["rds_sample_idx"]]
+    assert np.abs(got - g["rds_sample_val"]).max() <= 2e-6 * g["rds_abs_max"]
+
+
+def test_detection_indices_exact(case):
+    pk, det = case["pk"], case["det"]
+    assert int(det.overflow.sum()) == 0
+    d = det.frame(0)
+    want = (pk["antenna"].astype(np.uint32) << 24) | (pk["range_bin"].astype(np.uint32) << 12) | pk["doppler_bin"].astype(np.uint32)
+    got = d["key"]
+    if np.array_equal(got, want):
+        return
+    # any disagreement must sit inside the fp32 guard band (and, if reported, carry the flag)
+    ref_p = np.abs(case["rds_ref"]) ** 2
+    thr = 10 ** (case["cfg"]["thr"] / 10) - 1e-12
+    from scipy.ndimage import maximum_filter
+    foot = np.ones((1, 3, 3), bool)
+    foot[0, 1, 1] = False
+    nb = maximum_filter(ref_p, footprint=foot, mode="reflect")
+    for k in np.setxor1d(got, want):
+        a, r, dd = int(k >> 24), int((k >> 12) & 0xFFF), int(k & 0xFFF)
+        pc = ref_p[a, r, dd]
+        margin = min(abs(pc - nb[a, r, dd]) / pc, abs(pc - thr) / max(thr, 1e-30))
+        assert margin < 1e-5, (a, r, dd, margin)
+        hit = np.nonzero(got == k)[0]
+        if len(hit):
+            assert d["flags"][hit[0]] & FLAG_NEARMAX
+
+
+def test_detection_power(case):
+    pk = case["pk"]
+    d = case["det"].frame(0)
+    want = (pk["antenna"].astype(np.uint32) << 24) | (pk["range_bin"].astype(np.uint32) << 12) | pk["doppler_bin"].astype(np.uint32)
+    common, ia, ib = np.intersect1d(d["key"], want, return_indices=True)
+    db = 10 * np.log10(d["power"][ia].astype(np.float64) + 1e-12)
+    assert np.abs(db - pk["power_db"][ib]).max() < 1e-4
+
+
+def _angle_check(case, method):
+    cfg, p, pk, pipe = case["cfg"], case["p"], case["pk"], case["pipe"]
+    det = pipe.detect(case["rds"])
+    pipe.angles(case["rds"], det, method=method)
+    torch.cuda.synchronize()
+    d = det.frame(0)
+    want = (pk["antenna"].astype(np.uint32) << 24) | (pk["range_bin"].astype(np.uint32) << 12) | pk["doppler_bin"].astype(np.uint32)
+    common, ia, ib = np.intersect1d(d["key"], want, return_indices=True)
+    assert len(common) >= 0.999 * len(want)
+    sigs = orc.spatial_signatures(case["rds_ref"], pk["range_bin"][ib], pk["doppler_bin"][ib])
+    return d, ia, ib, sigs
+
+
+@pytest.mark.parametrize("method", ["music", "beamforming"])
+def test_grid_angles(case, method):
+    cfg, p = case["cfg"], case["p"]
+    d, ia, ib, sigs = _angle_check(case, method)
+    grid = orc.azimuth_grid((-90, 90), cfg["res"])
+    steer = orc.steering_matrix(grid, p.antenna_positions, p.lambda_c)
+    spec = orc.beamforming_spectra(sigs, steer)          # argmax-equivalent to MUSIC outside the guard
+    if method == "music":
+        den = p.num_antennas - spec
+        spec = np.where(np.abs(den) > 1e-12, 1.0 / np.abs(den), 0.0)
+    idx = np.argmax(spec, axis=1)
+    srt = np.sort(orc.beamforming_spectra(sigs, steer), axis=1)
+    gap = (srt[:, -1] - srt[:, -2]) / srt[:, -1]
+    got_idx = d["aidx"][ia]
+    bad = got_idx != idx
+    # BASELINE tolerance 0.05 deg == exact grid index; disagreements only inside the tie band, and flagged
+    assert np.all(gap[bad] < 1e-5), (int(bad.sum()), gap[bad])
+    assert np.all(d["flags"][ia][bad] & (FLAG_TIE | FLAG_GUARD))
+    assert np.abs(d["adeg"][ia][~bad] - grid[idx[~bad]]).max() < 0.05
+    assert bad.mean() < 2e-3
+    # flags stay rare
+    assert (d["flags"][ia] & FLAG_TIE).astype(bool).mean() < 0.02
+
+
+def test_esprit_angles(case):
+    p = case["p"]
+    d, ia, ib, sigs = _angle_check(case, "esprit")
+    want = orc.esprit_angles(sigs, p.lambda_c, p.spacing)
+    assert np.abs(d["adeg"][ia] - want).max() < 0.05
+
+
+def test_committed_reference_angles(case):
+    """The reference's own MUSIC / ESPRIT / beamforming outputs on the stated subsample."""
+    g, cfg, pk = case["g"], case["cfg"], case["pk"]
+    sub = g["ang_sub"]
+    want_key = (pk["antenna"][sub].astype(np.uint32) << 24) | (pk["range_bin"][sub].astype(np.uint32) << 12) | pk["doppler_bin"][sub].astype(np.uint32)
+    for method, name in (("music", "music_deg"), ("beamforming", "beam_deg"), ("esprit", "esprit_deg")):
+        det = case["pipe"].detect(case["rds"])
+        case["pipe"].angles(case["rds"], det, method=method)
+        d = det.frame(0)
+        pos = np.searchsorted(d["key"], want_key)
+        ok = (pos < len(d["key"])) & (d["key"][np.minimum(pos, len(d["key"]) - 1)] == want_key)
+        assert ok.mean() > 0.999
+        got = d["adeg"][pos[ok]]
+        diff = np.abs(got - g[name][ok])
+        flagged = (d["flags"][pos[ok]] & (FLAG_TIE | FLAG_GUARD)).astype(bool)
+        assert np.all(diff[~flagged] < 0.05), (method, diff[~flagged].max())
+        if method != "esprit":
+            assert np.all(g["music_top2_gap"][ok][diff >= 0.05] < 1e-4)
+
+
+def test_velocity(case):
+    cfg, p, pk = case["cfg"], case["p"], case["pk"]
+    grid = orc.azimuth_grid((-90, 90), cfg["res"])
+    steer = orc.steering_matrix(grid, p.antenna_positions, p.lambda_c)
+    sigs = orc.spatial_signatures(case["rds_ref"], pk["range_bin"], pk["doppler_bin"])
+    _, ang = orc.argmax_angles(orc.beamforming_spectra(sigs, steer), grid)
+    want = orc.solve_velocity(pk["range_m"], np.radians(ang), sigs, p.lambda_c, 0.1)
+    vel = case["vel"][0].cpu().numpy()
+    assert vel[6] == 1.0 and int(vel[7]) == len(pk["antenna"])
+    assert np.abs(vel[:2] - want["velocity"][:2]).max() < 1e-3
+    assert np.all(vel[2:6] == 0.0)
+
+
+def test_batch_is_frame_independent(case):
+    """Frames are independent: a batch of [x, y, x] gives bitwise identical results for both x."""
+    cfg, p, pipe = case["cfg"], case["p"], case["pipe"]
+    np.random.seed(cfg["seed"] + 500)
+    other = orc.synthesize_frame(p, np.array([[15.0, 0.2, -5.0, 0.0]])).astype(np.complex64)
+    dev = torch.from_numpy(np.stack([case["cube"], other, case["cube"]])).cuda()
+    vel, rds, det = pipe.process(dev, chunk_frames=4, keep=True)
+    torch.cuda.synchronize()
+    assert torch.equal(rds[0], rds[2]) and torch.equal(rds[0], case["rds"][0])
+    assert torch.equal(vel[0], vel[2]) and torch.equal(vel[0], case["vel"][0])
+    f0, f2 = det.frame(0), det.frame(2)
+    for k in ("key", "aidx", "phase", "power"):
+        assert np.array_equal(f0[k], f2[k])
+    # chunked processing changes nothing
+    vel2 = pipe.process(dev, chunk_frames=2)
+    torch.cuda.synchronize()
+    assert torch.equal(vel, vel2)
