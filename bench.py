@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""Benchmark of the radar-slam per-frame hot path on B200 (contract in the task statement).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--frames F] [--chunk B] [--impl reference]
+
+A "step" is one pass of the hot path (dechirp -> range FFT -> Doppler FFT -> peak detection ->
+MUSIC -> least-squares ego-velocity) over one batch of F synthetic frames per GPU.  Workload at any
+N: BASELINE.json configs[1] -- 1k frames of 256 samples x 128 chirps x 8 channels per GPU, MUSIC on
+a 1 degree grid, reference-default noise and threshold -- weak scaling, frames sharded by rank with
+no data-path collective except the all-gather of the per-frame velocity rows.
+
+The JSON line carries: value (frames/s, inputs resident in HBM), e2e (same metric through
+FramePipeline.process_host with pinned HOST buffers), roofline of the dominant kernel and of every
+stage, cpu_baseline (the oracle port timed on this box's host cores), clocks, gpu_launches.
+`--impl reference` times the reference algorithm's CPU port (oracle/) on all host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "frames/s dechirp->range-Doppler->MUSIC->LS ego-velocity"
+WORKLOAD = "configs[1]: 1k-frame synthetic batch per GPU, 256 samples x 128 chirps x 8 channels, MUSIC 1 deg grid, noise_power 0.01, threshold -20 dB"
+
+
+def radar_config(args):
+    from radar_slam_b200 import RadarConfig
+    return RadarConfig(fc=77e9, bandwidth=1e9, chirp_duration=args.samples / 10e6, pri=100e-6, num_chirps=args.chirps,
+                       sampling_rate=10e6, num_antennas=args.antennas, search_resolution=args.grid_res,
+                       method="music", threshold_db=args.threshold_db)
+
+
+def oracle_params(args):
+    from oracle import radar_oracle as orc
+    return orc.RadarParams(chirp_duration=args.samples / 10e6, num_chirps=args.chirps, num_antennas=args.antennas)
+
+
+# ---------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            p = [x.strip() for x in r.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0]))
+                mx.append(float(p[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------- CPU arms
+def _oracle_worker(payload):
+    frames, pdict, res, thr = payload
+    from oracle import radar_oracle as orc
+    p = orc.RadarParams(**pdict)
+    tim = {}
+    out = []
+    for fr in frames:
+        r = orc.process_frame(fr.astype(np.complex128), p, "music", res, thr, timings=tim)
+        out.append((r["velocity"].get("velocity", np.zeros(3))[:2], len(r["peaks"]["antenna"])))
+    return out, tim
+
+
+def cpu_oracle_rate(frames: np.ndarray, args, procs: int):
+    """Frames/s of the oracle port (vectorised numpy restatement of the reference) on `procs` processes."""
+    from dataclasses import asdict
+    p = oracle_params(args)
+    pdict = asdict(p)
+    parts = [frames[i::procs] for i in range(procs)]
+    parts = [x for x in parts if len(x)]
+    t0 = time.perf_counter()
+    if len(parts) == 1:
+        res = [_oracle_worker((parts[0], pdict, args.grid_res, args.threshold_db))]
+    else:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(len(parts)) as pool:
+            res = pool.map(_oracle_worker, [(x, pdict, args.grid_res, args.threshold_db) for x in parts])
+    dt = time.perf_counter() - t0
+    tim = {}
+    ndet = []
+    for out, t in res:
+        for k, v in t.items():
+            tim[k] = tim.get(k, 0.0) + v
+        ndet += [n for _, n in out]
+    return len(frames) / dt, dt, tim, float(np.mean(ndet)), res
+
+
+def host_frames(args, n: int, seed: int) -> np.ndarray:
+    """n frames of the benchmark workload generated on the HOST (numpy) for the CPU arms."""
+    from radar_slam_b200 import synth
+    cfg = radar_config(args)
+    sig = synth.scatterer_term(cfg).astype(np.complex64)
+    rs = np.random.RandomState(seed)
+    A, C, S = args.antennas, args.chirps, args.samples
+    out = np.empty((n, A, C, S), dtype=np.complex64)
+    for i in range(n):
+        noise = np.sqrt(0.01) * (rs.randn(A, C, S) + 1j * rs.randn(A, C, S))
+        out[i] = (sig[:, None, :] + noise).astype(np.complex64)
+    return out
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    procs = max(1, min(cores, args.ref_procs or cores))
+    per_step = max(procs, args.ref_frames_per_step or procs)
+    frames = host_frames(args, per_step, 4242)
+    for _ in range(args.warmup):
+        cpu_oracle_rate(frames[:procs], args, procs)
+    t0 = time.perf_counter()
+    ndet = 0.0
+    for _ in range(args.steps):
+        _, _, _, ndet, _ = cpu_oracle_rate(frames, args, procs)
+    dt = time.perf_counter() - t0
+    value = per_step * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "frames_per_step": per_step, "detections_per_frame": ndet},
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": procs, "kind": "port",
+                         "sample": f"{per_step} frames/step of the same workload through oracle.radar_oracle.process_frame "
+                                   f"(vectorised fp64 numpy port of the reference; the reference itself is Python and cannot "
+                                   f"travel to this box), {procs} processes"},
+        "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------- GPU arm
+def stage_bytes(name, F, A, C, S, n_det):
+    cells = F * A * C * S
+    if name in ("rs_range_fft", "rs_doppler_fft"):
+        return 16 * cells                                   # read c64 + write c64 per cell
+    if name == "rs_detect":
+        return 8 * cells + 9 * n_det                        # read RDS once; key + power + flag per detection
+    if name == "rs_angles":
+        return (8 * A + 4 + 2 + 12) * n_det                 # snapshot gather + key + flag r/w + aidx/adeg/phase
+    if name == "rs_velocity_ls":
+        return 9 * n_det + 64 * F                           # aidx + phase + flag per detection; one row per frame
+    return 0
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from radar_slam_b200 import FramePipeline, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = radar_config(args)
+    pipe = FramePipeline(cfg, device=str(dev))
+    F, A, C, S = args.frames, args.antennas, args.chirps, args.samples
+
+    cube = synth.synth_cubes(cfg, F, seed=1234, first_frame=rank * F, device=dev)
+    gathered = torch.zeros((world, F, 8), dtype=torch.float64, device=dev)      # NCCL all-gather target
+    vel = gathered[rank]                                                          # the solve writes its own slot
+
+    def step():
+        pipe.process(cube, chunk_frames=args.chunk, vel_out=vel)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered.view(-1), vel.reshape(-1))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    pipe.launches = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    launches = pipe.launches
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end to end through the public API with HOST buffers (pinned), H2D + D2H inside the timed region
+    n_e2e = min(F, args.e2e_frames)
+    host = torch.empty((n_e2e, A, C, S), dtype=torch.complex64, pin_memory=True)
+    host.copy_(cube[:n_e2e])
+    torch.cuda.synchronize(dev)
+    for _ in range(max(1, min(args.warmup, 2))):
+        pipe.process_host(host, chunk_frames=args.chunk)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, 3))
+    for _ in range(e2e_steps):
+        vel_host = pipe.process_host(host, chunk_frames=args.chunk)          # returns after the D2H completed
+    torch.cuda.synchronize(dev)
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = world * n_e2e * e2e_steps / float(e2e_s.item())
+    assert torch.allclose(vel_host.to(dev), vel[:n_e2e], atol=0, rtol=0), "host path and device path disagree"
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- per-stage device times (CUDA events on the launching stream) for the roofline
+    pipe.profile = []
+    pipe.process(cube, chunk_frames=args.chunk, vel_out=vel)
+    torch.cuda.synchronize(dev)
+    stage_ms, stage_n = {}, {}
+    for name, a, b in pipe.profile:
+        stage_ms[name] = stage_ms.get(name, 0.0) + a.elapsed_time(b)
+        stage_n[name] = stage_n.get(name, 0) + 1
+    pipe.profile = None
+    # detections per frame (for the algorithmic bytes of the list-driven stages)
+    rds = pipe.range_doppler(cube[: args.chunk])
+    det = pipe.detect(rds)
+    n_det_frame = float(det.per_frame_counts().double().mean().item())
+    overflow = int(det.overflow.sum().item())
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    stages = []
+    tot = sum(stage_ms.values())
+    for name, msv in stage_ms.items():
+        by = stage_bytes(name, F, A, C, S, n_det_frame * F)
+        stages.append({"kernel": name, "ms_per_step": msv, "share": msv / tot, "launches": stage_n[name],
+                       "alg_bytes_per_step": by, "achieved_gbs": by / msv / 1e6, "frac_hbm": by / msv / 1e6 / peak})
+    dom = max(stages, key=lambda s: s["ms_per_step"])
+    per_launch_bytes = dom["alg_bytes_per_step"] / dom["launches"]
+    roofline = {"kernel": dom["kernel"], "bound": "hbm", "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                "frac": dom["frac_hbm"], "traffic": None, "peak_source": peak_src,
+                "alg_bytes_per_launch": per_launch_bytes, "avg_launch_ms": dom["ms_per_step"] / dom["launches"],
+                "stages": stages}
+    if dom["kernel"] == "rs_angles":
+        G = len(pipe._angle_tables(A)["grid"])
+        ap = 2 if A <= 2 else 4 if A <= 4 else 8 if A <= 8 else 16
+        flops = n_det_frame * F * (G * (4 * (ap - 1) + 4) + 8 * ap * ap)
+        roofline["note"] = ("dominant kernel is the per-detection MUSIC scan, which is FP32-issue bound, not HBM bound; "
+                            "its HBM fraction is reported for the contract, its FP32 rate below")
+        roofline["fp32_tflops"] = flops / dom["ms_per_step"] / 1e9
+
+    # ---- CPU baseline: the oracle port on a bounded sample of the SAME frames, one core
+    n_cpu = args.cpu_frames
+    sample = cube[:n_cpu].cpu().numpy()
+    rate, dt, tim, ndet_cpu, res = cpu_oracle_rate(sample, args, 1)
+    v_cpu = np.stack([v for v, _ in res[0][0]])
+    v_gpu = vel[:n_cpu, :2].cpu().numpy()
+    parity = float(np.abs(v_cpu - v_gpu).max())
+
+    value = world * F * args.steps / (ms_total / 1e3)
+    line = {
+        "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "frames_per_gpu": F, "samples": S, "chirps": C, "channels": A,
+                   "grid_points": len(pipe._angle_tables(A)["grid"]), "chunk_frames": args.chunk,
+                   "detections_per_frame": n_det_frame, "detection_overflow": overflow,
+                   "cache": "inputs larger than L2 (%.2f GiB cube per GPU)" % (cube.numel() * 8 / 2 ** 30),
+                   "parallelism": f"frames sharded over {world} GPU(s), all-gather of [F,8] velocity rows"},
+        "roofline": roofline,
+        "cpu_baseline": {"value": rate, "unit": "frames/s", "cores": 1, "kind": "port",
+                         "sample": f"{n_cpu} frames of the same batch through the oracle port in {dt:.1f}s "
+                                   f"(stage seconds {json.dumps({k: round(v, 2) for k, v in tim.items()})}); "
+                                   f"{ndet_cpu:.0f} detections/frame",
+                         "max_abs_velocity_diff_vs_gpu": parity},
+        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": n_e2e * A * C * S * 8,
+                "d2h_bytes_per_step": n_e2e * 64, "frames_per_step": n_e2e},
+        "gpu_launches": launches, "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--frames", type=int, default=1000)
+    ap.add_argument("--samples", type=int, default=256)
+    ap.add_argument("--chirps", type=int, default=128)
+    ap.add_argument("--antennas", type=int, default=8)
+    ap.add_argument("--grid-res", type=float, default=1.0)
+    ap.add_argument("--threshold-db", type=float, default=-20.0)
+    ap.add_argument("--chunk", type=int, default=50)
+    ap.add_argument("--e2e-frames", type=int, default=1000)
+    ap.add_argument("--cpu-frames", type=int, default=8)
+    ap.add_argument("--ref-procs", type=int, default=0)
+    ap.add_argument("--ref-frames-per-step", type=int, default=0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

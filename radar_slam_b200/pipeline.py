@@ -122,6 +122,19 @@ class FramePipeline:
         self._tab: Dict = {}
         self._ws: Dict = {}
         self.launches = 0          # kernels of libradarslam_b200 launched since the last reset
+        self.profile = None        # set to a list to collect (stage, start_event, end_event) per launch
+
+    def _call(self, name: str, *args) -> None:
+        fn = getattr(self.lib, name)
+        if self.profile is None:
+            _lib.check(fn(*args), name)
+        else:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _lib.check(fn(*args), name)
+            e1.record()
+            self.profile.append((name, e0, e1))
+        self.launches += 1
 
     # ------------------------------------------------------------------ host tables (cached)
     def _dev(self, arr: np.ndarray) -> torch.Tensor:
@@ -185,10 +198,9 @@ class FramePipeline:
         mid = self._buf("mid", (F, S, A, Cu), torch.complex64)
         rds = out if out is not None else torch.empty((F, S, Cu, A), dtype=torch.complex64, device=self.device)
         st = self.stream
-        _lib.check(self.lib.rs_range_fft(cube.data_ptr(), tab.data_ptr(), tw_s.data_ptr(), mid.data_ptr(),
-                                         F, A, C, c0, Cu, S, int(self.cfg.dc_removal), st), "rs_range_fft")
-        _lib.check(self.lib.rs_doppler_fft(mid.data_ptr(), tw_c.data_ptr(), rds.data_ptr(), F, A, Cu, S, st),
-                   "rs_doppler_fft")
+        self._call("rs_range_fft", cube.data_ptr(), tab.data_ptr(), tw_s.data_ptr(), mid.data_ptr(),
+                   F, A, C, c0, Cu, S, int(self.cfg.dc_removal), st)
+        self._call("rs_doppler_fft", mid.data_ptr(), tw_c.data_ptr(), rds.data_ptr(), F, A, Cu, S, st)
         return rds
 
     def seg_cap_for(self, R: int, D: int, A: int) -> Tuple[int, int]:
@@ -213,9 +225,9 @@ class FramePipeline:
             adeg=alloc("det_adeg", (n,), torch.float32), phase=alloc("det_phase", (n,), torch.float32),
             count=alloc("det_count", (F * ntiles,), torch.int32), overflow=alloc("det_overflow", (F,), torch.int32),
             seg_cap=cap, ntiles=ntiles, F=F, R=R, D=D, A=A)
-        _lib.check(self.lib.rs_detect(rds.data_ptr(), gate.data_ptr(), thr, c.det_eps, det.key.data_ptr(),
-                                      det.power.data_ptr(), det.flags.data_ptr(), det.count.data_ptr(),
-                                      det.overflow.data_ptr(), cap, F, R, D, A, self.stream), "rs_detect")
+        self._call("rs_detect", rds.data_ptr(), gate.data_ptr(), thr, c.det_eps, det.key.data_ptr(),
+                   det.power.data_ptr(), det.flags.data_ptr(), det.count.data_ptr(),
+                   det.overflow.data_ptr(), cap, F, R, D, A, self.stream)
         return det
 
     def angles(self, rds: torch.Tensor, det: Detections, method: Optional[str] = None) -> Detections:
@@ -225,11 +237,12 @@ class FramePipeline:
             raise ValueError(f"Unknown method: {method}")
         t = self._angle_tables(det.A)
         esprit_scale = c.lambda_c / (2 * np.pi * c.spacing)                       # angle_estimation.py:218
-        _lib.check(self.lib.rs_angles(
+        self._call(
+            "rs_angles",
             rds.data_ptr(), t["scan"].data_ptr(), t["stride"], _lib.ptr(t["steer64"]), t["grid_f32"].data_ptr(), t["G"],
             _lib.METHODS[method], c.tie_eps, esprit_scale, det.key.data_ptr(), det.count.data_ptr(),
             det.flags.data_ptr(), det.aidx.data_ptr(), det.adeg.data_ptr(), det.phase.data_ptr(),
-            det.seg_cap, det.ntiles, det.F, det.R, det.D, det.A, self.stream), "rs_angles")
+            det.seg_cap, det.ntiles, det.F, det.R, det.D, det.A, self.stream)
         return det
 
     def velocity(self, det: Detections, out: Optional[torch.Tensor] = None, lambda_c: Optional[float] = None,
@@ -241,10 +254,11 @@ class FramePipeline:
         t = self._angle_tables(det.A)
         vel = out if out is not None else torch.empty((det.F, 8), dtype=torch.float64, device=self.device)
         assert vel.is_contiguous() and vel.dtype == torch.float64
-        _lib.check(self.lib.rs_velocity_ls(
+        self._call(
+            "rs_velocity_ls",
             det.aidx.data_ptr(), det.adeg.data_ptr(), det.phase.data_ptr(), det.flags.data_ptr(), det.count.data_ptr(),
             t["grid_cs"].data_ptr() if use_grid else 0, k, c.velocity_bound, c.irls_iters, c.huber_delta,
-            vel.data_ptr(), det.seg_cap, det.ntiles, det.F, self.stream), "rs_velocity_ls")
+            vel.data_ptr(), det.seg_cap, det.ntiles, det.F, self.stream)
         return vel
 
     # ------------------------------------------------------------------ whole path
@@ -263,7 +277,6 @@ class FramePipeline:
             det = self.detect(rds, workspace=not keep)
             self.angles(rds, det)
             self.velocity(det, out=vel[lo:hi])
-            self.launches += 5
             last = (rds, det)
         return (vel, last[0], last[1]) if keep else vel
 
