@@ -133,6 +133,31 @@ int rs_signatures_f64(const void* rds, const uint32_t* keys, const int32_t* fram
 int rs_spectra_f64(const void* sig128, const void* steer128, int method, int n, int A, int G,
                    double* out, int32_t* aidx, void* stream);
 
+/* 10 log10(|X|^2 + 1e-12) of the cell-major RDS in the reference layout: out double [F][A][S][C]
+ * (power_spectrum_db of extract_range_doppler_peaks, dechirp.py:235-238, 277). */
+int rs_power_db_f64(const void* rds, double* out, int F, int A, int C, int S, void* stream);
+
+/* SignalPreprocessor.process_chirp for `rows` chirps in fp64: (x conj(ref)) w - mean (dechirp.py:143-166).
+ * in128/out128 complex128 [rows][S], ref128 complex128 [S], window double [S]. */
+int rs_process_chirps_f64(const void* in128, const void* ref128, const double* window, int rows, int S,
+                          int dc_removal, void* out128, void* stream);
+
+/* AngleEstimator.estimate_angle_esprit for n snapshots in fp64 (angle_estimation.py:178-225): out double [n] deg. */
+int rs_esprit_f64(const void* sig128, int n, int A, double esprit_scale, double* out, void* stream);
+
+/* VelocitySolver.two_step_optimization for arbitrary positions/angles (velocity_solver.py:178-307):
+ * bounded-variable least squares of  k [d_i, r_i x d_i].[v, w] = y_i  over the box lo..hi (double [6]).
+ * nvar = 3 pins w = 0 (step 1), nvar = 6 is the full problem (step 2).  pos double [n][3], ang double [n][2]
+ * (azimuth, elevation), y double [n];  out7 = v[3], w[3], cost;  pred double [n] = predicted phases. */
+int rs_velocity_ls6(const double* pos, const double* ang, const double* y, int n, double k_phase,
+                    const double* lo, const double* hi, int nvar, double* out7, double* pred, void* stream);
+
+/* RobustAngleEstimator.compute_angle_confidence (robust_angle_estimation.py:88-138) for n unit-energy
+ * snapshots at their estimated angles: 0.4 |a^H s|/|s| + 0.3 exp(-mean|phase error|) + 0.3 min(1, log10(SNR)/3),
+ * clipped to [0, 1].  positions double [A] (metres). */
+int rs_robust_confidence_f64(const void* sig128, const double* angle_deg, const double* positions,
+                             double lambda_c, int n, int A, double* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

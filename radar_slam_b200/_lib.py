@@ -31,6 +31,11 @@ _SIGNATURES = {
     "rs_rds_from_reference_layout": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "rs_signatures_f64": (_i, [_vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp]),
     "rs_spectra_f64": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "rs_power_db_f64": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "rs_process_chirps_f64": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "rs_esprit_f64": (_i, [_vp, _i, _i, _d, _vp, _vp]),
+    "rs_velocity_ls6": (_i, [_vp, _vp, _vp, _i, _d, _vp, _vp, _i, _vp, _vp, _vp]),
+    "rs_robust_confidence_f64": (_i, [_vp, _vp, _vp, _d, _i, _i, _vp, _vp]),
 }
 
 _lib = None

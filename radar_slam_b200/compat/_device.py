@@ -1,0 +1,102 @@
+"""Shared device plumbing of the legacy adapters: pipeline cache, RDS upload cache, small ctypes helpers."""
+from __future__ import annotations
+
+import weakref
+from collections import OrderedDict
+from dataclasses import replace
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from .. import _lib
+from ..pipeline import FramePipeline, RadarConfig
+
+_pipes: "OrderedDict[tuple, FramePipeline]" = OrderedDict()
+_rds_cache: "OrderedDict[int, tuple]" = OrderedDict()
+
+
+def pipeline(**kw) -> FramePipeline:
+    """A FramePipeline for these radar parameters (cached; parameters are read at call time, so mutating
+    an attribute of a legacy object after construction behaves like the reference)."""
+    key = tuple(sorted((k, (tuple(v) if isinstance(v, (list, tuple)) else v)) for k, v in kw.items()))
+    p = _pipes.get(key)
+    if p is None:
+        p = FramePipeline(RadarConfig(**kw))
+        _pipes[key] = p
+        while len(_pipes) > 16:
+            _pipes.popitem(last=False)
+    return p
+
+
+def _sample(arr: np.ndarray) -> complex:
+    flat = arr.reshape(-1)
+    step = max(1, flat.size // 61)
+    return complex(flat[::step].sum())
+
+
+def remember_rds(arr: np.ndarray, dev: torch.Tensor) -> None:
+    """Remember the device copy (cell-major, [1,S,C,A]) of an RDS array handed to the caller."""
+    try:
+        ref = weakref.ref(arr)
+    except TypeError:
+        return
+    _rds_cache[id(arr)] = (ref, _sample(arr), dev)
+    while len(_rds_cache) > 2:
+        _rds_cache.popitem(last=False)
+
+
+def rds_to_device(rds: np.ndarray, pipe: FramePipeline) -> torch.Tensor:
+    """Reference-layout RDS [A, R, D] (any complex dtype, host) -> cell-major complex64 [1, R, D, A] on the
+    device.  Re-uses the device copy when `rds` is the very array this library returned."""
+    ent = _rds_cache.get(id(rds))
+    if ent is not None and ent[0]() is rds and ent[1] == _sample(rds):
+        return ent[2]
+    rds = np.asarray(rds)
+    if rds.ndim != 3:
+        raise ValueError("rds must be [num_antennas, range_bins, doppler_bins]")
+    A, R, D = rds.shape
+    host = torch.from_numpy(np.ascontiguousarray(rds, dtype=np.complex64))
+    ref_layout = host.to(pipe.device).view(1, A, R, D)
+    out = torch.empty((1, R, D, A), dtype=torch.complex64, device=pipe.device)
+    pipe._call("rs_rds_from_reference_layout", ref_layout.data_ptr(), out.data_ptr(), 1, A, D, R, pipe.stream)
+    remember_rds(rds, out)
+    return out
+
+
+def keys_tensor(antenna, range_bin, doppler_bin, device) -> torch.Tensor:
+    a = np.asarray(antenna, dtype=np.int64)
+    r = np.asarray(range_bin, dtype=np.int64)
+    d = np.asarray(doppler_bin, dtype=np.int64)
+    key = ((a & 0xFF) << 24) | (r << 12) | d
+    return torch.from_numpy(key.astype(np.uint32).view(np.int32)).to(device)
+
+
+def signatures(pipe: FramePipeline, rds_dev: torch.Tensor, range_bin, doppler_bin) -> torch.Tensor:
+    """Unit-energy snapshots complex128 [n, A] for cells of frame 0 (angle_estimation.py:83-88)."""
+    _, R, D, A = rds_dev.shape
+    n = len(range_bin)
+    keys = keys_tensor(np.zeros(n, dtype=np.int64), range_bin, doppler_bin, pipe.device)
+    frames = torch.zeros(n, dtype=torch.int32, device=pipe.device)
+    out = torch.empty((n, A), dtype=torch.complex128, device=pipe.device)
+    pipe._call("rs_signatures_f64", rds_dev.data_ptr(), keys.data_ptr(), frames.data_ptr(), n, out.data_ptr(),
+               1, R, D, A, pipe.stream)
+    return out
+
+
+def spectra(pipe: FramePipeline, sig128: torch.Tensor, steer128: torch.Tensor, method: str) -> Tuple[torch.Tensor, torch.Tensor]:
+    """fp64 pseudo-spectra [n, G] and first-index argmax [n] for snapshots complex128 [n, A]."""
+    n, A = sig128.shape
+    G = steer128.shape[1]
+    out = torch.empty((n, G), dtype=torch.float64, device=pipe.device)
+    aidx = torch.empty((n,), dtype=torch.int32, device=pipe.device)
+    pipe._call("rs_spectra_f64", sig128.data_ptr(), steer128.data_ptr(), _lib.METHODS[method], n, A, G,
+               out.data_ptr(), aidx.data_ptr(), pipe.stream)
+    return out, aidx
+
+
+def esprit(pipe: FramePipeline, sig128: torch.Tensor, scale: float) -> torch.Tensor:
+    n, A = sig128.shape
+    out = torch.empty((n,), dtype=torch.float64, device=pipe.device)
+    pipe._call("rs_esprit_f64", sig128.data_ptr(), n, A, float(scale), out.data_ptr(), pipe.stream)
+    return out

@@ -297,6 +297,9 @@ __global__ void spectra_f64_kernel(const double2* __restrict__ sig, const double
     const int i = blockIdx.x;
     for (int m = threadIdx.x; m < A; m += blockDim.x) sm_s[m] = sig[(size_t)i * A + m];
     __syncthreads();
+    // eigenvectors of s s^H do not depend on |s|: MUSIC sees the unit-energy snapshot
+    double energy = 0;
+    for (int m = 0; m < A; ++m) energy += sm_s[m].x * sm_s[m].x + sm_s[m].y * sm_s[m].y;
     double best = -1.0;
     int bi = 0x7fffffff;
     for (int g = threadIdx.x; g < G; g += blockDim.x) {
@@ -310,7 +313,8 @@ __global__ void spectra_f64_kernel(const double2* __restrict__ sig, const double
         double v = ar * ar + ai * ai;
         if (method == RS_METHOD_MUSIC) {
             // a^H E_n E_n^H a = M - |a^H s|^2 for a unit-energy snapshot; guard at angle_estimation.py:149
-            const double den = fabs((double)A - v);
+            // (a zero snapshot gives eigh(0) = I: the noise subspace is M-1 unit vectors, den = M-1)
+            const double den = fabs((double)A - (energy > 0 ? v / energy : 1.0));
             v = den > 1e-12 ? 1.0 / den : 0.0;
         }
         out[(size_t)i * G + g] = v;
