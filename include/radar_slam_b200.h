@@ -98,12 +98,22 @@ int rs_detect(const void* rds, const uint8_t* range_gate, float thr_power, float
  *                   scan_stride = 2 * (A_pad - 1) rounded up to 4        (A <= 16 path)
  *       steer       complex64 [A][G] exp(+i m phi_g)                      (A > 16 path; may be NULL otherwise)
  *       grid_deg    float [G]
- *       esprit_scale  lambda / (2 pi d)   (angle_estimation.py:218) */
+ *       esprit_scale  lambda / (2 pi d)   (angle_estimation.py:218)
+ *       grid_symmetric  1 when grid_deg[G-1-g] == -grid_deg[g] exactly (halves the scan work)
+ *       ls_partials   optional double [F*nseg_per_frame][8]: per-segment fp64 sums
+ *                     (sum c^2, sum s^2, sum cs, sum yc, sum ys, sum y^2, n, 0) of the velocity normal
+ *                     equations with c,s = grid_cs[aidx]; needs grid_cs (double [G][2]); grid methods, A <= 16 */
 int rs_angles(const void* rds, const float* scan_table, int scan_stride, const void* steer, const float* grid_deg, int G,
               int method, float tie_eps, double esprit_scale,
               const uint32_t* det_key, const int32_t* det_count, uint8_t* det_flags,
               int32_t* det_aidx, float* det_adeg, float* det_phase,
-              int seg_cap, int nseg_per_frame, int F, int R, int D, int A, void* stream);
+              int seg_cap, int nseg_per_frame, int F, int R, int D, int A,
+              const double* grid_cs, double* ls_partials, int grid_symmetric, void* stream);
+
+/* (d')  the velocity solve of rs_velocity_ls from the per-segment sums rs_angles already produced
+ *       (no second pass over the detection lists); same output row layout. */
+int rs_velocity_from_partials(const double* ls_partials, int nseg_per_frame, int F, double k_phase, double bound,
+                              double* vel, void* stream);
 
 /* (d)   replaces VelocitySolver.solve_velocity / two_step_optimization (velocity_solver.py:178-355):
  *       fp64 normal equations of  y = k (v_x cos az + v_y sin az),  k = 4 pi dt / lambda, solved under

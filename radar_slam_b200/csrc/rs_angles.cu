@@ -154,6 +154,202 @@ __global__ void __launch_bounds__(ANG_THREADS) angles_small_kernel(AngleArgs p) 
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Scan kernel, A <= AP: each thread carries ND detections through the grid at once so one
+// broadcast shared-memory read of the (cos k phi, sin k phi) row feeds ND * 2(AP-1) FMAs.
+// SYM: the grid is symmetric about 0 (grid[G-1-g] == -grid[g]), so cos k phi is shared by the
+// pair and sin k phi flips sign:  P(+-theta) = E +- O  with  E = sum Re R_k cos, O = sum Im R_k sin,
+// i.e. (AP-1) FMAs per grid point instead of 2(AP-1).  First-index argmax (np.argmax) is kept by
+// tracking the ascending left half with '>' and the descending right half with '>='.
+// The fp64 normal-equation sums of the velocity solve are accumulated here per segment
+// (deterministic block reduction), so the solve does not re-read the detection lists.
+// ---------------------------------------------------------------------------------------------
+struct Track {
+    float best, second;
+    int idx;
+};
+__device__ __forceinline__ void track_first(Track& t, float v, int g) {     // keeps the earliest index on ties
+    const bool up = v > t.best;
+    t.second = fmaxf(t.second, fminf(t.best, v));
+    t.best = fmaxf(t.best, v);
+    t.idx = up ? g : t.idx;
+}
+__device__ __forceinline__ void track_last(Track& t, float v, int g) {      // keeps the latest processed on ties
+    const bool up = v >= t.best;
+    t.second = fmaxf(t.second, fminf(t.best, v));
+    t.best = fmaxf(t.best, v);
+    t.idx = up ? g : t.idx;
+}
+
+template <int AP, int ND, bool SYM>
+__global__ void __launch_bounds__(ANG_THREADS) angles_scan_kernel(AngleArgs p, const double* __restrict__ grid_cs,
+                                                                   double* __restrict__ ls_partials) {
+    extern __shared__ float tab[];   // [rows][scan_stride]
+    __shared__ double red[ANG_THREADS / 32][8];
+    const int seg = blockIdx.x;
+    const int n = p.det_count[seg];
+    double acc_ls[7] = {0, 0, 0, 0, 0, 0, 0};
+    if (n > 0) {
+        const int rows = SYM ? (p.G + 1) / 2 : p.G;
+        for (int i = threadIdx.x; i < rows * p.scan_stride; i += blockDim.x) tab[i] = p.scan_table[i];
+        __syncthreads();
+        const int f = seg / p.nseg_per_frame;
+        const float2* frame = p.rds + (size_t)f * p.R * p.D * p.A;
+        const int M = p.A;
+        for (int base = 0; base < n; base += ND * ANG_THREADS) {
+            float rr[ND][AP], ri[ND][AP], yv[ND];
+            size_t o[ND];
+            bool valid[ND];
+#pragma unroll
+            for (int q = 0; q < ND; ++q) {
+                const int i = base + q * ANG_THREADS + threadIdx.x;
+                valid[q] = i < n;
+                o[q] = (size_t)seg * p.seg_cap + (valid[q] ? i : 0);
+                float2 s[AP];
+                if (valid[q]) {
+                    int a, r, d;
+                    rs_split_key(p.det_key[o[q]], a, r, d);
+                    const float2* cell = frame + ((size_t)r * p.D + d) * M;
+                    if (AP == 8 && M == 8) {
+                        const float4* c4 = reinterpret_cast<const float4*>(cell);
+#pragma unroll
+                        for (int m = 0; m < 4; ++m) {
+                            const float4 v = __ldg(c4 + m);
+                            s[2 * m] = make_float2(v.x, v.y);
+                            s[2 * m + 1] = make_float2(v.z, v.w);
+                        }
+                    } else {
+#pragma unroll
+                        for (int m = 0; m < AP; ++m) s[m] = (m < M) ? __ldg(cell + m) : make_float2(0.f, 0.f);
+                    }
+                    const float pr = s[1].x * s[0].x + s[1].y * s[0].y;
+                    const float pi = s[1].y * s[0].x - s[1].x * s[0].y;
+                    yv[q] = atan2f(pi, pr);
+                    p.det_phase[o[q]] = yv[q];
+                } else {
+                    yv[q] = 0.f;
+#pragma unroll
+                    for (int m = 0; m < AP; ++m) s[m] = make_float2(0.f, 0.f);
+                }
+#pragma unroll
+                for (int k = 0; k < AP; ++k) {
+                    float xr = 0.f, xi = 0.f;
+#pragma unroll
+                    for (int m = 0; m + k < AP; ++m) {
+                        xr = fmaf(s[m + k].x, s[m].x, xr);
+                        xr = fmaf(s[m + k].y, s[m].y, xr);
+                        xi = fmaf(s[m + k].y, s[m].x, xi);
+                        xi = fmaf(-s[m + k].x, s[m].y, xi);
+                    }
+                    rr[q][k] = xr;
+                    ri[q][k] = xi;
+                }
+            }
+
+            Track L[ND], Rt[ND];
+#pragma unroll
+            for (int q = 0; q < ND; ++q) {
+                L[q] = Track{-3.0e38f, -3.0e38f, 0};
+                Rt[q] = Track{-3.0e38f, -3.0e38f, 0};
+            }
+            if (SYM) {
+                const int half = p.G / 2;
+                const float* t = tab;
+                for (int g = 0; g < half; ++g, t += p.scan_stride) {
+                    float tv[2 * (AP - 1)];
+#pragma unroll
+                    for (int k4 = 0; k4 < (2 * (AP - 1) + 3) / 4; ++k4) {
+                        const float4 v = *reinterpret_cast<const float4*>(t + 4 * k4);
+                        if (4 * k4 + 0 < 2 * (AP - 1)) tv[4 * k4 + 0] = v.x;
+                        if (4 * k4 + 1 < 2 * (AP - 1)) tv[4 * k4 + 1] = v.y;
+                        if (4 * k4 + 2 < 2 * (AP - 1)) tv[4 * k4 + 2] = v.z;
+                        if (4 * k4 + 3 < 2 * (AP - 1)) tv[4 * k4 + 3] = v.w;
+                    }
+#pragma unroll
+                    for (int q = 0; q < ND; ++q) {
+                        float e = 0.f, od = 0.f;
+#pragma unroll
+                        for (int k = 1; k < AP; ++k) {
+                            e = fmaf(rr[q][k], tv[2 * (k - 1)], e);
+                            od = fmaf(ri[q][k], tv[2 * (k - 1) + 1], od);
+                        }
+                        track_first(L[q], e + od, g);
+                        track_last(Rt[q], e - od, p.G - 1 - g);
+                    }
+                }
+                if (p.G & 1) {      // the middle angle (0 deg for a symmetric grid): its own row, no partner
+#pragma unroll
+                    for (int q = 0; q < ND; ++q) {
+                        float e = 0.f;
+#pragma unroll
+                        for (int k = 1; k < AP; ++k) {
+                            e = fmaf(rr[q][k], t[2 * (k - 1)], e);
+                            e = fmaf(ri[q][k], t[2 * (k - 1) + 1], e);
+                        }
+                        track_first(L[q], e, half);     // larger than every left index, '>' keeps earlier ties
+                    }
+                }
+            } else {
+                const float* t = tab;
+                for (int g = 0; g < p.G; ++g, t += p.scan_stride) {
+#pragma unroll
+                    for (int q = 0; q < ND; ++q) {
+                        float e = 0.f;
+#pragma unroll
+                        for (int k = 1; k < AP; ++k) {
+                            e = fmaf(rr[q][k], t[2 * (k - 1)], e);
+                            e = fmaf(ri[q][k], t[2 * (k - 1) + 1], e);
+                        }
+                        track_first(L[q], e, g);
+                    }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < ND; ++q) {
+                if (!valid[q]) continue;
+                // merge: left indices are all smaller than right indices, so a tie goes to the left
+                const bool left = L[q].best >= Rt[q].best;
+                const float best = left ? L[q].best : Rt[q].best;
+                const float second = left ? fmaxf(Rt[q].best, L[q].second) : fmaxf(L[q].best, Rt[q].second);
+                const int bi = left ? L[q].idx : Rt[q].idx;
+                const float pbest = rr[q][0] + 2.f * best;
+                uint8_t flags = p.det_flags[o[q]];
+                if (2.f * (best - second) <= p.tie_eps * fabsf(pbest)) flags |= RS_FLAG_TIE;
+                if (p.method == RS_METHOD_MUSIC) {
+                    const float full = (float)M * rr[q][0];
+                    if (full - pbest <= 1e-4f * full) flags |= RS_FLAG_GUARD;
+                }
+                p.det_aidx[o[q]] = bi;
+                p.det_adeg[o[q]] = p.grid_deg[bi];
+                p.det_flags[o[q]] = flags;
+                if (ls_partials != nullptr) {
+                    const double c = grid_cs[2 * bi], sn = grid_cs[2 * bi + 1], y = (double)yv[q];
+                    acc_ls[0] += c * c; acc_ls[1] += sn * sn; acc_ls[2] += c * sn;
+                    acc_ls[3] += y * c; acc_ls[4] += y * sn; acc_ls[5] += y * y; acc_ls[6] += 1.0;
+                }
+            }
+        }
+    }
+    if (ls_partials == nullptr) return;
+    // deterministic block reduction of the seven sums -> ls_partials[seg][0..6]
+#pragma unroll
+    for (int q = 0; q < 7; ++q) {
+#pragma unroll
+        for (int off = 16; off; off >>= 1) acc_ls[q] += __shfl_xor_sync(0xffffffffu, acc_ls[q], off);
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < 7; ++q) red[wid][q] = acc_ls[q];
+    }
+    __syncthreads();
+    if (threadIdx.x < 7) {
+        double t = 0;
+        for (int w = 0; w < ANG_THREADS / 32; ++w) t += red[w][threadIdx.x];
+        ls_partials[(size_t)seg * 8 + threadIdx.x] = t;
+    }
+}
+
 // warp-per-detection kernel for any A (used for A > 16): lanes scan the grid, snapshot in smem
 __global__ void __launch_bounds__(ANG_THREADS) angles_large_kernel(AngleArgs p) {
     extern __shared__ float2 snap[];   // [warps][A]
@@ -343,8 +539,9 @@ extern "C" int rs_angles(const void* rds, const float* scan_table, int scan_stri
                          const float* grid_deg, int G, int method, float tie_eps, double esprit_scale,
                          const uint32_t* det_key, const int32_t* det_count, uint8_t* det_flags, int32_t* det_aidx,
                          float* det_adeg, float* det_phase, int seg_cap, int nseg_per_frame, int F, int R, int D, int A,
-                         void* stream) {
+                         const double* grid_cs, double* ls_partials, int grid_symmetric, void* stream) {
     RS_CHECK_ARG(rds && det_key && det_count && det_flags && det_aidx && det_adeg && det_phase, "rs_angles: null pointer");
+    RS_CHECK_ARG(ls_partials == nullptr || grid_cs != nullptr, "rs_angles: ls_partials needs grid_cs");
     RS_CHECK_ARG(method >= 0 && method <= 2, "rs_angles: unknown method %d", method);
     RS_CHECK_ARG(A >= 2 && A <= RS_MAX_ANTENNAS, "rs_angles: need 2 <= A <= %d", RS_MAX_ANTENNAS);
     RS_CHECK_ARG(F > 0 && R > 0 && D > 0 && seg_cap > 0 && nseg_per_frame > 0, "rs_angles: bad dims");
@@ -362,20 +559,39 @@ extern "C" int rs_angles(const void* rds, const float* scan_table, int scan_stri
         int need_stride = 2 * (ap - 1);
         need_stride = (need_stride + 3) & ~3;
         RS_CHECK_ARG(!scan || scan_stride == need_stride, "rs_angles: scan_stride must be %d for A=%d", need_stride, A);
-        const size_t smem = scan ? (size_t)G * scan_stride * sizeof(float) : 0;
+        const int rows = (scan && grid_symmetric) ? (G + 1) / 2 : G;
+        const size_t smem = scan ? (size_t)rows * scan_stride * sizeof(float) : 0;
         if (smem > (size_t)rs_smem_optin_limit()) {
             rs_set_error("rs_angles: grid table needs %zu B of shared memory", smem);
             return RS_ECAPACITY;
         }
-#define LAUNCH_SMALL(AP)                                                                                     \
-    cudaFuncSetAttribute(angles_small_kernel<AP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
-    angles_small_kernel<AP><<<(unsigned)blocks, ANG_THREADS, smem, st>>>(p)
-        if (ap == 2) { LAUNCH_SMALL(2); }
-        else if (ap == 4) { LAUNCH_SMALL(4); }
-        else if (ap == 8) { LAUNCH_SMALL(8); }
-        else { LAUNCH_SMALL(16); }
+        if (!scan) {
+            RS_CHECK_ARG(ls_partials == nullptr, "rs_angles: ls_partials is only produced by the grid methods");
+#define LAUNCH_SMALL(AP) angles_small_kernel<AP><<<(unsigned)blocks, ANG_THREADS, 0, st>>>(p)
+            if (ap == 2) { LAUNCH_SMALL(2); }
+            else if (ap == 4) { LAUNCH_SMALL(4); }
+            else if (ap == 8) { LAUNCH_SMALL(8); }
+            else { LAUNCH_SMALL(16); }
 #undef LAUNCH_SMALL
+        } else {
+#define LAUNCH_SCAN(AP, ND)                                                                                              \
+    do {                                                                                                                 \
+        if (grid_symmetric) {                                                                                            \
+            cudaFuncSetAttribute(angles_scan_kernel<AP, ND, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            angles_scan_kernel<AP, ND, true><<<(unsigned)blocks, ANG_THREADS, smem, st>>>(p, grid_cs, ls_partials);      \
+        } else {                                                                                                         \
+            cudaFuncSetAttribute(angles_scan_kernel<AP, ND, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            angles_scan_kernel<AP, ND, false><<<(unsigned)blocks, ANG_THREADS, smem, st>>>(p, grid_cs, ls_partials);     \
+        }                                                                                                                \
+    } while (0)
+            if (ap == 2) LAUNCH_SCAN(2, 4);
+            else if (ap == 4) LAUNCH_SCAN(4, 4);
+            else if (ap == 8) LAUNCH_SCAN(8, 4);
+            else LAUNCH_SCAN(16, 2);
+#undef LAUNCH_SCAN
+        }
     } else {
+        RS_CHECK_ARG(ls_partials == nullptr, "rs_angles: ls_partials is not produced for A > 16 (use rs_velocity_ls)");
         RS_CHECK_ARG(!scan || steer, "rs_angles: steer table required for A > 16");
         const size_t smem = (size_t)(ANG_THREADS / 32) * A * sizeof(float2);
         angles_large_kernel<<<(unsigned)blocks, ANG_THREADS, smem, st>>>(p);

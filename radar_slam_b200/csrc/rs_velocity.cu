@@ -125,7 +125,45 @@ velocity_kernel(const int32_t* __restrict__ det_aidx, const float* __restrict__ 
     }
 }
 
+// One warp per frame: add the per-segment partial sums written by rs_angles in segment order
+// (lane-strided, then a fixed shuffle tree: deterministic) and solve.
+__global__ void __launch_bounds__(128)
+velocity_from_partials_kernel(const double* __restrict__ partials, int nseg, int F, double kph, double bound,
+                              double* __restrict__ vel) {
+    const int lane = threadIdx.x & 31;
+    const int f = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (f >= F) return;
+    double s[7] = {0, 0, 0, 0, 0, 0, 0};
+    for (int sg = lane; sg < nseg; sg += 32) {
+        const double* q = partials + ((size_t)f * nseg + sg) * 8;
+#pragma unroll
+        for (int j = 0; j < 7; ++j) s[j] += q[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {
+#pragma unroll
+        for (int off = 16; off; off >>= 1) s[j] += __shfl_xor_sync(0xffffffffu, s[j], off);
+    }
+    if (lane == 0) {
+        double vx = 0, vy = 0;
+        const bool ok = s[6] >= 3.0;
+        if (ok) box_ls(kph * kph * s[0], kph * kph * s[1], kph * kph * s[2], kph * s[3], kph * s[4], bound, &vx, &vy);
+        double* o = vel + (size_t)f * 8;
+        o[0] = vx; o[1] = vy; o[2] = 0.0; o[3] = 0.0; o[4] = 0.0; o[5] = 0.0;
+        o[6] = ok ? 1.0 : 0.0; o[7] = s[6];
+    }
+}
+
 }  // namespace
+
+extern "C" int rs_velocity_from_partials(const double* ls_partials, int nseg_per_frame, int F, double k_phase,
+                                         double bound, double* vel, void* stream) {
+    RS_CHECK_ARG(ls_partials && vel && nseg_per_frame > 0 && F > 0 && bound > 0, "rs_velocity_from_partials: bad args");
+    velocity_from_partials_kernel<<<(F + 3) / 4, 128, 0, (cudaStream_t)stream>>>(ls_partials, nseg_per_frame, F, k_phase,
+                                                                              bound, vel);
+    RS_CHECK_LAUNCH("rs_velocity_from_partials");
+    return RS_OK;
+}
 
 extern "C" int rs_velocity_ls(const int32_t* det_aidx, const float* det_adeg, const float* det_phase,
                               const uint8_t* det_flags, const int32_t* det_count, const double* grid_cs, double k_phase,

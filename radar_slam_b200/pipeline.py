@@ -80,6 +80,7 @@ class Detections:
     R: int
     D: int
     A: int
+    ls_partials: Optional[torch.Tensor] = None     # per-segment normal-equation sums written by rs_angles
 
     def valid_mask(self) -> torch.Tensor:
         n = self.F * self.ntiles
@@ -162,6 +163,7 @@ class FramePipeline:
                 "scan": self._dev(scan), "grid_f32": self._dev(grid.astype(np.float32)),
                 "steer64": self._dev(steer.astype(np.complex64)) if A > 16 else None,
                 "steer128": self._dev(steer), "grid_cs": self._dev(tables.grid_cos_sin(grid)),
+                "symmetric": bool(np.array_equal(grid[::-1], -grid)),
             }
         return self._tab[key]
 
@@ -230,19 +232,23 @@ class FramePipeline:
                    det.overflow.data_ptr(), cap, F, R, D, A, self.stream)
         return det
 
-    def angles(self, rds: torch.Tensor, det: Detections, method: Optional[str] = None) -> Detections:
+    def angles(self, rds: torch.Tensor, det: Detections, method: Optional[str] = None,
+               fuse_ls: bool = True) -> Detections:
         c = self.cfg
         method = method or c.method
         if method not in _lib.METHODS:
             raise ValueError(f"Unknown method: {method}")
         t = self._angle_tables(det.A)
         esprit_scale = c.lambda_c / (2 * np.pi * c.spacing)                       # angle_estimation.py:218
+        fuse = fuse_ls and method != "esprit" and det.A <= 16
+        det.ls_partials = self._buf("ls_partials", (det.F * det.ntiles, 8), torch.float64) if fuse else None
         self._call(
             "rs_angles",
             rds.data_ptr(), t["scan"].data_ptr(), t["stride"], _lib.ptr(t["steer64"]), t["grid_f32"].data_ptr(), t["G"],
             _lib.METHODS[method], c.tie_eps, esprit_scale, det.key.data_ptr(), det.count.data_ptr(),
             det.flags.data_ptr(), det.aidx.data_ptr(), det.adeg.data_ptr(), det.phase.data_ptr(),
-            det.seg_cap, det.ntiles, det.F, det.R, det.D, det.A, self.stream)
+            det.seg_cap, det.ntiles, det.F, det.R, det.D, det.A,
+            t["grid_cs"].data_ptr(), _lib.ptr(det.ls_partials), int(t["symmetric"]), self.stream)
         return det
 
     def velocity(self, det: Detections, out: Optional[torch.Tensor] = None, lambda_c: Optional[float] = None,
@@ -254,6 +260,10 @@ class FramePipeline:
         t = self._angle_tables(det.A)
         vel = out if out is not None else torch.empty((det.F, 8), dtype=torch.float64, device=self.device)
         assert vel.is_contiguous() and vel.dtype == torch.float64
+        if det.ls_partials is not None and use_grid and c.irls_iters == 0:
+            self._call("rs_velocity_from_partials", det.ls_partials.data_ptr(), det.ntiles, det.F, k, c.velocity_bound,
+                       vel.data_ptr(), self.stream)
+            return vel
         self._call(
             "rs_velocity_ls",
             det.aidx.data_ptr(), det.adeg.data_ptr(), det.phase.data_ptr(), det.flags.data_ptr(), det.count.data_ptr(),
