@@ -8,7 +8,9 @@
 // passes out of a host-built fp64-accurate twiddle table, and stores with the transpose fused so
 // that the next stage reads contiguous memory.  Any length whose prime factors are <= 13 is
 // supported (the reference's defaults are S=400, C=64; BASELINE configs are powers of two).
+#include <algorithm>
 #include "rs_common.cuh"
+#include "rs_fft_pow2.cuh"
 
 namespace {
 
@@ -242,6 +244,37 @@ __global__ void ref_to_cell_kernel(const float2* __restrict__ in, float2* __rest
     }
 }
 
+// ---- power-of-two fast paths (rs_fft_pow2.cuh) ---------------------------------------------------
+template <int R1, int R2, int CB>
+static int launch_range_pow2(const float2* cube, const float2* table, const float2* tw, float2* mid, int F, int A,
+                             int C_total, int chirp0, int C_used, int dc, cudaStream_t st) {
+    using G = pow2::Geo<R1, R2>;
+    const size_t smem = (size_t)(2 * G::N + CB * G::ROWP_RANGE) * sizeof(float2);
+    auto kern = pow2::range_fft_pow2_kernel<R1, R2, CB>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const long long nblocks = (long long)F * A * (C_used / CB);
+    if (nblocks >= (1ll << 31)) return 1;
+    const int per_sm = (int)((size_t)rs_smem_optin_limit() / smem);
+    const long long grid = std::min<long long>(nblocks, (long long)rs_sm_count() * std::max(1, std::min(per_sm, 4)));
+    kern<<<(unsigned)grid, pow2::THREADS, smem, st>>>(cube, table, tw, mid, A, C_total, chirp0, C_used, dc, (int)nblocks);
+    return 0;
+}
+
+template <int R1, int R2, int NB>
+static int launch_doppler_pow2(const float2* mid, const float2* tw, float2* rds, int A, int lanes_a, long long nrows,
+                               cudaStream_t st) {
+    using G = pow2::Geo<R1, R2>;
+    const size_t smem = (size_t)(G::N + NB * G::ROWP_DOPP) * sizeof(float2);
+    auto kern = pow2::doppler_fft_pow2_kernel<R1, R2, NB>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const long long nblocks = (nrows + NB - 1) / NB;
+    if (nblocks >= (1ll << 31)) return 1;
+    const int per_sm = (int)((size_t)rs_smem_optin_limit() / smem);
+    const long long grid = std::min<long long>(nblocks, (long long)rs_sm_count() * std::max(1, std::min(per_sm, 4)));
+    kern<<<(unsigned)grid, pow2::THREADS, smem, st>>>(mid, tw, rds, A, lanes_a, nrows, (int)nblocks);
+    return 0;
+}
+
 static int largest_divisor_le(int n, int cap) {
     int best = 1;
     for (int d = 1; d <= cap && d <= n; ++d)
@@ -257,6 +290,18 @@ extern "C" int rs_range_fft(const void* cube, const void* table, const void* twi
     RS_CHECK_ARG(F > 0 && A > 0 && A <= RS_MAX_ANTENNAS && S > 0 && S <= RS_MAX_RANGE_BINS, "rs_range_fft: bad F/A/S");
     RS_CHECK_ARG(C_used > 0 && chirp0 >= 0 && chirp0 + C_used <= C_total && C_used <= RS_MAX_DOPPLER_BINS,
                  "rs_range_fft: bad chirp subset");
+    if (C_used % 32 == 0 && (S == 64 || S == 128 || S == 256)) {
+        const float2 *cu = (const float2*)cube, *tb = (const float2*)table, *tw = (const float2*)twiddle_s;
+        cudaStream_t st = (cudaStream_t)stream;
+        int rc = 1;
+        if (S == 256) rc = launch_range_pow2<16, 16, 32>(cu, tb, tw, (float2*)mid, F, A, C_total, chirp0, C_used, dc_removal, st);
+        else if (S == 128) rc = launch_range_pow2<16, 8, 32>(cu, tb, tw, (float2*)mid, F, A, C_total, chirp0, C_used, dc_removal, st);
+        else rc = launch_range_pow2<8, 8, 32>(cu, tb, tw, (float2*)mid, F, A, C_total, chirp0, C_used, dc_removal, st);
+        if (rc == 0) {
+            RS_CHECK_LAUNCH("rs_range_fft(pow2)");
+            return RS_OK;
+        }
+    }
     FftPlan plan;
     RS_CHECK_ARG(make_plan(S, &plan), "rs_range_fft: S=%d has a prime factor > 13", S);
     const int limit = rs_smem_optin_limit();
@@ -282,6 +327,21 @@ extern "C" int rs_doppler_fft(const void* mid, const void* twiddle_c, void* rds,
     RS_CHECK_ARG(mid && twiddle_c && rds, "rs_doppler_fft: null pointer");
     RS_CHECK_ARG(F > 0 && A > 0 && A <= RS_MAX_ANTENNAS && S > 0 && C > 0 && C <= RS_MAX_DOPPLER_BINS,
                  "rs_doppler_fft: bad dims");
+    {
+        const int lanes_a = (A % 32 == 0) ? 32 : (A == 16 || A == 8 || A == 4) ? A : 0;
+        if (lanes_a && (C == 64 || C == 128 || C == 256)) {
+            const long long nrows = (long long)F * S * A;
+            cudaStream_t st = (cudaStream_t)stream;
+            int rc = 1;
+            if (C == 256) rc = launch_doppler_pow2<16, 16, 32>((const float2*)mid, (const float2*)twiddle_c, (float2*)rds, A, lanes_a, nrows, st);
+            else if (C == 128) rc = launch_doppler_pow2<16, 8, 64>((const float2*)mid, (const float2*)twiddle_c, (float2*)rds, A, lanes_a, nrows, st);
+            else rc = launch_doppler_pow2<8, 8, 64>((const float2*)mid, (const float2*)twiddle_c, (float2*)rds, A, lanes_a, nrows, st);
+            if (rc == 0) {
+                RS_CHECK_LAUNCH("rs_doppler_fft(pow2)");
+                return RS_OK;
+            }
+        }
+    }
     FftPlan plan;
     RS_CHECK_ARG(make_plan(C, &plan), "rs_doppler_fft: C=%d has a prime factor > 13", C);
     const int limit = rs_smem_optin_limit();

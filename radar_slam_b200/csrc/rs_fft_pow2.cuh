@@ -1,0 +1,217 @@
+// Two-pass register FFT kernels for power-of-two lengths N = R1 * R2 (R1 >= R2, both in {4, 8, 16}).
+//
+// Pass 1: a thread owns x[t + R2 j], j < R1 (lanes run along the FFT axis -> coalesced loads),
+//         does the R1-point DFT in registers, applies the inter-pass twiddle w_N^{t k1} and writes
+//         Y[row][k1][t] to shared memory (padded, conflict-free).
+// Pass 2: a thread owns one (row, k1): reads Y[row][k1][0..R2), does the R2-point DFT and stores
+//         X[k1 + R1 k2] straight to global memory.  The lane -> (row, k1) map of pass 2 is chosen per
+//         kernel so that the TRANSPOSED store of each stage is coalesced:
+//           range stage   lanes = 32 consecutive chirps            -> mid[f][s][a][c..c+31]   (256 B runs)
+//           Doppler stage lanes = (antenna, 4 consecutive k1)      -> rds[f][s][k..k+3][a]    (256 B runs, A = 8)
+// One shared-memory round trip per element, no staging copies.
+#pragma once
+#include "rs_common.cuh"
+
+namespace pow2 {
+
+template <int R>
+__device__ __forceinline__ void dft(float2 (&v)[R]);
+
+template <>
+__device__ __forceinline__ void dft<2>(float2 (&v)[2]) {
+    const float2 a = v[0], b = v[1];
+    v[0] = cadd(a, b);
+    v[1] = csub(a, b);
+}
+template <>
+__device__ __forceinline__ void dft<4>(float2 (&v)[4]) {
+    const float2 t0 = cadd(v[0], v[2]), t1 = csub(v[0], v[2]);
+    const float2 t2 = cadd(v[1], v[3]), t3 = cmul_mi(csub(v[1], v[3]));
+    v[0] = cadd(t0, t2);
+    v[1] = cadd(t1, t3);
+    v[2] = csub(t0, t2);
+    v[3] = csub(t1, t3);
+}
+template <>
+__device__ __forceinline__ void dft<8>(float2 (&v)[8]) {
+    float2 e[4] = {v[0], v[2], v[4], v[6]};
+    float2 o[4] = {v[1], v[3], v[5], v[7]};
+    dft<4>(e);
+    dft<4>(o);
+    const float h = 0.70710678118654752440f;
+    o[1] = make_float2(h * (o[1].x + o[1].y), h * (o[1].y - o[1].x));
+    o[2] = cmul_mi(o[2]);
+    o[3] = make_float2(h * (o[3].y - o[3].x), -h * (o[3].x + o[3].y));
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        v[k] = cadd(e[k], o[k]);
+        v[k + 4] = csub(e[k], o[k]);
+    }
+}
+// 16 = 4 x 4: U[a][q] = sum_b v[a + 4b] w4^{bq};  X[q + 4r] = sum_a w4^{ar} (w16^{aq} U[a][q])
+template <>
+__device__ __forceinline__ void dft<16>(float2 (&v)[16]) {
+    const float c1 = 0.92387953251128675613f, s1 = 0.38268343236508977173f;   // cos, sin (pi/8)
+    const float h = 0.70710678118654752440f;
+    float2 u[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        float2 w[4] = {v[a], v[a + 4], v[a + 8], v[a + 12]};
+        dft<4>(w);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) u[a][q] = w[q];
+    }
+    // w16^m = exp(-2 pi i m / 16)
+    auto mul_w = [&](float2 x, int m) -> float2 {
+        switch (m) {
+            case 0: return x;
+            case 1: return make_float2(c1 * x.x + s1 * x.y, c1 * x.y - s1 * x.x);
+            case 2: return make_float2(h * (x.x + x.y), h * (x.y - x.x));
+            case 3: return make_float2(s1 * x.x + c1 * x.y, s1 * x.y - c1 * x.x);
+            case 4: return cmul_mi(x);
+            case 6: return make_float2(h * (x.y - x.x), -h * (x.x + x.y));
+            default: /* 9 */ return make_float2(-c1 * x.x - s1 * x.y, s1 * x.x - c1 * x.y);
+        }
+    };
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        float2 w[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) w[a] = mul_w(u[a][q], a * q);
+        dft<4>(w);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) v[q + 4 * r] = w[r];
+    }
+}
+
+constexpr int THREADS = 256;
+
+template <int R1, int R2>
+struct Geo {
+    static constexpr int N = R1 * R2;
+    static constexpr int K1P = R2 + 1;            // pitch of one k1 line (complex); odd -> conflict-free pass-2 reads
+    static constexpr int ROWP_RANGE = R1 * K1P + ((R1 * K1P) % 2 == 0 ? 1 : 0);    // odd: lanes along rows
+    static constexpr int ROWP_DOPP = R1 * K1P + ((18 - (R1 * K1P) % 16) % 16);     // == 2 (mod 16): lanes (a, k1)
+};
+
+// ---- pass 1 for `nrows` rows whose element (row, n) is at src[row * row_stride + n] -------------
+template <int R1, int R2, bool TABLE>
+__device__ __forceinline__ void pass1(const float2* __restrict__ src, size_t row_stride, int nrows, int rowp,
+                                      const float2* __restrict__ tabs, const float2* __restrict__ tw1,
+                                      float2* __restrict__ Y) {
+    using G = Geo<R1, R2>;
+    for (int it = threadIdx.x; it < nrows * R2; it += THREADS) {
+        const int row = it / R2, t = it - row * R2;
+        const float2* x = src + (size_t)row * row_stride + t;
+        float2 v[R1];
+#pragma unroll
+        for (int j = 0; j < R1; ++j) v[j] = __ldcs(x + R2 * j);          // streamed once: evict-first
+        if (TABLE) {
+#pragma unroll
+            for (int j = 0; j < R1; ++j) v[j] = cmul(v[j], tabs[t + R2 * j]);
+        }
+        dft<R1>(v);
+        float2* y = Y + row * rowp + t;
+#pragma unroll
+        for (int k1 = 0; k1 < R1; ++k1) y[k1 * G::K1P] = (k1 == 0) ? v[0] : cmul(v[k1], tw1[k1 * R2 + t]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// range stage: CTA = CB consecutive chirps of one (frame, antenna)
+// ---------------------------------------------------------------------------------------------
+template <int R1, int R2, int CB>
+__global__ void __launch_bounds__(THREADS)
+range_fft_pow2_kernel(const float2* __restrict__ cube, const float2* __restrict__ table, const float2* __restrict__ tw_g,
+                      float2* __restrict__ mid, int A, int C_total, int chirp0, int C_used, int dc_removal,
+                      int nblocks) {
+    using G = Geo<R1, R2>;
+    constexpr int S = G::N, RP = G::ROWP_RANGE;
+    extern __shared__ float2 sm[];
+    float2* tabs = sm;               // [S]
+    float2* tw1 = tabs + S;          // [R1][R2]
+    float2* Y = tw1 + S;             // [CB][RP]
+    for (int i = threadIdx.x; i < S; i += THREADS) {
+        tabs[i] = table[i];
+        const int k1 = i / R2, t = i - k1 * R2;
+        tw1[i] = tw_g[(k1 * t) % S];
+    }
+    __syncthreads();
+    const int per_fa = C_used / CB;
+    for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+        const int fa = blk / per_fa;
+        const int c0 = (blk - fa * per_fa) * CB;
+        const int f = fa / A, a = fa - f * A;
+        pass1<R1, R2, true>(cube + ((size_t)fa * C_total + chirp0 + c0) * S, S, CB, RP, tabs, tw1, Y);
+        __syncthreads();
+        float2* dst = mid + ((size_t)f * S * A + a) * C_used + c0;
+        for (int it = threadIdx.x; it < CB * R1; it += THREADS) {
+            const int row = it % CB, k1 = it / CB;          // lanes along chirps
+            const float2* y = Y + row * RP + k1 * G::K1P;
+            float2 u[R2];
+#pragma unroll
+            for (int n2 = 0; n2 < R2; ++n2) u[n2] = y[n2];
+            dft<R2>(u);
+#pragma unroll
+            for (int k2 = 0; k2 < R2; ++k2) {
+                const int k = k1 + R1 * k2;
+                float2 val = u[k2];
+                if (dc_removal && k == 0) val = make_float2(0.f, 0.f);
+                const int p = (k + S / 2) & (S - 1);                    // range fftshift
+                dst[(size_t)p * A * C_used + row] = val;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Doppler stage: rows of mid are (f, s, a) flattened, C contiguous; CTA = NB rows (NB % A == 0 or A % NB == 0)
+// ---------------------------------------------------------------------------------------------
+template <int R1, int R2, int NB>
+__global__ void __launch_bounds__(THREADS)
+doppler_fft_pow2_kernel(const float2* __restrict__ mid, const float2* __restrict__ tw_g, float2* __restrict__ rds, int A,
+                        int lanes_a, long long nrows_total, int nblocks) {
+    using G = Geo<R1, R2>;
+    constexpr int C = G::N, RP = G::ROWP_DOPP;
+    extern __shared__ float2 sm[];
+    float2* tw1 = sm;                // [R1][R2]
+    float2* Y = tw1 + C;             // [NB][RP]
+    for (int i = threadIdx.x; i < C; i += THREADS) {
+        const int k1 = i / R2, t = i - k1 * R2;
+        tw1[i] = tw_g[(k1 * t) % C];
+    }
+    __syncthreads();
+    const int kl = 32 / lanes_a;                                     // consecutive k1 per warp
+    for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+        const long long row0 = (long long)blk * NB;
+        const int nb = (int)min((long long)NB, nrows_total - row0);
+        pass1<R1, R2, false>(mid + row0 * C, C, nb, RP, nullptr, tw1, Y);
+        __syncthreads();
+        // item -> (a_l, k1lo) inside the warp, (row group, k1hi) across warps
+        const int groups = nb / lanes_a;                             // groups of lanes_a consecutive rows (antennas)
+        for (int it = threadIdx.x; it < groups * 32 * (R1 / kl); it += THREADS) {
+            const int lane = it & 31, w = it >> 5;
+            const int a_l = lane % lanes_a, k1lo = lane / lanes_a;
+            const int grp = w % groups, k1 = (w / groups) * kl + k1lo;
+            const int b = grp * lanes_a + a_l;
+            const float2* y = Y + b * RP + k1 * G::K1P;
+            float2 u[R2];
+#pragma unroll
+            for (int n2 = 0; n2 < R2; ++n2) u[n2] = y[n2];
+            dft<R2>(u);
+            const long long gr = row0 + b;
+            const long long fs = gr / A;
+            const int a = (int)(gr - fs * A);
+            float2* dst = rds + fs * C * A + a;
+#pragma unroll
+            for (int k2 = 0; k2 < R2; ++k2) {
+                const int p = (k1 + R1 * k2 + C / 2) & (C - 1);        // Doppler fftshift
+                dst[(size_t)p * A] = u[k2];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace pow2
