@@ -209,13 +209,13 @@ def run_gpu(args):
     F, A, C, S = args.frames, args.antennas, args.chirps, args.samples
 
     cube = synth.synth_cubes(cfg, F, seed=1234, first_frame=rank * F, device=dev)
-    gathered = torch.zeros((world, F, 8), dtype=torch.float64, device=dev)      # NCCL all-gather target
-    vel = gathered[rank]                                                          # the solve writes its own slot
+    from radar_slam_b200.sharding import VelocityGather
+    gather = VelocityGather(world * F, dev)       # all-gather target; this rank's slot is the solve's output
+    vel = gather.slot()
 
     def step():
         pipe.process(cube, chunk_frames=args.chunk, vel_out=vel)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered.view(-1), vel.reshape(-1))
+        gather.gather()                           # NCCL all_gather_into_tensor of the [F, 8] rows (no-op at N=1)
 
     def barrier():
         if world > 1:
@@ -248,12 +248,12 @@ def run_gpu(args):
     host.copy_(cube[:n_e2e])
     torch.cuda.synchronize(dev)
     for _ in range(max(1, min(args.warmup, 2))):
-        pipe.process_host(host, chunk_frames=args.chunk)
+        pipe.process_host(host, chunk_frames=args.host_chunk)
     barrier()
     t0 = time.perf_counter()
     e2e_steps = max(1, min(args.steps, 3))
     for _ in range(e2e_steps):
-        vel_host = pipe.process_host(host, chunk_frames=args.chunk)          # returns after the D2H completed
+        vel_host = pipe.process_host(host, chunk_frames=args.host_chunk)          # returns after the D2H completed
     torch.cuda.synchronize(dev)
     e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if world > 1:
@@ -276,7 +276,7 @@ def run_gpu(args):
         stage_n[name] = stage_n.get(name, 0) + 1
     pipe.profile = None
     # detections per frame (for the algorithmic bytes of the list-driven stages)
-    rds = pipe.range_doppler(cube[: args.chunk])
+    rds = pipe.range_doppler(cube[: min(F, 64)])
     det = pipe.detect(rds)
     n_det_frame = float(det.per_frame_counts().double().mean().item())
     overflow = int(det.overflow.sum().item())
@@ -317,7 +317,7 @@ def run_gpu(args):
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "frames_per_gpu": F, "samples": S, "chirps": C, "channels": A,
-                   "grid_points": len(pipe._angle_tables(A)["grid"]), "chunk_frames": args.chunk,
+                   "grid_points": len(pipe._angle_tables(A)["grid"]), "chunk_frames": args.chunk, "host_chunk_frames": args.host_chunk,
                    "detections_per_frame": n_det_frame, "detection_overflow": overflow,
                    "cache": "inputs larger than L2 (%.2f GiB cube per GPU)" % (cube.numel() * 8 / 2 ** 30),
                    "parallelism": f"frames sharded over {world} GPU(s), all-gather of [F,8] velocity rows"},
@@ -348,7 +348,8 @@ def main():
     ap.add_argument("--antennas", type=int, default=8)
     ap.add_argument("--grid-res", type=float, default=1.0)
     ap.add_argument("--threshold-db", type=float, default=-20.0)
-    ap.add_argument("--chunk", type=int, default=50)
+    ap.add_argument("--chunk", type=int, default=500, help="frames per launch set, device-resident path")
+    ap.add_argument("--host-chunk", type=int, default=32, help="frames per H2D chunk, host-buffer path")
     ap.add_argument("--e2e-frames", type=int, default=1000)
     ap.add_argument("--cpu-frames", type=int, default=8)
     ap.add_argument("--ref-procs", type=int, default=0)

@@ -166,6 +166,127 @@ detect_kernel(const float2* __restrict__ rds, const uint8_t* __restrict__ gate, 
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fast path: antenna chunks of 8 (A % 8 == 0), tile = TR range bins x 128 Doppler bins x 8 antennas.
+// 256 threads; thread = (doppler bin, antenna quad).  Loads are float4 (two antennas), the power plane
+// is [row][doppler+1][8] floats so a thread reads its 4 antennas and both Doppler neighbours with three
+// LDS.128 per row step; ~20 instructions per cell instead of ~150 in the generic kernel.
+// ---------------------------------------------------------------------------------------------
+template <int TR>
+__global__ void __launch_bounds__(DET_THREADS)
+detect_a8_kernel(const float2* __restrict__ rds, const uint8_t* __restrict__ gate, float thr, float eps,
+                 uint32_t* __restrict__ det_key, float* __restrict__ det_power, uint8_t* __restrict__ det_flags,
+                 int32_t* __restrict__ det_count, int32_t* __restrict__ det_overflow, int seg_cap, int R, int D, int A,
+                 Tiling tl) {
+    constexpr int TD = 128, AC = 8, W = (TD + 2) * AC;
+    extern __shared__ float pw[];   // [(TR+2)][W]
+    __shared__ int warp_sums[DET_THREADS / 32];
+    __shared__ int total_s;
+
+    const int tile = blockIdx.x % tl.ntiles;
+    const int f = blockIdx.x / tl.ntiles;
+    const int ia = tile % tl.nac;
+    const int id = (tile / tl.nac) % tl.ntd;
+    const int ir = tile / (tl.nac * tl.ntd);
+    const int r0 = ir * TR, d0 = id * TD, a0 = ia * AC;
+    const float2* frame = rds + (size_t)f * R * D * A;
+    const int tid = threadIdx.x;
+
+    // ---- halo columns (only when the frame is wider than one tile) and out-of-range fill
+    for (int i = tid; i < (TR + 2) * 2 * AC; i += DET_THREADS) {
+        const int rr = i / (2 * AC), rem = i - rr * 2 * AC;
+        const int side = rem / AC, ac = rem - side * AC;
+        const int r = r0 - 1 + rr, d = side ? d0 + TD : d0 - 1;
+        float p = -1.f;
+        if (r >= 0 && r < R && d >= 0 && d < D) {
+            const float2 x = __ldg(frame + ((size_t)r * D + d) * A + a0 + ac);
+            p = fmaf(x.x, x.x, x.y * x.y);
+        }
+        pw[rr * W + (side ? (TD + 1) * AC : 0) + ac] = p;
+    }
+    // ---- interior: each row is TD cells x 4 float4 (= 2 antennas each); 2 float4 per thread per row
+#pragma unroll 3
+    for (int rr = 0; rr < TR + 2; ++rr) {
+        const int r = r0 - 1 + rr;
+        const bool ok = r >= 0 && r < R;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int i4 = tid + DET_THREADS * k;
+            const int cell = i4 >> 2, part = i4 & 3;
+            float2 p2 = make_float2(-1.f, -1.f);
+            if (ok) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(frame + ((size_t)r * D + d0 + cell) * A + a0) + part);
+                p2.x = fmaf(v.x, v.x, v.y * v.y);
+                p2.y = fmaf(v.z, v.z, v.w * v.w);
+            }
+            *reinterpret_cast<float2*>(pw + rr * W + (cell + 1) * AC + part * 2) = p2;
+        }
+    }
+    __syncthreads();
+
+    // ---- column walk: thread = (doppler bin dd, antenna quad aq)
+    const int dd = (tid >> 1) + 1, aq = (tid & 1) * 4;
+    uint32_t hit[4] = {0u, 0u, 0u, 0u}, near[4] = {0u, 0u, 0u, 0u};
+    int my_count = 0;
+    {
+        const float* base = pw + dd * AC + aq;
+        auto ld4 = [&](const float* p, float (&o)[4]) {
+            const float4 v = *reinterpret_cast<const float4*>(p);
+            o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+        };
+        float l0[4], c0[4], q0[4], l1[4], c1[4], q1[4], hp[4];
+        ld4(base - AC, l0); ld4(base, c0); ld4(base + AC, q0);
+        ld4(base + W - AC, l1); ld4(base + W, c1); ld4(base + W + AC, q1);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) hp[j] = fmaxf(fmaxf(l0[j], c0[j]), q0[j]);
+#pragma unroll
+        for (int rr = 1; rr <= TR; ++rr) {
+            float l2[4], c2[4], q2[4];
+            const float* nx = base + (rr + 1) * W;
+            ld4(nx - AC, l2); ld4(nx, c2); ld4(nx + AC, q2);
+            const int r = r0 + rr - 1;
+            const bool row_ok = r < R && gate[r < R ? r : 0];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float hn = fmaxf(fmaxf(l2[j], c2[j]), q2[j]);
+                const float m = fmaxf(fmaxf(hp[j], hn), fmaxf(l1[j], q1[j]));
+                const float c = c1[j];
+                if (row_ok && c >= m && c > thr) {
+                    hit[j] |= 1u << (rr - 1);
+                    ++my_count;
+                    if ((c - m) <= eps * c || (c - thr) <= eps * fabsf(thr)) near[j] |= 1u << (rr - 1);
+                }
+                hp[j] = fmaxf(fmaxf(l1[j], c), q1[j]);
+                l1[j] = l2[j]; c1[j] = c2[j]; q1[j] = q2[j];
+            }
+        }
+    }
+
+    const int offset = block_exclusive_scan(my_count, warp_sums, &total_s);
+    const int total = total_s;
+    const size_t seg = (size_t)blockIdx.x;
+    if (tid == 0) {
+        det_count[seg] = total < seg_cap ? total : seg_cap;
+        if (total > seg_cap) det_overflow[f] = 1;
+    }
+    int pos = offset;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        uint32_t m = hit[j];
+        while (m) {
+            const int b = __ffs(m) - 1;
+            m &= m - 1;
+            if (pos < seg_cap) {
+                const size_t o = seg * seg_cap + pos;
+                det_key[o] = rs_make_key(a0 + aq + j, r0 + b, d0 + dd - 1);
+                det_power[o] = pw[(b + 1) * W + dd * AC + aq + j];
+                det_flags[o] = (near[j] >> b) & 1u ? RS_FLAG_NEARMAX : 0;
+            }
+            ++pos;
+        }
+    }
+}
+
 }  // namespace
 
 extern "C" int rs_detect_tiling(int R, int D, int A, int* tile_r, int* tile_d, int* ntiles) {
@@ -196,6 +317,14 @@ extern "C" int rs_detect(const void* rds, const uint8_t* range_gate, float thr_p
     const long long blocks = (long long)F * t.ntiles;
     RS_CHECK_ARG(blocks < (1ll << 31), "rs_detect: too many blocks");
     cudaMemsetAsync(det_overflow, 0, sizeof(int32_t) * F, (cudaStream_t)stream);
+    if (A % 8 == 0 && D % 128 == 0 && t.TD == 128 && t.AC == 8 && t.TR == 16 && R % 16 == 0) {
+        cudaFuncSetAttribute(detect_a8_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        detect_a8_kernel<16><<<(unsigned)blocks, DET_THREADS, smem, (cudaStream_t)stream>>>(
+            (const float2*)rds, range_gate, thr_power, det_eps, det_key, det_power, det_flags, det_count, det_overflow,
+            seg_cap, R, D, A, t);
+        RS_CHECK_LAUNCH("rs_detect(a8)");
+        return RS_OK;
+    }
     detect_kernel<<<(unsigned)blocks, DET_THREADS, smem, (cudaStream_t)stream>>>(
         (const float2*)rds, range_gate, thr_power, det_eps, det_key, det_power, det_flags, det_count, det_overflow,
         seg_cap, R, D, A, t);

@@ -9,6 +9,7 @@
 // that the next stage reads contiguous memory.  Any length whose prime factors are <= 13 is
 // supported (the reference's defaults are S=400, C=64; BASELINE configs are powers of two).
 #include <algorithm>
+#include <cstdlib>
 #include "rs_common.cuh"
 #include "rs_fft_pow2.cuh"
 
@@ -255,7 +256,7 @@ static int launch_range_pow2(const float2* cube, const float2* table, const floa
     const long long nblocks = (long long)F * A * (C_used / CB);
     if (nblocks >= (1ll << 31)) return 1;
     const int per_sm = (int)((size_t)rs_smem_optin_limit() / smem);
-    const long long grid = std::min<long long>(nblocks, (long long)rs_sm_count() * std::max(1, std::min(per_sm, 4)));
+    const long long grid = std::min<long long>(nblocks, (long long)rs_sm_count() * std::max(1, std::min(per_sm, 6)));
     kern<<<(unsigned)grid, pow2::THREADS, smem, st>>>(cube, table, tw, mid, A, C_total, chirp0, C_used, dc, (int)nblocks);
     return 0;
 }
@@ -270,7 +271,7 @@ static int launch_doppler_pow2(const float2* mid, const float2* tw, float2* rds,
     const long long nblocks = (nrows + NB - 1) / NB;
     if (nblocks >= (1ll << 31)) return 1;
     const int per_sm = (int)((size_t)rs_smem_optin_limit() / smem);
-    const long long grid = std::min<long long>(nblocks, (long long)rs_sm_count() * std::max(1, std::min(per_sm, 4)));
+    const long long grid = std::min<long long>(nblocks, (long long)rs_sm_count() * std::max(1, std::min(per_sm, 6)));
     kern<<<(unsigned)grid, pow2::THREADS, smem, st>>>(mid, tw, rds, A, lanes_a, nrows, (int)nblocks);
     return 0;
 }
@@ -294,7 +295,10 @@ extern "C" int rs_range_fft(const void* cube, const void* table, const void* twi
         const float2 *cu = (const float2*)cube, *tb = (const float2*)table, *tw = (const float2*)twiddle_s;
         cudaStream_t st = (cudaStream_t)stream;
         int rc = 1;
-        if (S == 256) rc = launch_range_pow2<16, 16, 32>(cu, tb, tw, (float2*)mid, F, A, C_total, chirp0, C_used, dc_removal, st);
+        const char* cb_env = getenv("RS_FFT_CB");
+        // measured on B200 (1k frames 256x128x8): CB=16 0.94 ms, CB=32 1.02 ms -- occupancy beats longer store runs
+        if (S == 256 && !(cb_env && atoi(cb_env) == 32)) rc = launch_range_pow2<16, 16, 16>(cu, tb, tw, (float2*)mid, F, A, C_total, chirp0, C_used, dc_removal, st);
+        else if (S == 256) rc = launch_range_pow2<16, 16, 32>(cu, tb, tw, (float2*)mid, F, A, C_total, chirp0, C_used, dc_removal, st);
         else if (S == 128) rc = launch_range_pow2<16, 8, 32>(cu, tb, tw, (float2*)mid, F, A, C_total, chirp0, C_used, dc_removal, st);
         else rc = launch_range_pow2<8, 8, 32>(cu, tb, tw, (float2*)mid, F, A, C_total, chirp0, C_used, dc_removal, st);
         if (rc == 0) {
@@ -334,6 +338,7 @@ extern "C" int rs_doppler_fft(const void* mid, const void* twiddle_c, void* rds,
             cudaStream_t st = (cudaStream_t)stream;
             int rc = 1;
             if (C == 256) rc = launch_doppler_pow2<16, 16, 32>((const float2*)mid, (const float2*)twiddle_c, (float2*)rds, A, lanes_a, nrows, st);
+            else if (C == 128 && !(getenv("RS_FFT_NB") && atoi(getenv("RS_FFT_NB")) == 64)) rc = /* NB=32 0.91 ms vs NB=64 1.04 ms */ launch_doppler_pow2<16, 8, 32>((const float2*)mid, (const float2*)twiddle_c, (float2*)rds, A, lanes_a, nrows, st);
             else if (C == 128) rc = launch_doppler_pow2<16, 8, 64>((const float2*)mid, (const float2*)twiddle_c, (float2*)rds, A, lanes_a, nrows, st);
             else rc = launch_doppler_pow2<8, 8, 64>((const float2*)mid, (const float2*)twiddle_c, (float2*)rds, A, lanes_a, nrows, st);
             if (rc == 0) {

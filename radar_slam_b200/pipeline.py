@@ -272,7 +272,7 @@ class FramePipeline:
         return vel
 
     # ------------------------------------------------------------------ whole path
-    def process(self, cube: torch.Tensor, chunk_frames: int = 64, vel_out: Optional[torch.Tensor] = None,
+    def process(self, cube: torch.Tensor, chunk_frames: int = 512, vel_out: Optional[torch.Tensor] = None,
                 keep: bool = False):
         """Device-resident batch: returns vel float64 [F, 8] (and the last chunk's RDS / detections when
         keep=True and the batch is a single chunk)."""
@@ -290,7 +290,7 @@ class FramePipeline:
             last = (rds, det)
         return (vel, last[0], last[1]) if keep else vel
 
-    def process_host(self, cube_host: torch.Tensor, chunk_frames: int = 64) -> torch.Tensor:
+    def process_host(self, cube_host: torch.Tensor, chunk_frames: int = 32) -> torch.Tensor:
         """End-to-end with HOST buffers: pinned cube[F,A,C,S] -> pinned vel[F,8]; H2D and D2H copies run on
         a second stream and overlap the kernels of the neighbouring chunk."""
         assert not cube_host.is_cuda and cube_host.dtype == torch.complex64
