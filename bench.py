@@ -279,6 +279,10 @@ def run_gpu(args):
     rds = pipe.range_doppler(cube[: min(F, 64)])
     det = pipe.detect(rds)
     n_det_frame = float(det.per_frame_counts().double().mean().item())
+    pipe.angles(rds, det)
+    vm = det.valid_mask().reshape(-1)
+    fl = det.flags[: vm.numel()][vm]
+    flagged = {name: float(((fl & bit) != 0).sum().item()) / det.F for name, bit in (("tie", 1), ("nearmax", 2), ("guard", 4))}
     overflow = int(det.overflow.sum().item())
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
     peak = float(peaks.get("hbm_gbs", 6650.0))
@@ -319,6 +323,7 @@ def run_gpu(args):
         "config": {"workload": WORKLOAD, "frames_per_gpu": F, "samples": S, "chirps": C, "channels": A,
                    "grid_points": len(pipe._angle_tables(A)["grid"]), "chunk_frames": args.chunk, "host_chunk_frames": args.host_chunk,
                    "detections_per_frame": n_det_frame, "detection_overflow": overflow,
+                   "undecided_in_fp32_per_frame": flagged,
                    "cache": "inputs larger than L2 (%.2f GiB cube per GPU)" % (cube.numel() * 8 / 2 ** 30),
                    "parallelism": f"frames sharded over {world} GPU(s), all-gather of [F,8] velocity rows"},
         "roofline": roofline,
