@@ -86,9 +86,14 @@ int rs_doppler_fft(const void* mid, const void* twiddle_c, void* rds, int F, int
  *       thr_power   p > thr_power  <=>  10 log10(p + 1e-12) > threshold_db  (host computes in fp64)
  *       range_gate  uint8 [R], 1 where min_range <= range_bins_m[i] <= max_range
  *       det_eps     relative guard band for RS_FLAG_NEARMAX
- *       det_overflow int32 [F], set to 1 when a tile had more than seg_cap detections */
+ *       det_overflow int32 [F], set to 1 when a tile had more than seg_cap detections
+ *       det_lead   uint32 [F*ntiles*seg_cap]; det_nlead int32 [F*ntiles]: one LEADER per distinct
+ *                   range-Doppler cell of a segment, position | (multiplicity << 16).  A cell flagged on k
+ *                   antennas occupies k consecutive detection slots that share one snapshot, so the angle
+ *                   stage evaluates each leader once.   seg_cap <= 65535. */
 int rs_detect(const void* rds, const uint8_t* range_gate, float thr_power, float det_eps,
-              uint32_t* det_key, float* det_power, uint8_t* det_flags, int32_t* det_count, int32_t* det_overflow,
+              uint32_t* det_key, float* det_power, uint8_t* det_flags, uint32_t* det_lead,
+              int32_t* det_count, int32_t* det_nlead, int32_t* det_overflow,
               int seg_cap, int F, int R, int D, int A, void* stream);
 
 /* (c)   replaces AngleEstimator.process_targets (angle_estimation.py:253-309) for every detection:
@@ -105,7 +110,7 @@ int rs_detect(const void* rds, const uint8_t* range_gate, float thr_power, float
  *                     equations with c,s = grid_cs[aidx]; needs grid_cs (double [G][2]); grid methods, A <= 16 */
 int rs_angles(const void* rds, const float* scan_table, int scan_stride, const void* steer, const float* grid_deg, int G,
               int method, float tie_eps, double esprit_scale,
-              const uint32_t* det_key, const int32_t* det_count, uint8_t* det_flags,
+              const uint32_t* det_key, const uint32_t* det_lead, const int32_t* det_nlead, uint8_t* det_flags,
               int32_t* det_aidx, float* det_adeg, float* det_phase,
               int seg_cap, int nseg_per_frame, int F, int R, int D, int A,
               const double* grid_cs, double* ls_partials, int grid_symmetric, void* stream);

@@ -30,13 +30,25 @@ struct AngleArgs {
     float tie_eps;
     double esprit_scale;
     const uint32_t* det_key;
-    const int32_t* det_count;
+    const uint32_t* det_lead;     // per segment: position | multiplicity << 16 of each distinct cell
+    const int32_t* det_nlead;
     uint8_t* det_flags;
     int32_t* det_aidx;
     float* det_adeg;
     float* det_phase;
     int seg_cap, nseg_per_frame, R, D, A;
 };
+
+// write one cell's result to all of its detections (same snapshot on every antenna that flagged the cell)
+__device__ __forceinline__ void emit(const AngleArgs& p, size_t o, int k, int aidx, float adeg, float phase,
+                                     uint8_t extra_flags) {
+    for (int e = 0; e < k; ++e) {
+        p.det_aidx[o + e] = aidx;
+        p.det_adeg[o + e] = adeg;
+        p.det_phase[o + e] = phase;
+        if (extra_flags) p.det_flags[o + e] |= extra_flags;
+    }
+}
 
 // ESPRIT closed form from a snapshot held in registers (s[0..M-1]); returns degrees.
 template <int AP>
@@ -84,7 +96,7 @@ template <int AP>
 __global__ void __launch_bounds__(ANG_THREADS) angles_small_kernel(AngleArgs p) {
     extern __shared__ float tab[];   // [G][scan_stride]
     const int seg = blockIdx.x;
-    const int n = p.det_count[seg];
+    const int n = p.det_nlead[seg];
     if (n == 0) return;
     const bool scan = p.method != RS_METHOD_ESPRIT;
     if (scan) {
@@ -96,7 +108,9 @@ __global__ void __launch_bounds__(ANG_THREADS) angles_small_kernel(AngleArgs p) 
     const float2* frame = p.rds + (size_t)f * p.R * p.D * p.A;
     const int M = p.A;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const size_t o = (size_t)seg * p.seg_cap + i;
+        const uint32_t ld = p.det_lead[(size_t)seg * p.seg_cap + i];
+        const size_t o = (size_t)seg * p.seg_cap + (ld & 0xFFFFu);
+        const int mult = (int)(ld >> 16);
         int a, r, d;
         rs_split_key(p.det_key[o], a, r, d);
         const float2* cell = frame + ((size_t)r * p.D + d) * M;
@@ -107,12 +121,11 @@ __global__ void __launch_bounds__(ANG_THREADS) angles_small_kernel(AngleArgs p) 
         // inter-antenna phase angle(s[1] conj(s[0]))  (velocity_solver.py:136)
         const float pr = s[1].x * s[0].x + s[1].y * s[0].y;
         const float pi = s[1].y * s[0].x - s[1].x * s[0].y;
-        p.det_phase[o] = atan2f(pi, pr);
+        const float phase = atan2f(pi, pr);
 
-        uint8_t flags = p.det_flags[o];
+        uint8_t flags = 0;
         if (!scan) {
-            p.det_adeg[o] = esprit_deg<AP>(s, M, p.esprit_scale);
-            p.det_aidx[o] = -1;
+            emit(p, o, mult, -1, esprit_deg<AP>(s, M, p.esprit_scale), phase, 0);
             continue;
         }
         // lags R_k, k = 0..AP-1
@@ -149,9 +162,7 @@ __global__ void __launch_bounds__(ANG_THREADS) angles_small_kernel(AngleArgs p) 
             const float full = (float)M * rr[0];
             if (full - pbest <= 1e-4f * full) flags |= RS_FLAG_GUARD;
         }
-        p.det_aidx[o] = bi;
-        p.det_adeg[o] = p.grid_deg[bi];
-        p.det_flags[o] = flags;
+        emit(p, o, mult, bi, p.grid_deg[bi], phase, flags);
     }
 }
 
@@ -188,7 +199,7 @@ __global__ void __launch_bounds__(ANG_THREADS) angles_scan_kernel(AngleArgs p, c
     extern __shared__ float tab[];   // [rows][scan_stride]
     __shared__ double red[ANG_THREADS / 32][8];
     const int seg = blockIdx.x;
-    const int n = p.det_count[seg];
+    const int n = p.det_nlead[seg];
     double acc_ls[7] = {0, 0, 0, 0, 0, 0, 0};
     if (n > 0) {
         const int rows = SYM ? (p.G + 1) / 2 : p.G;
@@ -200,12 +211,15 @@ __global__ void __launch_bounds__(ANG_THREADS) angles_scan_kernel(AngleArgs p, c
         for (int base = 0; base < n; base += ND * ANG_THREADS) {
             float rr[ND][AP], ri[ND][AP], yv[ND];
             size_t o[ND];
+            int mult[ND];
             bool valid[ND];
 #pragma unroll
             for (int q = 0; q < ND; ++q) {
                 const int i = base + q * ANG_THREADS + threadIdx.x;
                 valid[q] = i < n;
-                o[q] = (size_t)seg * p.seg_cap + (valid[q] ? i : 0);
+                const uint32_t ld = valid[q] ? p.det_lead[(size_t)seg * p.seg_cap + i] : (1u << 16);
+                o[q] = (size_t)seg * p.seg_cap + (ld & 0xFFFFu);
+                mult[q] = (int)(ld >> 16);
                 float2 s[AP];
                 if (valid[q]) {
                     int a, r, d;
@@ -226,7 +240,6 @@ __global__ void __launch_bounds__(ANG_THREADS) angles_scan_kernel(AngleArgs p, c
                     const float pr = s[1].x * s[0].x + s[1].y * s[0].y;
                     const float pi = s[1].y * s[0].x - s[1].x * s[0].y;
                     yv[q] = atan2f(pi, pr);
-                    p.det_phase[o[q]] = yv[q];
                 } else {
                     yv[q] = 0.f;
 #pragma unroll
@@ -314,19 +327,17 @@ __global__ void __launch_bounds__(ANG_THREADS) angles_scan_kernel(AngleArgs p, c
                 const float second = left ? fmaxf(Rt[q].best, L[q].second) : fmaxf(L[q].best, Rt[q].second);
                 const int bi = left ? L[q].idx : Rt[q].idx;
                 const float pbest = rr[q][0] + 2.f * best;
-                uint8_t flags = p.det_flags[o[q]];
+                uint8_t flags = 0;
                 if (2.f * (best - second) <= p.tie_eps * fabsf(pbest)) flags |= RS_FLAG_TIE;
                 if (p.method == RS_METHOD_MUSIC) {
                     const float full = (float)M * rr[q][0];
                     if (full - pbest <= 1e-4f * full) flags |= RS_FLAG_GUARD;
                 }
-                p.det_aidx[o[q]] = bi;
-                p.det_adeg[o[q]] = p.grid_deg[bi];
-                p.det_flags[o[q]] = flags;
-                if (ls_partials != nullptr) {
-                    const double c = grid_cs[2 * bi], sn = grid_cs[2 * bi + 1], y = (double)yv[q];
-                    acc_ls[0] += c * c; acc_ls[1] += sn * sn; acc_ls[2] += c * sn;
-                    acc_ls[3] += y * c; acc_ls[4] += y * sn; acc_ls[5] += y * y; acc_ls[6] += 1.0;
+                emit(p, o[q], mult[q], bi, p.grid_deg[bi], yv[q], flags);
+                if (ls_partials != nullptr) {      // every antenna's detection of the cell adds the same row
+                    const double c = grid_cs[2 * bi], sn = grid_cs[2 * bi + 1], y = (double)yv[q], w = (double)mult[q];
+                    acc_ls[0] += w * c * c; acc_ls[1] += w * sn * sn; acc_ls[2] += w * c * sn;
+                    acc_ls[3] += w * y * c; acc_ls[4] += w * y * sn; acc_ls[5] += w * y * y; acc_ls[6] += w;
                 }
             }
         }
@@ -355,7 +366,7 @@ __global__ void __launch_bounds__(ANG_THREADS) angles_scan_kernel(AngleArgs p, c
 __global__ void __launch_bounds__(ANG_THREADS) angles_large_kernel(AngleArgs p) {
     extern __shared__ float2 snap[];   // [warps][A]
     const int seg = blockIdx.x;
-    const int n = p.det_count[seg];
+    const int n = p.det_nlead[seg];
     if (n == 0) return;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const int f = seg / p.nseg_per_frame;
@@ -363,7 +374,9 @@ __global__ void __launch_bounds__(ANG_THREADS) angles_large_kernel(AngleArgs p) 
     const float2* frame = p.rds + (size_t)f * p.R * p.D * M;
     float2* s = snap + wid * M;
     for (int i = wid; i < n; i += nw) {
-        const size_t o = (size_t)seg * p.seg_cap + i;
+        const uint32_t ld = p.det_lead[(size_t)seg * p.seg_cap + i];
+        const size_t o = (size_t)seg * p.seg_cap + (ld & 0xFFFFu);
+        const int mult = (int)(ld >> 16);
         int a, r, d;
         rs_split_key(p.det_key[o], a, r, d);
         const float2* cell = frame + ((size_t)r * p.D + d) * M;
@@ -377,12 +390,8 @@ __global__ void __launch_bounds__(ANG_THREADS) angles_large_kernel(AngleArgs p) 
 #pragma unroll
         for (int off = 16; off; off >>= 1) e += __shfl_xor_sync(0xffffffffu, e, off);
         __syncwarp();
-        uint8_t flags = p.det_flags[o];
-        if (lane == 0) {
-            const float pr = s[1].x * s[0].x + s[1].y * s[0].y;
-            const float pi = s[1].y * s[0].x - s[1].x * s[0].y;
-            p.det_phase[o] = atan2f(pi, pr);
-        }
+        uint8_t flags = 0;
+        const float phase = atan2f(s[1].y * s[0].x - s[1].x * s[0].y, s[1].x * s[0].x + s[1].y * s[0].y);
         if (p.method == RS_METHOD_ESPRIT) {
             // warp-cooperative sums in fp64
             double alpha = 0, gamma = 0, br = 0, bi = 0;
@@ -418,10 +427,9 @@ __global__ void __launch_bounds__(ANG_THREADS) angles_large_kernel(AngleArgs p) 
                 nr += __shfl_xor_sync(0xffffffffu, nr, off);
                 ni += __shfl_xor_sync(0xffffffffu, ni, off);
             }
-            if (lane == 0) {
-                p.det_adeg[o] = (float)(asin(atan2(ni, nr) * p.esprit_scale) * (180.0 / 3.14159265358979323846));
-                p.det_aidx[o] = -1;
-            }
+            if (lane == 0)
+                emit(p, o, mult, -1, (float)(asin(atan2(ni, nr) * p.esprit_scale) * (180.0 / 3.14159265358979323846)),
+                     phase, 0);
             continue;
         }
         float best = -1.f, second = -1.f;
@@ -454,9 +462,7 @@ __global__ void __launch_bounds__(ANG_THREADS) angles_large_kernel(AngleArgs p) 
                 const float full = (float)M * e;
                 if (full - best <= 1e-4f * full) flags |= RS_FLAG_GUARD;
             }
-            p.det_aidx[o] = bi;
-            p.det_adeg[o] = p.grid_deg[bi];
-            p.det_flags[o] = flags;
+            emit(p, o, mult, bi, p.grid_deg[bi], phase, flags);
         }
     }
 }
@@ -538,10 +544,12 @@ __global__ void spectra_f64_kernel(const double2* __restrict__ sig, const double
 
 extern "C" int rs_angles(const void* rds, const float* scan_table, int scan_stride, const void* steer,
                          const float* grid_deg, int G, int method, float tie_eps, double esprit_scale,
-                         const uint32_t* det_key, const int32_t* det_count, uint8_t* det_flags, int32_t* det_aidx,
+                         const uint32_t* det_key, const uint32_t* det_lead, const int32_t* det_nlead, uint8_t* det_flags,
+                         int32_t* det_aidx,
                          float* det_adeg, float* det_phase, int seg_cap, int nseg_per_frame, int F, int R, int D, int A,
                          const double* grid_cs, double* ls_partials, int grid_symmetric, void* stream) {
-    RS_CHECK_ARG(rds && det_key && det_count && det_flags && det_aidx && det_adeg && det_phase, "rs_angles: null pointer");
+    RS_CHECK_ARG(rds && det_key && det_lead && det_nlead && det_flags && det_aidx && det_adeg && det_phase,
+                 "rs_angles: null pointer");
     RS_CHECK_ARG(ls_partials == nullptr || grid_cs != nullptr, "rs_angles: ls_partials needs grid_cs");
     RS_CHECK_ARG(method >= 0 && method <= 2, "rs_angles: unknown method %d", method);
     RS_CHECK_ARG(A >= 2 && A <= RS_MAX_ANTENNAS, "rs_angles: need 2 <= A <= %d", RS_MAX_ANTENNAS);
@@ -549,7 +557,7 @@ extern "C" int rs_angles(const void* rds, const float* scan_table, int scan_stri
     const bool scan = method != RS_METHOD_ESPRIT;
     RS_CHECK_ARG(!scan || (G > 0 && grid_deg), "rs_angles: grid required");
     AngleArgs p{(const float2*)rds, scan_table, scan_stride, (const float2*)steer, grid_deg, G, method, tie_eps,
-                esprit_scale, det_key, det_count, det_flags, det_aidx, det_adeg, det_phase, seg_cap, nseg_per_frame,
+                esprit_scale, det_key, det_lead, det_nlead, det_flags, det_aidx, det_adeg, det_phase, seg_cap, nseg_per_frame,
                 R, D, A};
     const long long blocks = (long long)F * nseg_per_frame;
     RS_CHECK_ARG(blocks < (1ll << 31), "rs_angles: too many segments");

@@ -81,6 +81,8 @@ class Detections:
     D: int
     A: int
     ls_partials: Optional[torch.Tensor] = None     # per-segment normal-equation sums written by rs_angles
+    lead: Optional[torch.Tensor] = None            # one leader per distinct cell: position | multiplicity << 16
+    nlead: Optional[torch.Tensor] = None
 
     def valid_mask(self) -> torch.Tensor:
         n = self.F * self.ntiles
@@ -226,10 +228,11 @@ class FramePipeline:
             flags=alloc("det_flags", (n,), torch.uint8), aidx=alloc("det_aidx", (n,), torch.int32),
             adeg=alloc("det_adeg", (n,), torch.float32), phase=alloc("det_phase", (n,), torch.float32),
             count=alloc("det_count", (F * ntiles,), torch.int32), overflow=alloc("det_overflow", (F,), torch.int32),
-            seg_cap=cap, ntiles=ntiles, F=F, R=R, D=D, A=A)
+            seg_cap=cap, ntiles=ntiles, F=F, R=R, D=D, A=A,
+            lead=alloc("det_lead", (n,), torch.int32), nlead=alloc("det_nlead", (F * ntiles,), torch.int32))
         self._call("rs_detect", rds.data_ptr(), gate.data_ptr(), thr, c.det_eps, det.key.data_ptr(),
-                   det.power.data_ptr(), det.flags.data_ptr(), det.count.data_ptr(),
-                   det.overflow.data_ptr(), cap, F, R, D, A, self.stream)
+                   det.power.data_ptr(), det.flags.data_ptr(), det.lead.data_ptr(), det.count.data_ptr(),
+                   det.nlead.data_ptr(), det.overflow.data_ptr(), cap, F, R, D, A, self.stream)
         return det
 
     def angles(self, rds: torch.Tensor, det: Detections, method: Optional[str] = None,
@@ -245,8 +248,8 @@ class FramePipeline:
         self._call(
             "rs_angles",
             rds.data_ptr(), t["scan"].data_ptr(), t["stride"], _lib.ptr(t["steer64"]), t["grid_f32"].data_ptr(), t["G"],
-            _lib.METHODS[method], c.tie_eps, esprit_scale, det.key.data_ptr(), det.count.data_ptr(),
-            det.flags.data_ptr(), det.aidx.data_ptr(), det.adeg.data_ptr(), det.phase.data_ptr(),
+            _lib.METHODS[method], c.tie_eps, esprit_scale, det.key.data_ptr(), det.lead.data_ptr(),
+            det.nlead.data_ptr(), det.flags.data_ptr(), det.aidx.data_ptr(), det.adeg.data_ptr(), det.phase.data_ptr(),
             det.seg_cap, det.ntiles, det.F, det.R, det.D, det.A,
             t["grid_cs"].data_ptr(), _lib.ptr(det.ls_partials), int(t["symmetric"]), self.stream)
         return det
