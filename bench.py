@@ -38,7 +38,8 @@ def radar_config(args):
     from radar_slam_b200 import RadarConfig
     return RadarConfig(fc=77e9, bandwidth=1e9, chirp_duration=args.samples / 10e6, pri=100e-6, num_chirps=args.chirps,
                        sampling_rate=10e6, num_antennas=args.antennas, search_resolution=args.grid_res,
-                       method="music", threshold_db=args.threshold_db)
+                       method="music", threshold_db=args.threshold_db, recheck=not args.no_recheck,
+                       fft_eps=args.fft_eps)
 
 
 def oracle_params(args):
@@ -284,6 +285,13 @@ def run_gpu(args):
     fl = det.flags[: vm.numel()][vm]
     flagged = {name: float(((fl & bit) != 0).sum().item()) / det.F for name, bit in (("tie", 1), ("nearmax", 2), ("guard", 4))}
     overflow = int(det.overflow.sum().item())
+    recheck_stats = None
+    if cfg.recheck:
+        ds = pipe.recheck_detections(cube[: det.F], det).cpu().numpy().astype(float) / det.F
+        pipe.angles(rds, det)
+        as_ = pipe.recheck_angles(cube[: det.F], rds, det).cpu().numpy().astype(float) / det.F
+        recheck_stats = {"detections_per_frame": dict(zip(("rechecked", "dropped", "promoted", "unresolved"), ds.tolist())),
+                         "angles_per_frame": dict(zip(("rechecked", "index_changed", "fp64_snapshot", "unresolved"), as_.tolist()))}
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
@@ -323,7 +331,7 @@ def run_gpu(args):
         "config": {"workload": WORKLOAD, "frames_per_gpu": F, "samples": S, "chirps": C, "channels": A,
                    "grid_points": len(pipe._angle_tables(A)["grid"]), "chunk_frames": args.chunk, "host_chunk_frames": args.host_chunk,
                    "detections_per_frame": n_det_frame, "detection_overflow": overflow,
-                   "undecided_in_fp32_per_frame": flagged,
+                   "undecided_in_fp32_per_frame": flagged, "fp64_recheck": recheck_stats,
                    "cache": "inputs larger than L2 (%.2f GiB cube per GPU)" % (cube.numel() * 8 / 2 ** 30),
                    "parallelism": f"frames sharded over {world} GPU(s), all-gather of [F,8] velocity rows"},
         "roofline": roofline,
@@ -355,6 +363,8 @@ def main():
     ap.add_argument("--threshold-db", type=float, default=-20.0)
     ap.add_argument("--chunk", type=int, default=500, help="frames per launch set, device-resident path")
     ap.add_argument("--host-chunk", type=int, default=32, help="frames per H2D chunk, host-buffer path")
+    ap.add_argument("--no-recheck", action="store_true", help="skip the fp64 recheck of flagged decisions (fp32 path only)")
+    ap.add_argument("--fft-eps", type=float, default=1e-6, help="error bound of the fp32 FFT used by the recheck, in rms units")
     ap.add_argument("--e2e-frames", type=int, default=1000)
     ap.add_argument("--cpu-frames", type=int, default=8)
     ap.add_argument("--ref-procs", type=int, default=0)

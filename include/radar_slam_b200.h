@@ -54,8 +54,9 @@ extern "C" {
 #define RS_FLAG_TIE        1   /* top-2 grid values closer than tie_eps: argmax not trustworthy in fp32 */
 #define RS_FLAG_NEARMAX    2   /* cell within det_eps of a neighbour or of the threshold */
 #define RS_FLAG_GUARD      4   /* MUSIC denominator inside the 1e-12 guard zone (angle_estimation.py:149) */
-#define RS_FLAG_FIXED      8   /* decision re-evaluated in fp64 by rs_recheck_f64 */
-#define RS_FLAG_DROPPED   16   /* fp64 recheck says this is not a detection; consumers skip it */
+#define RS_FLAG_FIXED      8   /* angle decision re-evaluated in fp64 by rs_recheck_angles_f64 */
+#define RS_FLAG_DROPPED   16   /* not a detection (near-miss candidate, or dropped by the fp64 recheck); consumers skip it */
+#define RS_FLAG_DETFIXED  32   /* detection decision re-evaluated in fp64 by rs_recheck_detections_f64 */
 
 #define RS_MAX_RANGE_BINS   4096
 #define RS_MAX_DOPPLER_BINS 4096
@@ -90,10 +91,13 @@ int rs_doppler_fft(const void* mid, const void* twiddle_c, void* rds, int F, int
  *       det_lead   uint32 [F*ntiles*seg_cap]; det_nlead int32 [F*ntiles]: one LEADER per distinct
  *                   range-Doppler cell of a segment, position | (multiplicity << 16).  A cell flagged on k
  *                   antennas occupies k consecutive detection slots that share one snapshot, so the angle
- *                   stage evaluates each leader once.   seg_cap <= 65535. */
+ *                   stage evaluates each leader once.   seg_cap <= 65535.
+ *       det_nnear   optional int32 [F*ntiles]: RS_FLAG_NEARMAX entries per segment (recheck skips clean segments)
+ *       det_psum    optional float [F*ntiles]: sum of |X|^2 over the tile (frame noise level, used by the
+ *                   recheck's error bound) */
 int rs_detect(const void* rds, const uint8_t* range_gate, float thr_power, float det_eps,
               uint32_t* det_key, float* det_power, uint8_t* det_flags, uint32_t* det_lead,
-              int32_t* det_count, int32_t* det_nlead, int32_t* det_overflow,
+              int32_t* det_count, int32_t* det_nlead, int32_t* det_overflow, int32_t* det_nnear, float* det_psum,
               int seg_cap, int F, int R, int D, int A, void* stream);
 
 /* (c)   replaces AngleEstimator.process_targets (angle_estimation.py:253-309) for every detection:
@@ -107,13 +111,14 @@ int rs_detect(const void* rds, const uint8_t* range_gate, float thr_power, float
  *       grid_symmetric  1 when grid_deg[G-1-g] == -grid_deg[g] exactly (halves the scan work)
  *       ls_partials   optional double [F*nseg_per_frame][8]: per-segment fp64 sums
  *                     (sum c^2, sum s^2, sum cs, sum yc, sum ys, sum y^2, n, 0) of the velocity normal
- *                     equations with c,s = grid_cs[aidx]; needs grid_cs (double [G][2]); grid methods, A <= 16 */
+ *                     equations with c,s = grid_cs[aidx]; needs grid_cs (double [G][2]); grid methods, A <= 16
+ *       det_ntie      optional int32 [F*nseg_per_frame]: cells flagged TIE / GUARD per segment */
 int rs_angles(const void* rds, const float* scan_table, int scan_stride, const void* steer, const float* grid_deg, int G,
               int method, float tie_eps, double esprit_scale,
               const uint32_t* det_key, const uint32_t* det_lead, const int32_t* det_nlead, uint8_t* det_flags,
               int32_t* det_aidx, float* det_adeg, float* det_phase,
               int seg_cap, int nseg_per_frame, int F, int R, int D, int A,
-              const double* grid_cs, double* ls_partials, int grid_symmetric, void* stream);
+              const double* grid_cs, double* ls_partials, int grid_symmetric, int32_t* det_ntie, void* stream);
 
 /* (d')  the velocity solve of rs_velocity_ls from the per-segment sums rs_angles already produced
  *       (no second pass over the detection lists); same output row layout. */
@@ -129,6 +134,33 @@ int rs_velocity_ls(const int32_t* det_aidx, const float* det_adeg, const float* 
                    const int32_t* det_count, const double* grid_cs, double k_phase, double bound,
                    int irls_iters, double huber_delta,
                    double* vel, int seg_cap, int nseg_per_frame, int F, void* stream);
+
+/* fp64 re-evaluation of the decisions the fp32 kernels flag as undecidable, straight from the raw cube
+ * (direct fp64 DFT of the cells involved; table128 = conj(ref)*window complex128 [S]).  One CTA per
+ * detection segment, items in list order: deterministic.  stats int32 [4] is zeroed and filled.
+ *
+ * rs_recheck_detections_f64: RS_FLAG_NEARMAX entries (detections and the near-miss candidates rs_detect emits
+ *   as RS_FLAG_DROPPED): exact 3x3 local-maximum and threshold test (dechirp.py:250-254,
+ *   thr_power64 = 10^(threshold_db/10), test p + 1e-12 > thr_power64); sets/clears RS_FLAG_DROPPED, sets
+ *   RS_FLAG_DETFIXED.  Run it BEFORE rs_angles.  stats = {rechecked, dropped, promoted, unresolved}.
+ * rs_recheck_angles_f64: RS_FLAG_TIE / RS_FLAG_GUARD cells.  Stage A: fp64 grid scan of the fp32 snapshot; the
+ *   snapshot's rounding error is bounded by fft_eps * rms(|X|) per element (rms from det_psum), which bounds how far
+ *   P_g - P_h can move; if the winner beats every other grid point by more than its bound the decision is final.
+ *   Stage B (otherwise, and near the MUSIC 1e-12 guard): the snapshot is recomputed in fp64 from the cube.
+ *   First-index argmax of the method's pseudo-spectrum (angle_estimation.py:143-152, 173); rewrites
+ *   det_aidx/det_adeg, sets RS_FLAG_FIXED and corrects ls_partials.
+ *   stats = {rechecked, index changed, needed the fp64 snapshot, unresolved}. */
+int rs_recheck_detections_f64(const void* cube, const void* table128, int C_total, int chirp0, int dc_removal,
+                              double thr_power64, const uint32_t* det_key, uint8_t* det_flags,
+                              const int32_t* det_count, const int32_t* det_nnear, int seg_cap, int nseg_per_frame,
+                              int F, int A, int C, int S, int32_t* stats, void* stream);
+int rs_recheck_angles_f64(const void* cube, const void* table128, int C_total, int chirp0, int dc_removal,
+                          const void* rds, const void* steer128, const float* grid_deg, const double* grid_cs,
+                          int G, int method, double fft_eps, const float* det_psum, const int32_t* det_ntie,
+                          const uint32_t* det_key, const uint32_t* det_lead, const int32_t* det_nlead,
+                          uint8_t* det_flags, int32_t* det_aidx, float* det_adeg, const float* det_phase,
+                          double* ls_partials, int seg_cap, int nseg_per_frame, int F, int A, int C, int S,
+                          int32_t* stats, void* stream);
 
 /* helpers for the legacy (list-of-dict) adapters ---------------------------------------------- */
 

@@ -12,7 +12,7 @@ import os
 from . import build as _build
 
 RS_METHOD_MUSIC, RS_METHOD_BEAMFORMING, RS_METHOD_ESPRIT = 0, 1, 2
-RS_FLAG_TIE, RS_FLAG_NEARMAX, RS_FLAG_GUARD, RS_FLAG_FIXED, RS_FLAG_DROPPED = 1, 2, 4, 8, 16
+RS_FLAG_TIE, RS_FLAG_NEARMAX, RS_FLAG_GUARD, RS_FLAG_FIXED, RS_FLAG_DROPPED, RS_FLAG_DETFIXED = 1, 2, 4, 8, 16, 32
 METHODS = {"music": RS_METHOD_MUSIC, "beamforming": RS_METHOD_BEAMFORMING, "esprit": RS_METHOD_ESPRIT}
 
 _vp, _i, _f, _d = C.c_void_p, C.c_int, C.c_float, C.c_double
@@ -23,10 +23,13 @@ _SIGNATURES = {
     "rs_detect_tiling": (_i, [_i, _i, _i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
     "rs_range_fft": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "rs_doppler_fft": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
-    "rs_detect": (_i, [_vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "rs_detect": (_i, [_vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "rs_angles": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _f, _d, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
-                       _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
+                       _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
     "rs_velocity_from_partials": (_i, [_vp, _i, _i, _d, _d, _vp, _vp]),
+    "rs_recheck_detections_f64": (_i, [_vp, _vp, _i, _i, _i, _d, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "rs_recheck_angles_f64": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _d, _vp, _vp, _vp, _vp, _vp,
+                                   _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "rs_velocity_ls": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _d, _d, _i, _d, _vp, _i, _i, _i, _vp]),
     "rs_rds_to_reference_layout": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "rs_rds_from_reference_layout": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),

@@ -32,6 +32,7 @@ struct AngleArgs {
     const uint32_t* det_key;
     const uint32_t* det_lead;     // per segment: position | multiplicity << 16 of each distinct cell
     const int32_t* det_nlead;
+    int32_t* det_ntie;            // per segment: cells flagged TIE / GUARD (zeroed by the entry point; may be null)
     uint8_t* det_flags;
     int32_t* det_aidx;
     float* det_adeg;
@@ -40,14 +41,20 @@ struct AngleArgs {
 };
 
 // write one cell's result to all of its detections (same snapshot on every antenna that flagged the cell)
-__device__ __forceinline__ void emit(const AngleArgs& p, size_t o, int k, int aidx, float adeg, float phase,
-                                     uint8_t extra_flags) {
+// returns how many of them are live (not RS_FLAG_DROPPED): the weight of the cell in the velocity sums
+__device__ __forceinline__ int emit(const AngleArgs& p, int seg, size_t o, int k, int aidx, float adeg, float phase,
+                                    uint8_t extra_flags) {
+    int live = 0;
+    if ((extra_flags & (RS_FLAG_TIE | RS_FLAG_GUARD)) && p.det_ntie) atomicAdd(p.det_ntie + seg, 1);
     for (int e = 0; e < k; ++e) {
         p.det_aidx[o + e] = aidx;
         p.det_adeg[o + e] = adeg;
         p.det_phase[o + e] = phase;
-        if (extra_flags) p.det_flags[o + e] |= extra_flags;
+        const uint8_t fl = p.det_flags[o + e];
+        live += (fl & RS_FLAG_DROPPED) ? 0 : 1;
+        if (extra_flags) p.det_flags[o + e] = fl | extra_flags;
     }
+    return live;
 }
 
 // ESPRIT closed form from a snapshot held in registers (s[0..M-1]); returns degrees.
@@ -125,7 +132,7 @@ __global__ void __launch_bounds__(ANG_THREADS) angles_small_kernel(AngleArgs p) 
 
         uint8_t flags = 0;
         if (!scan) {
-            emit(p, o, mult, -1, esprit_deg<AP>(s, M, p.esprit_scale), phase, 0);
+            emit(p, seg, o, mult, -1, esprit_deg<AP>(s, M, p.esprit_scale), phase, 0);
             continue;
         }
         // lags R_k, k = 0..AP-1
@@ -162,7 +169,7 @@ __global__ void __launch_bounds__(ANG_THREADS) angles_small_kernel(AngleArgs p) 
             const float full = (float)M * rr[0];
             if (full - pbest <= 1e-4f * full) flags |= RS_FLAG_GUARD;
         }
-        emit(p, o, mult, bi, p.grid_deg[bi], phase, flags);
+        emit(p, seg, o, mult, bi, p.grid_deg[bi], phase, flags);
     }
 }
 
@@ -333,9 +340,9 @@ __global__ void __launch_bounds__(ANG_THREADS) angles_scan_kernel(AngleArgs p, c
                     const float full = (float)M * rr[q][0];
                     if (full - pbest <= 1e-4f * full) flags |= RS_FLAG_GUARD;
                 }
-                emit(p, o[q], mult[q], bi, p.grid_deg[bi], yv[q], flags);
+                const int live = emit(p, seg, o[q], mult[q], bi, p.grid_deg[bi], yv[q], flags);
                 if (ls_partials != nullptr) {      // every antenna's detection of the cell adds the same row
-                    const double c = grid_cs[2 * bi], sn = grid_cs[2 * bi + 1], y = (double)yv[q], w = (double)mult[q];
+                    const double c = grid_cs[2 * bi], sn = grid_cs[2 * bi + 1], y = (double)yv[q], w = (double)live;
                     acc_ls[0] += w * c * c; acc_ls[1] += w * sn * sn; acc_ls[2] += w * c * sn;
                     acc_ls[3] += w * y * c; acc_ls[4] += w * y * sn; acc_ls[5] += w * y * y; acc_ls[6] += w;
                 }
@@ -428,7 +435,7 @@ __global__ void __launch_bounds__(ANG_THREADS) angles_large_kernel(AngleArgs p) 
                 ni += __shfl_xor_sync(0xffffffffu, ni, off);
             }
             if (lane == 0)
-                emit(p, o, mult, -1, (float)(asin(atan2(ni, nr) * p.esprit_scale) * (180.0 / 3.14159265358979323846)),
+                emit(p, seg, o, mult, -1, (float)(asin(atan2(ni, nr) * p.esprit_scale) * (180.0 / 3.14159265358979323846)),
                      phase, 0);
             continue;
         }
@@ -462,7 +469,7 @@ __global__ void __launch_bounds__(ANG_THREADS) angles_large_kernel(AngleArgs p) 
                 const float full = (float)M * e;
                 if (full - best <= 1e-4f * full) flags |= RS_FLAG_GUARD;
             }
-            emit(p, o, mult, bi, p.grid_deg[bi], phase, flags);
+            emit(p, seg, o, mult, bi, p.grid_deg[bi], phase, flags);
         }
     }
 }
@@ -547,7 +554,7 @@ extern "C" int rs_angles(const void* rds, const float* scan_table, int scan_stri
                          const uint32_t* det_key, const uint32_t* det_lead, const int32_t* det_nlead, uint8_t* det_flags,
                          int32_t* det_aidx,
                          float* det_adeg, float* det_phase, int seg_cap, int nseg_per_frame, int F, int R, int D, int A,
-                         const double* grid_cs, double* ls_partials, int grid_symmetric, void* stream) {
+                         const double* grid_cs, double* ls_partials, int grid_symmetric, int32_t* det_ntie, void* stream) {
     RS_CHECK_ARG(rds && det_key && det_lead && det_nlead && det_flags && det_aidx && det_adeg && det_phase,
                  "rs_angles: null pointer");
     RS_CHECK_ARG(ls_partials == nullptr || grid_cs != nullptr, "rs_angles: ls_partials needs grid_cs");
@@ -557,11 +564,13 @@ extern "C" int rs_angles(const void* rds, const float* scan_table, int scan_stri
     const bool scan = method != RS_METHOD_ESPRIT;
     RS_CHECK_ARG(!scan || (G > 0 && grid_deg), "rs_angles: grid required");
     AngleArgs p{(const float2*)rds, scan_table, scan_stride, (const float2*)steer, grid_deg, G, method, tie_eps,
-                esprit_scale, det_key, det_lead, det_nlead, det_flags, det_aidx, det_adeg, det_phase, seg_cap, nseg_per_frame,
+                esprit_scale, det_key, det_lead, det_nlead, det_ntie, det_flags, det_aidx, det_adeg, det_phase, seg_cap,
+                nseg_per_frame,
                 R, D, A};
     const long long blocks = (long long)F * nseg_per_frame;
     RS_CHECK_ARG(blocks < (1ll << 31), "rs_angles: too many segments");
     cudaStream_t st = (cudaStream_t)stream;
+    if (det_ntie) cudaMemsetAsync(det_ntie, 0, sizeof(int32_t) * (size_t)blocks, st);
     if (A <= 16) {
         RS_CHECK_ARG(!scan || scan_table, "rs_angles: scan_table required for A <= 16");
         const int ap = A <= 2 ? 2 : A <= 4 ? 4 : A <= 8 ? 8 : 16;

@@ -66,6 +66,20 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* warp_sums, int* 
     return warp_sums[wid] + inc - v;
 }
 
+// 0: not a detection; 1: detection; 3: detection whose margin to the best neighbour / threshold is inside
+// the fp32 guard band; 7: NOT a detection in fp32 but inside the band (a candidate the fp64 recheck may promote).
+__device__ __forceinline__ int classify(float c, float m, float thr, float eps) {
+    // cheap reject (91 % of the cells): more than 2 eps below the best neighbour or the threshold
+    const float cu = fmaf(c, 2.f * eps, c);
+    if (cu < m || cu <= thr) return 0;
+    const bool ge_m = c >= m, gt_t = c > thr;
+    const bool near_m = fabsf(c - m) <= eps * fmaxf(c, m);
+    const bool near_t = fabsf(c - thr) <= eps * fabsf(thr);
+    if (ge_m && gt_t) return (near_m || near_t) ? 3 : 1;
+    if ((ge_m || near_m) && (gt_t || near_t)) return 7;
+    return 0;
+}
+
 struct DetOut {
     uint32_t* key;
     float* power;
@@ -74,8 +88,33 @@ struct DetOut {
     int32_t* count;
     int32_t* nlead;
     int32_t* overflow;
+    int32_t* nnear;      // per segment: entries carrying RS_FLAG_NEARMAX (lets the fp64 recheck skip clean segments)
+    float* psum;         // per segment: sum of |X|^2 over the tile (frame noise level for the recheck's error bound)
     int seg_cap;
 };
+
+// block-wide sums of an int and a float into shared scalars (integer sum is order independent; the float sum is
+// reduced in a fixed shuffle/warp order, so both are deterministic)
+__device__ __forceinline__ void block_sums(int iv, float fv, int* s_i, float* s_f) {
+    __shared__ float wf[DET_THREADS / 32];
+    __shared__ int wi[DET_THREADS / 32];
+#pragma unroll
+    for (int off = 16; off; off >>= 1) {
+        iv += __shfl_xor_sync(0xffffffffu, iv, off);
+        fv += __shfl_xor_sync(0xffffffffu, fv, off);
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) { wi[wid] = iv; wf[wid] = fv; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int ti = 0;
+        float tf = 0.f;
+        for (int w = 0; w < DET_THREADS / 32; ++w) { ti += wi[w]; tf += wf[w]; }
+        *s_i = ti;
+        *s_f = tf;
+    }
+    __syncthreads();
+}
 
 // ---------------------------------------------------------------------------------------------
 // generic kernel: any A / D / R (every detection is its own leader)
@@ -115,12 +154,14 @@ detect_kernel(const float2* __restrict__ rds, const uint8_t* __restrict__ gate, 
 
     // ---- column walk: masks of hits / near-ties per column, kept in registers
     const int ncols = TD * AC;
-    uint32_t hit[DET_MAX_COLS_PER_THREAD], near[DET_MAX_COLS_PER_THREAD];
-    int my_count = 0;
+    uint32_t hit[DET_MAX_COLS_PER_THREAD], near[DET_MAX_COLS_PER_THREAD], cand[DET_MAX_COLS_PER_THREAD];
+    int my_count = 0, my_near = 0;
+    float my_psum = 0.f;
 #pragma unroll
     for (int q = 0; q < DET_MAX_COLS_PER_THREAD; ++q) {
         hit[q] = 0u;
         near[q] = 0u;
+        cand[q] = 0u;
         const int col = threadIdx.x + q * DET_THREADS;
         if (col < ncols) {
             const int dd = col / AC + 1, ac = col - (col / AC) * AC;
@@ -137,11 +178,14 @@ detect_kernel(const float2* __restrict__ rds, const uint8_t* __restrict__ gate, 
                     const int r = r0 + rr - 1;
                     if (r < R) {
                         const float m = fmaxf(fmaxf(h_prev, h_next), fmaxf(l1, rt1));
-                        if (c1 >= m && c1 > thr && gate[r]) {
+                        const int cls = classify(c1, m, thr, eps);
+                        if (cls && gate[r]) {
                             hit[q] |= 1u << (rr - 1);
                             ++my_count;
-                            if ((c1 - m) <= eps * c1 || (c1 - thr) <= eps * fabsf(thr)) near[q] |= 1u << (rr - 1);
+                            if (cls & 2) { near[q] |= 1u << (rr - 1); ++my_near; }
+                            if (cls & 4) cand[q] |= 1u << (rr - 1);
                         }
+                        my_psum += c1;
                     }
                     h_prev = fmaxf(fmaxf(l1, c1), rt1);
                     l1 = l2; c1 = c2; rt1 = rt2;
@@ -151,6 +195,9 @@ detect_kernel(const float2* __restrict__ rds, const uint8_t* __restrict__ gate, 
     }
 
     // ---- deterministic compaction into this tile's segment
+    __shared__ int near_s;
+    __shared__ float psum_s;
+    block_sums(my_near, my_psum, &near_s, &psum_s);
     const int offset = block_exclusive_scan(my_count, warp_sums, &total_s);
     const int total = total_s;
     const size_t seg = (size_t)blockIdx.x;
@@ -159,6 +206,8 @@ detect_kernel(const float2* __restrict__ rds, const uint8_t* __restrict__ gate, 
         out.count[seg] = n;
         out.nlead[seg] = n;
         if (total > out.seg_cap) out.overflow[f] = 1;
+        if (out.nnear) out.nnear[seg] = near_s;
+        if (out.psum) out.psum[seg] = psum_s;
     }
     int pos = offset;
 #pragma unroll
@@ -174,7 +223,8 @@ detect_kernel(const float2* __restrict__ rds, const uint8_t* __restrict__ gate, 
                     const size_t o = seg * out.seg_cap + pos;
                     out.key[o] = rs_make_key(a0 + ac, r0 + b, d0 + dd - 1);
                     out.power[o] = pw[(b + 1) * W + dd * AC + ac];
-                    out.flags[o] = (near[q] >> b) & 1u ? RS_FLAG_NEARMAX : 0;
+                    out.flags[o] = ((cand[q] >> b) & 1u) ? (RS_FLAG_NEARMAX | RS_FLAG_DROPPED)
+                                                        : ((near[q] >> b) & 1u) ? RS_FLAG_NEARMAX : 0;
                     out.lead[o] = (uint32_t)pos | (1u << 16);
                 }
                 ++pos;
@@ -197,7 +247,7 @@ __device__ __forceinline__ int a8_off(int rr, int ddp, int quad) {          // f
     return rr * A8_W + ddp * A8_AC + ((quad ^ ((ddp >> 2) & 1)) << 2);
 }
 
-__global__ void __launch_bounds__(DET_THREADS)
+__global__ void __launch_bounds__(DET_THREADS, 2)
 detect_a8_kernel(const float2* __restrict__ rds, const uint8_t* __restrict__ gate, float thr, float eps, DetOut out, int R,
                  int D, int A, Tiling tl) {
     extern __shared__ float pw[];   // [(TR+2)][W]
@@ -248,7 +298,9 @@ detect_a8_kernel(const float2* __restrict__ rds, const uint8_t* __restrict__ gat
     // ---- walk: thread = (doppler bin, row half); 8 antennas per cell
     const int ddp = (tid & (A8_TD - 1)) + 1, rh = tid >> 7;
     const int rbase = rh * A8_HALF;                  // tile rows rbase+1 .. rbase+8 (1-based incl. halo)
-    uint32_t hit[2] = {0u, 0u}, near[2] = {0u, 0u};  // byte per row: antenna mask
+    uint32_t hit[2] = {0u, 0u}, near[2] = {0u, 0u}, cand[2] = {0u, 0u};  // byte per row: antenna mask
+    int my_near = 0;
+    float my_psum = 0.f;
     {
         auto ld8 = [&](int rr, int dp, float (&o)[8]) {
             const float4 v0 = *reinterpret_cast<const float4*>(pw + a8_off(rr, dp, 0));
@@ -271,21 +323,25 @@ detect_a8_kernel(const float2* __restrict__ rds, const uint8_t* __restrict__ gat
             ld8(rr + 1, ddp - 1, l2); ld8(rr + 1, ddp, c2); ld8(rr + 1, ddp + 1, q2);
             const int r = r0 + rr - 1;
             const bool row_ok = r < R && gate[r < R ? r : 0];
-            uint32_t hm = 0u, nm = 0u;
+            uint32_t hm = 0u, nm = 0u, cm = 0u;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const float hn = fmaxf(fmaxf(l2[j], c2[j]), q2[j]);
                 const float m = fmaxf(fmaxf(hp[j], hn), fmaxf(l1[j], q1[j]));
                 const float c = c1[j];
-                if (row_ok && c >= m && c > thr) {
+                const int cls = row_ok ? classify(c, m, thr, eps) : 0;
+                my_psum += c;
+                if (cls) {
                     hm |= 1u << j;
-                    if ((c - m) <= eps * c || (c - thr) <= eps * fabsf(thr)) nm |= 1u << j;
+                    if (cls & 2) { nm |= 1u << j; ++my_near; }
+                    if (cls & 4) cm |= 1u << j;
                 }
                 hp[j] = fmaxf(fmaxf(l1[j], c), q1[j]);
                 l1[j] = l2[j]; c1[j] = c2[j]; q1[j] = q2[j];
             }
             hit[i >> 2] |= hm << ((i & 3) * 8);
             near[i >> 2] |= nm << ((i & 3) * 8);
+            cand[i >> 2] |= cm << ((i & 3) * 8);
         }
     }
     // entries and leaders of this thread, scanned together (entries <= 2^14 per tile)
@@ -301,6 +357,15 @@ detect_a8_kernel(const float2* __restrict__ rds, const uint8_t* __restrict__ gat
         out.count[seg] = total < out.seg_cap ? total : out.seg_cap;
         if (total > out.seg_cap) out.overflow[f] = 1;
     }
+    {
+        __shared__ int near_s;
+        __shared__ float psum_s;
+        block_sums(my_near, my_psum, &near_s, &psum_s);
+        if (tid == 0) {
+            if (out.nnear) out.nnear[seg] = near_s;
+            if (out.psum) out.psum[seg] = psum_s;
+        }
+    }
     // a leader is kept only if all of its cell's entries fit; because entries are emitted in order, the kept
     // leaders are a prefix of the leader list -> nlead = number of leaders whose last entry fits
     int kept = 0;
@@ -309,6 +374,7 @@ detect_a8_kernel(const float2* __restrict__ rds, const uint8_t* __restrict__ gat
         uint32_t m = (hit[i >> 2] >> ((i & 3) * 8)) & 0xFFu;
         if (!m) continue;
         const uint32_t nb = (near[i >> 2] >> ((i & 3) * 8)) & 0xFFu;
+        const uint32_t cb = (cand[i >> 2] >> ((i & 3) * 8)) & 0xFFu;
         const int k = __popc(m);
         const int rr = rbase + 1 + i;
         if (pos + k <= out.seg_cap) {
@@ -323,17 +389,19 @@ detect_a8_kernel(const float2* __restrict__ rds, const uint8_t* __restrict__ gat
                 const size_t o = seg * out.seg_cap + pos;
                 out.key[o] = rs_make_key(a0 + j, r0 + rr - 1, d0 + ddp - 1);
                 out.power[o] = pw[a8_off(rr, ddp, j >> 2) + (j & 3)];
-                out.flags[o] = (nb >> j) & 1u ? RS_FLAG_NEARMAX : 0;
+                out.flags[o] = ((cb >> j) & 1u) ? (RS_FLAG_NEARMAX | RS_FLAG_DROPPED) : ((nb >> j) & 1u) ? RS_FLAG_NEARMAX : 0;
             }
             ++pos;
         }
     }
-    // number of kept leaders: block sum (reuses the scan scratch after a barrier)
-    __syncthreads();
-    const int kept_before = block_exclusive_scan(kept, warp_sums, &total_s);
-    (void)kept_before;
-    if (tid == 0) out.nlead[seg] = total_s;
-    (void)total_lead;
+    // number of kept leaders: all of them unless the segment overflowed (then a block sum, uniform branch)
+    if (total <= out.seg_cap) {
+        if (tid == 0) out.nlead[seg] = total_lead;
+    } else {
+        __syncthreads();
+        block_exclusive_scan(kept, warp_sums, &total_s);
+        if (tid == 0) out.nlead[seg] = total_s;
+    }
 }
 
 }  // namespace
@@ -350,8 +418,8 @@ extern "C" int rs_detect_tiling(int R, int D, int A, int* tile_r, int* tile_d, i
 
 extern "C" int rs_detect(const void* rds, const uint8_t* range_gate, float thr_power, float det_eps, uint32_t* det_key,
                          float* det_power, uint8_t* det_flags, uint32_t* det_lead, int32_t* det_count,
-                         int32_t* det_nlead, int32_t* det_overflow, int seg_cap, int F, int R, int D, int A,
-                         void* stream) {
+                         int32_t* det_nlead, int32_t* det_overflow, int32_t* det_nnear, float* det_psum, int seg_cap,
+                         int F, int R, int D, int A, void* stream) {
     RS_CHECK_ARG(rds && range_gate && det_key && det_power && det_flags && det_lead && det_count && det_nlead &&
                      det_overflow,
                  "rs_detect: null pointer");
@@ -361,7 +429,7 @@ extern "C" int rs_detect(const void* rds, const uint8_t* range_gate, float thr_p
     Tiling t = make_tiling(R, D, A);
     const long long blocks = (long long)F * t.ntiles;
     RS_CHECK_ARG(blocks < (1ll << 31), "rs_detect: too many blocks");
-    DetOut out{det_key, det_power, det_flags, det_lead, det_count, det_nlead, det_overflow, seg_cap};
+    DetOut out{det_key, det_power, det_flags, det_lead, det_count, det_nlead, det_overflow, det_nnear, det_psum, seg_cap};
     cudaMemsetAsync(det_overflow, 0, sizeof(int32_t) * F, (cudaStream_t)stream);
     if (A % 8 == 0 && D % A8_TD == 0 && R % A8_TR == 0 && t.TD == A8_TD && t.AC == A8_AC && t.TR == A8_TR) {
         const size_t smem = (size_t)(A8_TR + 2) * A8_W * sizeof(float);

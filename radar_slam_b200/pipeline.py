@@ -41,6 +41,8 @@ class RadarConfig:
     huber_delta: float = 1.0
     det_eps: float = 2e-6                        # guard bands for decisions fp32 cannot settle
     tie_eps: float = 4e-6
+    recheck: bool = True                         # settle the flagged decisions in fp64 from the raw cube
+    fft_eps: float = 1e-6                        # bound on the fp32 FFT's per-element error, in units of rms(|X|)
 
     @property
     def lambda_c(self) -> float:
@@ -83,6 +85,11 @@ class Detections:
     ls_partials: Optional[torch.Tensor] = None     # per-segment normal-equation sums written by rs_angles
     lead: Optional[torch.Tensor] = None            # one leader per distinct cell: position | multiplicity << 16
     nlead: Optional[torch.Tensor] = None
+    nnear: Optional[torch.Tensor] = None           # per segment: entries flagged NEARMAX
+    psum: Optional[torch.Tensor] = None            # per segment: sum of |X|^2 (noise level for the recheck bound)
+    ntie: Optional[torch.Tensor] = None            # per segment: cells flagged TIE / GUARD
+    threshold_db: float = -20.0                    # the threshold rs_detect ran with (needed by the fp64 recheck)
+    method: Optional[str] = None                   # the method rs_angles ran with
 
     def valid_mask(self) -> torch.Tensor:
         n = self.F * self.ntiles
@@ -229,10 +236,14 @@ class FramePipeline:
             adeg=alloc("det_adeg", (n,), torch.float32), phase=alloc("det_phase", (n,), torch.float32),
             count=alloc("det_count", (F * ntiles,), torch.int32), overflow=alloc("det_overflow", (F,), torch.int32),
             seg_cap=cap, ntiles=ntiles, F=F, R=R, D=D, A=A,
-            lead=alloc("det_lead", (n,), torch.int32), nlead=alloc("det_nlead", (F * ntiles,), torch.int32))
+            threshold_db=float(c.threshold_db if threshold_db is None else threshold_db),
+            lead=alloc("det_lead", (n,), torch.int32), nlead=alloc("det_nlead", (F * ntiles,), torch.int32),
+            nnear=alloc("det_nnear", (F * ntiles,), torch.int32), psum=alloc("det_psum", (F * ntiles,), torch.float32),
+            ntie=alloc("det_ntie", (F * ntiles,), torch.int32))
         self._call("rs_detect", rds.data_ptr(), gate.data_ptr(), thr, c.det_eps, det.key.data_ptr(),
                    det.power.data_ptr(), det.flags.data_ptr(), det.lead.data_ptr(), det.count.data_ptr(),
-                   det.nlead.data_ptr(), det.overflow.data_ptr(), cap, F, R, D, A, self.stream)
+                   det.nlead.data_ptr(), det.overflow.data_ptr(), det.nnear.data_ptr(), det.psum.data_ptr(),
+                   cap, F, R, D, A, self.stream)
         return det
 
     def angles(self, rds: torch.Tensor, det: Detections, method: Optional[str] = None,
@@ -243,6 +254,7 @@ class FramePipeline:
             raise ValueError(f"Unknown method: {method}")
         t = self._angle_tables(det.A)
         esprit_scale = c.lambda_c / (2 * np.pi * c.spacing)                       # angle_estimation.py:218
+        det.method = method
         fuse = fuse_ls and method != "esprit" and det.A <= 16
         det.ls_partials = self._buf("ls_partials", (det.F * det.ntiles, 8), torch.float64) if fuse else None
         self._call(
@@ -251,7 +263,7 @@ class FramePipeline:
             _lib.METHODS[method], c.tie_eps, esprit_scale, det.key.data_ptr(), det.lead.data_ptr(),
             det.nlead.data_ptr(), det.flags.data_ptr(), det.aidx.data_ptr(), det.adeg.data_ptr(), det.phase.data_ptr(),
             det.seg_cap, det.ntiles, det.F, det.R, det.D, det.A,
-            t["grid_cs"].data_ptr(), _lib.ptr(det.ls_partials), int(t["symmetric"]), self.stream)
+            t["grid_cs"].data_ptr(), _lib.ptr(det.ls_partials), int(t["symmetric"]), det.ntie.data_ptr(), self.stream)
         return det
 
     def velocity(self, det: Detections, out: Optional[torch.Tensor] = None, lambda_c: Optional[float] = None,
@@ -274,6 +286,46 @@ class FramePipeline:
             vel.data_ptr(), det.seg_cap, det.ntiles, det.F, self.stream)
         return vel
 
+    # ------------------------------------------------------------------ fp64 recheck of flagged decisions
+    def _stats_buf(self, name: str) -> torch.Tensor:
+        return self._buf(name, (4,), torch.int32)
+
+    def recheck_detections(self, cube: torch.Tensor, det: Detections,
+                           chirp_subset: Optional[Tuple[int, int]] = None) -> torch.Tensor:
+        """Exact (fp64, from the raw cube) local-maximum / threshold decision for every RS_FLAG_NEARMAX entry.
+        Run before angles().  Returns the device stats int32 [4] = rechecked, dropped, promoted, unresolved."""
+        F, A, C, S = cube.shape
+        c0, c1 = (0, C) if chirp_subset is None else chirp_subset
+        tab128 = self._fft_tables(S, c1 - c0)[3]
+        stats = self._stats_buf("recheck_det_stats")
+        self._call("rs_recheck_detections_f64", cube.data_ptr(), tab128.data_ptr(), C, c0, int(self.cfg.dc_removal),
+                   float(10.0 ** (det.threshold_db / 10.0)), det.key.data_ptr(), det.flags.data_ptr(),
+                   det.count.data_ptr(), det.nnear.data_ptr(), det.seg_cap, det.ntiles, F, A, c1 - c0, S,
+                   stats.data_ptr(), self.stream)
+        return stats
+
+    def recheck_angles(self, cube: torch.Tensor, rds: torch.Tensor, det: Detections,
+                       chirp_subset: Optional[Tuple[int, int]] = None) -> torch.Tensor:
+        """Exact grid argmax for every RS_FLAG_TIE / RS_FLAG_GUARD cell (grid methods).  Run after angles().
+        Returns the device stats int32 [4] = rechecked, index changed, needed the fp64 snapshot, unresolved."""
+        method = det.method or self.cfg.method
+        stats = self._stats_buf("recheck_ang_stats")
+        if method == "esprit":
+            stats.zero_()
+            return stats
+        F, A, C, S = cube.shape
+        c0, c1 = (0, C) if chirp_subset is None else chirp_subset
+        tab128 = self._fft_tables(S, c1 - c0)[3]
+        t = self._angle_tables(A)
+        self._call("rs_recheck_angles_f64", cube.data_ptr(), tab128.data_ptr(), C, c0, int(self.cfg.dc_removal),
+                   rds.data_ptr(), t["steer128"].data_ptr(), t["grid_f32"].data_ptr(), t["grid_cs"].data_ptr(), t["G"],
+                   _lib.METHODS[method], float(self.cfg.fft_eps), det.psum.data_ptr(), det.ntie.data_ptr(),
+                   det.key.data_ptr(), det.lead.data_ptr(),
+                   det.nlead.data_ptr(), det.flags.data_ptr(), det.aidx.data_ptr(), det.adeg.data_ptr(),
+                   det.phase.data_ptr(), _lib.ptr(det.ls_partials), det.seg_cap, det.ntiles, F, A, c1 - c0, S,
+                   stats.data_ptr(), self.stream)
+        return stats
+
     # ------------------------------------------------------------------ whole path
     def process(self, cube: torch.Tensor, chunk_frames: int = 512, vel_out: Optional[torch.Tensor] = None,
                 keep: bool = False):
@@ -288,7 +340,11 @@ class FramePipeline:
             _, A, C, S = cube.shape
             rds = self.range_doppler(cube[lo:hi], out=None if keep else self._buf("rds", (n, S, C, A), torch.complex64))
             det = self.detect(rds, workspace=not keep)
+            if self.cfg.recheck:
+                self.recheck_detections(cube[lo:hi], det)
             self.angles(rds, det)
+            if self.cfg.recheck:
+                self.recheck_angles(cube[lo:hi], rds, det)
             self.velocity(det, out=vel[lo:hi])
             last = (rds, det)
         return (vel, last[0], last[1]) if keep else vel
