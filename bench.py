@@ -364,7 +364,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=500, help="frames per launch set, device-resident path")
     ap.add_argument("--host-chunk", type=int, default=32, help="frames per H2D chunk, host-buffer path")
     ap.add_argument("--no-recheck", action="store_true", help="skip the fp64 recheck of flagged decisions (fp32 path only)")
-    ap.add_argument("--fft-eps", type=float, default=1e-6, help="error bound of the fp32 FFT used by the recheck, in rms units")
+    ap.add_argument("--fft-eps", type=float, default=4e-7, help="error bound of the fp32 FFT used by the recheck, in rms units")
     ap.add_argument("--e2e-frames", type=int, default=1000)
     ap.add_argument("--cpu-frames", type=int, default=8)
     ap.add_argument("--ref-procs", type=int, default=0)

@@ -142,25 +142,31 @@ int rs_velocity_ls(const int32_t* det_aidx, const float* det_adeg, const float* 
  * rs_recheck_detections_f64: RS_FLAG_NEARMAX entries (detections and the near-miss candidates rs_detect emits
  *   as RS_FLAG_DROPPED): exact 3x3 local-maximum and threshold test (dechirp.py:250-254,
  *   thr_power64 = 10^(threshold_db/10), test p + 1e-12 > thr_power64); sets/clears RS_FLAG_DROPPED, sets
- *   RS_FLAG_DETFIXED.  Run it BEFORE rs_angles.  stats = {rechecked, dropped, promoted, unresolved}.
+ *   RS_FLAG_DETFIXED.  Run it BEFORE rs_angles (last four pointers NULL), or AFTER it with det_aidx, det_phase,
+ *   grid_cs and ls_partials so a detection that changes state is moved into / out of the velocity sums.
+ *   stats = {rechecked, dropped, promoted, unresolved}.
  * rs_recheck_angles_f64: RS_FLAG_TIE / RS_FLAG_GUARD cells.  Stage A: fp64 grid scan of the fp32 snapshot; the
  *   snapshot's rounding error is bounded by fft_eps * rms(|X|) per element (rms from det_psum), which bounds how far
  *   P_g - P_h can move; if the winner beats every other grid point by more than its bound the decision is final.
  *   Stage B (otherwise, and near the MUSIC 1e-12 guard): the snapshot is recomputed in fp64 from the cube.
  *   First-index argmax of the method's pseudo-spectrum (angle_estimation.py:143-152, 173); rewrites
  *   det_aidx/det_adeg, sets RS_FLAG_FIXED and corrects ls_partials.
- *   stats = {rechecked, index changed, needed the fp64 snapshot, unresolved}. */
+ *   Stage B reads each (frame, antenna) plane of the cube once for all undecided cells of the frame.
+ *   Workspace (caller-allocated): work_idx int32 [F*nseg*16], work_cnt int32 [F*nseg], work_snap complex128
+ *   [F*nseg*16*A].   stats = {rechecked, index changed, needed the fp64 snapshot, unresolved}. */
 int rs_recheck_detections_f64(const void* cube, const void* table128, int C_total, int chirp0, int dc_removal,
                               double thr_power64, const uint32_t* det_key, uint8_t* det_flags,
                               const int32_t* det_count, const int32_t* det_nnear, int seg_cap, int nseg_per_frame,
-                              int F, int A, int C, int S, int32_t* stats, void* stream);
+                              int F, int A, int C, int S,
+                              const int32_t* det_aidx, const float* det_phase, const double* grid_cs, double* ls_partials,
+                              int32_t* stats, void* stream);
 int rs_recheck_angles_f64(const void* cube, const void* table128, int C_total, int chirp0, int dc_removal,
                           const void* rds, const void* steer128, const float* grid_deg, const double* grid_cs,
                           int G, int method, double fft_eps, const float* det_psum, const int32_t* det_ntie,
                           const uint32_t* det_key, const uint32_t* det_lead, const int32_t* det_nlead,
                           uint8_t* det_flags, int32_t* det_aidx, float* det_adeg, const float* det_phase,
                           double* ls_partials, int seg_cap, int nseg_per_frame, int F, int A, int C, int S,
-                          int32_t* stats, void* stream);
+                          int32_t* work_idx, int32_t* work_cnt, void* work_snap, int32_t* stats, void* stream);
 
 /* helpers for the legacy (list-of-dict) adapters ---------------------------------------------- */
 

@@ -27,9 +27,10 @@ _SIGNATURES = {
     "rs_angles": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _f, _d, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                        _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
     "rs_velocity_from_partials": (_i, [_vp, _i, _i, _d, _d, _vp, _vp]),
-    "rs_recheck_detections_f64": (_i, [_vp, _vp, _i, _i, _i, _d, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "rs_recheck_detections_f64": (_i, [_vp, _vp, _i, _i, _i, _d, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i,
+                                       _vp, _vp, _vp, _vp, _vp, _vp]),
     "rs_recheck_angles_f64": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _d, _vp, _vp, _vp, _vp, _vp,
-                                   _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+                                   _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "rs_velocity_ls": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _d, _d, _i, _d, _vp, _i, _i, _i, _vp]),
     "rs_rds_to_reference_layout": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "rs_rds_from_reference_layout": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),

@@ -193,7 +193,9 @@ __device__ int collect_items(int n, PosFn pos_of, const uint8_t* flags, uint8_t 
 __global__ void __launch_bounds__(RC_THREADS)
 recheck_detect_kernel(CubeView v, double thr64, const uint32_t* __restrict__ det_key, uint8_t* __restrict__ det_flags,
                       const int32_t* __restrict__ det_count, const int32_t* __restrict__ det_nnear, int seg_cap,
-                      int nseg, int R, int D, int32_t* __restrict__ stats) {
+                      int nseg, int R, int D, const int32_t* __restrict__ det_aidx, const float* __restrict__ det_phase,
+                      const double* __restrict__ grid_cs, double* __restrict__ ls_partials,
+                      int32_t* __restrict__ stats) {
     extern __shared__ double2 smd[];
     double2* ws = smd;
     double2* wc = ws + v.S;
@@ -238,7 +240,17 @@ recheck_detect_kernel(CubeView v, double thr64, const uint32_t* __restrict__ det
             const bool is_det = (c >= m) && (c + 1e-12 > thr64);
             uint8_t fl = det_flags[o];
             const bool was_det = !(fl & RS_FLAG_DROPPED);
-            if (is_det != was_det) atomicAdd(stats + (is_det ? 2 : 1), 1);
+            if (is_det != was_det) {
+                atomicAdd(stats + (is_det ? 2 : 1), 1);
+                // run after rs_angles: move this detection's row into / out of the velocity sums
+                if (ls_partials != nullptr && det_aidx[o] >= 0) {
+                    const double sg = is_det ? 1.0 : -1.0, y = (double)det_phase[o];
+                    const double cc = grid_cs[2 * det_aidx[o]], ss = grid_cs[2 * det_aidx[o] + 1];
+                    double* ps = ls_partials + (size_t)seg * 8;
+                    ps[0] += sg * cc * cc; ps[1] += sg * ss * ss; ps[2] += sg * cc * ss;
+                    ps[3] += sg * y * cc;  ps[4] += sg * y * ss;  ps[5] += sg * y * y;  ps[6] += sg;
+                }
+            }
             fl = is_det ? (fl & ~RS_FLAG_DROPPED) : (fl | RS_FLAG_DROPPED);
             det_flags[o] = fl | RS_FLAG_DETFIXED;
             atomicAdd(stats + 0, 1);
@@ -351,71 +363,111 @@ __device__ ScanRes scan_f64(const AngleFix& q, const double2* snap, int A, doubl
     return res;
 }
 
-// warp-level variant of scan_f64 for stage A: lanes over grid points, snapshot in shared memory
+// writes one settled cell to all of its detections; dl = correction of the segment's velocity sums
+__device__ void apply_angle(const AngleFix& q, size_t o, int k, int idx, double* dl, int32_t* stats, int stage) {
+    const int old = q.det_aidx[o];
+    int live = 0;
+    for (int e = 0; e < k; ++e) {
+        const uint8_t fl = q.det_flags[o + e];
+        live += (fl & RS_FLAG_DROPPED) ? 0 : 1;
+        q.det_flags[o + e] = fl | RS_FLAG_FIXED;
+        q.det_aidx[o + e] = idx;
+        q.det_adeg[o + e] = q.grid_deg[idx];
+    }
+    if (old != idx && live > 0) {
+        const double w = (double)live, y = (double)q.det_phase[o];
+        const double c0 = q.grid_cs[2 * old], s0 = q.grid_cs[2 * old + 1];
+        const double c1 = q.grid_cs[2 * idx], s1 = q.grid_cs[2 * idx + 1];
+        dl[0] = w * (c1 * c1 - c0 * c0); dl[1] = w * (s1 * s1 - s0 * s0); dl[2] = w * (c1 * s1 - c0 * s0);
+        dl[3] = w * y * (c1 - c0);       dl[4] = w * y * (s1 - s0);
+    }
+    atomicAdd(stats + 0, 1);
+    if (old != idx) atomicAdd(stats + 1, 1);
+    if (stage) atomicAdd(stats + 2, 1);
+}
+
+// warp-level variant of scan_f64 for stage A: lanes over grid points, snapshot in shared memory.
+// Outside the MUSIC guard zone 1/(M - P/E) is monotone in the beam power P, so the argmax is taken on P; the
+// guard zone and every pair that the error bound cannot separate go to stage B.
+constexpr int SW_MAX_PER_LANE = 12;            // grids up to 384 points keep (b_h, P_h) in registers
 __device__ ScanRes scan_warp(const AngleFix& q, const double2* snap, int A, double energy, double ds_norm) {
     const int lane = threadIdx.x & 31;
-    double best = -1.0, bestp = -1.0;
+    double2 bl[SW_MAX_PER_LANE];
+    double bestp = -1.0;
     int bi = 0x7fffffff;
-    for (int g = lane; g < q.G; g += 32) {
+    const bool cached = q.G <= 32 * SW_MAX_PER_LANE;
+#pragma unroll
+    for (int j = 0; j < SW_MAX_PER_LANE; ++j) {
+        const int g = lane + 32 * j;
+        if (g < q.G) {
+            const double2 b = beam(q, snap, A, g);
+            bl[j] = b;
+            const double pwr = b.x * b.x + b.y * b.y;
+            if (pwr > bestp) { bestp = pwr; bi = g; }
+        }
+    }
+    for (int g = lane + 32 * SW_MAX_PER_LANE; g < q.G; g += 32) {
         const double2 b = beam(q, snap, A, g);
         const double pwr = b.x * b.x + b.y * b.y;
-        double val = pwr;
-        if (q.method == RS_METHOD_MUSIC) {
-            const double den = fabs((double)A - (energy > 0 ? pwr / energy : 1.0));
-            val = den > 1e-12 ? 1.0 / den : 0.0;
-        }
-        if (val > best) { best = val; bi = g; }
-        bestp = fmax(bestp, pwr);
+        if (pwr > bestp) { bestp = pwr; bi = g; }
     }
 #pragma unroll
     for (int off = 16; off; off >>= 1) {
-        const double ov = __shfl_xor_sync(0xffffffffu, best, off);
-        const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
         const double op = __shfl_xor_sync(0xffffffffu, bestp, off);
-        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
-        bestp = fmax(bestp, op);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+        if (op > bestp || (op == bestp && oi < bi)) { bestp = op; bi = oi; }
     }
     ScanRes res;
     res.idx = bi;
     bool und = (q.method == RS_METHOD_MUSIC) && ((double)A * energy - bestp <= 1e-6 * (double)A * energy);
     const double2 bg = beam(q, snap, A, bi);
-    const double pg = bg.x * bg.x + bg.y * bg.y;
-    for (int h = lane; h < q.G && !und; h += 32) {
-        if (h == bi) continue;
-        const double2 bh = beam(q, snap, A, h);
+    const double pg = bestp;
+    const double wg = sqrt((double)A * pg);
+    auto test = [&](int h, double2 bh) {
+        if (h == bi || und) return;
         const double ph = bh.x * bh.x + bh.y * bh.y;
+        const double gap = pg - ph;
+        // cheap sufficient test: |conj(b_g) a_g - conj(b_h) a_h| <= sqrt(A) (|b_g| + |b_h|)
+        if (gap > 2.0 * (wg + sqrt((double)A * ph)) * ds_norm) return;
         double cr = 0, ci = 0;
         for (int m = 0; m < A; ++m) {
-            const double2 wg = q.steer[(size_t)m * q.G + bi], wh = q.steer[(size_t)m * q.G + h];
-            cr += wg.x * wh.x + wg.y * wh.y;
-            ci += wg.x * wh.y - wg.y * wh.x;
+            const double2 wgm = q.steer[(size_t)m * q.G + bi], wh = q.steer[(size_t)m * q.G + h];
+            cr += wgm.x * wh.x + wgm.y * wh.y;
+            ci += wgm.x * wh.y - wgm.y * wh.x;
         }
         const double tr = bg.x * bh.x + bg.y * bh.y, ti = bg.y * bh.x - bg.x * bh.y;
         const double n2 = fmax(0.0, (double)A * (pg + ph) - 2.0 * (tr * cr - ti * ci));
-        if (pg - ph <= 2.0 * sqrt(n2) * ds_norm) und = true;
+        if (gap <= 2.0 * sqrt(n2) * ds_norm) und = true;
+    };
+    if (cached) {
+#pragma unroll
+        for (int j = 0; j < SW_MAX_PER_LANE; ++j) {
+            const int h = lane + 32 * j;
+            if (h < q.G) test(h, bl[j]);
+        }
+    } else {
+        for (int h = lane; h < q.G; h += 32) test(h, beam(q, snap, A, h));
     }
     res.undecided = __any_sync(0xffffffffu, und);
     return res;
 }
 
 constexpr int RA_MAX_ITEMS = 256;
+constexpr int RB_MAX = 16;          // undecided cells per segment handed to stage B
+constexpr int RB_BATCH = 4;         // cells whose range twiddles are staged together in stage B
 
+// -------- stage A: one CTA per segment, one warp per flagged cell; undecided cells go to the stage-B list
 __global__ void __launch_bounds__(RC_THREADS)
-recheck_angles_kernel(CubeView v, AngleFix q, int32_t* __restrict__ stats) {
+recheck_angles_kernel(CubeView v, AngleFix q, int32_t* __restrict__ work_idx, int32_t* __restrict__ work_cnt,
+                      int32_t* __restrict__ stats) {
     extern __shared__ double2 smd[];
-    double2* ws = smd;
-    double2* wc = ws + v.S;
-    double2* T = wc + v.C;               // [C]
-    double2* z = T + v.C;                // [S]
-    double2* u = z + v.S;                // [C]
-    double2* snap = u + v.C;             // [warps + 1][A]: one per warp for stage A, the last for stage B
+    double2* snap = smd;                 // [warps][A]
     __shared__ int items[RC_MAX_ITEMS];
     __shared__ int scratch[RC_THREADS + 1];
-    __shared__ double red_v[RC_THREADS];
-    __shared__ int red_i[RC_THREADS];
     __shared__ double delta[RA_MAX_ITEMS][5];
     __shared__ unsigned char need_b[RA_MAX_ITEMS];
     const int seg = blockIdx.x;
+    if (threadIdx.x == 0) work_cnt[seg] = 0;
     if (q.det_ntie != nullptr && q.det_ntie[seg] == 0) return;
     const int n = q.det_nlead[seg];
     if (n == 0) return;
@@ -431,39 +483,10 @@ recheck_angles_kernel(CubeView v, AngleFix q, int32_t* __restrict__ stats) {
     for (int sg = 0; sg < q.nseg; ++sg) psum += (double)q.det_psum[(size_t)f * q.nseg + sg];
     const double ds_norm = fmax(q.fft_eps * sqrt(psum / ((double)q.R * q.D * A)) * sqrt((double)A), 1e-300);
     const int todo = min(total, RA_MAX_ITEMS);
-
-    // writes one settled cell; returns nothing, records the velocity-sum correction of the item
-    auto apply = [&](int it, int idx, int stage) {
-        const uint32_t ld = q.det_lead[base + items[it]];
-        const size_t o = base + (ld & 0xFFFFu);
-        const int k = (int)(ld >> 16);
-        const int old = q.det_aidx[o];
-        int live = 0;
-        for (int e = 0; e < k; ++e) {
-            const uint8_t fl = q.det_flags[o + e];
-            live += (fl & RS_FLAG_DROPPED) ? 0 : 1;
-            q.det_flags[o + e] = fl | RS_FLAG_FIXED;
-            q.det_aidx[o + e] = idx;
-            q.det_adeg[o + e] = q.grid_deg[idx];
-        }
-        double dl[5] = {0, 0, 0, 0, 0};
-        if (old != idx && live > 0) {
-            const double w = (double)live, y = (double)q.det_phase[o];
-            const double c0 = q.grid_cs[2 * old], s0 = q.grid_cs[2 * old + 1];
-            const double c1 = q.grid_cs[2 * idx], s1 = q.grid_cs[2 * idx + 1];
-            dl[0] = w * (c1 * c1 - c0 * c0); dl[1] = w * (s1 * s1 - s0 * s0); dl[2] = w * (c1 * s1 - c0 * s0);
-            dl[3] = w * y * (c1 - c0);       dl[4] = w * y * (s1 - s0);
-        }
-        for (int j = 0; j < 5; ++j) delta[it][j] = dl[j];
-        atomicAdd(stats + 0, 1);
-        if (old != idx) atomicAdd(stats + 1, 1);
-        if (stage) atomicAdd(stats + 2, 1);
-    };
-
-    // ---- stage A: one warp per item
     for (int it = wid; it < todo; it += nw) {
         const uint32_t ld = q.det_lead[base + items[it]];
         const size_t o = base + (ld & 0xFFFFu);
+        const int k = (int)(ld >> 16);
         int a, r, d;
         rs_split_key(q.det_key[o], a, r, d);
         const float2* cell = q.rds + (((size_t)f * q.R + r) * q.D + d) * A;
@@ -473,39 +496,178 @@ recheck_angles_kernel(CubeView v, AngleFix q, int32_t* __restrict__ stats) {
         __syncwarp();
         double energy = 0;
         for (int m = 0; m < A; ++m) energy += sw[m].x * sw[m].x + sw[m].y * sw[m].y;
-        const ScanRes sr = scan_warp(q, sw, A, energy, ds_norm);
+        // |dS|_2 <= fft_eps * rms * sqrt(A)  (noise-like part)  +  1.5e-7 |s|_2  (part that scales with the cell itself)
+        const ScanRes sr = scan_warp(q, sw, A, energy, ds_norm + 1.5e-7 * sqrt(energy));
         if (lane == 0) {
             need_b[it] = sr.undecided ? 1 : 0;
-            if (!sr.undecided) apply(it, sr.idx, 0);
+            double dl[5] = {0, 0, 0, 0, 0};
+            if (!sr.undecided) apply_angle(q, o, k, sr.idx, dl, stats, 0);
+            for (int j = 0; j < 5; ++j) delta[it][j] = dl[j];
         }
     }
     __syncthreads();
+    if (threadIdx.x == 0) {
+        int nb = 0, lost = total > RA_MAX_ITEMS ? total - RA_MAX_ITEMS : 0;
+        double* ps = q.ls_partials ? q.ls_partials + (size_t)seg * 8 : nullptr;
+        for (int it = 0; it < todo; ++it) {
+            if (ps) for (int j = 0; j < 5; ++j) ps[j] += delta[it][j];       // item order: deterministic
+            if (need_b[it]) {
+                if (nb < RB_MAX) work_idx[(size_t)seg * RB_MAX + nb++] = items[it];
+                else ++lost;
+            }
+        }
+        work_cnt[seg] = nb;
+        if (lost) atomicAdd(stats + 3, lost);
+    }
+}
 
-    // ---- stage B: the undecided items, whole CTA per item, snapshot in fp64 from the raw cube
-    bool have_tw = false;
-    double2* sb = snap + nw * A;
-    for (int it = 0; it < todo; ++it) {
-        if (!need_b[it]) continue;                      // block-uniform
-        if (!have_tw) { build_twiddles(ws, v.S, wc, v.C); have_tw = true; }
-        const uint32_t ld = q.det_lead[base + items[it]];
-        const size_t o = base + (ld & 0xFFFFu);
-        int a, r, d;
-        rs_split_key(q.det_key[o], a, r, d);
-        snapshot_f64(v, f, r, d, ws, wc, z, u, T, sb);
-        double energy = 0;
-        for (int m = 0; m < A; ++m) energy += sb[m].x * sb[m].x + sb[m].y * sb[m].y;
-        const ScanRes sr = scan_f64(q, sb, A, energy, 0.0, red_v, red_i);
-        if (threadIdx.x == 0) apply(it, sr.idx, 1);
-        __syncthreads();
+// inner loop of stage B1 for NB cells at once: every raw sample is converted to fp64 once and multiplied into
+// NB accumulators; the Doppler twiddle index advances incrementally (no integer division in the loop)
+template <int NB>
+__device__ __forceinline__ void b1_accumulate(const float2* __restrict__ plane, int S, int C, const double2* z,
+                                              const double2* wc, const int* kd, double2* acc) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    int ci[NB], cstep[NB];
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+        ci[i] = (int)(((long long)wid * kd[i]) % C);
+        cstep[i] = (int)(((long long)nw * kd[i]) % C);
+    }
+    for (int c = wid; c < C; c += nw) {
+        const float2* x = plane + (size_t)c * S;
+        double tr[NB], ti[NB];
+#pragma unroll
+        for (int i = 0; i < NB; ++i) { tr[i] = 0; ti[i] = 0; }
+#pragma unroll 2
+        for (int s = lane; s < S; s += 32) {
+            const float2 xv = __ldg(x + s);
+            const double xr = (double)xv.x, xi = (double)xv.y;
+#pragma unroll
+            for (int i = 0; i < NB; ++i) {
+                const double2 w = z[i * S + s];
+                tr[i] = fma(xr, w.x, fma(-xi, w.y, tr[i]));
+                ti[i] = fma(xr, w.y, fma(xi, w.x, ti[i]));
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+            const double2 u = wc[ci[i]];
+            acc[i].x += tr[i] * u.x - ti[i] * u.y;       // per-lane partial times the Doppler twiddle
+            acc[i].y += tr[i] * u.y + ti[i] * u.x;
+            ci[i] += cstep[i];
+            if (ci[i] >= C) ci[i] -= C;
+        }
+    }
+}
+
+// -------- stage B1: one CTA per (frame, antenna) reads that antenna's raw rows ONCE and forms its element of the
+// fp64 snapshot of every undecided cell of the frame
+__global__ void __launch_bounds__(RC_THREADS)
+recheck_snapshots_kernel(CubeView v, AngleFix q, const int32_t* __restrict__ work_idx,
+                         const int32_t* __restrict__ work_cnt, double2* __restrict__ work_snap) {
+    extern __shared__ double2 smd[];
+    double2* ws = smd;                          // [S]
+    double2* wc = ws + v.S;                     // [C]
+    double2* z = wc + v.C;                      // [RB_BATCH][S]
+    double2* red = z + RB_BATCH * v.S;          // [warps][RB_BATCH]
+    __shared__ int cell_r[RB_MAX * 64], cell_d[RB_MAX * 64], cell_slot[RB_MAX * 64];
+    __shared__ int n_cells;
+    const int a = blockIdx.x, f = blockIdx.y;
+    if (threadIdx.x == 0) {
+        int nc = 0;
+        for (int sg = 0; sg < q.nseg; ++sg) {
+            const int seg = f * q.nseg + sg;
+            const int cnt = work_cnt[seg];
+            for (int k = 0; k < cnt && nc < RB_MAX * 64; ++k) {       // same cap in recheck_finish_kernel
+                const size_t base = (size_t)seg * q.seg_cap;
+                const uint32_t ld = q.det_lead[base + work_idx[(size_t)seg * RB_MAX + k]];
+                int aa, r, d;
+                rs_split_key(q.det_key[base + (ld & 0xFFFFu)], aa, r, d);
+                cell_r[nc] = r; cell_d[nc] = d; cell_slot[nc] = seg * RB_MAX + k;
+                ++nc;
+            }
+        }
+        n_cells = nc;
     }
     __syncthreads();
-    // ---- corrections to the velocity sums, in item order (deterministic)
-    if (threadIdx.x == 0 && q.ls_partials != nullptr) {
-        double* ps = q.ls_partials + (size_t)seg * 8;
-        for (int it = 0; it < todo; ++it)
-            for (int j = 0; j < 5; ++j) ps[j] += delta[it][j];
+    const int nc = n_cells;
+    if (nc == 0) return;
+    build_twiddles(ws, v.S, wc, v.C);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int b0 = 0; b0 < nc; b0 += RB_BATCH) {
+        const int nb = min(RB_BATCH, nc - b0);
+        int kd[RB_BATCH];
+        for (int i = 0; i < RB_BATCH; ++i) kd[i] = i < nb ? (cell_d[b0 + i] - v.C / 2 + v.C) % v.C : 0;
+        for (int i = 0; i < nb; ++i) {
+            const int kr = (cell_r[b0 + i] - v.S / 2 + v.S) % v.S;
+            for (int s = threadIdx.x; s < v.S; s += blockDim.x)
+                z[i * v.S + s] = dmul(v.tab[s], ws[(int)(((long long)s * kr) % v.S)]);
+        }
+        __syncthreads();
+        double2 acc[RB_BATCH];
+        for (int i = 0; i < RB_BATCH; ++i) acc[i] = make_double2(0, 0);
+        const float2* plane = v.cube + (((size_t)f * v.A + a) * v.C_total + v.chirp0) * v.S;
+        switch (nb) {
+            case 1: b1_accumulate<1>(plane, v.S, v.C, z, wc, kd, acc); break;
+            case 2: b1_accumulate<2>(plane, v.S, v.C, z, wc, kd, acc); break;
+            case 3: b1_accumulate<3>(plane, v.S, v.C, z, wc, kd, acc); break;
+            default: b1_accumulate<4>(plane, v.S, v.C, z, wc, kd, acc); break;
+        }
+        for (int i = 0; i < nb; ++i) {
+            const double re = warp_sum(acc[i].x), im = warp_sum(acc[i].y);
+            if (lane == 0) red[wid * RB_BATCH + i] = make_double2(re, im);
+        }
+        __syncthreads();
+        if (threadIdx.x < nb) {
+            const int i = threadIdx.x;
+            double re = 0, im = 0;
+            for (int w = 0; w < nw; ++w) { re += red[w * RB_BATCH + i].x; im += red[w * RB_BATCH + i].y; }
+            const int kr = (cell_r[b0 + i] - v.S / 2 + v.S) % v.S;
+            work_snap[(size_t)cell_slot[b0 + i] * v.A + a] = (v.dc && kr == 0) ? make_double2(0, 0) : make_double2(re, im);
+        }
+        __syncthreads();
     }
-    if (threadIdx.x == 0 && total > RA_MAX_ITEMS) atomicAdd(stats + 3, total - RA_MAX_ITEMS);
+}
+
+// -------- stage B2: one CTA per segment scans the exact snapshots and settles the remaining cells
+__global__ void __launch_bounds__(RC_THREADS)
+recheck_finish_kernel(CubeView v, AngleFix q, const int32_t* __restrict__ work_idx, const int32_t* __restrict__ work_cnt,
+                      const double2* __restrict__ work_snap, int32_t* __restrict__ stats) {
+    extern __shared__ double2 smd[];
+    double2* snap = smd;                 // [A]
+    __shared__ double red_v[RC_THREADS];
+    __shared__ int red_i[RC_THREADS];
+    const int seg = blockIdx.x;
+    const int cnt = work_cnt[seg];
+    if (cnt == 0) return;
+    const int A = v.A;
+    const size_t base = (size_t)seg * q.seg_cap;
+    // cells of earlier segments of this frame (stage B1 handles at most RB_MAX * 64 cells per frame)
+    int before = 0;
+    for (int sg = (seg / q.nseg) * q.nseg; sg < seg; ++sg) before += work_cnt[sg];
+    for (int k = 0; k < cnt; ++k) {
+        if (before + k >= RB_MAX * 64) {
+            if (threadIdx.x == 0) atomicAdd(stats + 3, 1);
+            continue;
+        }
+        const uint32_t ld = q.det_lead[base + work_idx[(size_t)seg * RB_MAX + k]];
+        const size_t o = base + (ld & 0xFFFFu);
+        const int mult = (int)(ld >> 16);
+        for (int m = threadIdx.x; m < A; m += blockDim.x) snap[m] = work_snap[((size_t)seg * RB_MAX + k) * A + m];
+        __syncthreads();
+        double energy = 0;
+        for (int m = 0; m < A; ++m) energy += snap[m].x * snap[m].x + snap[m].y * snap[m].y;
+        const ScanRes sr = scan_f64(q, snap, A, energy, 0.0, red_v, red_i);
+        if (threadIdx.x == 0) {
+            double dl[5] = {0, 0, 0, 0, 0};
+            apply_angle(q, o, mult, sr.idx, dl, stats, 1);
+            if (q.ls_partials) {
+                double* ps = q.ls_partials + (size_t)seg * 8;
+                for (int j = 0; j < 5; ++j) ps[j] += dl[j];
+            }
+        }
+        __syncthreads();
+    }
 }
 
 }  // namespace
@@ -513,8 +675,12 @@ recheck_angles_kernel(CubeView v, AngleFix q, int32_t* __restrict__ stats) {
 extern "C" int rs_recheck_detections_f64(const void* cube, const void* table128, int C_total, int chirp0, int dc_removal,
                                          double thr_power64, const uint32_t* det_key, uint8_t* det_flags,
                                          const int32_t* det_count, const int32_t* det_nnear, int seg_cap,
-                                         int nseg_per_frame, int F, int A, int C, int S, int32_t* stats, void* stream) {
+                                         int nseg_per_frame, int F, int A, int C, int S, const int32_t* det_aidx,
+                                         const float* det_phase, const double* grid_cs, double* ls_partials,
+                                         int32_t* stats, void* stream) {
     RS_CHECK_ARG(cube && table128 && det_key && det_flags && det_count && stats, "rs_recheck_detections_f64: null pointer");
+    RS_CHECK_ARG(ls_partials == nullptr || (det_aidx && det_phase && grid_cs),
+                 "rs_recheck_detections_f64: ls_partials needs det_aidx, det_phase and grid_cs");
     RS_CHECK_ARG(F > 0 && A > 0 && C > 0 && S > 0 && chirp0 >= 0 && chirp0 + C <= C_total && seg_cap > 0 &&
                      nseg_per_frame > 0,
                  "rs_recheck_detections_f64: bad dims");
@@ -528,7 +694,8 @@ extern "C" int rs_recheck_detections_f64(const void* cube, const void* table128,
     cudaMemsetAsync(stats, 0, 4 * sizeof(int32_t), (cudaStream_t)stream);
     const long long blocks = (long long)F * nseg_per_frame;
     recheck_detect_kernel<<<(unsigned)blocks, RC_THREADS, smem, (cudaStream_t)stream>>>(
-        v, thr_power64, det_key, det_flags, det_count, det_nnear, seg_cap, nseg_per_frame, S, C, stats);
+        v, thr_power64, det_key, det_flags, det_count, det_nnear, seg_cap, nseg_per_frame, S, C, det_aidx, det_phase,
+        grid_cs, ls_partials, stats);
     RS_CHECK_LAUNCH("rs_recheck_detections_f64");
     return RS_OK;
 }
@@ -539,26 +706,39 @@ extern "C" int rs_recheck_angles_f64(const void* cube, const void* table128, int
                                      const uint32_t* det_key, const uint32_t* det_lead, const int32_t* det_nlead,
                                      uint8_t* det_flags, int32_t* det_aidx, float* det_adeg, const float* det_phase,
                                      double* ls_partials, int seg_cap, int nseg_per_frame, int F, int A, int C, int S,
-                                     int32_t* stats, void* stream) {
+                                     int32_t* work_idx, int32_t* work_cnt, void* work_snap, int32_t* stats,
+                                     void* stream) {
     RS_CHECK_ARG(cube && table128 && rds && steer128 && grid_deg && grid_cs && det_psum && det_key && det_lead &&
-                     det_nlead && det_flags && det_aidx && det_adeg && det_phase && stats,
+                     det_nlead && det_flags && det_aidx && det_adeg && det_phase && work_idx && work_cnt && work_snap &&
+                     stats,
                  "rs_recheck_angles_f64: null pointer");
     RS_CHECK_ARG(method == RS_METHOD_MUSIC || method == RS_METHOD_BEAMFORMING, "rs_recheck_angles_f64: grid methods only");
-    RS_CHECK_ARG(F > 0 && A >= 2 && C > 0 && S > 0 && G > 0 && chirp0 >= 0 && chirp0 + C <= C_total && fft_eps >= 0,
+    RS_CHECK_ARG(F > 0 && F <= 65535 && A >= 2 && C > 0 && S > 0 && G > 0 && chirp0 >= 0 && chirp0 + C <= C_total &&
+                     fft_eps >= 0 && nseg_per_frame > 0,
                  "rs_recheck_angles_f64: bad dims");
     CubeView v{(const float2*)cube, (const double2*)table128, A, C_total, chirp0, C, S, dc_removal};
     AngleFix q{(const float2*)rds, (const double2*)steer128, grid_deg, grid_cs, G, method, fft_eps, det_psum, det_ntie,
                det_key, det_lead, det_nlead, det_flags, det_aidx, det_adeg, det_phase, ls_partials, seg_cap,
                nseg_per_frame, S, C};
-    const size_t smem = (size_t)(2 * S + 3 * C + (RC_THREADS / 32 + 1) * A) * sizeof(double2);
-    if (smem > (size_t)rs_smem_optin_limit()) {
-        rs_set_error("rs_recheck_angles_f64: needs %zu B of shared memory", smem);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t smem_a = (size_t)(RC_THREADS / 32) * A * sizeof(double2);
+    const size_t smem_b1 = (size_t)(S + C + RB_BATCH * S + (RC_THREADS / 32) * RB_BATCH) * sizeof(double2);
+    const size_t smem_b2 = (size_t)A * sizeof(double2);
+    if (smem_b1 > (size_t)rs_smem_optin_limit()) {
+        rs_set_error("rs_recheck_angles_f64: needs %zu B of shared memory", smem_b1);
         return RS_ECAPACITY;
     }
-    cudaFuncSetAttribute(recheck_angles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaMemsetAsync(stats, 0, 4 * sizeof(int32_t), (cudaStream_t)stream);
+    cudaFuncSetAttribute(recheck_angles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a);
+    cudaFuncSetAttribute(recheck_snapshots_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b1);
+    cudaMemsetAsync(stats, 0, 4 * sizeof(int32_t), st);
     const long long blocks = (long long)F * nseg_per_frame;
-    recheck_angles_kernel<<<(unsigned)blocks, RC_THREADS, smem, (cudaStream_t)stream>>>(v, q, stats);
-    RS_CHECK_LAUNCH("rs_recheck_angles_f64");
+    recheck_angles_kernel<<<(unsigned)blocks, RC_THREADS, smem_a, st>>>(v, q, work_idx, work_cnt, stats);
+    RS_CHECK_LAUNCH("rs_recheck_angles_f64(stage A)");
+    recheck_snapshots_kernel<<<dim3((unsigned)A, (unsigned)F), RC_THREADS, smem_b1, st>>>(v, q, work_idx, work_cnt,
+                                                                                        (double2*)work_snap);
+    RS_CHECK_LAUNCH("rs_recheck_angles_f64(stage B1)");
+    recheck_finish_kernel<<<(unsigned)blocks, RC_THREADS, smem_b2, st>>>(v, q, work_idx, work_cnt,
+                                                                        (const double2*)work_snap, stats);
+    RS_CHECK_LAUNCH("rs_recheck_angles_f64(stage B2)");
     return RS_OK;
 }

@@ -6,6 +6,7 @@ fallback: constructing a pipeline without a CUDA device or without the library r
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass, field
 from typing import Dict, Optional, Tuple
 
@@ -42,7 +43,8 @@ class RadarConfig:
     det_eps: float = 2e-6                        # guard bands for decisions fp32 cannot settle
     tie_eps: float = 4e-6
     recheck: bool = True                         # settle the flagged decisions in fp64 from the raw cube
-    fft_eps: float = 1e-6                        # bound on the fp32 FFT's per-element error, in units of rms(|X|)
+    fft_eps: float = 4e-7                        # 2-norm bound of the fp32 FFT error per element, in units of rms(|X|):
+                                                 # measured rms error 1.4e-7 (profiles/fft_error_probe.py), x2.9 margin
 
     @property
     def lambda_c(self) -> float:
@@ -90,6 +92,7 @@ class Detections:
     ntie: Optional[torch.Tensor] = None            # per segment: cells flagged TIE / GUARD
     threshold_db: float = -20.0                    # the threshold rs_detect ran with (needed by the fp64 recheck)
     method: Optional[str] = None                   # the method rs_angles ran with
+    tag: str = ""                                  # workspace set the buffers came from
 
     def valid_mask(self) -> torch.Tensor:
         n = self.F * self.ntiles
@@ -220,7 +223,7 @@ class FramePipeline:
         return cap, ntiles
 
     def detect(self, rds: torch.Tensor, threshold_db: Optional[float] = None, min_range: Optional[float] = None,
-               max_range: Optional[float] = None, workspace: bool = False) -> Detections:
+               max_range: Optional[float] = None, workspace=False) -> Detections:
         assert rds.is_cuda and rds.dtype == torch.complex64 and rds.dim() == 4 and rds.is_contiguous()
         F, R, D, A = rds.shape
         c = self.cfg
@@ -228,7 +231,8 @@ class FramePipeline:
         gate = self._gate(R, c.min_range if min_range is None else min_range, c.max_range if max_range is None else max_range)
         cap, ntiles = self.seg_cap_for(R, D, A)
         n = F * ntiles * cap
-        alloc = (lambda nm, shp, dt: self._buf(nm, shp, dt)) if workspace else \
+        tag = workspace if isinstance(workspace, str) else ""      # "0" / "1": double-buffered workspaces
+        alloc = (lambda nm, shp, dt: self._buf(nm + tag, shp, dt)) if workspace else \
             (lambda nm, shp, dt: torch.empty(shp, dtype=dt, device=self.device))
         det = Detections(
             key=alloc("det_key", (n,), torch.int32), power=alloc("det_power", (n,), torch.float32),
@@ -236,7 +240,7 @@ class FramePipeline:
             adeg=alloc("det_adeg", (n,), torch.float32), phase=alloc("det_phase", (n,), torch.float32),
             count=alloc("det_count", (F * ntiles,), torch.int32), overflow=alloc("det_overflow", (F,), torch.int32),
             seg_cap=cap, ntiles=ntiles, F=F, R=R, D=D, A=A,
-            threshold_db=float(c.threshold_db if threshold_db is None else threshold_db),
+            threshold_db=float(c.threshold_db if threshold_db is None else threshold_db), tag=tag,
             lead=alloc("det_lead", (n,), torch.int32), nlead=alloc("det_nlead", (F * ntiles,), torch.int32),
             nnear=alloc("det_nnear", (F * ntiles,), torch.int32), psum=alloc("det_psum", (F * ntiles,), torch.float32),
             ntie=alloc("det_ntie", (F * ntiles,), torch.int32))
@@ -256,7 +260,7 @@ class FramePipeline:
         esprit_scale = c.lambda_c / (2 * np.pi * c.spacing)                       # angle_estimation.py:218
         det.method = method
         fuse = fuse_ls and method != "esprit" and det.A <= 16
-        det.ls_partials = self._buf("ls_partials", (det.F * det.ntiles, 8), torch.float64) if fuse else None
+        det.ls_partials = self._buf("ls_partials" + det.tag, (det.F * det.ntiles, 8), torch.float64) if fuse else None
         self._call(
             "rs_angles",
             rds.data_ptr(), t["scan"].data_ptr(), t["stride"], _lib.ptr(t["steer64"]), t["grid_f32"].data_ptr(), t["G"],
@@ -293,23 +297,29 @@ class FramePipeline:
     def recheck_detections(self, cube: torch.Tensor, det: Detections,
                            chirp_subset: Optional[Tuple[int, int]] = None) -> torch.Tensor:
         """Exact (fp64, from the raw cube) local-maximum / threshold decision for every RS_FLAG_NEARMAX entry.
-        Run before angles().  Returns the device stats int32 [4] = rechecked, dropped, promoted, unresolved."""
+        Before angles() it only edits the flags; after angles() (det.method set) it also moves a detection that
+        changes state into / out of the fused velocity sums.  Must precede recheck_angles().
+        Returns the device stats int32 [4] = rechecked, dropped, promoted, unresolved."""
         F, A, C, S = cube.shape
         c0, c1 = (0, C) if chirp_subset is None else chirp_subset
         tab128 = self._fft_tables(S, c1 - c0)[3]
-        stats = self._stats_buf("recheck_det_stats")
+        stats = self._stats_buf("recheck_det_stats" + det.tag)
+        post = det.method is not None and det.ls_partials is not None
+        t = self._angle_tables(A)
         self._call("rs_recheck_detections_f64", cube.data_ptr(), tab128.data_ptr(), C, c0, int(self.cfg.dc_removal),
                    float(10.0 ** (det.threshold_db / 10.0)), det.key.data_ptr(), det.flags.data_ptr(),
                    det.count.data_ptr(), det.nnear.data_ptr(), det.seg_cap, det.ntiles, F, A, c1 - c0, S,
+                   det.aidx.data_ptr() if post else 0, det.phase.data_ptr() if post else 0,
+                   t["grid_cs"].data_ptr() if post else 0, det.ls_partials.data_ptr() if post else 0,
                    stats.data_ptr(), self.stream)
         return stats
 
     def recheck_angles(self, cube: torch.Tensor, rds: torch.Tensor, det: Detections,
-                       chirp_subset: Optional[Tuple[int, int]] = None) -> torch.Tensor:
+                       chirp_subset: Optional[Tuple[int, int]] = None, exhaustive: bool = False) -> torch.Tensor:
         """Exact grid argmax for every RS_FLAG_TIE / RS_FLAG_GUARD cell (grid methods).  Run after angles().
         Returns the device stats int32 [4] = rechecked, index changed, needed the fp64 snapshot, unresolved."""
         method = det.method or self.cfg.method
-        stats = self._stats_buf("recheck_ang_stats")
+        stats = self._stats_buf("recheck_ang_stats" + det.tag)
         if method == "esprit":
             stats.zero_()
             return stats
@@ -323,7 +333,21 @@ class FramePipeline:
                    det.key.data_ptr(), det.lead.data_ptr(),
                    det.nlead.data_ptr(), det.flags.data_ptr(), det.aidx.data_ptr(), det.adeg.data_ptr(),
                    det.phase.data_ptr(), _lib.ptr(det.ls_partials), det.seg_cap, det.ntiles, F, A, c1 - c0, S,
+                   self._buf("rc_idx" + det.tag, (F * det.ntiles * 16,), torch.int32).data_ptr(),
+                   self._buf("rc_cnt" + det.tag, (F * det.ntiles,), torch.int32).data_ptr(),
+                   self._buf("rc_snap" + det.tag, (F * det.ntiles * 16 * A,), torch.complex128).data_ptr(),
                    stats.data_ptr(), self.stream)
+        if exhaustive:
+            # one pass settles at most 16 undecided cells per segment / 1024 per frame; adversarial inputs (e.g. a
+            # noise-free frame where every cell sits on the MUSIC guard) need more passes -- each syncs on the stats
+            total = stats.clone()
+            for _ in range(256):
+                if int(stats[3].item()) == 0:
+                    break
+                self.recheck_angles(cube, rds, det, chirp_subset, exhaustive=False)
+                total[:3] += stats[:3]
+                total[3] = stats[3]
+            stats.copy_(total)
         return stats
 
     # ------------------------------------------------------------------ whole path
@@ -334,19 +358,42 @@ class FramePipeline:
         F = cube.shape[0]
         vel = vel_out if vel_out is not None else torch.empty((F, 8), dtype=torch.float64, device=self.device)
         last = None
-        for lo in range(0, F, chunk_frames):
+        # The fp64 recheck and the solve of chunk i run on a side stream while the main stream already works on
+        # chunk i+1 (two workspace sets): the recheck kernels are latency bound on a handful of CTAs and hide
+        # behind the bandwidth / issue bound main kernels.
+        main = torch.cuda.current_stream(self.device)
+        side = self._ws.setdefault("side_stream", torch.cuda.Stream(self.device))
+        side_done = self._ws.setdefault("side_done", [None, None])
+        overlap = self.cfg.recheck and not keep and os.environ.get("RS_NO_OVERLAP") != "1"
+        for ci, lo in enumerate(range(0, F, chunk_frames)):
             hi = min(F, lo + chunk_frames)
             n = hi - lo
             _, A, C, S = cube.shape
-            rds = self.range_doppler(cube[lo:hi], out=None if keep else self._buf("rds", (n, S, C, A), torch.complex64))
-            det = self.detect(rds, workspace=not keep)
-            if self.cfg.recheck:
-                self.recheck_detections(cube[lo:hi], det)
+            tag = str(ci & 1)
+            if overlap and side_done[ci & 1] is not None:
+                main.wait_event(side_done[ci & 1])                 # workspace set free again
+            rds = self.range_doppler(cube[lo:hi], out=None if keep else self._buf("rds" + tag, (n, S, C, A), torch.complex64))
+            det = self.detect(rds, workspace=False if keep else tag)
             self.angles(rds, det)
-            if self.cfg.recheck:
-                self.recheck_angles(cube[lo:hi], rds, det)
-            self.velocity(det, out=vel[lo:hi])
+            if overlap:
+                ready = torch.cuda.Event()
+                ready.record(main)
+                with torch.cuda.stream(side):
+                    side.wait_event(ready)
+                    self.recheck_detections(cube[lo:hi], det)
+                    self.recheck_angles(cube[lo:hi], rds, det)
+                    self.velocity(det, out=vel[lo:hi])
+                    done = torch.cuda.Event()
+                    done.record(side)
+                    side_done[ci & 1] = done
+            else:
+                if self.cfg.recheck:
+                    self.recheck_detections(cube[lo:hi], det)
+                    self.recheck_angles(cube[lo:hi], rds, det, exhaustive=keep)
+                self.velocity(det, out=vel[lo:hi])
             last = (rds, det)
+        if overlap:
+            main.wait_stream(side)
         return (vel, last[0], last[1]) if keep else vel
 
     def process_host(self, cube_host: torch.Tensor, chunk_frames: int = 32) -> torch.Tensor:
