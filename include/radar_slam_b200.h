@@ -168,6 +168,16 @@ int rs_recheck_angles_f64(const void* cube, const void* table128, int C_total, i
                           double* ls_partials, int seg_cap, int nseg_per_frame, int F, int A, int C, int S,
                           int32_t* work_idx, int32_t* work_cnt, void* work_snap, int32_t* stats, void* stream);
 
+/* (c')  General-covariance MUSIC (angle_estimation.py:109-154 for an ARBITRARY Hermitian R: multi-snapshot or
+ *       smoothed covariances, num_sources >= 1): Hermitian Jacobi eigendecomposition in registers, one warp per
+ *       matrix (parallel cyclic Jacobi, columns across lanes, rotations by shuffle), descending eigenvalue order,
+ *       noise subspace V[:, num_sources:], pseudo-spectrum 1/|a^H E_n E_n^H a| with the 1e-12 guard, first-index
+ *       argmax.  cov64 complex64 [n][A][A] (row-major), 2 <= A <= 32; steer64 complex64 [A][G] or NULL (eigen only);
+ *       outputs (each optional): eigvals float [n][A] descending, eigvecs64 complex64 [n][A][A] (columns),
+ *       spectrum float [n][G], aidx int32 [n]. */
+int rs_music_covariance(const void* cov64, int n, int A, int num_sources, const void* steer64, int G, int sweeps,
+                        float* eigvals, void* eigvecs64, float* spectrum, int32_t* aidx, void* stream);
+
 /* helpers for the legacy (list-of-dict) adapters ---------------------------------------------- */
 
 /* rds [F][S][C][A] -> reference layout [F][A][S][C] (complex64) */

@@ -27,6 +27,7 @@ _SIGNATURES = {
     "rs_angles": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _f, _d, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                        _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
     "rs_velocity_from_partials": (_i, [_vp, _i, _i, _d, _d, _vp, _vp]),
+    "rs_music_covariance": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "rs_recheck_detections_f64": (_i, [_vp, _vp, _i, _i, _i, _d, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i,
                                        _vp, _vp, _vp, _vp, _vp, _vp]),
     "rs_recheck_angles_f64": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _d, _vp, _vp, _vp, _vp, _vp,

@@ -35,13 +35,15 @@ def _sample(arr: np.ndarray) -> complex:
     return complex(flat[::step].sum())
 
 
-def remember_rds(arr: np.ndarray, dev: torch.Tensor) -> None:
-    """Remember the device copy (cell-major, [1,S,C,A]) of an RDS array handed to the caller."""
+def remember_rds(arr: np.ndarray, dev: torch.Tensor, cube: Optional[torch.Tensor] = None,
+                 chirp_subset: Optional[Tuple[int, int]] = None) -> None:
+    """Remember the device copy (cell-major, [1,S,C,A]) of an RDS array handed to the caller, and the raw cube it
+    came from when known (lets the peak extractor settle fp32-undecidable cells in fp64)."""
     try:
         ref = weakref.ref(arr)
     except TypeError:
         return
-    _rds_cache[id(arr)] = (ref, _sample(arr), dev)
+    _rds_cache[id(arr)] = (ref, _sample(arr), dev, cube, chirp_subset)
     while len(_rds_cache) > 2:
         _rds_cache.popitem(last=False)
 
@@ -100,3 +102,11 @@ def esprit(pipe: FramePipeline, sig128: torch.Tensor, scale: float) -> torch.Ten
     out = torch.empty((n,), dtype=torch.float64, device=pipe.device)
     pipe._call("rs_esprit_f64", sig128.data_ptr(), n, A, float(scale), out.data_ptr(), pipe.stream)
     return out
+
+
+def cube_of(rds: np.ndarray):
+    """(device cube, chirp_subset) the RDS array was computed from in this process, or (None, None)."""
+    ent = _rds_cache.get(id(rds))
+    if ent is not None and ent[0]() is rds and ent[1] == _sample(rds) and ent[3] is not None:
+        return ent[3], ent[4]
+    return None, None

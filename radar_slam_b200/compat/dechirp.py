@@ -105,7 +105,7 @@ class SignalPreprocessor:
         ref_layout = torch.empty((1, A, S, Cu), dtype=torch.complex64, device=pipe.device)
         pipe._call("rs_rds_to_reference_layout", rds_dev.data_ptr(), ref_layout.data_ptr(), 1, A, Cu, S, pipe.stream)
         out = ref_layout[0].cpu().numpy().astype(np.complex128)
-        _device.remember_rds(out, rds_dev)
+        _device.remember_rds(out, rds_dev, cube, chirp_subset)
         return out
 
     def extract_range_doppler_peaks(self, rds: np.ndarray, threshold_db: float = -20.0, min_range: float = 1.0,
@@ -115,6 +115,10 @@ class SignalPreprocessor:
         rds_dev = _device.rds_to_device(rds, pipe)
         _, R, D, A = rds_dev.shape
         det = pipe.detect(rds_dev, threshold_db=threshold_db, min_range=min_range, max_range=max_range)
+        cube_dev, subset = _device.cube_of(rds)
+        if cube_dev is not None:
+            # the RDS was computed here from a known cube: cells fp32 cannot decide are settled in fp64
+            pipe.recheck_detections(cube_dev, det, subset)
         if int(det.overflow.sum().item()):
             # plateau-heavy input: rerun with segments that can hold every cell of a tile
             from ..pipeline import FramePipeline

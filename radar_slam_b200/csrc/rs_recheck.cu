@@ -73,8 +73,9 @@ __device__ void dft_cells(const CubeView& v, int f, int a, const int* rp, int nr
             idx[i] = (int)(((long long)lane * kr[i]) % v.S);
             step[i] = (int)((32ll * kr[i]) % v.S);
         }
-        for (int s = lane; s < v.S; s += 32) {
-            const float2 xv = x[s];
+#pragma unroll 8
+        for (int s = lane; s < v.S; s += 32) {        // unrolled: the loads of a row are in flight together
+            const float2 xv = __ldg(x + s);
             const double2 y = dmul(make_double2((double)xv.x, (double)xv.y), v.tab[s]);
             for (int i = 0; i < nr; ++i) {
                 const double2 t = dmul(y, ws[idx[i]]);
@@ -538,7 +539,7 @@ __device__ __forceinline__ void b1_accumulate(const float2* __restrict__ plane, 
         double tr[NB], ti[NB];
 #pragma unroll
         for (int i = 0; i < NB; ++i) { tr[i] = 0; ti[i] = 0; }
-#pragma unroll 2
+#pragma unroll 4
         for (int s = lane; s < S; s += 32) {
             const float2 xv = __ldg(x + s);
             const double xr = (double)xv.x, xi = (double)xv.y;

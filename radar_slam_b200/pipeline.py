@@ -290,6 +290,34 @@ class FramePipeline:
             vel.data_ptr(), det.seg_cap, det.ntiles, det.F, self.stream)
         return vel
 
+    # ------------------------------------------------------------------ general-covariance MUSIC (Jacobi)
+    def music_covariance(self, cov: torch.Tensor, num_sources: int = 1, sweeps: int = 10, want_vectors: bool = False):
+        """MUSIC for arbitrary Hermitian covariances complex64 [n, A, A] (2 <= A <= 32): Jacobi eigendecomposition in
+        registers, noise subspace V[:, num_sources:], pseudo-spectrum over this pipeline's azimuth grid
+        (angle_estimation.py:109-154 generalised beyond the rank-1 single-snapshot case).
+        Returns dict(eigvals [n,A] descending, spectrum [n,G], aidx [n], angle_deg [n], eigvecs [n,A,A] optional)."""
+        assert cov.is_cuda and cov.dtype == torch.complex64 and cov.dim() == 3 and cov.shape[1] == cov.shape[2]
+        cov = cov.contiguous()
+        n, A, _ = cov.shape
+        c = self.cfg
+        key = ("steer64_any", A)
+        if key not in self._tab:
+            grid = tables.azimuth_grid(c.search_range, c.search_resolution)
+            self._tab[key] = (self._dev(tables.steering(grid, np.arange(A) * c.spacing, c.lambda_c).astype(np.complex64)),
+                              self._dev(grid.astype(np.float32)))
+        steer, grid = self._tab[key]
+        G = steer.shape[1]
+        vals = torch.empty((n, A), dtype=torch.float32, device=self.device)
+        spec = torch.empty((n, G), dtype=torch.float32, device=self.device)
+        aidx = torch.empty((n,), dtype=torch.int32, device=self.device)
+        vecs = torch.empty((n, A, A), dtype=torch.complex64, device=self.device) if want_vectors else None
+        self._call("rs_music_covariance", cov.data_ptr(), n, A, int(num_sources), steer.data_ptr(), G, int(sweeps),
+                   vals.data_ptr(), _lib.ptr(vecs), spec.data_ptr(), aidx.data_ptr(), self.stream)
+        out = {"eigvals": vals, "spectrum": spec, "aidx": aidx, "angle_deg": grid[aidx.long()]}
+        if want_vectors:
+            out["eigvecs"] = vecs
+        return out
+
     # ------------------------------------------------------------------ fp64 recheck of flagged decisions
     def _stats_buf(self, name: str) -> torch.Tensor:
         return self._buf(name, (4,), torch.int32)
