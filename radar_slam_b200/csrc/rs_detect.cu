@@ -247,7 +247,7 @@ __device__ __forceinline__ int a8_off(int rr, int ddp, int quad) {          // f
     return rr * A8_W + ddp * A8_AC + ((quad ^ ((ddp >> 2) & 1)) << 2);
 }
 
-__global__ void __launch_bounds__(DET_THREADS, 2)
+__global__ void __launch_bounds__(DET_THREADS, 3)
 detect_a8_kernel(const float2* __restrict__ rds, const uint8_t* __restrict__ gate, float thr, float eps, DetOut out, int R,
                  int D, int A, Tiling tl) {
     extern __shared__ float pw[];   // [(TR+2)][W]
@@ -301,31 +301,32 @@ detect_a8_kernel(const float2* __restrict__ rds, const uint8_t* __restrict__ gat
     uint32_t hit[2] = {0u, 0u}, near[2] = {0u, 0u}, cand[2] = {0u, 0u};  // byte per row: antenna mask
     int my_near = 0;
     float my_psum = 0.f;
-    {
-        auto ld8 = [&](int rr, int dp, float (&o)[8]) {
-            const float4 v0 = *reinterpret_cast<const float4*>(pw + a8_off(rr, dp, 0));
-            const float4 v1 = *reinterpret_cast<const float4*>(pw + a8_off(rr, dp, 1));
-            o[0] = v0.x; o[1] = v0.y; o[2] = v0.z; o[3] = v0.w;
-            o[4] = v1.x; o[5] = v1.y; o[6] = v1.z; o[7] = v1.w;
-        };
-        float l1[8], c1[8], q1[8], hp[8];
-        {
-            float l0[8], c0[8], q0[8];
-            ld8(rbase, ddp - 1, l0); ld8(rbase, ddp, c0); ld8(rbase, ddp + 1, q0);
+    // the two antenna quads of the cell are walked one after the other (half the live registers of an
+    // 8-wide walk, so three CTAs fit per SM); their hit bits land in the same per-row antenna mask
 #pragma unroll
-            for (int j = 0; j < 8; ++j) hp[j] = fmaxf(fmaxf(l0[j], c0[j]), q0[j]);
+    for (int quad = 0; quad < 2; ++quad) {
+        auto ld4 = [&](int rr, int dp, float (&o)[4]) {
+            const float4 v0 = *reinterpret_cast<const float4*>(pw + a8_off(rr, dp, quad));
+            o[0] = v0.x; o[1] = v0.y; o[2] = v0.z; o[3] = v0.w;
+        };
+        float l1[4], c1[4], q1[4], hp[4];
+        {
+            float l0[4], c0[4], q0[4];
+            ld4(rbase, ddp - 1, l0); ld4(rbase, ddp, c0); ld4(rbase, ddp + 1, q0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) hp[j] = fmaxf(fmaxf(l0[j], c0[j]), q0[j]);
         }
-        ld8(rbase + 1, ddp - 1, l1); ld8(rbase + 1, ddp, c1); ld8(rbase + 1, ddp + 1, q1);
+        ld4(rbase + 1, ddp - 1, l1); ld4(rbase + 1, ddp, c1); ld4(rbase + 1, ddp + 1, q1);
 #pragma unroll
         for (int i = 0; i < A8_HALF; ++i) {
             const int rr = rbase + 1 + i;
-            float l2[8], c2[8], q2[8];
-            ld8(rr + 1, ddp - 1, l2); ld8(rr + 1, ddp, c2); ld8(rr + 1, ddp + 1, q2);
+            float l2[4], c2[4], q2[4];
+            ld4(rr + 1, ddp - 1, l2); ld4(rr + 1, ddp, c2); ld4(rr + 1, ddp + 1, q2);
             const int r = r0 + rr - 1;
             const bool row_ok = r < R && gate[r < R ? r : 0];
             uint32_t hm = 0u, nm = 0u, cm = 0u;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < 4; ++j) {
                 const float hn = fmaxf(fmaxf(l2[j], c2[j]), q2[j]);
                 const float m = fmaxf(fmaxf(hp[j], hn), fmaxf(l1[j], q1[j]));
                 const float c = c1[j];
@@ -339,9 +340,10 @@ detect_a8_kernel(const float2* __restrict__ rds, const uint8_t* __restrict__ gat
                 hp[j] = fmaxf(fmaxf(l1[j], c), q1[j]);
                 l1[j] = l2[j]; c1[j] = c2[j]; q1[j] = q2[j];
             }
-            hit[i >> 2] |= hm << ((i & 3) * 8);
-            near[i >> 2] |= nm << ((i & 3) * 8);
-            cand[i >> 2] |= cm << ((i & 3) * 8);
+            const int sh = (i & 3) * 8 + quad * 4;
+            hit[i >> 2] |= hm << sh;
+            near[i >> 2] |= nm << sh;
+            cand[i >> 2] |= cm << sh;
         }
     }
     // entries and leaders of this thread, scanned together (entries <= 2^14 per tile)

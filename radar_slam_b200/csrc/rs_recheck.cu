@@ -73,16 +73,30 @@ __device__ void dft_cells(const CubeView& v, int f, int a, const int* rp, int nr
             idx[i] = (int)(((long long)lane * kr[i]) % v.S);
             step[i] = (int)((32ll * kr[i]) % v.S);
         }
-#pragma unroll 8
-        for (int s = lane; s < v.S; s += 32) {        // unrolled: the loads of a row are in flight together
-            const float2 xv = __ldg(x + s);
-            const double2 y = dmul(make_double2((double)xv.x, (double)xv.y), v.tab[s]);
-            for (int i = 0; i < nr; ++i) {
-                const double2 t = dmul(y, ws[idx[i]]);
-                acc[i].x += t.x;
-                acc[i].y += t.y;
-                idx[i] += step[i];
-                if (idx[i] >= v.S) idx[i] -= v.S;
+        for (int s0 = lane; s0 < v.S; s0 += 256) {
+            // eight loads in flight per lane before any of them is consumed (the item is latency bound)
+            float2 xs[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int s = s0 + 32 * j;
+                xs[j] = s < v.S ? __ldg(x + s) : make_float2(0.f, 0.f);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int s = s0 + 32 * j;
+                if (s < v.S) {
+                    const double2 y = dmul(make_double2((double)xs[j].x, (double)xs[j].y), v.tab[s]);
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        if (i < nr) {
+                            const double2 t = dmul(y, ws[idx[i]]);
+                            acc[i].x += t.x;
+                            acc[i].y += t.y;
+                            idx[i] += step[i];
+                            if (idx[i] >= v.S) idx[i] -= v.S;
+                        }
+                    }
+                }
             }
         }
         for (int i = 0; i < nr; ++i) {
