@@ -112,13 +112,17 @@ int rs_detect(const void* rds, const uint8_t* range_gate, float thr_power, float
  *       ls_partials   optional double [F*nseg_per_frame][8]: per-segment fp64 sums
  *                     (sum c^2, sum s^2, sum cs, sum yc, sum ys, sum y^2, n, 0) of the velocity normal
  *                     equations with c,s = grid_cs[aidx]; needs grid_cs (double [G][2]); grid methods, A <= 16
- *       det_ntie      optional int32 [F*nseg_per_frame]: cells flagged TIE / GUARD per segment */
+ *       det_ntie      optional int32 [F*nseg_per_frame]: cells flagged TIE / GUARD per segment
+ *       det_tielist   optional int32 [F*nseg_per_frame][RS_TIE_LIST_CAP]: leader indices of the first RS_TIE_LIST_CAP
+ *                     flagged cells of each segment, in arbitrary order (lets the fp64 recheck skip the list scan) */
+#define RS_TIE_LIST_CAP 32
 int rs_angles(const void* rds, const float* scan_table, int scan_stride, const void* steer, const float* grid_deg, int G,
               int method, float tie_eps, double esprit_scale,
               const uint32_t* det_key, const uint32_t* det_lead, const int32_t* det_nlead, uint8_t* det_flags,
               int32_t* det_aidx, float* det_adeg, float* det_phase,
               int seg_cap, int nseg_per_frame, int F, int R, int D, int A,
-              const double* grid_cs, double* ls_partials, int grid_symmetric, int32_t* det_ntie, void* stream);
+              const double* grid_cs, double* ls_partials, int grid_symmetric, int32_t* det_ntie, int32_t* det_tielist,
+              void* stream);
 
 /* (d')  the velocity solve of rs_velocity_ls from the per-segment sums rs_angles already produced
  *       (no second pass over the detection lists); same output row layout. */
@@ -136,8 +140,8 @@ int rs_velocity_ls(const int32_t* det_aidx, const float* det_adeg, const float* 
                    double* vel, int seg_cap, int nseg_per_frame, int F, void* stream);
 
 /* fp64 re-evaluation of the decisions the fp32 kernels flag as undecidable, straight from the raw cube
- * (direct fp64 DFT of the cells involved; table128 = conj(ref)*window complex128 [S]).  One CTA per
- * detection segment, items in list order: deterministic.  stats int32 [4] is zeroed and filled.
+ * (direct fp64 DFT of the cells involved; table128 = conj(ref)*window complex128 [S]).  A segment's items are
+ * settled in list order by one owner (CTA or warp): deterministic.  stats int32 [4] is zeroed and filled.
  *
  * rs_recheck_detections_f64: RS_FLAG_NEARMAX entries (detections and the near-miss candidates rs_detect emits
  *   as RS_FLAG_DROPPED): exact 3x3 local-maximum and threshold test (dechirp.py:250-254,
@@ -151,22 +155,31 @@ int rs_velocity_ls(const int32_t* det_aidx, const float* det_adeg, const float* 
  *   Stage B (otherwise, and near the MUSIC 1e-12 guard): the snapshot is recomputed in fp64 from the cube.
  *   First-index argmax of the method's pseudo-spectrum (angle_estimation.py:143-152, 173); rewrites
  *   det_aidx/det_adeg, sets RS_FLAG_FIXED and corrects ls_partials.
- *   Stage B reads each (frame, antenna) plane of the cube once for all undecided cells of the frame.
+ *   Stage B reads each (frame, antenna) plane of the cube once per 8 undecided cells of the frame.
+ *   det_tielist: the list rs_angles wrote (NULL, or more than RS_TIE_LIST_CAP flagged cells: the leaders are scanned).
+ *   tw_s128 / tw_c128: complex128 exp(-2 pi i k / S) [S] and exp(-2 pi i k / C) [C], built in fp64 by the host.
  *   Workspace (caller-allocated): work_idx int32 [F*nseg*16], work_cnt int32 [F*nseg], work_snap complex128
- *   [F*nseg*16*A].   stats = {rechecked, index changed, needed the fp64 snapshot, unresolved}. */
-int rs_recheck_detections_f64(const void* cube, const void* table128, int C_total, int chirp0, int dc_removal,
+ *   [F*nseg*16*A], frame_cnt int32 [F], frame_list int32 [F][RS_RECHECK_FRAME_CAP][4] (16-byte aligned).
+ *   One pass settles at most 16 undecided cells per segment and RS_RECHECK_FRAME_CAP per frame in stage B; the rest
+ *   is counted in stats[3] and left unflagged-as-fixed for another pass.
+ *   stats = {rechecked, index changed, needed the fp64 snapshot, unresolved}. */
+#define RS_RECHECK_FRAME_CAP 256
+int rs_recheck_detections_f64(const void* cube, const void* table128, const void* tw_s128, const void* tw_c128,
+                              int C_total, int chirp0, int dc_removal,
                               double thr_power64, const uint32_t* det_key, uint8_t* det_flags,
                               const int32_t* det_count, const int32_t* det_nnear, int seg_cap, int nseg_per_frame,
                               int F, int A, int C, int S,
                               const int32_t* det_aidx, const float* det_phase, const double* grid_cs, double* ls_partials,
                               int32_t* stats, void* stream);
-int rs_recheck_angles_f64(const void* cube, const void* table128, int C_total, int chirp0, int dc_removal,
+int rs_recheck_angles_f64(const void* cube, const void* table128, const void* tw_s128, const void* tw_c128,
+                          int C_total, int chirp0, int dc_removal,
                           const void* rds, const void* steer128, const float* grid_deg, const double* grid_cs,
                           int G, int method, double fft_eps, const float* det_psum, const int32_t* det_ntie,
-                          const uint32_t* det_key, const uint32_t* det_lead, const int32_t* det_nlead,
+                          const int32_t* det_tielist, const uint32_t* det_key, const uint32_t* det_lead, const int32_t* det_nlead,
                           uint8_t* det_flags, int32_t* det_aidx, float* det_adeg, const float* det_phase,
                           double* ls_partials, int seg_cap, int nseg_per_frame, int F, int A, int C, int S,
-                          int32_t* work_idx, int32_t* work_cnt, void* work_snap, int32_t* stats, void* stream);
+                          int32_t* work_idx, int32_t* work_cnt, void* work_snap, int32_t* frame_cnt,
+                          int32_t* frame_list, int32_t* stats, void* stream);
 
 /* (c')  General-covariance MUSIC (angle_estimation.py:109-154 for an ARBITRARY Hermitian R: multi-snapshot or
  *       smoothed covariances, num_sources >= 1): Hermitian Jacobi eigendecomposition in registers, one warp per

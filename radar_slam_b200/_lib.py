@@ -12,6 +12,8 @@ import os
 from . import build as _build
 
 RS_METHOD_MUSIC, RS_METHOD_BEAMFORMING, RS_METHOD_ESPRIT = 0, 1, 2
+RS_RECHECK_FRAME_CAP = 256
+RS_TIE_LIST_CAP = 32
 RS_FLAG_TIE, RS_FLAG_NEARMAX, RS_FLAG_GUARD, RS_FLAG_FIXED, RS_FLAG_DROPPED, RS_FLAG_DETFIXED = 1, 2, 4, 8, 16, 32
 METHODS = {"music": RS_METHOD_MUSIC, "beamforming": RS_METHOD_BEAMFORMING, "esprit": RS_METHOD_ESPRIT}
 
@@ -25,13 +27,14 @@ _SIGNATURES = {
     "rs_doppler_fft": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "rs_detect": (_i, [_vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "rs_angles": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _f, _d, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
-                       _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
+                       _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp]),
     "rs_velocity_from_partials": (_i, [_vp, _i, _i, _d, _d, _vp, _vp]),
     "rs_music_covariance": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
-    "rs_recheck_detections_f64": (_i, [_vp, _vp, _i, _i, _i, _d, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i,
+    "rs_recheck_detections_f64": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _d, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i,
                                        _vp, _vp, _vp, _vp, _vp, _vp]),
-    "rs_recheck_angles_f64": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _d, _vp, _vp, _vp, _vp, _vp,
-                                   _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "rs_recheck_angles_f64": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _d, _vp, _vp, _vp, _vp, _vp,
+                                   _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp,
+                                   _vp, _vp]),
     "rs_velocity_ls": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _d, _d, _i, _d, _vp, _i, _i, _i, _vp]),
     "rs_rds_to_reference_layout": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "rs_rds_from_reference_layout": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),

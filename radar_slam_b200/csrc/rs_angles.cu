@@ -33,6 +33,7 @@ struct AngleArgs {
     const uint32_t* det_lead;     // per segment: position | multiplicity << 16 of each distinct cell
     const int32_t* det_nlead;
     int32_t* det_ntie;            // per segment: cells flagged TIE / GUARD (zeroed by the entry point; may be null)
+    int32_t* det_tielist;         // per segment: leader indices of the first RS_TIE_LIST_CAP flagged cells (unordered; may be null)
     uint8_t* det_flags;
     int32_t* det_aidx;
     float* det_adeg;
@@ -42,10 +43,13 @@ struct AngleArgs {
 
 // write one cell's result to all of its detections (same snapshot on every antenna that flagged the cell)
 // returns how many of them are live (not RS_FLAG_DROPPED): the weight of the cell in the velocity sums
-__device__ __forceinline__ int emit(const AngleArgs& p, int seg, size_t o, int k, int aidx, float adeg, float phase,
-                                    uint8_t extra_flags) {
+__device__ __forceinline__ int emit(const AngleArgs& p, int seg, int lead_i, size_t o, int k, int aidx, float adeg,
+                                    float phase, uint8_t extra_flags) {
     int live = 0;
-    if ((extra_flags & (RS_FLAG_TIE | RS_FLAG_GUARD)) && p.det_ntie) atomicAdd(p.det_ntie + seg, 1);
+    if ((extra_flags & (RS_FLAG_TIE | RS_FLAG_GUARD)) && p.det_ntie) {
+        const int slot = atomicAdd(p.det_ntie + seg, 1);
+        if (p.det_tielist && slot < RS_TIE_LIST_CAP) p.det_tielist[(size_t)seg * RS_TIE_LIST_CAP + slot] = lead_i;
+    }
     for (int e = 0; e < k; ++e) {
         p.det_aidx[o + e] = aidx;
         p.det_adeg[o + e] = adeg;
@@ -132,7 +136,7 @@ __global__ void __launch_bounds__(ANG_THREADS) angles_small_kernel(AngleArgs p) 
 
         uint8_t flags = 0;
         if (!scan) {
-            emit(p, seg, o, mult, -1, esprit_deg<AP>(s, M, p.esprit_scale), phase, 0);
+            emit(p, seg, i, o, mult, -1, esprit_deg<AP>(s, M, p.esprit_scale), phase, 0);
             continue;
         }
         // lags R_k, k = 0..AP-1
@@ -169,7 +173,7 @@ __global__ void __launch_bounds__(ANG_THREADS) angles_small_kernel(AngleArgs p) 
             const float full = (float)M * rr[0];
             if (full - pbest <= 1e-4f * full) flags |= RS_FLAG_GUARD;
         }
-        emit(p, seg, o, mult, bi, p.grid_deg[bi], phase, flags);
+        emit(p, seg, i, o, mult, bi, p.grid_deg[bi], phase, flags);
     }
 }
 
@@ -340,7 +344,7 @@ __global__ void __launch_bounds__(ANG_THREADS) angles_scan_kernel(AngleArgs p, c
                     const float full = (float)M * rr[q][0];
                     if (full - pbest <= 1e-4f * full) flags |= RS_FLAG_GUARD;
                 }
-                const int live = emit(p, seg, o[q], mult[q], bi, p.grid_deg[bi], yv[q], flags);
+                const int live = emit(p, seg, base + q * ANG_THREADS + threadIdx.x, o[q], mult[q], bi, p.grid_deg[bi], yv[q], flags);
                 if (ls_partials != nullptr) {      // every antenna's detection of the cell adds the same row
                     const double c = grid_cs[2 * bi], sn = grid_cs[2 * bi + 1], y = (double)yv[q], w = (double)live;
                     acc_ls[0] += w * c * c; acc_ls[1] += w * sn * sn; acc_ls[2] += w * c * sn;
@@ -435,7 +439,7 @@ __global__ void __launch_bounds__(ANG_THREADS) angles_large_kernel(AngleArgs p) 
                 ni += __shfl_xor_sync(0xffffffffu, ni, off);
             }
             if (lane == 0)
-                emit(p, seg, o, mult, -1, (float)(asin(atan2(ni, nr) * p.esprit_scale) * (180.0 / 3.14159265358979323846)),
+                emit(p, seg, i, o, mult, -1, (float)(asin(atan2(ni, nr) * p.esprit_scale) * (180.0 / 3.14159265358979323846)),
                      phase, 0);
             continue;
         }
@@ -469,7 +473,7 @@ __global__ void __launch_bounds__(ANG_THREADS) angles_large_kernel(AngleArgs p) 
                 const float full = (float)M * e;
                 if (full - best <= 1e-4f * full) flags |= RS_FLAG_GUARD;
             }
-            emit(p, seg, o, mult, bi, p.grid_deg[bi], phase, flags);
+            emit(p, seg, i, o, mult, bi, p.grid_deg[bi], phase, flags);
         }
     }
 }
@@ -554,7 +558,8 @@ extern "C" int rs_angles(const void* rds, const float* scan_table, int scan_stri
                          const uint32_t* det_key, const uint32_t* det_lead, const int32_t* det_nlead, uint8_t* det_flags,
                          int32_t* det_aidx,
                          float* det_adeg, float* det_phase, int seg_cap, int nseg_per_frame, int F, int R, int D, int A,
-                         const double* grid_cs, double* ls_partials, int grid_symmetric, int32_t* det_ntie, void* stream) {
+                         const double* grid_cs, double* ls_partials, int grid_symmetric, int32_t* det_ntie,
+                         int32_t* det_tielist, void* stream) {
     RS_CHECK_ARG(rds && det_key && det_lead && det_nlead && det_flags && det_aidx && det_adeg && det_phase,
                  "rs_angles: null pointer");
     RS_CHECK_ARG(ls_partials == nullptr || grid_cs != nullptr, "rs_angles: ls_partials needs grid_cs");
@@ -564,7 +569,7 @@ extern "C" int rs_angles(const void* rds, const float* scan_table, int scan_stri
     const bool scan = method != RS_METHOD_ESPRIT;
     RS_CHECK_ARG(!scan || (G > 0 && grid_deg), "rs_angles: grid required");
     AngleArgs p{(const float2*)rds, scan_table, scan_stride, (const float2*)steer, grid_deg, G, method, tie_eps,
-                esprit_scale, det_key, det_lead, det_nlead, det_ntie, det_flags, det_aidx, det_adeg, det_phase, seg_cap,
+                esprit_scale, det_key, det_lead, det_nlead, det_ntie, det_tielist, det_flags, det_aidx, det_adeg, det_phase, seg_cap,
                 nseg_per_frame,
                 R, D, A};
     const long long blocks = (long long)F * nseg_per_frame;

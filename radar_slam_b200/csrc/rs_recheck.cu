@@ -17,18 +17,31 @@
 //     nearly equal, have a tiny bound, so almost all fp32 ties are settled here.
 //   * angles, stage B (the rest, and anything near the MUSIC guard): the snapshot itself is recomputed in
 //     fp64 from the raw cube and scanned exactly.
-// One CTA per detection segment walks its flagged items in list order, so results (and the corrections
-// to the velocity sums) are deterministic.  Segments without flagged items exit on a per-segment counter.
+// Work decomposition.  A segment's flagged items are always settled in list order by ONE owner, so the results and
+// the corrections to the velocity sums are deterministic:
+//   * detections: one CTA per 8 segments; segments without NEARMAX entries are skipped on a per-segment counter.
+//   * angles, stage A and the final exact scan: one WARP per segment (lanes over grid points).
+//   * angles, stage B snapshots: stage A appends the undecided cells of a frame to one per-frame list; one CTA per
+//     (frame, antenna) then reads that antenna's raw plane ONCE for up to 8 cells at a time.
+// The direct DFT is organised by fast-time column: a thread owns sample index s, walks the chirps with eight
+// coalesced loads in flight, applies the Doppler twiddle of every requested cell (broadcast from shared memory)
+// and only at the end the range factor table[s] w_S^{s k_r}; a block reduction over s finishes the cell.
 #include "rs_common.cuh"
 
 namespace {
 
 constexpr int RC_THREADS = 256;
+constexpr int RC_WARPS = RC_THREADS / 32;
 constexpr int RC_MAX_ITEMS = 512;
+constexpr int RB_MAX = 16;                       // undecided cells per segment handed to stage B
+constexpr int FB_CAP = RS_RECHECK_FRAME_CAP;     // undecided cells per frame handed to stage B
+constexpr int NB_MAX = 8;                        // cells accumulated per pass over a raw plane
 
 struct CubeView {
     const float2* cube;    // [F][A][C_total][S]
     const double2* tab;    // [S] conj(ref) * window, fp64
+    const double2* tw_s;   // [S] exp(-2 pi i k / S), fp64
+    const double2* tw_c;   // [C] exp(-2 pi i k / C), fp64
     int A, C_total, chirp0, C, S, dc;
 };
 
@@ -40,166 +53,61 @@ __device__ __forceinline__ double warp_sum(double v) {
     for (int off = 16; off; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
     return v;
 }
+__device__ __forceinline__ int unshift(int pos, int n) { return (pos - n / 2 + n) % n; }      // undo np.fft.fftshift
 
-__device__ void build_twiddles(double2* ws, int S, double2* wc, int C) {
-    for (int m = threadIdx.x; m < S; m += blockDim.x) {
-        double sn, cs;
-        sincospi(-2.0 * (double)m / (double)S, &sn, &cs);
-        ws[m] = make_double2(cs, sn);
+// Y[i] = sum_c x[c][s] u[i][c]  for one fast-time column (col = plane + s); eight loads in flight
+template <int NB>
+__device__ __forceinline__ void column_dft(const float2* __restrict__ col, int S, int C, const double2* __restrict__ u,
+                                           double2 (&Y)[NB]) {
+#pragma unroll
+    for (int i = 0; i < NB; ++i) Y[i] = make_double2(0, 0);
+    int c = 0;
+    for (; c + 8 <= C; c += 8) {
+        float2 x[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = __ldg(col + (size_t)(c + j) * S);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const double xr = (double)x[j].x, xi = (double)x[j].y;
+#pragma unroll
+            for (int i = 0; i < NB; ++i) {
+                const double2 w = u[i * C + c + j];
+                Y[i].x = fma(xr, w.x, fma(-xi, w.y, Y[i].x));
+                Y[i].y = fma(xr, w.y, fma(xi, w.x, Y[i].y));
+            }
+        }
     }
-    for (int m = threadIdx.x; m < C; m += blockDim.x) {
-        double sn, cs;
-        sincospi(-2.0 * (double)m / (double)C, &sn, &cs);
-        wc[m] = make_double2(cs, sn);
+    for (; c < C; ++c) {
+        const float2 xv = __ldg(col + (size_t)c * S);
+        const double xr = (double)xv.x, xi = (double)xv.y;
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+            const double2 w = u[i * C + c];
+            Y[i].x = fma(xr, w.x, fma(-xi, w.y, Y[i].x));
+            Y[i].y = fma(xr, w.y, fma(xi, w.x, Y[i].y));
+        }
     }
-    __syncthreads();
 }
 
-// X[a][rp_i][dp_j] (shifted bin positions, as stored in the RDS) for i < nr, j < nd, in fp64 from the raw cube.
-// Whole CTA participates; out[i * 3 + j] in shared memory.  T: scratch double2 [3][C].
-__device__ void dft_cells(const CubeView& v, int f, int a, const int* rp, int nr, const int* dp, int nd,
-                          const double2* ws, const double2* wc, double2* T, double2* out) {
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    int kr[3], kd[3];
-    for (int i = 0; i < 3; ++i) {
-        kr[i] = i < nr ? (rp[i] - v.S / 2 + v.S) % v.S : 0;          // undo np.fft.fftshift
-        kd[i] = i < nd ? (dp[i] - v.C / 2 + v.C) % v.C : 0;
-    }
-    for (int c = wid; c < v.C; c += nw) {
-        const float2* x = v.cube + (((size_t)f * v.A + a) * v.C_total + v.chirp0 + c) * v.S;
-        double2 acc[3] = {{0, 0}, {0, 0}, {0, 0}};
-        int idx[3], step[3];                       // (s * kr_i) mod S, advanced incrementally
-        for (int i = 0; i < 3; ++i) {
-            idx[i] = (int)(((long long)lane * kr[i]) % v.S);
-            step[i] = (int)((32ll * kr[i]) % v.S);
-        }
-        for (int s0 = lane; s0 < v.S; s0 += 256) {
-            // eight loads in flight per lane before any of them is consumed (the item is latency bound)
-            float2 xs[8];
+// block sums of n complex values held per thread; result of value i lands in out[i] (thread 0 .. n-1 write)
+template <int N>
+__device__ __forceinline__ void block_reduce(const double2 (&acc)[N], int n, double2* red /* [RC_WARPS][N] */,
+                                             double2* out) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int s = s0 + 32 * j;
-                xs[j] = s < v.S ? __ldg(x + s) : make_float2(0.f, 0.f);
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int s = s0 + 32 * j;
-                if (s < v.S) {
-                    const double2 y = dmul(make_double2((double)xs[j].x, (double)xs[j].y), v.tab[s]);
-#pragma unroll
-                    for (int i = 0; i < 3; ++i) {
-                        if (i < nr) {
-                            const double2 t = dmul(y, ws[idx[i]]);
-                            acc[i].x += t.x;
-                            acc[i].y += t.y;
-                            idx[i] += step[i];
-                            if (idx[i] >= v.S) idx[i] -= v.S;
-                        }
-                    }
-                }
-            }
-        }
-        for (int i = 0; i < nr; ++i) {
+    for (int i = 0; i < N; ++i) {
+        if (i < n) {
             const double re = warp_sum(acc[i].x), im = warp_sum(acc[i].y);
-            if (lane == 0) T[i * v.C + c] = make_double2(re, im);
+            if (lane == 0) red[wid * N + i] = make_double2(re, im);
         }
     }
     __syncthreads();
-    for (int o = wid; o < nr * nd; o += nw) {
-        const int i = o / nd, j = o - i * nd;
-        double ar = 0, ai = 0;
-        for (int c = lane; c < v.C; c += 32) {
-            const double2 t = dmul(T[i * v.C + c], wc[(int)(((long long)c * kd[j]) % v.C)]);
-            ar += t.x;
-            ai += t.y;
-        }
-        ar = warp_sum(ar);
-        ai = warp_sum(ai);
-        // the reference subtracts the per-chirp mean (dechirp.py:120): range bin 0 is ~1e-15, taken as 0
-        if (lane == 0) out[i * 3 + j] = (v.dc && kr[i] == 0) ? make_double2(0, 0) : make_double2(ar, ai);
+    if ((int)threadIdx.x < n) {
+        double re = 0, im = 0;
+        for (int w = 0; w < RC_WARPS; ++w) { re += red[w * N + threadIdx.x].x; im += red[w * N + threadIdx.x].y; }
+        out[threadIdx.x] = make_double2(re, im);
     }
     __syncthreads();
-}
-
-// The A-channel snapshot of ONE cell in fp64: z[s] = table[s] w_S^{s kr} and u[c] = w_C^{c kd} are formed once,
-// then every antenna costs one complex multiply-add per raw sample.
-__device__ void snapshot_f64(const CubeView& v, int f, int rpos, int dpos, const double2* ws, const double2* wc,
-                             double2* z, double2* u, double2* T, double2* snap) {
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    const int kr = (rpos - v.S / 2 + v.S) % v.S, kd = (dpos - v.C / 2 + v.C) % v.C;
-    for (int s = threadIdx.x; s < v.S; s += blockDim.x) z[s] = dmul(v.tab[s], ws[(int)(((long long)s * kr) % v.S)]);
-    for (int c = threadIdx.x; c < v.C; c += blockDim.x) u[c] = wc[(int)(((long long)c * kd) % v.C)];
-    __syncthreads();
-    for (int a = 0; a < v.A; ++a) {
-        for (int c = wid; c < v.C; c += nw) {
-            const float2* x = v.cube + (((size_t)f * v.A + a) * v.C_total + v.chirp0 + c) * v.S;
-            // four independent accumulator pairs: the fp64 pipe is latency bound on a single chain
-            double ar0 = 0, ai0 = 0, ar1 = 0, ai1 = 0, ar2 = 0, ai2 = 0, ar3 = 0, ai3 = 0;
-            int s = lane;
-            for (; s + 96 < v.S; s += 128) {
-                const float2 x0 = x[s], x1 = x[s + 32], x2 = x[s + 64], x3 = x[s + 96];
-                const double2 w0 = z[s], w1 = z[s + 32], w2 = z[s + 64], w3 = z[s + 96];
-                ar0 += (double)x0.x * w0.x - (double)x0.y * w0.y; ai0 += (double)x0.x * w0.y + (double)x0.y * w0.x;
-                ar1 += (double)x1.x * w1.x - (double)x1.y * w1.y; ai1 += (double)x1.x * w1.y + (double)x1.y * w1.x;
-                ar2 += (double)x2.x * w2.x - (double)x2.y * w2.y; ai2 += (double)x2.x * w2.y + (double)x2.y * w2.x;
-                ar3 += (double)x3.x * w3.x - (double)x3.y * w3.y; ai3 += (double)x3.x * w3.y + (double)x3.y * w3.x;
-            }
-            for (; s < v.S; s += 32) {
-                const float2 xv = x[s];
-                const double2 w = z[s];
-                ar0 += (double)xv.x * w.x - (double)xv.y * w.y;
-                ai0 += (double)xv.x * w.y + (double)xv.y * w.x;
-            }
-            double ar = warp_sum((ar0 + ar1) + (ar2 + ar3));
-            double ai = warp_sum((ai0 + ai1) + (ai2 + ai3));
-            if (lane == 0) T[c] = dmul(make_double2(ar, ai), u[c]);
-        }
-        __syncthreads();
-        if (wid == 0) {
-            double ar = 0, ai = 0;
-            for (int c = lane; c < v.C; c += 32) { ar += T[c].x; ai += T[c].y; }
-            ar = warp_sum(ar);
-            ai = warp_sum(ai);
-            if (lane == 0) snap[a] = (v.dc && kr == 0) ? make_double2(0, 0) : make_double2(ar, ai);
-        }
-        __syncthreads();
-    }
-}
-
-// ordered list of the flagged items of a segment: item i qualifies when flags[pos(i)] & mask and not & done
-template <typename PosFn>
-__device__ int collect_items(int n, PosFn pos_of, const uint8_t* flags, uint8_t mask, uint8_t done, int* items,
-                             int* scratch) {
-    const int per = (n + blockDim.x - 1) / blockDim.x;
-    const int lo = threadIdx.x * per, hi = min(n, lo + per);
-    int cnt = 0;
-    for (int i = lo; i < hi; ++i) {
-        const uint8_t fl = flags[pos_of(i)];
-        cnt += ((fl & mask) && !(fl & done)) ? 1 : 0;
-    }
-    scratch[threadIdx.x] = cnt;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int run = 0;
-        for (int t = 0; t < (int)blockDim.x; ++t) {
-            const int c = scratch[t];
-            scratch[t] = run;
-            run += c;
-        }
-        scratch[blockDim.x] = run;
-    }
-    __syncthreads();
-    int at = scratch[threadIdx.x];
-    const int total = scratch[blockDim.x];
-    for (int i = lo; i < hi; ++i) {
-        const uint8_t fl = flags[pos_of(i)];
-        if ((fl & mask) && !(fl & done)) {
-            if (at < RC_MAX_ITEMS) items[at] = i;
-            ++at;
-        }
-    }
-    __syncthreads();
-    return total;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -208,71 +116,118 @@ __device__ int collect_items(int n, PosFn pos_of, const uint8_t* flags, uint8_t 
 __global__ void __launch_bounds__(RC_THREADS)
 recheck_detect_kernel(CubeView v, double thr64, const uint32_t* __restrict__ det_key, uint8_t* __restrict__ det_flags,
                       const int32_t* __restrict__ det_count, const int32_t* __restrict__ det_nnear, int seg_cap,
-                      int nseg, int R, int D, const int32_t* __restrict__ det_aidx, const float* __restrict__ det_phase,
-                      const double* __restrict__ grid_cs, double* __restrict__ ls_partials,
-                      int32_t* __restrict__ stats) {
+                      int nseg, int nseg_total, int R, int D, const int32_t* __restrict__ det_aidx,
+                      const float* __restrict__ det_phase, const double* __restrict__ grid_cs,
+                      double* __restrict__ ls_partials, int32_t* __restrict__ stats) {
     extern __shared__ double2 smd[];
-    double2* ws = smd;
-    double2* wc = ws + v.S;
-    double2* T = wc + v.C;
+    double2* u = smd;                    // [3][C] Doppler twiddles of the three columns
+    double2* red = u + 3 * v.C;          // [RC_WARPS][9]
     __shared__ double2 out[9];
     __shared__ int items[RC_MAX_ITEMS];
-    __shared__ int scratch[RC_THREADS + 1];
-    __shared__ int rp[3], dp[3];
-    const int seg = blockIdx.x;
-    if (det_nnear != nullptr && det_nnear[seg] == 0) return;
-    const int n = det_count[seg];
-    if (n == 0) return;
-    const size_t base = (size_t)seg * seg_cap;
-    const int total = collect_items(n, [&](int i) { return base + i; }, det_flags, RS_FLAG_NEARMAX, RS_FLAG_DETFIXED, items,
-                                    scratch);
-    if (total == 0) return;
-    build_twiddles(ws, v.S, wc, v.C);
-    const int f = seg / nseg;
-    const int todo = min(total, RC_MAX_ITEMS);
-    for (int it = 0; it < todo; ++it) {
-        const size_t o = base + items[it];
-        int a, r, d;
-        rs_split_key(det_key[o], a, r, d);
-        const int r_lo = max(r - 1, 0), r_hi = min(r + 1, R - 1), d_lo = max(d - 1, 0), d_hi = min(d + 1, D - 1);
-        const int nr = r_hi - r_lo + 1, nd = d_hi - d_lo + 1;
-        if (threadIdx.x < 3) {
-            rp[threadIdx.x] = r_lo + threadIdx.x;
-            dp[threadIdx.x] = d_lo + threadIdx.x;
+    __shared__ int wcnt[RC_WARPS];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int sg = 0; sg < RC_WARPS; ++sg) {
+        const int seg = blockIdx.x * RC_WARPS + sg;
+        if (seg >= nseg_total) break;
+        if (det_nnear != nullptr && det_nnear[seg] == 0) continue;
+        const int n = det_count[seg];
+        if (n == 0) continue;
+        const size_t base = (size_t)seg * seg_cap;
+        // ordered list of the segment's undecided entries
+        int total = 0;
+        for (int c0 = 0; c0 < n; c0 += RC_THREADS) {
+            const int i = c0 + threadIdx.x;
+            bool fl = false;
+            if (i < n) {
+                const uint8_t f8 = det_flags[base + i];
+                fl = (f8 & RS_FLAG_NEARMAX) && !(f8 & RS_FLAG_DETFIXED);
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, fl);
+            if (lane == 0) wcnt[wid] = __popc(m);
+            __syncthreads();
+            int off = total, all = 0;
+            for (int w = 0; w < RC_WARPS; ++w) {
+                if (w < wid) off += wcnt[w];
+                all += wcnt[w];
+            }
+            if (fl) {
+                const int at = off + __popc(m & ((1u << lane) - 1u));
+                if (at < RC_MAX_ITEMS) items[at] = i;
+            }
+            total += all;
+            __syncthreads();
         }
-        __syncthreads();
-        dft_cells(v, f, a, rp, nr, dp, nd, ws, wc, T, out);
-        if (threadIdx.x == 0) {
-            double c = 0, m = -1;
-            for (int i = 0; i < nr; ++i)
-                for (int j = 0; j < nd; ++j) {
-                    const double2 x = out[i * 3 + j];
-                    const double p = x.x * x.x + x.y * x.y;
-                    if (r_lo + i == r && d_lo + j == d) c = p;
-                    else m = fmax(m, p);
-                }
-            // dechirp.py:250-254 on exact powers: equality with the 3x3 maximum and dB strictly above threshold
-            const bool is_det = (c >= m) && (c + 1e-12 > thr64);
-            uint8_t fl = det_flags[o];
-            const bool was_det = !(fl & RS_FLAG_DROPPED);
-            if (is_det != was_det) {
-                atomicAdd(stats + (is_det ? 2 : 1), 1);
-                // run after rs_angles: move this detection's row into / out of the velocity sums
-                if (ls_partials != nullptr && det_aidx[o] >= 0) {
-                    const double sg = is_det ? 1.0 : -1.0, y = (double)det_phase[o];
-                    const double cc = grid_cs[2 * det_aidx[o]], ss = grid_cs[2 * det_aidx[o] + 1];
-                    double* ps = ls_partials + (size_t)seg * 8;
-                    ps[0] += sg * cc * cc; ps[1] += sg * ss * ss; ps[2] += sg * cc * ss;
-                    ps[3] += sg * y * cc;  ps[4] += sg * y * ss;  ps[5] += sg * y * y;  ps[6] += sg;
+        if (total == 0) continue;
+        const int f = seg / nseg;
+        const int todo = min(total, RC_MAX_ITEMS);
+        for (int it = 0; it < todo; ++it) {
+            const size_t o = base + items[it];
+            int a, r, d;
+            rs_split_key(det_key[o], a, r, d);
+            const int r_lo = max(r - 1, 0), r_hi = min(r + 1, R - 1), d_lo = max(d - 1, 0), d_hi = min(d + 1, D - 1);
+            const int nr = r_hi - r_lo + 1, nd = d_hi - d_lo + 1;
+            for (int idx = threadIdx.x; idx < 3 * v.C; idx += RC_THREADS) {
+                const int j = idx / v.C, c = idx - j * v.C;
+                const int kd = unshift(min(d_lo + j, D - 1), v.C);
+                u[idx] = j < nd ? v.tw_c[(int)(((long long)c * kd) % v.C)] : make_double2(0, 0);
+            }
+            __syncthreads();
+            int kr[3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) kr[i] = unshift(min(r_lo + i, R - 1), v.S);
+            const float2* plane = v.cube + (((size_t)f * v.A + a) * v.C_total + v.chirp0) * v.S;
+            double2 acc[9];
+#pragma unroll
+            for (int q = 0; q < 9; ++q) acc[q] = make_double2(0, 0);
+            for (int s = threadIdx.x; s < v.S; s += RC_THREADS) {
+                double2 Y[3];
+                column_dft<3>(plane + s, v.S, v.C, u, Y);
+                const double2 t = v.tab[s];
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    const double2 z = dmul(t, v.tw_s[(int)(((long long)s * kr[i]) % v.S)]);
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        const double2 p = dmul(Y[j], z);
+                        acc[i * 3 + j].x += p.x;
+                        acc[i * 3 + j].y += p.y;
+                    }
                 }
             }
-            fl = is_det ? (fl & ~RS_FLAG_DROPPED) : (fl | RS_FLAG_DROPPED);
-            det_flags[o] = fl | RS_FLAG_DETFIXED;
-            atomicAdd(stats + 0, 1);
+            block_reduce<9>(acc, 9, red, out);
+            if (threadIdx.x == 0) {
+                double c = 0, m = -1;
+                for (int i = 0; i < nr; ++i)
+                    for (int j = 0; j < nd; ++j) {
+                        // the reference subtracts the per-chirp mean (dechirp.py:120): range bin 0 is ~1e-15, taken as 0
+                        const double2 x = (v.dc && kr[i] == 0) ? make_double2(0, 0) : out[i * 3 + j];
+                        const double p = x.x * x.x + x.y * x.y;
+                        if (r_lo + i == r && d_lo + j == d) c = p;
+                        else m = fmax(m, p);
+                    }
+                // dechirp.py:250-254 on exact powers: equality with the 3x3 maximum and dB strictly above threshold
+                const bool is_det = (c >= m) && (c + 1e-12 > thr64);
+                uint8_t fl = det_flags[o];
+                const bool was_det = !(fl & RS_FLAG_DROPPED);
+                if (is_det != was_det) {
+                    atomicAdd(stats + (is_det ? 2 : 1), 1);
+                    // run after rs_angles: move this detection's row into / out of the velocity sums
+                    if (ls_partials != nullptr && det_aidx[o] >= 0) {
+                        const double sg2 = is_det ? 1.0 : -1.0, y = (double)det_phase[o];
+                        const double cc = grid_cs[2 * det_aidx[o]], ss = grid_cs[2 * det_aidx[o] + 1];
+                        double* ps = ls_partials + (size_t)seg * 8;
+                        ps[0] += sg2 * cc * cc; ps[1] += sg2 * ss * ss; ps[2] += sg2 * cc * ss;
+                        ps[3] += sg2 * y * cc;  ps[4] += sg2 * y * ss;  ps[5] += sg2 * y * y;  ps[6] += sg2;
+                    }
+                }
+                fl = is_det ? (fl & ~RS_FLAG_DROPPED) : (fl | RS_FLAG_DROPPED);
+                det_flags[o] = fl | RS_FLAG_DETFIXED;
+                atomicAdd(stats + 0, 1);
+            }
+            __syncthreads();
         }
-        __syncthreads();
+        if (threadIdx.x == 0 && total > RC_MAX_ITEMS) atomicAdd(stats + 3, total - RC_MAX_ITEMS);
     }
-    if (threadIdx.x == 0 && total > RC_MAX_ITEMS) atomicAdd(stats + 3, total - RC_MAX_ITEMS);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -287,6 +242,7 @@ struct AngleFix {
     double fft_eps;            // bound on the fp32 FFT's absolute error per element, in units of rms(|X|)
     const float* det_psum;     // per segment sum of |X|^2 (rs_detect)
     const int32_t* det_ntie;
+    const int32_t* det_tielist;   // [nseg_total][RS_TIE_LIST_CAP] leader indices flagged by rs_angles (unordered) or null
     const uint32_t* det_key;
     const uint32_t* det_lead;
     const int32_t* det_nlead;
@@ -295,7 +251,7 @@ struct AngleFix {
     float* det_adeg;
     const float* det_phase;
     double* ls_partials;
-    int seg_cap, nseg, R, D;
+    int seg_cap, nseg, nseg_total, R, D;
 };
 
 struct ScanRes {
@@ -303,7 +259,7 @@ struct ScanRes {
     bool undecided;     // some other grid point is within the error bound of the winner, or guard zone
 };
 
-// |a_g^H s| etc. for one grid point
+// a_g^H s for one grid point
 __device__ __forceinline__ double2 beam(const AngleFix& q, const double2* snap, int A, int g) {
     double ar = 0, ai = 0;
     for (int m = 0; m < A; ++m) {
@@ -315,70 +271,7 @@ __device__ __forceinline__ double2 beam(const AngleFix& q, const double2* snap, 
     return make_double2(ar, ai);
 }
 
-// ds_norm: bound on |dS|_2 of the snapshot (0 when the snapshot is exact)
-__device__ ScanRes scan_f64(const AngleFix& q, const double2* snap, int A, double energy, double ds_norm, double* red_v,
-                            int* red_i) {
-    double best = -1.0, bestp = -1.0;
-    int bi = 0x7fffffff;
-    for (int g = threadIdx.x; g < q.G; g += blockDim.x) {
-        const double2 b = beam(q, snap, A, g);
-        const double pwr = b.x * b.x + b.y * b.y;
-        double val = pwr;
-        if (q.method == RS_METHOD_MUSIC) {
-            const double den = fabs((double)A - (energy > 0 ? pwr / energy : 1.0));
-            val = den > 1e-12 ? 1.0 / den : 0.0;                   // angle_estimation.py:149-152
-        }
-        if (val > best) { best = val; bi = g; }
-        bestp = fmax(bestp, pwr);
-    }
-    __shared__ double r_p[RC_THREADS];
-    red_v[threadIdx.x] = best; red_i[threadIdx.x] = bi; r_p[threadIdx.x] = bestp;
-    __syncthreads();
-    for (int s = blockDim.x >> 1; s; s >>= 1) {
-        if (threadIdx.x < s) {
-            const double ov = red_v[threadIdx.x + s];
-            const int oi = red_i[threadIdx.x + s];
-            if (ov > red_v[threadIdx.x] || (ov == red_v[threadIdx.x] && oi < red_i[threadIdx.x])) {
-                red_v[threadIdx.x] = ov;
-                red_i[threadIdx.x] = oi;
-            }
-            r_p[threadIdx.x] = fmax(r_p[threadIdx.x], r_p[threadIdx.x + s]);
-        }
-        __syncthreads();
-    }
-    ScanRes res;
-    res.idx = red_i[0];
-    const double pmax = r_p[0];
-    __syncthreads();
-    bool und = false;
-    if (ds_norm > 0) {
-        // near the guard the pseudo-spectrum is not monotone in the beam power: needs the exact snapshot
-        if (q.method == RS_METHOD_MUSIC && ((double)A * energy - pmax <= 1e-6 * (double)A * energy)) und = true;
-        const int gs = res.idx;
-        const double2 bg = beam(q, snap, A, gs);
-        const double pg = bg.x * bg.x + bg.y * bg.y;
-        for (int h = threadIdx.x; h < q.G && !und; h += blockDim.x) {
-            if (h == gs) continue;
-            const double2 bh = beam(q, snap, A, h);
-            const double ph = bh.x * bh.x + bh.y * bh.y;
-            // |conj(b_g) a_g - conj(b_h) a_h|^2 = A (|b_g|^2 + |b_h|^2) - 2 Re(b_g conj(b_h) (a_g^H a_h))
-            double cr = 0, ci = 0;
-            for (int m = 0; m < A; ++m) {
-                const double2 wg = q.steer[(size_t)m * q.G + gs], wh = q.steer[(size_t)m * q.G + h];
-                cr += wg.x * wh.x + wg.y * wh.y;                   // conj(a_g) a_h
-                ci += wg.x * wh.y - wg.y * wh.x;
-            }
-            const double tr = bg.x * bh.x + bg.y * bh.y, ti = bg.y * bh.x - bg.x * bh.y;      // b_g conj(b_h)
-            const double n2 = fmax(0.0, (double)A * (pg + ph) - 2.0 * (tr * cr - ti * ci));
-            const double bound = 2.0 * sqrt(n2) * ds_norm;
-            if (pg - ph <= bound) und = true;
-        }
-    }
-    res.undecided = __syncthreads_or(und ? 1 : 0) != 0;
-    return res;
-}
-
-// writes one settled cell to all of its detections; dl = correction of the segment's velocity sums
+// writes one settled cell to all of its detections; dl += correction of the segment's velocity sums
 __device__ void apply_angle(const AngleFix& q, size_t o, int k, int idx, double* dl, int32_t* stats, int stage) {
     const int old = q.det_aidx[o];
     int live = 0;
@@ -393,31 +286,31 @@ __device__ void apply_angle(const AngleFix& q, size_t o, int k, int idx, double*
         const double w = (double)live, y = (double)q.det_phase[o];
         const double c0 = q.grid_cs[2 * old], s0 = q.grid_cs[2 * old + 1];
         const double c1 = q.grid_cs[2 * idx], s1 = q.grid_cs[2 * idx + 1];
-        dl[0] = w * (c1 * c1 - c0 * c0); dl[1] = w * (s1 * s1 - s0 * s0); dl[2] = w * (c1 * s1 - c0 * s0);
-        dl[3] = w * y * (c1 - c0);       dl[4] = w * y * (s1 - s0);
+        dl[0] += w * (c1 * c1 - c0 * c0); dl[1] += w * (s1 * s1 - s0 * s0); dl[2] += w * (c1 * s1 - c0 * s0);
+        dl[3] += w * y * (c1 - c0);       dl[4] += w * y * (s1 - s0);
     }
     atomicAdd(stats + 0, 1);
     if (old != idx) atomicAdd(stats + 1, 1);
     if (stage) atomicAdd(stats + 2, 1);
 }
 
-// warp-level variant of scan_f64 for stage A: lanes over grid points, snapshot in shared memory.
-// Outside the MUSIC guard zone 1/(M - P/E) is monotone in the beam power P, so the argmax is taken on P; the
-// guard zone and every pair that the error bound cannot separate go to stage B.
-constexpr int SW_MAX_PER_LANE = 12;            // grids up to 384 points keep (b_h, P_h) in registers
+// Stage A scan by one warp: lanes over grid points, snapshot in shared memory.  Outside the MUSIC guard zone
+// 1/(M - P/E) is monotone in the beam power P, so the argmax is taken on P; the guard zone and every pair that the
+// error bound cannot separate go to stage B.  ds_norm bounds |dS|_2 of the snapshot.
+constexpr int SW_MAX_PER_LANE = 12;            // grids up to 384 points keep P_h in registers
 __device__ ScanRes scan_warp(const AngleFix& q, const double2* snap, int A, double energy, double ds_norm) {
     const int lane = threadIdx.x & 31;
-    double2 bl[SW_MAX_PER_LANE];
+    double pl[SW_MAX_PER_LANE];
     double bestp = -1.0;
     int bi = 0x7fffffff;
-    const bool cached = q.G <= 32 * SW_MAX_PER_LANE;
 #pragma unroll
     for (int j = 0; j < SW_MAX_PER_LANE; ++j) {
         const int g = lane + 32 * j;
+        pl[j] = -1.0;
         if (g < q.G) {
             const double2 b = beam(q, snap, A, g);
-            bl[j] = b;
             const double pwr = b.x * b.x + b.y * b.y;
+            pl[j] = pwr;
             if (pwr > bestp) { bestp = pwr; bi = g; }
         }
     }
@@ -438,322 +331,337 @@ __device__ ScanRes scan_warp(const AngleFix& q, const double2* snap, int A, doub
     const double2 bg = beam(q, snap, A, bi);
     const double pg = bestp;
     const double wg = sqrt((double)A * pg);
-    auto test = [&](int h, double2 bh) {
+    auto test = [&](int h, double ph) {
         if (h == bi || und) return;
-        const double ph = bh.x * bh.x + bh.y * bh.y;
         const double gap = pg - ph;
-        // cheap sufficient test: |conj(b_g) a_g - conj(b_h) a_h| <= sqrt(A) (|b_g| + |b_h|)
+        // cheap sufficient tests: |conj(b_g) a_g - conj(b_h) a_h| <= sqrt(A) (|b_g| + |b_h|) <= 2 sqrt(A) |b_g|
+        if (gap > 4.0 * wg * ds_norm) return;
         if (gap > 2.0 * (wg + sqrt((double)A * ph)) * ds_norm) return;
+        const double2 bh = beam(q, snap, A, h);
         double cr = 0, ci = 0;
         for (int m = 0; m < A; ++m) {
             const double2 wgm = q.steer[(size_t)m * q.G + bi], wh = q.steer[(size_t)m * q.G + h];
-            cr += wgm.x * wh.x + wgm.y * wh.y;
+            cr += wgm.x * wh.x + wgm.y * wh.y;      // conj(a_g) a_h
             ci += wgm.x * wh.y - wgm.y * wh.x;
         }
+        // |conj(b_g) a_g - conj(b_h) a_h|^2 = A (|b_g|^2 + |b_h|^2) - 2 Re(b_g conj(b_h) (a_g^H a_h))
         const double tr = bg.x * bh.x + bg.y * bh.y, ti = bg.y * bh.x - bg.x * bh.y;
         const double n2 = fmax(0.0, (double)A * (pg + ph) - 2.0 * (tr * cr - ti * ci));
         if (gap <= 2.0 * sqrt(n2) * ds_norm) und = true;
     };
-    if (cached) {
 #pragma unroll
-        for (int j = 0; j < SW_MAX_PER_LANE; ++j) {
-            const int h = lane + 32 * j;
-            if (h < q.G) test(h, bl[j]);
-        }
-    } else {
-        for (int h = lane; h < q.G; h += 32) test(h, beam(q, snap, A, h));
+    for (int j = 0; j < SW_MAX_PER_LANE; ++j) {
+        const int h = lane + 32 * j;
+        if (h < q.G) test(h, pl[j]);
+    }
+    for (int h = lane + 32 * SW_MAX_PER_LANE; h < q.G; h += 32) {
+        const double2 bh = beam(q, snap, A, h);
+        test(h, bh.x * bh.x + bh.y * bh.y);
     }
     res.undecided = __any_sync(0xffffffffu, und);
     return res;
 }
 
-constexpr int RA_MAX_ITEMS = 256;
-constexpr int RB_MAX = 16;          // undecided cells per segment handed to stage B
-constexpr int RB_BATCH = 4;         // cells whose range twiddles are staged together in stage B
+// exact scan of an exact snapshot by one warp: the method's pseudo-spectrum with the reference's guard
+// (angle_estimation.py:143-152), first-index argmax (:173)
+__device__ int scan_exact_warp(const AngleFix& q, const double2* snap, int A, double energy) {
+    const int lane = threadIdx.x & 31;
+    double best = -1.0;
+    int bi = 0x7fffffff;
+    for (int g = lane; g < q.G; g += 32) {
+        const double2 b = beam(q, snap, A, g);
+        const double pwr = b.x * b.x + b.y * b.y;
+        double val = pwr;
+        if (q.method == RS_METHOD_MUSIC) {
+            const double den = fabs((double)A - (energy > 0 ? pwr / energy : 1.0));
+            val = den > 1e-12 ? 1.0 / den : 0.0;
+        }
+        if (val > best) { best = val; bi = g; }
+    }
+#pragma unroll
+    for (int off = 16; off; off >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, best, off);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    return bi;
+}
 
-// -------- stage A: one CTA per segment, one warp per flagged cell; undecided cells go to the stage-B list
-__global__ void __launch_bounds__(RC_THREADS)
+// -------- stage A: one warp per segment walks the flagged leaders in list order
+__global__ void __launch_bounds__(RC_THREADS, 2)
 recheck_angles_kernel(CubeView v, AngleFix q, int32_t* __restrict__ work_idx, int32_t* __restrict__ work_cnt,
-                      int32_t* __restrict__ stats) {
+                      int32_t* __restrict__ frame_cnt, int4* __restrict__ frame_list, int32_t* __restrict__ stats) {
     extern __shared__ double2 smd[];
-    double2* snap = smd;                 // [warps][A]
-    __shared__ int items[RC_MAX_ITEMS];
-    __shared__ int scratch[RC_THREADS + 1];
-    __shared__ double delta[RA_MAX_ITEMS][5];
-    __shared__ unsigned char need_b[RA_MAX_ITEMS];
-    const int seg = blockIdx.x;
-    if (threadIdx.x == 0) work_cnt[seg] = 0;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int seg = blockIdx.x * RC_WARPS + wid;
+    if (seg >= q.nseg_total) return;
+    if (lane == 0) work_cnt[seg] = 0;
     if (q.det_ntie != nullptr && q.det_ntie[seg] == 0) return;
     const int n = q.det_nlead[seg];
     if (n == 0) return;
-    const size_t base = (size_t)seg * q.seg_cap;
-    const int total = collect_items(n, [&](int i) { return base + (q.det_lead[base + i] & 0xFFFFu); }, q.det_flags,
-                                    RS_FLAG_TIE | RS_FLAG_GUARD, RS_FLAG_FIXED, items, scratch);
-    if (total == 0) return;
-    const int f = seg / q.nseg;
     const int A = v.A;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    double2* sw = smd + wid * A;         // this warp's snapshot
+    const size_t base = (size_t)seg * q.seg_cap;
+    const int f = seg / q.nseg;
     // rms(|X|) of the frame from the per-tile power sums; |dS|_2 <= fft_eps * rms * sqrt(A)
     double psum = 0;
-    for (int sg = 0; sg < q.nseg; ++sg) psum += (double)q.det_psum[(size_t)f * q.nseg + sg];
+    for (int sg = lane; sg < q.nseg; sg += 32) psum += (double)q.det_psum[(size_t)f * q.nseg + sg];
+    psum = warp_sum(psum);
     const double ds_norm = fmax(q.fft_eps * sqrt(psum / ((double)q.R * q.D * A)) * sqrt((double)A), 1e-300);
-    const int todo = min(total, RA_MAX_ITEMS);
-    for (int it = wid; it < todo; it += nw) {
-        const uint32_t ld = q.det_lead[base + items[it]];
-        const size_t o = base + (ld & 0xFFFFu);
-        const int k = (int)(ld >> 16);
+    double dl[5] = {0, 0, 0, 0, 0};
+    int nb = 0, lost = 0;
+    // one flagged cell: leader index li, whole warp
+    auto settle = [&](int li) {
+        const uint32_t ldj = q.det_lead[base + li];
+        const size_t o = base + (ldj & 0xFFFFu);
+        const int k = (int)(ldj >> 16);
         int a, r, d;
         rs_split_key(q.det_key[o], a, r, d);
         const float2* cell = q.rds + (((size_t)f * q.R + r) * q.D + d) * A;
-        double2* sw = snap + wid * A;
         __syncwarp();
         for (int m = lane; m < A; m += 32) sw[m] = make_double2((double)cell[m].x, (double)cell[m].y);
         __syncwarp();
         double energy = 0;
         for (int m = 0; m < A; ++m) energy += sw[m].x * sw[m].x + sw[m].y * sw[m].y;
-        // |dS|_2 <= fft_eps * rms * sqrt(A)  (noise-like part)  +  1.5e-7 |s|_2  (part that scales with the cell itself)
+        // |dS|_2 <= fft_eps * rms * sqrt(A)  (noise-like part)  +  1.5e-7 |s|_2  (part that scales with the cell)
         const ScanRes sr = scan_warp(q, sw, A, energy, ds_norm + 1.5e-7 * sqrt(energy));
         if (lane == 0) {
-            need_b[it] = sr.undecided ? 1 : 0;
-            double dl[5] = {0, 0, 0, 0, 0};
-            if (!sr.undecided) apply_angle(q, o, k, sr.idx, dl, stats, 0);
-            for (int j = 0; j < 5; ++j) delta[it][j] = dl[j];
+            if (!sr.undecided) {
+                apply_angle(q, o, k, sr.idx, dl, stats, 0);
+            } else if (nb < RB_MAX) {
+                const int slot = atomicAdd(frame_cnt + f, 1);
+                if (slot < FB_CAP) {
+                    work_idx[(size_t)seg * RB_MAX + nb] = li;
+                    frame_list[(size_t)f * FB_CAP + slot] = make_int4(seg * RB_MAX + nb, r, d, 0);
+                    ++nb;
+                } else {
+                    ++lost;
+                }
+            } else {
+                ++lost;
+            }
+        }
+    };
+    auto undecided = [&](int li) {
+        const uint8_t f8 = q.det_flags[base + (q.det_lead[base + li] & 0xFFFFu)];
+        return (f8 & (RS_FLAG_TIE | RS_FLAG_GUARD)) && !(f8 & RS_FLAG_FIXED);
+    };
+    const int ntie = q.det_ntie != nullptr ? q.det_ntie[seg] : 0x7fffffff;
+    if (q.det_tielist != nullptr && ntie <= RS_TIE_LIST_CAP) {
+        // the list rs_angles wrote (in atomic order): rank-sort it so the items are settled in list order
+        int li = lane < ntie ? q.det_tielist[(size_t)seg * RS_TIE_LIST_CAP + lane] : 0x7fffffff;
+        const bool live = lane < ntie && li >= 0 && li < n && undecided(li);
+        if (!live) li = 0x7fffffff;
+        int rank = 0;
+        for (int t = 0; t < ntie; ++t) rank += __shfl_sync(0xffffffffu, li, t) < li ? 1 : 0;
+        const int nlive = __popc(__ballot_sync(0xffffffffu, live));
+        for (int rk = 0; rk < nlive; ++rk) {
+            const unsigned who = __ballot_sync(0xffffffffu, live && rank == rk);
+            settle(__shfl_sync(0xffffffffu, li, __ffs(who) - 1));
+        }
+    } else {
+        for (int c0 = 0; c0 < n; c0 += 32) {
+            const int i = c0 + lane;
+            unsigned mask = __ballot_sync(0xffffffffu, i < n && undecided(i));
+            while (mask) {
+                const int j = __ffs(mask) - 1;
+                mask &= mask - 1;
+                settle(c0 + j);
+            }
         }
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int nb = 0, lost = total > RA_MAX_ITEMS ? total - RA_MAX_ITEMS : 0;
-        double* ps = q.ls_partials ? q.ls_partials + (size_t)seg * 8 : nullptr;
-        for (int it = 0; it < todo; ++it) {
-            if (ps) for (int j = 0; j < 5; ++j) ps[j] += delta[it][j];       // item order: deterministic
-            if (need_b[it]) {
-                if (nb < RB_MAX) work_idx[(size_t)seg * RB_MAX + nb++] = items[it];
-                else ++lost;
-            }
+    if (lane == 0) {
+        if (q.ls_partials) {
+            double* ps = q.ls_partials + (size_t)seg * 8;
+            for (int j = 0; j < 5; ++j) ps[j] += dl[j];
         }
         work_cnt[seg] = nb;
         if (lost) atomicAdd(stats + 3, lost);
     }
 }
 
-// inner loop of stage B1 for NB cells at once: every raw sample is converted to fp64 once and multiplied into
-// NB accumulators; the Doppler twiddle index advances incrementally (no integer division in the loop)
+// -------- stage B1: one CTA per (frame, antenna) reads that antenna's raw plane once per batch of NB_MAX undecided
+// cells of the frame and forms its element of their fp64 snapshots
 template <int NB>
-__device__ __forceinline__ void b1_accumulate(const float2* __restrict__ plane, int S, int C, const double2* z,
-                                              const double2* wc, const int* kd, double2* acc) {
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    int ci[NB], cstep[NB];
-#pragma unroll
-    for (int i = 0; i < NB; ++i) {
-        ci[i] = (int)(((long long)wid * kd[i]) % C);
-        cstep[i] = (int)(((long long)nw * kd[i]) % C);
-    }
-    for (int c = wid; c < C; c += nw) {
-        const float2* x = plane + (size_t)c * S;
-        double tr[NB], ti[NB];
-#pragma unroll
-        for (int i = 0; i < NB; ++i) { tr[i] = 0; ti[i] = 0; }
-#pragma unroll 4
-        for (int s = lane; s < S; s += 32) {
-            const float2 xv = __ldg(x + s);
-            const double xr = (double)xv.x, xi = (double)xv.y;
-#pragma unroll
-            for (int i = 0; i < NB; ++i) {
-                const double2 w = z[i * S + s];
-                tr[i] = fma(xr, w.x, fma(-xi, w.y, tr[i]));
-                ti[i] = fma(xr, w.y, fma(xi, w.x, ti[i]));
-            }
-        }
+__device__ __forceinline__ void b1_batch(const CubeView& v, const float2* plane, const double2* u, const int* kr,
+                                         double2 (&acc)[NB_MAX]) {
+    for (int s = threadIdx.x; s < v.S; s += RC_THREADS) {
+        double2 Y[NB];
+        column_dft<NB>(plane + s, v.S, v.C, u, Y);
+        const double2 t = v.tab[s];
 #pragma unroll
         for (int i = 0; i < NB; ++i) {
-            const double2 u = wc[ci[i]];
-            acc[i].x += tr[i] * u.x - ti[i] * u.y;       // per-lane partial times the Doppler twiddle
-            acc[i].y += tr[i] * u.y + ti[i] * u.x;
-            ci[i] += cstep[i];
-            if (ci[i] >= C) ci[i] -= C;
+            const double2 p = dmul(Y[i], dmul(t, v.tw_s[(int)(((long long)s * kr[i]) % v.S)]));
+            acc[i].x += p.x;
+            acc[i].y += p.y;
         }
     }
 }
 
-// -------- stage B1: one CTA per (frame, antenna) reads that antenna's raw rows ONCE and forms its element of the
-// fp64 snapshot of every undecided cell of the frame
 __global__ void __launch_bounds__(RC_THREADS)
-recheck_snapshots_kernel(CubeView v, AngleFix q, const int32_t* __restrict__ work_idx,
-                         const int32_t* __restrict__ work_cnt, double2* __restrict__ work_snap) {
+recheck_snapshots_kernel(CubeView v, const int32_t* __restrict__ frame_cnt, const int4* __restrict__ frame_list,
+                         double2* __restrict__ work_snap) {
     extern __shared__ double2 smd[];
-    double2* ws = smd;                          // [S]
-    double2* wc = ws + v.S;                     // [C]
-    double2* z = wc + v.C;                      // [RB_BATCH][S]
-    double2* red = z + RB_BATCH * v.S;          // [warps][RB_BATCH]
-    __shared__ int cell_r[RB_MAX * 64], cell_d[RB_MAX * 64], cell_slot[RB_MAX * 64];
-    __shared__ int n_cells;
+    double2* u = smd;                           // [NB_MAX][C]
+    double2* red = u + NB_MAX * v.C;            // [RC_WARPS][NB_MAX]
+    __shared__ double2 out[NB_MAX];
+    __shared__ int kr_s[NB_MAX], kd_s[NB_MAX], slot_s[NB_MAX];
     const int a = blockIdx.x, f = blockIdx.y;
-    if (threadIdx.x == 0) {
-        int nc = 0;
-        for (int sg = 0; sg < q.nseg; ++sg) {
-            const int seg = f * q.nseg + sg;
-            const int cnt = work_cnt[seg];
-            for (int k = 0; k < cnt && nc < RB_MAX * 64; ++k) {       // same cap in recheck_finish_kernel
-                const size_t base = (size_t)seg * q.seg_cap;
-                const uint32_t ld = q.det_lead[base + work_idx[(size_t)seg * RB_MAX + k]];
-                int aa, r, d;
-                rs_split_key(q.det_key[base + (ld & 0xFFFFu)], aa, r, d);
-                cell_r[nc] = r; cell_d[nc] = d; cell_slot[nc] = seg * RB_MAX + k;
-                ++nc;
+    const int nc = min(frame_cnt[f], FB_CAP);
+    if (nc == 0) return;
+    const float2* plane = v.cube + (((size_t)f * v.A + a) * v.C_total + v.chirp0) * v.S;
+    for (int b0 = 0; b0 < nc; b0 += NB_MAX) {
+        const int nb = min(NB_MAX, nc - b0);
+        if ((int)threadIdx.x < NB_MAX) {
+            const int i = threadIdx.x;
+            if (i < nb) {
+                const int4 e = frame_list[(size_t)f * FB_CAP + b0 + i];
+                slot_s[i] = e.x;
+                kr_s[i] = unshift(e.y, v.S);
+                kd_s[i] = unshift(e.z, v.C);
+            } else {
+                slot_s[i] = -1; kr_s[i] = 0; kd_s[i] = 0;
             }
         }
-        n_cells = nc;
-    }
-    __syncthreads();
-    const int nc = n_cells;
-    if (nc == 0) return;
-    build_twiddles(ws, v.S, wc, v.C);
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    for (int b0 = 0; b0 < nc; b0 += RB_BATCH) {
-        const int nb = min(RB_BATCH, nc - b0);
-        int kd[RB_BATCH];
-        for (int i = 0; i < RB_BATCH; ++i) kd[i] = i < nb ? (cell_d[b0 + i] - v.C / 2 + v.C) % v.C : 0;
-        for (int i = 0; i < nb; ++i) {
-            const int kr = (cell_r[b0 + i] - v.S / 2 + v.S) % v.S;
-            for (int s = threadIdx.x; s < v.S; s += blockDim.x)
-                z[i * v.S + s] = dmul(v.tab[s], ws[(int)(((long long)s * kr) % v.S)]);
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < NB_MAX * v.C; idx += RC_THREADS) {
+            const int i = idx / v.C, c = idx - i * v.C;
+            u[idx] = i < nb ? v.tw_c[(int)(((long long)c * kd_s[i]) % v.C)] : make_double2(0, 0);
         }
         __syncthreads();
-        double2 acc[RB_BATCH];
-        for (int i = 0; i < RB_BATCH; ++i) acc[i] = make_double2(0, 0);
-        const float2* plane = v.cube + (((size_t)f * v.A + a) * v.C_total + v.chirp0) * v.S;
-        switch (nb) {
-            case 1: b1_accumulate<1>(plane, v.S, v.C, z, wc, kd, acc); break;
-            case 2: b1_accumulate<2>(plane, v.S, v.C, z, wc, kd, acc); break;
-            case 3: b1_accumulate<3>(plane, v.S, v.C, z, wc, kd, acc); break;
-            default: b1_accumulate<4>(plane, v.S, v.C, z, wc, kd, acc); break;
-        }
-        for (int i = 0; i < nb; ++i) {
-            const double re = warp_sum(acc[i].x), im = warp_sum(acc[i].y);
-            if (lane == 0) red[wid * RB_BATCH + i] = make_double2(re, im);
-        }
-        __syncthreads();
-        if (threadIdx.x < nb) {
+        int kr[NB_MAX];
+#pragma unroll
+        for (int i = 0; i < NB_MAX; ++i) kr[i] = kr_s[i];
+        double2 acc[NB_MAX];
+#pragma unroll
+        for (int i = 0; i < NB_MAX; ++i) acc[i] = make_double2(0, 0);
+        if (nb <= 1) b1_batch<1>(v, plane, u, kr, acc);
+        else if (nb <= 2) b1_batch<2>(v, plane, u, kr, acc);
+        else if (nb <= 4) b1_batch<4>(v, plane, u, kr, acc);
+        else b1_batch<8>(v, plane, u, kr, acc);
+        block_reduce<NB_MAX>(acc, nb, red, out);
+        if ((int)threadIdx.x < nb) {
             const int i = threadIdx.x;
-            double re = 0, im = 0;
-            for (int w = 0; w < nw; ++w) { re += red[w * RB_BATCH + i].x; im += red[w * RB_BATCH + i].y; }
-            const int kr = (cell_r[b0 + i] - v.S / 2 + v.S) % v.S;
-            work_snap[(size_t)cell_slot[b0 + i] * v.A + a] = (v.dc && kr == 0) ? make_double2(0, 0) : make_double2(re, im);
+            work_snap[(size_t)slot_s[i] * v.A + a] = (v.dc && kr_s[i] == 0) ? make_double2(0, 0) : out[i];
         }
         __syncthreads();
     }
 }
 
-// -------- stage B2: one CTA per segment scans the exact snapshots and settles the remaining cells
+// -------- stage B2: one warp per segment scans the exact snapshots and settles the remaining cells in list order
 __global__ void __launch_bounds__(RC_THREADS)
 recheck_finish_kernel(CubeView v, AngleFix q, const int32_t* __restrict__ work_idx, const int32_t* __restrict__ work_cnt,
                       const double2* __restrict__ work_snap, int32_t* __restrict__ stats) {
     extern __shared__ double2 smd[];
-    double2* snap = smd;                 // [A]
-    __shared__ double red_v[RC_THREADS];
-    __shared__ int red_i[RC_THREADS];
-    const int seg = blockIdx.x;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int seg = blockIdx.x * RC_WARPS + wid;
+    if (seg >= q.nseg_total) return;
     const int cnt = work_cnt[seg];
     if (cnt == 0) return;
     const int A = v.A;
+    double2* snap = smd + wid * A;
     const size_t base = (size_t)seg * q.seg_cap;
-    // cells of earlier segments of this frame (stage B1 handles at most RB_MAX * 64 cells per frame)
-    int before = 0;
-    for (int sg = (seg / q.nseg) * q.nseg; sg < seg; ++sg) before += work_cnt[sg];
+    double dl[5] = {0, 0, 0, 0, 0};
     for (int k = 0; k < cnt; ++k) {
-        if (before + k >= RB_MAX * 64) {
-            if (threadIdx.x == 0) atomicAdd(stats + 3, 1);
-            continue;
-        }
         const uint32_t ld = q.det_lead[base + work_idx[(size_t)seg * RB_MAX + k]];
         const size_t o = base + (ld & 0xFFFFu);
         const int mult = (int)(ld >> 16);
-        for (int m = threadIdx.x; m < A; m += blockDim.x) snap[m] = work_snap[((size_t)seg * RB_MAX + k) * A + m];
-        __syncthreads();
+        __syncwarp();
+        for (int m = lane; m < A; m += 32) snap[m] = work_snap[((size_t)seg * RB_MAX + k) * A + m];
+        __syncwarp();
         double energy = 0;
         for (int m = 0; m < A; ++m) energy += snap[m].x * snap[m].x + snap[m].y * snap[m].y;
-        const ScanRes sr = scan_f64(q, snap, A, energy, 0.0, red_v, red_i);
-        if (threadIdx.x == 0) {
-            double dl[5] = {0, 0, 0, 0, 0};
-            apply_angle(q, o, mult, sr.idx, dl, stats, 1);
-            if (q.ls_partials) {
-                double* ps = q.ls_partials + (size_t)seg * 8;
-                for (int j = 0; j < 5; ++j) ps[j] += dl[j];
-            }
-        }
-        __syncthreads();
+        const int idx = scan_exact_warp(q, snap, A, energy);
+        if (lane == 0) apply_angle(q, o, mult, idx, dl, stats, 1);
+    }
+    if (lane == 0 && q.ls_partials) {
+        double* ps = q.ls_partials + (size_t)seg * 8;
+        for (int j = 0; j < 5; ++j) ps[j] += dl[j];
     }
 }
 
 }  // namespace
 
-extern "C" int rs_recheck_detections_f64(const void* cube, const void* table128, int C_total, int chirp0, int dc_removal,
+extern "C" int rs_recheck_detections_f64(const void* cube, const void* table128, const void* tw_s128,
+                                         const void* tw_c128, int C_total, int chirp0, int dc_removal,
                                          double thr_power64, const uint32_t* det_key, uint8_t* det_flags,
                                          const int32_t* det_count, const int32_t* det_nnear, int seg_cap,
                                          int nseg_per_frame, int F, int A, int C, int S, const int32_t* det_aidx,
                                          const float* det_phase, const double* grid_cs, double* ls_partials,
                                          int32_t* stats, void* stream) {
-    RS_CHECK_ARG(cube && table128 && det_key && det_flags && det_count && stats, "rs_recheck_detections_f64: null pointer");
+    RS_CHECK_ARG(cube && table128 && tw_s128 && tw_c128 && det_key && det_flags && det_count && stats,
+                 "rs_recheck_detections_f64: null pointer");
     RS_CHECK_ARG(ls_partials == nullptr || (det_aidx && det_phase && grid_cs),
                  "rs_recheck_detections_f64: ls_partials needs det_aidx, det_phase and grid_cs");
     RS_CHECK_ARG(F > 0 && A > 0 && C > 0 && S > 0 && chirp0 >= 0 && chirp0 + C <= C_total && seg_cap > 0 &&
                      nseg_per_frame > 0,
                  "rs_recheck_detections_f64: bad dims");
-    CubeView v{(const float2*)cube, (const double2*)table128, A, C_total, chirp0, C, S, dc_removal};
-    const size_t smem = (size_t)(S + 4 * C) * sizeof(double2);
+    CubeView v{(const float2*)cube, (const double2*)table128, (const double2*)tw_s128, (const double2*)tw_c128,
+               A, C_total, chirp0, C, S, dc_removal};
+    const size_t smem = (size_t)(3 * C + RC_WARPS * 9) * sizeof(double2);
     if (smem > (size_t)rs_smem_optin_limit()) {
         rs_set_error("rs_recheck_detections_f64: needs %zu B of shared memory", smem);
         return RS_ECAPACITY;
     }
     cudaFuncSetAttribute(recheck_detect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaMemsetAsync(stats, 0, 4 * sizeof(int32_t), (cudaStream_t)stream);
-    const long long blocks = (long long)F * nseg_per_frame;
-    recheck_detect_kernel<<<(unsigned)blocks, RC_THREADS, smem, (cudaStream_t)stream>>>(
-        v, thr_power64, det_key, det_flags, det_count, det_nnear, seg_cap, nseg_per_frame, S, C, det_aidx, det_phase,
-        grid_cs, ls_partials, stats);
+    const long long nseg_total = (long long)F * nseg_per_frame;
+    RS_CHECK_ARG(nseg_total < (1ll << 31), "rs_recheck_detections_f64: too many segments");
+    const unsigned blocks = (unsigned)((nseg_total + RC_WARPS - 1) / RC_WARPS);
+    recheck_detect_kernel<<<blocks, RC_THREADS, smem, (cudaStream_t)stream>>>(
+        v, thr_power64, det_key, det_flags, det_count, det_nnear, seg_cap, nseg_per_frame, (int)nseg_total, S, C,
+        det_aidx, det_phase, grid_cs, ls_partials, stats);
     RS_CHECK_LAUNCH("rs_recheck_detections_f64");
     return RS_OK;
 }
 
-extern "C" int rs_recheck_angles_f64(const void* cube, const void* table128, int C_total, int chirp0, int dc_removal,
-                                     const void* rds, const void* steer128, const float* grid_deg, const double* grid_cs,
-                                     int G, int method, double fft_eps, const float* det_psum, const int32_t* det_ntie,
-                                     const uint32_t* det_key, const uint32_t* det_lead, const int32_t* det_nlead,
-                                     uint8_t* det_flags, int32_t* det_aidx, float* det_adeg, const float* det_phase,
-                                     double* ls_partials, int seg_cap, int nseg_per_frame, int F, int A, int C, int S,
-                                     int32_t* work_idx, int32_t* work_cnt, void* work_snap, int32_t* stats,
-                                     void* stream) {
-    RS_CHECK_ARG(cube && table128 && rds && steer128 && grid_deg && grid_cs && det_psum && det_key && det_lead &&
-                     det_nlead && det_flags && det_aidx && det_adeg && det_phase && work_idx && work_cnt && work_snap &&
-                     stats,
+extern "C" int rs_recheck_angles_f64(const void* cube, const void* table128, const void* tw_s128, const void* tw_c128,
+                                     int C_total, int chirp0, int dc_removal, const void* rds, const void* steer128,
+                                     const float* grid_deg, const double* grid_cs, int G, int method, double fft_eps,
+                                     const float* det_psum, const int32_t* det_ntie, const int32_t* det_tielist,
+                                     const uint32_t* det_key,
+                                     const uint32_t* det_lead, const int32_t* det_nlead, uint8_t* det_flags,
+                                     int32_t* det_aidx, float* det_adeg, const float* det_phase, double* ls_partials,
+                                     int seg_cap, int nseg_per_frame, int F, int A, int C, int S, int32_t* work_idx,
+                                     int32_t* work_cnt, void* work_snap, int32_t* frame_cnt, int32_t* frame_list,
+                                     int32_t* stats, void* stream) {
+    RS_CHECK_ARG(cube && table128 && tw_s128 && tw_c128 && rds && steer128 && grid_deg && grid_cs && det_psum &&
+                     det_key && det_lead && det_nlead && det_flags && det_aidx && det_adeg && det_phase && work_idx &&
+                     work_cnt && work_snap && frame_cnt && frame_list && stats,
                  "rs_recheck_angles_f64: null pointer");
     RS_CHECK_ARG(method == RS_METHOD_MUSIC || method == RS_METHOD_BEAMFORMING, "rs_recheck_angles_f64: grid methods only");
     RS_CHECK_ARG(F > 0 && F <= 65535 && A >= 2 && C > 0 && S > 0 && G > 0 && chirp0 >= 0 && chirp0 + C <= C_total &&
                      fft_eps >= 0 && nseg_per_frame > 0,
                  "rs_recheck_angles_f64: bad dims");
-    CubeView v{(const float2*)cube, (const double2*)table128, A, C_total, chirp0, C, S, dc_removal};
+    RS_CHECK_ARG(((uintptr_t)frame_list & 15u) == 0, "rs_recheck_angles_f64: frame_list must be 16-byte aligned");
+    const long long nseg_total = (long long)F * nseg_per_frame;
+    RS_CHECK_ARG(nseg_total < (1ll << 27), "rs_recheck_angles_f64: too many segments");
+    CubeView v{(const float2*)cube, (const double2*)table128, (const double2*)tw_s128, (const double2*)tw_c128,
+               A, C_total, chirp0, C, S, dc_removal};
     AngleFix q{(const float2*)rds, (const double2*)steer128, grid_deg, grid_cs, G, method, fft_eps, det_psum, det_ntie,
-               det_key, det_lead, det_nlead, det_flags, det_aidx, det_adeg, det_phase, ls_partials, seg_cap,
-               nseg_per_frame, S, C};
+               det_tielist, det_key, det_lead, det_nlead, det_flags, det_aidx, det_adeg, det_phase, ls_partials, seg_cap,
+               nseg_per_frame, (int)nseg_total, S, C};
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t smem_a = (size_t)(RC_THREADS / 32) * A * sizeof(double2);
-    const size_t smem_b1 = (size_t)(S + C + RB_BATCH * S + (RC_THREADS / 32) * RB_BATCH) * sizeof(double2);
-    const size_t smem_b2 = (size_t)A * sizeof(double2);
-    if (smem_b1 > (size_t)rs_smem_optin_limit()) {
-        rs_set_error("rs_recheck_angles_f64: needs %zu B of shared memory", smem_b1);
+    const size_t smem_a = (size_t)RC_WARPS * A * sizeof(double2);
+    const size_t smem_b1 = (size_t)(NB_MAX * C + RC_WARPS * NB_MAX) * sizeof(double2);
+    if (smem_b1 > (size_t)rs_smem_optin_limit() || smem_a > (size_t)rs_smem_optin_limit()) {
+        rs_set_error("rs_recheck_angles_f64: needs %zu B of shared memory", smem_b1 > smem_a ? smem_b1 : smem_a);
         return RS_ECAPACITY;
     }
     cudaFuncSetAttribute(recheck_angles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a);
+    cudaFuncSetAttribute(recheck_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a);
     cudaFuncSetAttribute(recheck_snapshots_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b1);
     cudaMemsetAsync(stats, 0, 4 * sizeof(int32_t), st);
-    const long long blocks = (long long)F * nseg_per_frame;
-    recheck_angles_kernel<<<(unsigned)blocks, RC_THREADS, smem_a, st>>>(v, q, work_idx, work_cnt, stats);
+    cudaMemsetAsync(frame_cnt, 0, (size_t)F * sizeof(int32_t), st);
+    const unsigned blocks = (unsigned)((nseg_total + RC_WARPS - 1) / RC_WARPS);
+    recheck_angles_kernel<<<blocks, RC_THREADS, smem_a, st>>>(v, q, work_idx, work_cnt, frame_cnt, (int4*)frame_list,
+                                                              stats);
     RS_CHECK_LAUNCH("rs_recheck_angles_f64(stage A)");
-    recheck_snapshots_kernel<<<dim3((unsigned)A, (unsigned)F), RC_THREADS, smem_b1, st>>>(v, q, work_idx, work_cnt,
-                                                                                        (double2*)work_snap);
+    recheck_snapshots_kernel<<<dim3((unsigned)A, (unsigned)F), RC_THREADS, smem_b1, st>>>(
+        v, frame_cnt, (const int4*)frame_list, (double2*)work_snap);
     RS_CHECK_LAUNCH("rs_recheck_angles_f64(stage B1)");
-    recheck_finish_kernel<<<(unsigned)blocks, RC_THREADS, smem_b2, st>>>(v, q, work_idx, work_cnt,
-                                                                        (const double2*)work_snap, stats);
+    recheck_finish_kernel<<<blocks, RC_THREADS, smem_a, st>>>(v, q, work_idx, work_cnt, (const double2*)work_snap,
+                                                              stats);
     RS_CHECK_LAUNCH("rs_recheck_angles_f64(stage B2)");
     return RS_OK;
 }

@@ -90,6 +90,7 @@ class Detections:
     nnear: Optional[torch.Tensor] = None           # per segment: entries flagged NEARMAX
     psum: Optional[torch.Tensor] = None            # per segment: sum of |X|^2 (noise level for the recheck bound)
     ntie: Optional[torch.Tensor] = None            # per segment: cells flagged TIE / GUARD
+    tielist: Optional[torch.Tensor] = None         # per segment: leader indices of the first RS_TIE_LIST_CAP of them
     threshold_db: float = -20.0                    # the threshold rs_detect ran with (needed by the fp64 recheck)
     method: Optional[str] = None                   # the method rs_angles ran with
     tag: str = ""                                  # workspace set the buffers came from
@@ -159,7 +160,8 @@ class FramePipeline:
             c = self.cfg
             tab = tables.dechirp_table(c.fc, c.chirp_rate, c.chirp_duration, S, c.window_type)
             self._tab[key] = (self._dev(tab.astype(np.complex64)), self._dev(tables.twiddles(S)),
-                              self._dev(tables.twiddles(C)), self._dev(tab))
+                              self._dev(tables.twiddles(C)), self._dev(tab),
+                              self._dev(tables.twiddles128(S)), self._dev(tables.twiddles128(C)))
         return self._tab[key]
 
     def _angle_tables(self, A: int):
@@ -208,7 +210,7 @@ class FramePipeline:
         Cu = c1 - c0
         if Cu <= 0:
             raise ValueError("empty chirp subset")
-        tab, tw_s, tw_c, _ = self._fft_tables(S, Cu)
+        tab, tw_s, tw_c = self._fft_tables(S, Cu)[:3]
         mid = self._buf("mid", (F, S, A, Cu), torch.complex64)
         rds = out if out is not None else torch.empty((F, S, Cu, A), dtype=torch.complex64, device=self.device)
         st = self.stream
@@ -243,7 +245,8 @@ class FramePipeline:
             threshold_db=float(c.threshold_db if threshold_db is None else threshold_db), tag=tag,
             lead=alloc("det_lead", (n,), torch.int32), nlead=alloc("det_nlead", (F * ntiles,), torch.int32),
             nnear=alloc("det_nnear", (F * ntiles,), torch.int32), psum=alloc("det_psum", (F * ntiles,), torch.float32),
-            ntie=alloc("det_ntie", (F * ntiles,), torch.int32))
+            ntie=alloc("det_ntie", (F * ntiles,), torch.int32),
+            tielist=alloc("det_tielist", (F * ntiles * _lib.RS_TIE_LIST_CAP,), torch.int32))
         self._call("rs_detect", rds.data_ptr(), gate.data_ptr(), thr, c.det_eps, det.key.data_ptr(),
                    det.power.data_ptr(), det.flags.data_ptr(), det.lead.data_ptr(), det.count.data_ptr(),
                    det.nlead.data_ptr(), det.overflow.data_ptr(), det.nnear.data_ptr(), det.psum.data_ptr(),
@@ -267,7 +270,8 @@ class FramePipeline:
             _lib.METHODS[method], c.tie_eps, esprit_scale, det.key.data_ptr(), det.lead.data_ptr(),
             det.nlead.data_ptr(), det.flags.data_ptr(), det.aidx.data_ptr(), det.adeg.data_ptr(), det.phase.data_ptr(),
             det.seg_cap, det.ntiles, det.F, det.R, det.D, det.A,
-            t["grid_cs"].data_ptr(), _lib.ptr(det.ls_partials), int(t["symmetric"]), det.ntie.data_ptr(), self.stream)
+            t["grid_cs"].data_ptr(), _lib.ptr(det.ls_partials), int(t["symmetric"]), det.ntie.data_ptr(), det.tielist.data_ptr(),
+            self.stream)
         return det
 
     def velocity(self, det: Detections, out: Optional[torch.Tensor] = None, lambda_c: Optional[float] = None,
@@ -330,11 +334,12 @@ class FramePipeline:
         Returns the device stats int32 [4] = rechecked, dropped, promoted, unresolved."""
         F, A, C, S = cube.shape
         c0, c1 = (0, C) if chirp_subset is None else chirp_subset
-        tab128 = self._fft_tables(S, c1 - c0)[3]
+        _, _, _, tab128, tws128, twc128 = self._fft_tables(S, c1 - c0)
         stats = self._stats_buf("recheck_det_stats" + det.tag)
         post = det.method is not None and det.ls_partials is not None
         t = self._angle_tables(A)
-        self._call("rs_recheck_detections_f64", cube.data_ptr(), tab128.data_ptr(), C, c0, int(self.cfg.dc_removal),
+        self._call("rs_recheck_detections_f64", cube.data_ptr(), tab128.data_ptr(), tws128.data_ptr(), twc128.data_ptr(),
+                   C, c0, int(self.cfg.dc_removal),
                    float(10.0 ** (det.threshold_db / 10.0)), det.key.data_ptr(), det.flags.data_ptr(),
                    det.count.data_ptr(), det.nnear.data_ptr(), det.seg_cap, det.ntiles, F, A, c1 - c0, S,
                    det.aidx.data_ptr() if post else 0, det.phase.data_ptr() if post else 0,
@@ -353,20 +358,23 @@ class FramePipeline:
             return stats
         F, A, C, S = cube.shape
         c0, c1 = (0, C) if chirp_subset is None else chirp_subset
-        tab128 = self._fft_tables(S, c1 - c0)[3]
+        _, _, _, tab128, tws128, twc128 = self._fft_tables(S, c1 - c0)
         t = self._angle_tables(A)
-        self._call("rs_recheck_angles_f64", cube.data_ptr(), tab128.data_ptr(), C, c0, int(self.cfg.dc_removal),
+        self._call("rs_recheck_angles_f64", cube.data_ptr(), tab128.data_ptr(), tws128.data_ptr(), twc128.data_ptr(),
+                   C, c0, int(self.cfg.dc_removal),
                    rds.data_ptr(), t["steer128"].data_ptr(), t["grid_f32"].data_ptr(), t["grid_cs"].data_ptr(), t["G"],
                    _lib.METHODS[method], float(self.cfg.fft_eps), det.psum.data_ptr(), det.ntie.data_ptr(),
-                   det.key.data_ptr(), det.lead.data_ptr(),
+                   det.tielist.data_ptr(), det.key.data_ptr(), det.lead.data_ptr(),
                    det.nlead.data_ptr(), det.flags.data_ptr(), det.aidx.data_ptr(), det.adeg.data_ptr(),
                    det.phase.data_ptr(), _lib.ptr(det.ls_partials), det.seg_cap, det.ntiles, F, A, c1 - c0, S,
                    self._buf("rc_idx" + det.tag, (F * det.ntiles * 16,), torch.int32).data_ptr(),
                    self._buf("rc_cnt" + det.tag, (F * det.ntiles,), torch.int32).data_ptr(),
                    self._buf("rc_snap" + det.tag, (F * det.ntiles * 16 * A,), torch.complex128).data_ptr(),
+                   self._buf("rc_fcnt" + det.tag, (F,), torch.int32).data_ptr(),
+                   self._buf("rc_flist" + det.tag, (F * _lib.RS_RECHECK_FRAME_CAP * 4,), torch.int32).data_ptr(),
                    stats.data_ptr(), self.stream)
         if exhaustive:
-            # one pass settles at most 16 undecided cells per segment / 1024 per frame; adversarial inputs (e.g. a
+            # one pass settles at most 16 undecided cells per segment / 256 per frame; adversarial inputs (e.g. a
             # noise-free frame where every cell sits on the MUSIC guard) need more passes -- each syncs on the stats
             total = stats.clone()
             for _ in range(256):

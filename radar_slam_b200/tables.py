@@ -40,6 +40,12 @@ def twiddles(n: int) -> np.ndarray:
     return np.exp(-2j * np.pi * k / n).astype(np.complex64)
 
 
+def twiddles128(n: int) -> np.ndarray:
+    """exp(-2 pi i k / n), k < n, complex128 (the fp64 recheck's direct DFT)."""
+    k = np.arange(n)
+    return np.exp(-2j * np.pi * k / n)
+
+
 def azimuth_grid(search_range: Tuple[float, float], search_resolution: float) -> np.ndarray:
     """angle_estimation.py:59."""
     return np.arange(search_range[0], search_range[1] + search_resolution, search_resolution)
