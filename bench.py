@@ -190,6 +190,10 @@ def stage_bytes(name, F, A, C, S, n_det):
         return (8 * A + 4 + 2 + 12) * n_det                 # snapshot gather + key + flag r/w + aidx/adeg/phase
     if name == "rs_velocity_ls":
         return 9 * n_det + 64 * F                           # aidx + phase + flag per detection; one row per frame
+    if name == "rs_recheck_angles_f64":
+        return 8 * cells                                    # exact snapshots need every raw plane of the frame once
+    if name == "rs_velocity_from_partials":
+        return 64 * 16 * F + 64 * F                         # per-segment sums in, one row per frame out
     return 0
 
 
@@ -269,8 +273,10 @@ def run_gpu(args):
 
     # ---- per-stage device times (CUDA events on the launching stream) for the roofline
     pipe.profile = []
+    os.environ["RS_NO_OVERLAP"] = "1"             # stage times one after the other (the timed run above overlaps the recheck)
     pipe.process(cube, chunk_frames=args.chunk, vel_out=vel)
     torch.cuda.synchronize(dev)
+    os.environ.pop("RS_NO_OVERLAP")
     stage_ms, stage_n = {}, {}
     for name, a, b in pipe.profile:
         stage_ms[name] = stage_ms.get(name, 0.0) + a.elapsed_time(b)

@@ -537,7 +537,9 @@ recheck_snapshots_kernel(CubeView v, const int32_t* __restrict__ frame_cnt, cons
         for (int i = 0; i < NB_MAX; ++i) acc[i] = make_double2(0, 0);
         if (nb <= 1) b1_batch<1>(v, plane, u, kr, acc);
         else if (nb <= 2) b1_batch<2>(v, plane, u, kr, acc);
+        else if (nb <= 3) b1_batch<3>(v, plane, u, kr, acc);
         else if (nb <= 4) b1_batch<4>(v, plane, u, kr, acc);
+        else if (nb <= 6) b1_batch<6>(v, plane, u, kr, acc);
         else b1_batch<8>(v, plane, u, kr, acc);
         block_reduce<NB_MAX>(acc, nb, red, out);
         if ((int)threadIdx.x < nb) {

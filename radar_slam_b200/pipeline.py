@@ -398,9 +398,27 @@ class FramePipeline:
         # chunk i+1 (two workspace sets): the recheck kernels are latency bound on a handful of CTAs and hide
         # behind the bandwidth / issue bound main kernels.
         main = torch.cuda.current_stream(self.device)
-        side = self._ws.setdefault("side_stream", torch.cuda.Stream(self.device))
+        if "side_stream" not in self._ws:
+            prio = int(os.environ.get("RS_SIDE_PRIORITY", "-1"))     # high priority: its few CTAs slot in between the main kernels'
+            self._ws["side_stream"] = torch.cuda.Stream(self.device, priority=prio)
+        side = self._ws["side_stream"]
         side_done = self._ws.setdefault("side_done", [None, None])
         overlap = self.cfg.recheck and not keep and os.environ.get("RS_NO_OVERLAP") != "1"
+        pending = None          # (lo, hi, rds, det, ready) of the chunk whose recheck has not been enqueued yet
+
+        def enqueue_recheck(job, after: Optional[torch.cuda.Event]):
+            jlo, jhi, jrds, jdet, jready, jslot = job
+            with torch.cuda.stream(side):
+                side.wait_event(jready)
+                if after is not None:
+                    side.wait_event(after)
+                self.recheck_detections(cube[jlo:jhi], jdet)
+                self.recheck_angles(cube[jlo:jhi], jrds, jdet)
+                self.velocity(jdet, out=vel[jlo:jhi])
+                done = torch.cuda.Event()
+                done.record(side)
+                side_done[jslot] = done
+
         for ci, lo in enumerate(range(0, F, chunk_frames)):
             hi = min(F, lo + chunk_frames)
             n = hi - lo
@@ -408,20 +426,21 @@ class FramePipeline:
             tag = str(ci & 1)
             if overlap and side_done[ci & 1] is not None:
                 main.wait_event(side_done[ci & 1])                 # workspace set free again
+                side_done[ci & 1] = None
             rds = self.range_doppler(cube[lo:hi], out=None if keep else self._buf("rds" + tag, (n, S, C, A), torch.complex64))
             det = self.detect(rds, workspace=False if keep else tag)
+            if overlap and pending is not None:
+                # the recheck of the previous chunk (HBM + fp64 bound) starts once this chunk's bandwidth-bound
+                # kernels are through, so that it runs beside this chunk's FP32-issue-bound angle scan
+                after = torch.cuda.Event()
+                after.record(main)
+                enqueue_recheck(pending, after)
+                pending = None
             self.angles(rds, det)
             if overlap:
                 ready = torch.cuda.Event()
                 ready.record(main)
-                with torch.cuda.stream(side):
-                    side.wait_event(ready)
-                    self.recheck_detections(cube[lo:hi], det)
-                    self.recheck_angles(cube[lo:hi], rds, det)
-                    self.velocity(det, out=vel[lo:hi])
-                    done = torch.cuda.Event()
-                    done.record(side)
-                    side_done[ci & 1] = done
+                pending = (lo, hi, rds, det, ready, ci & 1)
             else:
                 if self.cfg.recheck:
                     self.recheck_detections(cube[lo:hi], det)
@@ -429,6 +448,8 @@ class FramePipeline:
                 self.velocity(det, out=vel[lo:hi])
             last = (rds, det)
         if overlap:
+            if pending is not None:
+                enqueue_recheck(pending, None)
             main.wait_stream(side)
         return (vel, last[0], last[1]) if keep else vel
 
