@@ -373,6 +373,229 @@ __global__ void __launch_bounds__(ANG_THREADS) angles_scan_kernel(AngleArgs p, c
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Tensor-core scan for 5 <= A <= 16 on a grid that is symmetric about 0.
+//
+// The lag-form scan is a dense contraction: for the grid pair (g, G-1-g)
+//     E[cell][g] = sum_k Re R_k cos(k phi_g),   O[cell][g] = sum_k Im R_k sin(k phi_g),   P(+-theta) = R_0 + 2 (E +- O),
+// i.e. [cells x K] . [K x pairs] with K = AP lags (k = 1 .. AP-1, zero padded).  It runs on the tensor cores through
+// mma.sync.m16n8k8 TF32 with the 3xTF32 split (x = hi + lo, both TF32: hi*hi + lo*hi + hi*lo, the two small products
+// in their own accumulator), which keeps ~2^-21 relative accuracy per product -- the same order as the fp32 FMA
+// chain; the B fragments (cos / sin tables) are split on the host.  A warp carries 32 cells (two 16-row tiles); lane L
+// computes the lags of cell L, publishes them through shared memory in fragment order, and every lane then tracks
+// (best, runner-up, pair index) for its two accumulator rows and two columns per tile.  The pair maximum is
+// E + |O| and the pair minimum E - |O|, so the tracking costs 6 ALU operations per pair instead of 10 per pair
+// in the CUDA-core scan; which side won is read off the sign of O once, after the scan (|O| ~ 0 means the two sides
+// tie, and a tie is flagged RS_FLAG_TIE anyway).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void track_pair(Track& t, float hi, float lo, int pair) {
+    const float m = fminf(t.best, hi);
+    const bool up = hi > t.best;
+    t.best = fmaxf(t.best, hi);
+    t.second = fmaxf(t.second, fmaxf(lo, m));
+    t.idx = up ? pair : t.idx;
+}
+
+template <int AP>
+__global__ void __launch_bounds__(ANG_THREADS) angles_mma_kernel(AngleArgs p, const float* __restrict__ mma_table,
+                                                                  int ntiles, const double* __restrict__ grid_cs,
+                                                                  double* __restrict__ ls_partials) {
+    constexpr int K = AP, KS = AP / 8, LSTRIDE = 2 * K + 4, TILE_FLOATS = 4 * KS * 64;
+    extern __shared__ float smf[];
+    float* tabs = smf;                              // [ntiles][cos, sin][hi, lo][KS][32 lanes][2]
+    float* Lx = tabs + (size_t)ntiles * TILE_FLOATS; // [warps][32 cells][LSTRIDE]: lags 1..K-1 of E, then of O
+    __shared__ double red[ANG_THREADS / 32][8];
+    const int seg = blockIdx.x;
+    const int n = p.det_nlead[seg];
+    double acc_ls[7] = {0, 0, 0, 0, 0, 0, 0};
+    if (n > 0) {
+        for (int i = threadIdx.x; i < ntiles * TILE_FLOATS / 4; i += blockDim.x)
+            reinterpret_cast<float4*>(tabs)[i] = __ldg(reinterpret_cast<const float4*>(mma_table) + i);
+        __syncthreads();
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        const int gq = lane >> 2, tq = lane & 3;
+        float* Lw = Lx + (size_t)wid * 32 * LSTRIDE;
+        const int f = seg / p.nseg_per_frame;
+        const float2* frame = p.rds + (size_t)f * p.R * p.D * p.A;
+        const int M = p.A, G = p.G;
+        const int half = G / 2, odd = G & 1, last_pair = (G + 1) / 2 - 1;
+        const float NEG = -3.0e38f;
+        for (int base = 0; base < n; base += ANG_THREADS) {
+            const int i = base + threadIdx.x;
+            const bool valid = i < n;
+            const uint32_t ld = valid ? p.det_lead[(size_t)seg * p.seg_cap + i] : (1u << 16);
+            const size_t o = (size_t)seg * p.seg_cap + (ld & 0xFFFFu);
+            const int mult = (int)(ld >> 16);
+            float rr0 = 0.f, yv = 0.f;
+            {
+                float2 s[AP];
+                if (valid) {
+                    int a, r, d;
+                    rs_split_key(p.det_key[o], a, r, d);
+                    const float2* cell = frame + ((size_t)r * p.D + d) * M;
+                    if (AP == 8 && M == 8) {
+                        const float4* c4 = reinterpret_cast<const float4*>(cell);
+#pragma unroll
+                        for (int m = 0; m < 4; ++m) {
+                            const float4 v = __ldg(c4 + m);
+                            s[2 * m] = make_float2(v.x, v.y);
+                            s[2 * m + 1] = make_float2(v.z, v.w);
+                        }
+                    } else {
+#pragma unroll
+                        for (int m = 0; m < AP; ++m) s[m] = (m < M) ? __ldg(cell + m) : make_float2(0.f, 0.f);
+                    }
+                    yv = atan2f(s[1].y * s[0].x - s[1].x * s[0].y, s[1].x * s[0].x + s[1].y * s[0].y);
+                } else {
+#pragma unroll
+                    for (int m = 0; m < AP; ++m) s[m] = make_float2(0.f, 0.f);
+                }
+                __syncwarp();                       // the previous pass no longer reads this warp's rows
+                float* row = Lw + lane * LSTRIDE;
+#pragma unroll
+                for (int k = 0; k < AP; ++k) {
+                    float xr = 0.f, xi = 0.f;
+#pragma unroll
+                    for (int m = 0; m + k < AP; ++m) {
+                        xr = fmaf(s[m + k].x, s[m].x, xr);
+                        xr = fmaf(s[m + k].y, s[m].y, xr);
+                        xi = fmaf(s[m + k].y, s[m].x, xi);
+                        xi = fmaf(-s[m + k].x, s[m].y, xi);
+                    }
+                    if (k == 0) rr0 = xr;
+                    else { row[k - 1] = xr; row[K + k - 1] = xi; }
+                }
+                row[K - 1] = 0.f;
+                row[2 * K - 1] = 0.f;
+                __syncwarp();
+            }
+            float my_best = NEG, my_second = NEG;
+            int my_pair = 0;
+#pragma unroll 1
+            for (int t = 0; t < 2; ++t) {
+                // A fragments of this 16-cell tile: rows gq, gq+8; columns tq + 8s, tq + 4 + 8s
+                uint32_t aEh[KS][4], aEl[KS][4], aOh[KS][4], aOl[KS][4];
+                const float* r0 = Lw + (16 * t + gq) * LSTRIDE;
+                const float* r1 = r0 + 8 * LSTRIDE;
+#pragma unroll
+                for (int s_ = 0; s_ < KS; ++s_) {
+                    const int c0 = tq + 8 * s_, c1 = c0 + 4;
+                    const float vE[4] = {r0[c0], r1[c0], r0[c1], r1[c1]};
+                    const float vO[4] = {r0[K + c0], r1[K + c0], r0[K + c1], r1[K + c1]};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        aEh[s_][q] = to_tf32(vE[q]);
+                        aEl[s_][q] = to_tf32(vE[q] - __uint_as_float(aEh[s_][q]));
+                        aOh[s_][q] = to_tf32(vO[q]);
+                        aOl[s_][q] = to_tf32(vO[q] - __uint_as_float(aOh[s_][q]));
+                    }
+                }
+                Track tr[2] = {Track{NEG, NEG, 0}, Track{NEG, NEG, 0}};
+                const float2* tb = reinterpret_cast<const float2*>(tabs) + lane;
+                for (int j = 0; j < ntiles; ++j, tb += TILE_FLOATS / 2) {
+                    float cEh[4] = {0.f, 0.f, 0.f, 0.f}, cEl[4] = {0.f, 0.f, 0.f, 0.f};
+                    float cOh[4] = {0.f, 0.f, 0.f, 0.f}, cOl[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                    for (int s_ = 0; s_ < KS; ++s_) {
+                        const float2 bEh = tb[(0 * KS + s_) * 32], bEl = tb[(1 * KS + s_) * 32];
+                        const float2 bOh = tb[(2 * KS + s_) * 32], bOl = tb[(3 * KS + s_) * 32];
+                        mma_tf32(cEh, aEh[s_], __float_as_uint(bEh.x), __float_as_uint(bEh.y));
+                        mma_tf32(cOh, aOh[s_], __float_as_uint(bOh.x), __float_as_uint(bOh.y));
+                        mma_tf32(cEl, aEl[s_], __float_as_uint(bEh.x), __float_as_uint(bEh.y));
+                        mma_tf32(cOl, aOl[s_], __float_as_uint(bOh.x), __float_as_uint(bOh.y));
+                        mma_tf32(cEl, aEh[s_], __float_as_uint(bEl.x), __float_as_uint(bEl.y));
+                        mma_tf32(cOl, aOh[s_], __float_as_uint(bOl.x), __float_as_uint(bOl.y));
+                    }
+                    const int pb = 8 * j + 2 * tq;
+                    const bool masked = j == ntiles - 1;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float e = cEh[q] + cEl[q], od = fabsf(cOh[q] + cOl[q]);
+                        float hi = e + od, lo = e - od;
+                        const int pair = pb + (q & 1);
+                        if (masked) {
+                            if (pair > last_pair) { hi = NEG; lo = NEG; }
+                            else if (odd && pair == half) lo = NEG;        // the middle angle has no partner
+                        }
+                        track_pair(tr[q >> 1], hi, lo, pair);
+                    }
+                }
+                // the four lanes of a quad hold different columns of the same rows: merge them
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+#pragma unroll
+                    for (int off = 1; off <= 2; off <<= 1) {
+                        const float ob = __shfl_xor_sync(0xffffffffu, tr[h].best, off);
+                        const float os = __shfl_xor_sync(0xffffffffu, tr[h].second, off);
+                        const int oi = __shfl_xor_sync(0xffffffffu, tr[h].idx, off);
+                        tr[h].second = fmaxf(fmaxf(tr[h].second, os), fminf(tr[h].best, ob));
+                        if (ob > tr[h].best || (ob == tr[h].best && oi < tr[h].idx)) { tr[h].best = ob; tr[h].idx = oi; }
+                    }
+                }
+                // row (t, h, gq) is cell 16 t + 8 h + gq of the warp: hand the result to the lane that owns the cell
+                const int src = 4 * (lane & 7);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const float vb = __shfl_sync(0xffffffffu, tr[h].best, src);
+                    const float vs = __shfl_sync(0xffffffffu, tr[h].second, src);
+                    const int vi = __shfl_sync(0xffffffffu, tr[h].idx, src);
+                    if ((lane >> 4) == t && ((lane >> 3) & 1) == h) { my_best = vb; my_second = vs; my_pair = vi; }
+                }
+            }
+            if (valid) {
+                // which side of the pair won: sign of the odd part, re-evaluated with the fp32 table
+                const float* row = Lw + lane * LSTRIDE + K;
+                const float* trow = p.scan_table + (size_t)my_pair * p.scan_stride;
+                float od = 0.f;
+#pragma unroll
+                for (int k = 1; k < AP; ++k) od = fmaf(row[k - 1], __ldg(trow + 2 * (k - 1) + 1), od);
+                const int bi = (odd && my_pair == half) ? half : (od >= 0.f ? my_pair : G - 1 - my_pair);
+                const float pbest = rr0 + 2.f * my_best;
+                uint8_t flags = 0;
+                if (2.f * (my_best - my_second) <= p.tie_eps * fabsf(pbest)) flags |= RS_FLAG_TIE;
+                if (p.method == RS_METHOD_MUSIC) {
+                    const float full = (float)M * rr0;
+                    if (full - pbest <= 1e-4f * full) flags |= RS_FLAG_GUARD;
+                }
+                const int live = emit(p, seg, i, o, mult, bi, p.grid_deg[bi], yv, flags);
+                if (ls_partials != nullptr) {
+                    const double c = grid_cs[2 * bi], sn = grid_cs[2 * bi + 1], y = (double)yv, w = (double)live;
+                    acc_ls[0] += w * c * c; acc_ls[1] += w * sn * sn; acc_ls[2] += w * c * sn;
+                    acc_ls[3] += w * y * c; acc_ls[4] += w * y * sn; acc_ls[5] += w * y * y; acc_ls[6] += w;
+                }
+            }
+        }
+    }
+    if (ls_partials == nullptr) return;
+#pragma unroll
+    for (int q = 0; q < 7; ++q) {
+#pragma unroll
+        for (int off = 16; off; off >>= 1) acc_ls[q] += __shfl_xor_sync(0xffffffffu, acc_ls[q], off);
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < 7; ++q) red[wid][q] = acc_ls[q];
+    }
+    __syncthreads();
+    if (threadIdx.x < 7) {
+        double t = 0;
+        for (int w = 0; w < ANG_THREADS / 32; ++w) t += red[w][threadIdx.x];
+        ls_partials[(size_t)seg * 8 + threadIdx.x] = t;
+    }
+}
+
 // warp-per-detection kernel for any A (used for A > 16): lanes scan the grid, snapshot in smem
 __global__ void __launch_bounds__(ANG_THREADS) angles_large_kernel(AngleArgs p) {
     extern __shared__ float2 snap[];   // [warps][A]
@@ -559,7 +782,7 @@ extern "C" int rs_angles(const void* rds, const float* scan_table, int scan_stri
                          int32_t* det_aidx,
                          float* det_adeg, float* det_phase, int seg_cap, int nseg_per_frame, int F, int R, int D, int A,
                          const double* grid_cs, double* ls_partials, int grid_symmetric, int32_t* det_ntie,
-                         int32_t* det_tielist, void* stream) {
+                         int32_t* det_tielist, const float* mma_table, int mma_tiles, void* stream) {
     RS_CHECK_ARG(rds && det_key && det_lead && det_nlead && det_flags && det_aidx && det_adeg && det_phase,
                  "rs_angles: null pointer");
     RS_CHECK_ARG(ls_partials == nullptr || grid_cs != nullptr, "rs_angles: ls_partials needs grid_cs");
@@ -607,6 +830,25 @@ extern "C" int rs_angles(const void* rds, const float* scan_table, int scan_stri
             angles_scan_kernel<AP, ND, false><<<(unsigned)blocks, ANG_THREADS, smem, st>>>(p, grid_cs, ls_partials);     \
         }                                                                                                                \
     } while (0)
+            const char* mma_env = getenv("RS_ANGLES_MMA");  // 0: force the CUDA-core scan
+            if (mma_table != nullptr && grid_symmetric && (ap == 8 || ap == 16) && !(mma_env && atoi(mma_env) == 0)) {
+                RS_CHECK_ARG(mma_tiles == ((G + 1) / 2 + 7) / 8, "rs_angles: mma_tiles must be ceil(ceil(G/2)/8)");
+                const size_t sm = ((size_t)mma_tiles * 4 * (ap / 8) * 64 + (size_t)(ANG_THREADS / 32) * 32 * (2 * ap + 4)) *
+                                  sizeof(float);
+                if (sm <= (size_t)rs_smem_optin_limit()) {
+                    if (ap == 8) {
+                        cudaFuncSetAttribute(angles_mma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+                        angles_mma_kernel<8><<<(unsigned)blocks, ANG_THREADS, sm, st>>>(p, mma_table, mma_tiles, grid_cs,
+                                                                                     ls_partials);
+                    } else {
+                        cudaFuncSetAttribute(angles_mma_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+                        angles_mma_kernel<16><<<(unsigned)blocks, ANG_THREADS, sm, st>>>(p, mma_table, mma_tiles, grid_cs,
+                                                                                      ls_partials);
+                    }
+                    RS_CHECK_LAUNCH("rs_angles(mma)");
+                    return RS_OK;
+                }
+            }
             const char* nd_env = getenv("RS_SCAN_ND");      // tuning knob (detections carried per thread)
             const int nd8 = nd_env ? atoi(nd_env) : 2;      // measured on B200: ND=2 4.12 ms, 3: 4.49, 4: 4.53 per 1k frames
             if (ap == 2) LAUNCH_SCAN(2, 4);

@@ -172,12 +172,14 @@ class FramePipeline:
             scan, stride = tables.scan_table(grid, c.spacing, c.lambda_c, A)
             pos = np.arange(A) * c.spacing
             steer = tables.steering(grid, pos, c.lambda_c)
+            symmetric = bool(np.array_equal(grid[::-1], -grid))
+            mma, mma_tiles = (tables.scan_mma_table(scan, len(grid), A) if symmetric and 4 < A <= 16 else (None, 0))
             self._tab[key] = {
                 "grid": grid, "G": len(grid), "stride": stride,
                 "scan": self._dev(scan), "grid_f32": self._dev(grid.astype(np.float32)),
                 "steer64": self._dev(steer.astype(np.complex64)) if A > 16 else None,
                 "steer128": self._dev(steer), "grid_cs": self._dev(tables.grid_cos_sin(grid)),
-                "symmetric": bool(np.array_equal(grid[::-1], -grid)),
+                "symmetric": symmetric, "mma": self._dev(mma) if mma is not None else None, "mma_tiles": mma_tiles,
             }
         return self._tab[key]
 
@@ -271,7 +273,7 @@ class FramePipeline:
             det.nlead.data_ptr(), det.flags.data_ptr(), det.aidx.data_ptr(), det.adeg.data_ptr(), det.phase.data_ptr(),
             det.seg_cap, det.ntiles, det.F, det.R, det.D, det.A,
             t["grid_cs"].data_ptr(), _lib.ptr(det.ls_partials), int(t["symmetric"]), det.ntie.data_ptr(), det.tielist.data_ptr(),
-            self.stream)
+            _lib.ptr(t["mma"]), t["mma_tiles"], self.stream)
         return det
 
     def velocity(self, det: Detections, out: Optional[torch.Tensor] = None, lambda_c: Optional[float] = None,

@@ -77,6 +77,47 @@ def scan_table(grid_deg: np.ndarray, spacing: float, lambda_c: float, A: int) ->
     return tab.astype(np.float32), stride
 
 
+def tf32_split(x32: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+    """x (float32) -> (hi, lo), both exactly representable in TF32 (10 explicit mantissa bits, rounded like
+    cvt.rna.tf32.f32: nearest, ties away from zero), with x = hi + lo up to 2^-22 |x|."""
+    def rna(v):
+        b = np.ascontiguousarray(v, dtype=np.float32).view(np.uint32).astype(np.uint64)
+        return ((b + 0x1000) & 0xFFFFE000).astype(np.uint32).view(np.float32)
+    hi = rna(x32)
+    lo = rna((x32.astype(np.float32) - hi).astype(np.float32))
+    return hi, lo
+
+
+def scan_mma_table(scan: np.ndarray, G: int, A: int) -> Tuple[np.ndarray, int]:
+    """B-operand fragments of the tensor-core angle scan (mma.sync m16n8k8 TF32, 3xTF32 split) for a grid that is
+    symmetric about 0: grid pairs (g, G-1-g), g < ceil(G/2), share cos(k phi_g) and differ in the sign of sin(k phi_g).
+    Layout float32 [ntiles][matrix: cos, sin][part: hi, lo][kstep][lane 32][2]: lane holds B[k = lane%4 + 4r + 8s]
+    [n = lane/4] of tile j, i.e. the table value for lag k+1 and pair 8j + n (0 beyond the last lag / pair).
+    `scan` is the float32 [G][stride] table of scan_table()."""
+    ap = padded_antennas(A)
+    assert ap in (8, 16)
+    npairs = (G + 1) // 2
+    nt = (npairs + 7) // 8
+    K, KS = ap, ap // 8
+    T = np.zeros((2, K, nt * 8), dtype=np.float32)
+    for k in range(K):
+        lag = k + 1
+        if lag <= ap - 1:
+            T[0, k, :npairs] = scan[:npairs, 2 * (lag - 1)]
+            T[1, k, :npairs] = scan[:npairs, 2 * (lag - 1) + 1]
+    hi, lo = tf32_split(T)
+    parts = np.stack([hi, lo], axis=1)                   # [matrix][part][K][pairs]
+    out = np.zeros((nt, 2, 2, KS, 32, 2), dtype=np.float32)
+    lane = np.arange(32)
+    for j in range(nt):
+        for s_ in range(KS):
+            for r in range(2):
+                k = (lane % 4) + 4 * r + 8 * s_
+                n = 8 * j + lane // 4
+                out[j, :, :, s_, :, r] = parts[:, :, k, n]
+    return out.reshape(-1), nt
+
+
 def grid_cos_sin(grid_deg: np.ndarray) -> np.ndarray:
     """(cos, sin) of np.radians(grid) -- what velocity_solver.py:94-97 evaluates per target. f64 [G][2]."""
     az = np.radians(grid_deg)
