@@ -379,8 +379,7 @@ __global__ void __launch_bounds__(ANG_THREADS) angles_scan_kernel(AngleArgs p, c
 // The lag-form scan is a dense contraction: for the grid pair (g, G-1-g)
 //     E[cell][g] = sum_k Re R_k cos(k phi_g),   O[cell][g] = sum_k Im R_k sin(k phi_g),   P(+-theta) = R_0 + 2 (E +- O),
 // i.e. [cells x K] . [K x pairs] with K = AP lags (k = 1 .. AP-1, zero padded).  It runs on the tensor cores through
-// mma.sync.m16n8k8 TF32 with the 3xTF32 split (x = hi + lo, both TF32: hi*hi + lo*hi + hi*lo, the two small products
-// in their own accumulator), which keeps ~2^-21 relative accuracy per product -- the same order as the fp32 FMA
+// mma.sync.m16n8k8 TF32 with the 3xTF32 split (x = hi + lo, both TF32: hi*hi + lo*hi + hi*lo), which keeps ~2^-21 relative accuracy per product -- the same order as the fp32 FMA
 // chain; the B fragments (cos / sin tables) are split on the host.  A warp carries 32 cells (two 16-row tiles); lane L
 // computes the lags of cell L, publishes them through shared memory in fragment order, and every lane then tracks
 // (best, runner-up, pair index) for its two accumulator rows and two columns per tile.  The pair maximum is
@@ -407,8 +406,8 @@ __device__ __forceinline__ void track_pair(Track& t, float hi, float lo, int pai
     t.idx = up ? pair : t.idx;
 }
 
-template <int AP>
-__global__ void __launch_bounds__(ANG_THREADS) angles_mma_kernel(AngleArgs p, const float* __restrict__ mma_table,
+template <int AP, int MINB>
+__global__ void __launch_bounds__(ANG_THREADS, MINB) angles_mma_kernel(AngleArgs p, const float* __restrict__ mma_table,
                                                                   int ntiles, const double* __restrict__ grid_cs,
                                                                   double* __restrict__ ls_partials) {
     constexpr int K = AP, KS = AP / 8, LSTRIDE = 2 * K + 4, TILE_FLOATS = 4 * KS * 64;
@@ -504,24 +503,24 @@ __global__ void __launch_bounds__(ANG_THREADS) angles_mma_kernel(AngleArgs p, co
                 Track tr[2] = {Track{NEG, NEG, 0}, Track{NEG, NEG, 0}};
                 const float2* tb = reinterpret_cast<const float2*>(tabs) + lane;
                 for (int j = 0; j < ntiles; ++j, tb += TILE_FLOATS / 2) {
-                    float cEh[4] = {0.f, 0.f, 0.f, 0.f}, cEl[4] = {0.f, 0.f, 0.f, 0.f};
-                    float cOh[4] = {0.f, 0.f, 0.f, 0.f}, cOl[4] = {0.f, 0.f, 0.f, 0.f};
+                    // one accumulator per matrix: the large product first, then the two small ones (E and O chains alternate)
+                    float cE[4] = {0.f, 0.f, 0.f, 0.f}, cO[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                     for (int s_ = 0; s_ < KS; ++s_) {
                         const float2 bEh = tb[(0 * KS + s_) * 32], bEl = tb[(1 * KS + s_) * 32];
                         const float2 bOh = tb[(2 * KS + s_) * 32], bOl = tb[(3 * KS + s_) * 32];
-                        mma_tf32(cEh, aEh[s_], __float_as_uint(bEh.x), __float_as_uint(bEh.y));
-                        mma_tf32(cOh, aOh[s_], __float_as_uint(bOh.x), __float_as_uint(bOh.y));
-                        mma_tf32(cEl, aEl[s_], __float_as_uint(bEh.x), __float_as_uint(bEh.y));
-                        mma_tf32(cOl, aOl[s_], __float_as_uint(bOh.x), __float_as_uint(bOh.y));
-                        mma_tf32(cEl, aEh[s_], __float_as_uint(bEl.x), __float_as_uint(bEl.y));
-                        mma_tf32(cOl, aOh[s_], __float_as_uint(bOl.x), __float_as_uint(bOl.y));
+                        mma_tf32(cE, aEh[s_], __float_as_uint(bEh.x), __float_as_uint(bEh.y));
+                        mma_tf32(cO, aOh[s_], __float_as_uint(bOh.x), __float_as_uint(bOh.y));
+                        mma_tf32(cE, aEl[s_], __float_as_uint(bEh.x), __float_as_uint(bEh.y));
+                        mma_tf32(cO, aOl[s_], __float_as_uint(bOh.x), __float_as_uint(bOh.y));
+                        mma_tf32(cE, aEh[s_], __float_as_uint(bEl.x), __float_as_uint(bEl.y));
+                        mma_tf32(cO, aOh[s_], __float_as_uint(bOl.x), __float_as_uint(bOl.y));
                     }
                     const int pb = 8 * j + 2 * tq;
                     const bool masked = j == ntiles - 1;
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        const float e = cEh[q] + cEl[q], od = fabsf(cOh[q] + cOl[q]);
+                        const float e = cE[q], od = fabsf(cO[q]);
                         float hi = e + od, lo = e - od;
                         const int pair = pb + (q & 1);
                         if (masked) {
@@ -836,14 +835,15 @@ extern "C" int rs_angles(const void* rds, const float* scan_table, int scan_stri
                 const size_t sm = ((size_t)mma_tiles * 4 * (ap / 8) * 64 + (size_t)(ANG_THREADS / 32) * 32 * (2 * ap + 4)) *
                                   sizeof(float);
                 if (sm <= (size_t)rs_smem_optin_limit()) {
+                    // occupancy beats per-warp ILP here (measured): 64 registers / 8 CTAs per SM at A <= 8
                     if (ap == 8) {
-                        cudaFuncSetAttribute(angles_mma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-                        angles_mma_kernel<8><<<(unsigned)blocks, ANG_THREADS, sm, st>>>(p, mma_table, mma_tiles, grid_cs,
-                                                                                     ls_partials);
+                        cudaFuncSetAttribute(angles_mma_kernel<8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+                        angles_mma_kernel<8, 8><<<(unsigned)blocks, ANG_THREADS, sm, st>>>(p, mma_table, mma_tiles, grid_cs,
+                                                                                        ls_partials);
                     } else {
-                        cudaFuncSetAttribute(angles_mma_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-                        angles_mma_kernel<16><<<(unsigned)blocks, ANG_THREADS, sm, st>>>(p, mma_table, mma_tiles, grid_cs,
-                                                                                      ls_partials);
+                        cudaFuncSetAttribute(angles_mma_kernel<16, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+                        angles_mma_kernel<16, 5><<<(unsigned)blocks, ANG_THREADS, sm, st>>>(p, mma_table, mma_tiles,
+                                                                                         grid_cs, ls_partials);
                     }
                     RS_CHECK_LAUNCH("rs_angles(mma)");
                     return RS_OK;
