@@ -298,9 +298,10 @@ detect_a8_kernel(const float2* __restrict__ rds, const uint8_t* __restrict__ gat
     // ---- walk: thread = (doppler bin, row half); 8 antennas per cell
     const int ddp = (tid & (A8_TD - 1)) + 1, rh = tid >> 7;
     const int rbase = rh * A8_HALF;                  // tile rows rbase+1 .. rbase+8 (1-based incl. halo)
-    uint32_t hit[2] = {0u, 0u}, near[2] = {0u, 0u}, cand[2] = {0u, 0u};  // byte per row: antenna mask
+    uint32_t hit[2] = {0u, 0u}, near[2] = {0u, 0u}, cand[2] = {0u, 0u}, unc[2] = {0u, 0u};  // byte per row: antenna mask
     int my_near = 0;
     float my_psum = 0.f;
+    const float band = 2.f * eps;
     // the two antenna quads of the cell are walked one after the other (half the live registers of an
     // 8-wide walk, so three CTAs fit per SM); their hit bits land in the same per-row antenna mask
 #pragma unroll
@@ -324,26 +325,46 @@ detect_a8_kernel(const float2* __restrict__ rds, const uint8_t* __restrict__ gat
             ld4(rr + 1, ddp - 1, l2); ld4(rr + 1, ddp, c2); ld4(rr + 1, ddp + 1, q2);
             const int r = r0 + rr - 1;
             const bool row_ok = r < R && gate[r < R ? r : 0];
-            uint32_t hm = 0u, nm = 0u, cm = 0u;
+            uint32_t hm = 0u, um = 0u;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const float hn = fmaxf(fmaxf(l2[j], c2[j]), q2[j]);
                 const float m = fmaxf(fmaxf(hp[j], hn), fmaxf(l1[j], q1[j]));
                 const float c = c1[j];
-                const int cls = row_ok ? classify(c, m, thr, eps) : 0;
                 my_psum += c;
-                if (cls) {
-                    hm |= 1u << j;
-                    if (cls & 2) { nm |= 1u << j; ++my_near; }
-                    if (cls & 4) cm |= 1u << j;
-                }
+                // three zones from two scaled copies of c: surely a detection (margin > 2 eps to the best neighbour and to
+                // the threshold), surely not one, and the thin band in between where the exact rule of classify() decides
+                const float cu = fmaf(c, band, c), cl = fmaf(c, -band, c);
+                const bool maybe = row_ok && cu >= m && cu > thr;
+                const bool sure = cl >= m && cl > thr;
+                hm |= maybe ? (1u << j) : 0u;
+                um |= (maybe && !sure) ? (1u << j) : 0u;          // ~1e-5 of the cells: settled after the walk
                 hp[j] = fmaxf(fmaxf(l1[j], c), q1[j]);
                 l1[j] = l2[j]; c1[j] = c2[j]; q1[j] = q2[j];
             }
             const int sh = (i & 3) * 8 + quad * 4;
             hit[i >> 2] |= hm << sh;
-            near[i >> 2] |= nm << sh;
-            cand[i >> 2] |= cm << sh;
+            unc[i >> 2] |= um << sh;
+        }
+    }
+    // cells inside the band: the exact rule on the nine powers, re-read from the tile
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+        uint32_t u = unc[w];
+        while (u) {
+            const int b = __ffs(u) - 1;
+            u &= u - 1;
+            const int i = w * 4 + (b >> 3), j = b & 7;
+            const int rr = rbase + 1 + i;
+            auto at = [&](int r_, int d_) { return pw[a8_off(r_, d_, j >> 2) + (j & 3)]; };
+            const float c = at(rr, ddp);
+            float m = fmaxf(fmaxf(at(rr - 1, ddp - 1), at(rr - 1, ddp)), at(rr - 1, ddp + 1));
+            m = fmaxf(m, fmaxf(at(rr, ddp - 1), at(rr, ddp + 1)));
+            m = fmaxf(m, fmaxf(fmaxf(at(rr + 1, ddp - 1), at(rr + 1, ddp)), at(rr + 1, ddp + 1)));
+            const int cls = classify(c, m, thr, eps);
+            if (cls == 0) hit[w] &= ~(1u << b);
+            if (cls & 2) { near[w] |= 1u << b; ++my_near; }
+            if (cls & 4) cand[w] |= 1u << b;
         }
     }
     // entries and leaders of this thread, scanned together (entries <= 2^14 per tile)
