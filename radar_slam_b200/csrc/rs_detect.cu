@@ -275,22 +275,43 @@ detect_a8_kernel(const float2* __restrict__ rds, const uint8_t* __restrict__ gat
         }
         pw[a8_off(rr, side ? A8_TD + 1 : 0, ac >> 2) + (ac & 3)] = p;
     }
-    // ---- interior: each row is 128 cells x 4 float4 (two antennas each); 2 float4 per thread per row
-#pragma unroll 3
-    for (int rr = 0; rr < A8_TR + 2; ++rr) {
-        const int r = r0 - 1 + rr;
-        const bool ok = r >= 0 && r < R;
+    // ---- interior: each row is 128 cells x 4 float4 (two antennas each); 2 float4 per thread per row.
+    // Row-invariant address parts are hoisted; six rows (12 loads) are in flight per thread before the first use.
+    {
+        const size_t row_f4 = (size_t)D * A / 2;                                    // float4 per RDS row
+        const float4* src[2];
+        float* dst[2];
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
             const int i4 = tid + DET_THREADS * k;
             const int cell = i4 >> 2, part = i4 & 3;
-            float2 p2 = make_float2(-1.f, -1.f);
-            if (ok) {
-                const float4 v = __ldg(reinterpret_cast<const float4*>(frame + ((size_t)r * D + d0 + cell) * A + a0) + part);
-                p2.x = fmaf(v.x, v.x, v.y * v.y);
-                p2.y = fmaf(v.z, v.z, v.w * v.w);
+            src[k] = reinterpret_cast<const float4*>(frame + ((size_t)d0 + cell) * A + a0) + part;
+            dst[k] = pw + a8_off(0, cell + 1, part >> 1) + (part & 1) * 2;
+        }
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {
+            constexpr int NR = (A8_TR + 2) / 3;
+            float4 v[NR][2];
+#pragma unroll
+            for (int q = 0; q < NR; ++q) {
+                const int r = r0 - 1 + g * NR + q;
+                const bool ok = r >= 0 && r < R;
+#pragma unroll
+                for (int k = 0; k < 2; ++k)
+                    v[q][k] = ok ? __ldg(src[k] + (size_t)r * row_f4) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            *reinterpret_cast<float2*>(pw + a8_off(rr, cell + 1, part >> 1) + (part & 1) * 2) = p2;
+#pragma unroll
+            for (int q = 0; q < NR; ++q) {
+                const int rr = g * NR + q, r = r0 - 1 + rr;
+                const bool ok = r >= 0 && r < R;
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    float2 p2;
+                    p2.x = ok ? fmaf(v[q][k].x, v[q][k].x, v[q][k].y * v[q][k].y) : -1.f;
+                    p2.y = ok ? fmaf(v[q][k].z, v[q][k].z, v[q][k].w * v[q][k].w) : -1.f;
+                    *reinterpret_cast<float2*>(dst[k] + rr * A8_W) = p2;
+                }
+            }
         }
     }
     __syncthreads();
