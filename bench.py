@@ -309,17 +309,38 @@ def run_gpu(args):
                        "alg_bytes_per_step": by, "achieved_gbs": by / msv / 1e6, "frac_hbm": by / msv / 1e6 / peak})
     dom = max(stages, key=lambda s: s["ms_per_step"])
     per_launch_bytes = dom["alg_bytes_per_step"] / dom["launches"]
+    # measured DRAM traffic of the same kernels from the committed ncu capture (per frame of this shape), if present
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_v5_traffic.json")
+    if os.path.exists(tpath) and (A, C, S) == (8, 128, 256):
+        per_frame = json.load(open(tpath))["dram_bytes_per_frame"]
+        for st in stages:
+            if st["kernel"] in per_frame:
+                st["ncu_dram_bytes_per_step"] = per_frame[st["kernel"]] * F
+        if dom["kernel"] in per_frame:
+            traffic = per_frame[dom["kernel"]] * F / dom["launches"]
     roofline = {"kernel": dom["kernel"], "bound": "hbm", "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                "frac": dom["frac_hbm"], "traffic": None, "peak_source": peak_src,
+                "frac": dom["frac_hbm"], "traffic": traffic, "peak_source": peak_src,
                 "alg_bytes_per_launch": per_launch_bytes, "avg_launch_ms": dom["ms_per_step"] / dom["launches"],
                 "stages": stages}
+    fft = [st for st in stages if st["kernel"] in ("rs_range_fft", "rs_doppler_fft")]
+    if fft:
+        ms_fft = sum(st["ms_per_step"] for st in fft)
+        roofline["fft_stages"] = {
+            "ms_per_step": ms_fft, "alg_bytes_per_step": 16 * F * A * C * S,
+            "frac_hbm_2d": 16 * F * A * C * S / ms_fft / 1e6 / peak,
+            "note": "both FFT kernels against the 16 B/cell of the whole 2-D transform (cube in, RDS out); each kernel "
+                    "alone moves 16 B/cell and is listed in stages"}
     if dom["kernel"] == "rs_angles":
         G = len(pipe._angle_tables(A)["grid"])
         ap = 2 if A <= 2 else 4 if A <= 4 else 8 if A <= 8 else 16
-        flops = n_det_frame * F * (G * (4 * (ap - 1) + 4) + 8 * ap * ap)
-        roofline["note"] = ("dominant kernel is the per-detection MUSIC scan, which is FP32-issue bound, not HBM bound; "
-                            "its HBM fraction is reported for the contract, its FP32 rate below")
-        roofline["fp32_tflops"] = flops / dom["ms_per_step"] / 1e9
+        cells = float(det.nlead[: det.F * det.ntiles].sum().item()) / det.F * F
+        flops = cells * (G * 2 * (ap - 1) + 8 * ap * ap)
+        roofline["note"] = ("dominant kernel is the per-cell MUSIC grid scan: a [cells x lags] . [lags x grid pairs] contraction "
+                            "on the tensor cores (mma.sync 3xTF32) whose argmax / runner-up tracking is ALU-issue bound, not "
+                            "HBM bound; its HBM fraction is reported for the contract, its arithmetic rate below")
+        roofline["distinct_cells_per_step"] = cells
+        roofline["scan_tflops_fp32_equivalent"] = flops / dom["ms_per_step"] / 1e9
 
     # ---- CPU baseline: the oracle port on a bounded sample of the SAME frames, one core
     n_cpu = args.cpu_frames
@@ -372,7 +393,7 @@ def main():
     ap.add_argument("--no-recheck", action="store_true", help="skip the fp64 recheck of flagged decisions (fp32 path only)")
     ap.add_argument("--fft-eps", type=float, default=4e-7, help="error bound of the fp32 FFT used by the recheck, in rms units")
     ap.add_argument("--e2e-frames", type=int, default=1000)
-    ap.add_argument("--cpu-frames", type=int, default=8)
+    ap.add_argument("--cpu-frames", type=int, default=24)
     ap.add_argument("--ref-procs", type=int, default=0)
     ap.add_argument("--ref-frames-per-step", type=int, default=0)
     args = ap.parse_args()

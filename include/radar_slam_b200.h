@@ -237,6 +237,20 @@ int rs_velocity_ls6(const double* pos, const double* ang, const double* y, int n
 int rs_robust_confidence_f64(const void* sig128, const double* angle_deg, const double* positions,
                              double lambda_c, int n, int A, double* out, void* stream);
 
+/* (f2)  FMCWRadarSimulator.synthesize_frame (scripts/simulate_raw.py:147-221) for F frames on the device:
+ *       cube[f][a][c][s] = sum over scatterers of amplitude exp(i(doppler + antenna phase)) delayed_chirp conj(ref_chirp)
+ *       (the same [A][S] plane for every chirp, :190-209) + sqrt(noise_power) (N(0,1) + i N(0,1))  (:216-219).
+ *       scatterers    double [F][n_max][4] = range_m, azimuth_rad, rcs_db, radial_velocity; rows that the reference
+ *                     skips (range <= 0, non-finite, :177) are skipped; n_scatterers int32 [F] or NULL (= n_max each)
+ *       antenna_pos   double [A] metres;  chirp_rate = bandwidth / chirp_duration;  t = linspace(0, chirp_duration, S)
+ *       noise         Philox4x32-10 keyed by seed, counter = (cell pair in frame, first_frame + f): frame k does not
+ *                     depend on the batch it is generated in.  Same distribution as the reference, not the same samples.
+ *       plane_ws      complex64 [F][A][S] workspace;  cube complex64 [F][A][C][S];  S even. */
+int rs_synthesize_frames(const double* scatterers, const int32_t* n_scatterers, int n_max, double fc,
+                         double chirp_rate, double chirp_duration, double lambda_c, const double* antenna_pos,
+                         double noise_power, unsigned long long seed, long long first_frame, void* plane_ws,
+                         void* cube, int F, int A, int C, int S, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

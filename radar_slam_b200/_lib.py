@@ -44,6 +44,8 @@ _SIGNATURES = {
     "rs_process_chirps_f64": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "rs_esprit_f64": (_i, [_vp, _i, _i, _d, _vp, _vp]),
     "rs_velocity_ls6": (_i, [_vp, _vp, _vp, _i, _d, _vp, _vp, _i, _vp, _vp, _vp]),
+    "rs_synthesize_frames": (_i, [_vp, _vp, _i, _d, _d, _d, _d, _vp, _d, C.c_ulonglong, C.c_longlong, _vp, _vp,
+                                  _i, _i, _i, _i, _vp]),
     "rs_robust_confidence_f64": (_i, [_vp, _vp, _vp, _d, _i, _i, _vp, _vp]),
 }
 

@@ -1,10 +1,10 @@
 """Synthetic FMCW cubes for benchmarks and smoke runs.
 
 Same signal model as the reference simulator (scripts/simulate_raw.py:102-221): the scatterer term
-is chirp-invariant (simulate_raw.py:190-209 never uses the chirp start time), so it is evaluated
-once on the host in fp64 -- the chirp phase needs fp64 -- and broadcast; the complex Gaussian noise
-(simulate_raw.py:216-219) is drawn on the device.  Frame k depends only on (seed, k-block), so
-every rank of a sharded run can generate exactly its own frames.
+is chirp-invariant (simulate_raw.py:190-209 never uses the chirp start time), so it is one
+[A, S] plane per frame; rs_synthesize_frames evaluates it in fp64 on the device and streams plane + Philox noise
+(simulate_raw.py:216-219) into the cube.  Frame k depends only on (seed, k), so every rank of a sharded run can
+generate exactly its own frames.  scatterer_term() is the host fp64 version of the same plane (tests, CPU arms).
 """
 from __future__ import annotations
 
@@ -40,26 +40,38 @@ def scatterer_term(cfg: RadarConfig, scatterers: np.ndarray = DEFAULT_SCENE) -> 
     return out
 
 
-def synth_cubes(cfg: RadarConfig, frames: int, seed: int, noise_power: float = 0.01,
-                scatterers: np.ndarray = DEFAULT_SCENE, device=None, first_frame: int = 0,
-                block: int = 64) -> torch.Tensor:
-    """complex64 [frames, A, C, S] on the device.  Noise is generated in blocks of `block` frames with
-    generator seed (seed, block index), so any rank can produce frames [first_frame, first_frame+frames)."""
+def synthesize_frames(cfg: RadarConfig, scatterers, frames: int, seed: int, noise_power: float = 0.01,
+                      device=None, first_frame: int = 0, out: torch.Tensor = None) -> torch.Tensor:
+    """FMCWRadarSimulator.synthesize_frame for `frames` frames on the device (rs_synthesize_frames).
+    scatterers: [n, 4] (the same scene in every frame) or [frames, n, 4] = range_m, azimuth_rad, rcs_db, radial velocity.
+    Returns complex64 [frames, A, C, S].  Frame k's noise depends only on (seed, first_frame + k)."""
+    from . import _lib
+    if not torch.cuda.is_available():
+        raise _lib.RadarSlamError("radar_slam_b200 needs a CUDA device (no CPU fallback)")
+    lib = _lib.load()
     device = torch.device(device or f"cuda:{torch.cuda.current_device()}")
     A, C, S = cfg.num_antennas, cfg.num_chirps, cfg.samples_per_chirp
-    cube = torch.empty((frames, A, C, S), dtype=torch.complex64, device=device)
-    sig = torch.from_numpy(scatterer_term(cfg, scatterers).astype(np.complex64)).to(device)
-    sigma = float(np.sqrt(noise_power))
-    gen = torch.Generator(device=device)
-    f = first_frame
-    while f < first_frame + frames:
-        b = f // block
-        lo, hi = b * block, (b + 1) * block
-        gen.manual_seed((seed << 20) + b)
-        blk = torch.empty((block, A, C, S, 2), dtype=torch.float32, device=device)
-        blk.normal_(0.0, sigma, generator=gen)
-        s0, s1 = max(lo, first_frame), min(hi, first_frame + frames)
-        cube[s0 - first_frame:s1 - first_frame] = torch.view_as_complex(blk[s0 - lo:s1 - lo])
-        f = hi
-    cube += sig[None, :, None, :]
+    sc = np.asarray(scatterers, dtype=np.float64)
+    if sc.ndim == 2:
+        sc = np.broadcast_to(sc[None, :, :4], (frames,) + sc[:, :4].shape)
+    sc = np.array(sc[:, :, :4], dtype=np.float64, order="C", copy=True)
+    assert sc.shape[0] == frames
+    n_max = sc.shape[1]
+    with torch.cuda.device(device):
+        sc_dev = torch.from_numpy(sc).to(device) if n_max else torch.zeros(1, dtype=torch.float64, device=device)
+        pos = torch.from_numpy(np.arange(A) * cfg.spacing).to(device)
+        plane = torch.empty((frames, A, S), dtype=torch.complex64, device=device)
+        cube = out if out is not None else torch.empty((frames, A, C, S), dtype=torch.complex64, device=device)
+        assert cube.is_contiguous() and cube.dtype == torch.complex64 and tuple(cube.shape) == (frames, A, C, S)
+        _lib.check(lib.rs_synthesize_frames(sc_dev.data_ptr(), 0, n_max, cfg.fc, cfg.chirp_rate, cfg.chirp_duration,
+                                            cfg.lambda_c, pos.data_ptr(), float(noise_power), int(seed) & (2 ** 64 - 1),
+                                            int(first_frame), plane.data_ptr(), cube.data_ptr(), frames, A, C, S,
+                                            torch.cuda.current_stream(device).cuda_stream), "rs_synthesize_frames")
     return cube
+
+
+def synth_cubes(cfg: RadarConfig, frames: int, seed: int, noise_power: float = 0.01,
+                scatterers: np.ndarray = DEFAULT_SCENE, device=None, first_frame: int = 0) -> torch.Tensor:
+    """complex64 [frames, A, C, S] on the device: the benchmark workload (same scene in every frame, fresh noise per
+    frame).  Any rank can produce frames [first_frame, first_frame + frames) of the same sequence."""
+    return synthesize_frames(cfg, scatterers, frames, seed, noise_power, device, first_frame)
