@@ -14,15 +14,15 @@ import torch
 
 from .. import tables
 from . import _device
+from .lazy import LazyRecords, column_of, records_of
 
 logger = logging.getLogger(__name__)
 
 
-def _peaks_list(peak_info) -> list:
-    peaks = peak_info['peaks']
-    if isinstance(peaks, np.ndarray):          # np.load(..., allow_pickle=True) gives an object array of dicts
-        peaks = peaks.tolist()
-    return list(peaks)
+def _peaks_list(peak_info):
+    """peak_info['peaks'] as a record sequence: LazyRecords (also unwrapped from the 0-d object array np.load
+    returns), the reference's 1-D object array of dicts, or a list."""
+    return records_of(peak_info['peaks'])
 
 
 class AngleEstimator:
@@ -112,20 +112,20 @@ class AngleEstimator:
         the RDS are skipped the same way."""
         peaks = _peaks_list(peak_info)
         if method not in ('music', 'esprit', 'beamforming'):
-            if peaks:
+            if len(peaks):
                 logger.warning(f"Error processing target: Unknown method: {method}")
             logger.info(f"Processed 0 targets using {method}")
             return []
         rds = np.asarray(rds) if not isinstance(rds, np.ndarray) else rds
         A, R, D = rds.shape
-        rb = np.array([int(p['range_bin']) for p in peaks], dtype=np.int64)
-        db = np.array([int(p['doppler_bin']) for p in peaks], dtype=np.int64)
+        rb = column_of(peaks, 'range_bin', np.int64).reshape(-1)
+        db = column_of(peaks, 'doppler_bin', np.int64).reshape(-1)
         ok = (rb >= -R) & (rb < R) & (db >= -D) & (db < D)
         for _ in range(int((~ok).sum())):
             logger.warning("Error processing target: index out of bounds")
         keep = np.nonzero(ok)[0]
         rbk, dbk = rb[keep] % R, db[keep] % D          # numpy negative indexing
-        targets: List[Dict] = []
+        targets = []
         if len(keep):
             pipe = self._pipe()
             rds_dev = _device.rds_to_device(rds, pipe)
@@ -139,15 +139,16 @@ class AngleEstimator:
                 angles = self.azimuth_grid[aidx.cpu().numpy()]
                 spec = spec_dev.cpu().numpy()
             sigs = sig_dev.cpu().numpy()
-            for j, i in enumerate(keep):
-                peak = peaks[i]
-                angle = angles[j]
-                targets.append({
-                    'range_m': peak['range_m'], 'doppler_hz': peak['doppler_hz'], 'power_db': peak['power_db'],
-                    'azimuth_deg': angle, 'azimuth_rad': np.radians(angle), 'antenna': peak['antenna'],
-                    'range_bin': peak['range_bin'], 'doppler_bin': peak['doppler_bin'],
-                    'spatial_signature': sigs[j], 'spectrum': None if spec is None else spec[j],
-                })
+            # angle_estimation.py:289-300: ten keys per target; columns now, dicts when somebody asks (compat/lazy.py)
+            def peak_col(name):
+                col = column_of(peaks, name)
+                return col[keep] if isinstance(col, np.ndarray) and col.ndim >= 1 else col
+            targets = LazyRecords({
+                'range_m': peak_col('range_m'), 'doppler_hz': peak_col('doppler_hz'), 'power_db': peak_col('power_db'),
+                'azimuth_deg': angles, 'azimuth_rad': np.radians(angles), 'antenna': peak_col('antenna'),
+                'range_bin': peak_col('range_bin'), 'doppler_bin': peak_col('doppler_bin'),
+                'spatial_signature': sigs, 'spectrum': spec,
+            })
         logger.info(f"Processed {len(targets)} targets using {method}")
         return targets
 

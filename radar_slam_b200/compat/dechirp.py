@@ -15,6 +15,7 @@ import torch
 
 from .. import tables
 from . import _device
+from .lazy import LazyRecords
 
 logger = logging.getLogger(__name__)
 
@@ -134,8 +135,9 @@ class SignalPreprocessor:
         doppler_bins_hz = tables.doppler_axis(self.sampling_rate, D)
         ant, rb, db = d["antenna"], d["range_bin"], d["doppler_bin"]
         rm, dh, pw = range_bins_m[rb], doppler_bins_hz[db], power_db[ant, rb, db]
-        peaks = [{'antenna': int(a), 'range_bin': i, 'doppler_bin': j, 'range_m': x, 'doppler_hz': y, 'power_db': z}
-                 for a, i, j, x, y, z in zip(ant, rb, db, rm, dh, pw)]
+        # dechirp.py:265-272: one dict per peak; kept as columns and materialised on access (compat/lazy.py)
+        peaks = LazyRecords({'antenna': ant, 'range_bin': rb, 'doppler_bin': db, 'range_m': rm, 'doppler_hz': dh,
+                             'power_db': pw})
         return {'peaks': peaks, 'range_bins_m': range_bins_m, 'doppler_bins_hz': doppler_bins_hz,
                 'power_spectrum_db': power_db}
 

@@ -19,6 +19,7 @@ import torch
 from .. import tables
 from . import _device
 from .angle_estimation import _peaks_list
+from .lazy import column_of
 
 logger = logging.getLogger(__name__)
 
@@ -144,9 +145,12 @@ class RobustAngleEstimator:
     def process_targets_robust(self, rds: np.ndarray, peak_info: Dict, frame_timestamp: float = None) -> List[Dict]:
         """robust_angle_estimation.py:346-411."""
         peaks = _peaks_list(peak_info)
-        filtered_peaks = [p for p in peaks if p['power_db'] > -25.0]
-        filtered_peaks.sort(key=lambda x: x['power_db'], reverse=True)
-        filtered_peaks = filtered_peaks[:self.max_targets]
+        # robust_angle_estimation.py:362-370: power filter, stable descending sort, top max_targets -- on the power
+        # column, so only the selected peaks are ever materialised as dicts
+        power = column_of(peaks, 'power_db', float).reshape(-1) if len(peaks) else np.zeros(0)
+        cand = np.nonzero(power > -25.0)[0]
+        cand = cand[np.argsort(-power[cand], kind='stable')][:self.max_targets]
+        filtered_peaks = [peaks[int(i)] for i in cand]
         targets: List[Dict] = []
         if filtered_peaks:
             A, R, D = rds.shape

@@ -19,17 +19,14 @@ import numpy as np
 import torch
 
 from . import _device
+from .lazy import LazyRecords, column_of, records_of
 
 logger = logging.getLogger(__name__)
 
 
-def _as_list(target_info) -> list:
-    if isinstance(target_info, np.ndarray):
-        if target_info.ndim == 0:
-            target_info = target_info.item()
-        else:
-            target_info = target_info.tolist()
-    return list(target_info)
+def _as_list(target_info):
+    """targets as a record sequence (LazyRecords, the reference's object array of dicts, or a list)."""
+    return records_of(target_info)
 
 
 class VelocitySolver:
@@ -61,8 +58,12 @@ class VelocitySolver:
         return (4 * np.pi * np.sum(rel * direction, axis=1) * dt) / self.lambda_c
 
     def compute_observed_phase_differences(self, rds_data: np.ndarray, target_info: List[Dict]) -> np.ndarray:
-        sig = np.array([[t['spatial_signature'][0], t['spatial_signature'][1]] for t in _as_list(target_info)],
-                       dtype=complex).reshape(-1, 2)
+        targets = _as_list(target_info)
+        if isinstance(targets, LazyRecords) and len(targets):
+            sig = np.asarray(targets.column('spatial_signature'))[:, :2].astype(complex)
+        else:
+            sig = np.array([[t['spatial_signature'][0], t['spatial_signature'][1]] for t in targets],
+                           dtype=complex).reshape(-1, 2)
         return np.angle(sig[:, 1] * np.conj(sig[:, 0]))
 
     def cost_function(self, motion_params: np.ndarray, target_positions: np.ndarray, target_angles: np.ndarray,
@@ -131,13 +132,13 @@ class VelocitySolver:
                        initial_guess: Optional[np.ndarray] = None) -> Dict:
         """velocity_solver.py:309-355."""
         targets = _as_list(target_info)
-        range_m = np.array([t['range_m'] for t in targets], dtype=float)
-        az = np.array([t['azimuth_rad'] for t in targets], dtype=float)
+        range_m = column_of(targets, 'range_m', float).reshape(-1)
+        az = column_of(targets, 'azimuth_rad', float).reshape(-1)
         el = np.zeros_like(az)                       # "Assume ground level" (velocity_solver.py:334)
         target_positions = np.stack([range_m * np.cos(el) * np.cos(az), range_m * np.cos(el) * np.sin(az),
                                      range_m * np.sin(el)], axis=1).reshape(-1, 3)
         target_angles = np.stack([az, el], axis=1).reshape(-1, 2)
-        observed_phases = self.compute_observed_phase_differences(rds_data, targets) if targets else np.zeros(0)
+        observed_phases = self.compute_observed_phase_differences(rds_data, targets) if len(targets) else np.zeros(0)
         return self.two_step_optimization(target_positions, target_angles, observed_phases, dt, initial_guess)
 
     def visualize_results(self, results: Dict, save_path: Optional[str] = None) -> None:
