@@ -99,14 +99,24 @@ class ClockSampler:
 
 # ---------------------------------------------------------------------------------- CPU arms
 def _oracle_worker(payload):
-    frames, pdict, res, thr = payload
+    frames, pdict, res, thr, blas_threads = payload
     from oracle import radar_oracle as orc
     p = orc.RadarParams(**pdict)
     tim = {}
     out = []
-    for fr in frames:
-        r = orc.process_frame(fr.astype(np.complex128), p, "music", res, thr, timings=tim)
-        out.append((r["velocity"].get("velocity", np.zeros(3))[:2], len(r["peaks"]["antenna"])))
+
+    def run():
+        for fr in frames:
+            r = orc.process_frame(fr.astype(np.complex128), p, "music", res, thr, timings=tim)
+            out.append((r["velocity"].get("velocity", np.zeros(3))[:2], len(r["peaks"]["antenna"])))
+
+    if blas_threads:
+        # one process per core: keep each worker's BLAS / OpenMP pools at one thread, or they oversubscribe the box
+        from threadpoolctl import threadpool_limits
+        with threadpool_limits(limits=blas_threads):
+            run()
+    else:
+        run()
     return out, tim
 
 
@@ -119,11 +129,11 @@ def cpu_oracle_rate(frames: np.ndarray, args, procs: int):
     parts = [x for x in parts if len(x)]
     t0 = time.perf_counter()
     if len(parts) == 1:
-        res = [_oracle_worker((parts[0], pdict, args.grid_res, args.threshold_db))]
+        res = [_oracle_worker((parts[0], pdict, args.grid_res, args.threshold_db, 1 if procs == 1 else 0))]
     else:
         import multiprocessing as mp
         with mp.get_context("fork").Pool(len(parts)) as pool:
-            res = pool.map(_oracle_worker, [(x, pdict, args.grid_res, args.threshold_db) for x in parts])
+            res = pool.map(_oracle_worker, [(x, pdict, args.grid_res, args.threshold_db, 1) for x in parts])
     dt = time.perf_counter() - t0
     tim = {}
     ndet = []
