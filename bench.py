@@ -192,8 +192,8 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------- GPU arm
 def stage_bytes(name, F, A, C, S, n_det):
     cells = F * A * C * S
-    if name in ("rs_range_fft", "rs_doppler_fft"):
-        return 16 * cells                                   # read c64 + write c64 per cell
+    if name in ("rs_range_fft", "rs_doppler_fft", "rs_range_doppler_fft"):
+        return 16 * cells                                   # read c64 + write c64 per cell (the fused 2-D kernel: cube in, RDS out)
     if name == "rs_detect":
         return 8 * cells + 9 * n_det                        # read RDS once; key + power + flag per detection
     if name == "rs_angles":
@@ -333,14 +333,14 @@ def run_gpu(args):
                 "frac": dom["frac_hbm"], "traffic": traffic, "peak_source": peak_src,
                 "alg_bytes_per_launch": per_launch_bytes, "avg_launch_ms": dom["ms_per_step"] / dom["launches"],
                 "stages": stages}
-    fft = [st for st in stages if st["kernel"] in ("rs_range_fft", "rs_doppler_fft")]
+    fft = [st for st in stages if st["kernel"] in ("rs_range_fft", "rs_doppler_fft", "rs_range_doppler_fft")]
     if fft:
         ms_fft = sum(st["ms_per_step"] for st in fft)
         roofline["fft_stages"] = {
             "ms_per_step": ms_fft, "alg_bytes_per_step": 16 * F * A * C * S,
             "frac_hbm_2d": 16 * F * A * C * S / ms_fft / 1e6 / peak,
-            "note": "both FFT kernels against the 16 B/cell of the whole 2-D transform (cube in, RDS out); each kernel "
-                    "alone moves 16 B/cell and is listed in stages"}
+            "note": "the whole 2-D transform (dechirp, window, range FFT, Doppler FFT, both shifts) against its 16 B/cell "
+                    "(cube in, RDS out); one cluster kernel when the plane fits distributed shared memory"}
     if dom["kernel"] == "rs_angles":
         G = len(pipe._angle_tables(A)["grid"])
         ap = 2 if A <= 2 else 4 if A <= 4 else 8 if A <= 8 else 16

@@ -78,8 +78,16 @@ int rs_range_fft(const void* cube, const void* table, const void* twiddle_s, voi
                  int F, int A, int C_total, int chirp0, int C_used, int S, int dc_removal, void* stream);
 
 /* (a2)  the Doppler half of fft2/fftshift (dechirp.py:208-211): FFT over slow time, Doppler
- *       fftshift, antenna-innermost store.   twiddle_c complex64 [C] */
+ *       fftshift, rows kept in place (rds row = mid row).   twiddle_c complex64 [C] */
 int rs_doppler_fft(const void* mid, const void* twiddle_c, void* rds, int F, int A, int C, int S, void* stream);
+
+/* (a1+a2) the whole 2-D transform in one call.  For power-of-two shapes whose plane fits the shared memory of a
+ *       thread-block cluster (S = 256, C_used = 128) one fused kernel keeps the plane on chip: 8 B in + 8 B out per
+ *       cell instead of the 32 B of the two-kernel path; other shapes run rs_range_fft + rs_doppler_fft through
+ *       mid_ws (complex64 [F][S][A][C_used]; may be NULL when the fused kernel applies). */
+int rs_range_doppler_fft(const void* cube, const void* table, const void* twiddle_s, const void* twiddle_c,
+                         void* mid_ws, void* rds, int F, int A, int C_total, int chirp0, int C_used, int S,
+                         int dc_removal, void* stream);
 
 /* (b)   replaces extract_range_doppler_peaks (dechirp.py:215-278): |X|^2, 3x3 local maximum per
  *       antenna plane (scipy maximum_filter 'reflect' == ignore out-of-range neighbours, ties

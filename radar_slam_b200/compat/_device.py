@@ -37,7 +37,7 @@ def _sample(arr: np.ndarray) -> complex:
 
 def remember_rds(arr: np.ndarray, dev: torch.Tensor, cube: Optional[torch.Tensor] = None,
                  chirp_subset: Optional[Tuple[int, int]] = None) -> None:
-    """Remember the device copy (cell-major, [1,S,C,A]) of an RDS array handed to the caller, and the raw cube it
+    """Remember the device copy ([1,S,A,C]) of an RDS array handed to the caller, and the raw cube it
     came from when known (lets the peak extractor settle fp32-undecidable cells in fp64)."""
     try:
         ref = weakref.ref(arr)
@@ -49,7 +49,7 @@ def remember_rds(arr: np.ndarray, dev: torch.Tensor, cube: Optional[torch.Tensor
 
 
 def rds_to_device(rds: np.ndarray, pipe: FramePipeline) -> torch.Tensor:
-    """Reference-layout RDS [A, R, D] (any complex dtype, host) -> cell-major complex64 [1, R, D, A] on the
+    """Reference-layout RDS [A, R, D] (any complex dtype, host) -> complex64 [1, R, A, D] on the
     device.  Re-uses the device copy when `rds` is the very array this library returned."""
     ent = _rds_cache.get(id(rds))
     if ent is not None and ent[0]() is rds and ent[1] == _sample(rds):
@@ -60,7 +60,7 @@ def rds_to_device(rds: np.ndarray, pipe: FramePipeline) -> torch.Tensor:
     A, R, D = rds.shape
     host = torch.from_numpy(np.ascontiguousarray(rds, dtype=np.complex64))
     ref_layout = host.to(pipe.device).view(1, A, R, D)
-    out = torch.empty((1, R, D, A), dtype=torch.complex64, device=pipe.device)
+    out = torch.empty((1, R, A, D), dtype=torch.complex64, device=pipe.device)
     pipe._call("rs_rds_from_reference_layout", ref_layout.data_ptr(), out.data_ptr(), 1, A, D, R, pipe.stream)
     remember_rds(rds, out)
     return out
@@ -76,7 +76,7 @@ def keys_tensor(antenna, range_bin, doppler_bin, device) -> torch.Tensor:
 
 def signatures(pipe: FramePipeline, rds_dev: torch.Tensor, range_bin, doppler_bin) -> torch.Tensor:
     """Unit-energy snapshots complex128 [n, A] for cells of frame 0 (angle_estimation.py:83-88)."""
-    _, R, D, A = rds_dev.shape
+    _, R, A, D = rds_dev.shape
     n = len(range_bin)
     keys = keys_tensor(np.zeros(n, dtype=np.int64), range_bin, doppler_bin, pipe.device)
     frames = torch.zeros(n, dtype=torch.int32, device=pipe.device)

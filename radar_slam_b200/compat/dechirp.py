@@ -102,7 +102,7 @@ class SignalPreprocessor:
         pipe = self._pipe()
         cube = torch.from_numpy(np.ascontiguousarray(frame_signals, dtype=np.complex64)[None]).to(pipe.device)
         rds_dev = pipe.range_doppler(cube, chirp_subset)
-        _, S, Cu, A = rds_dev.shape
+        _, S, A, Cu = rds_dev.shape
         ref_layout = torch.empty((1, A, S, Cu), dtype=torch.complex64, device=pipe.device)
         pipe._call("rs_rds_to_reference_layout", rds_dev.data_ptr(), ref_layout.data_ptr(), 1, A, Cu, S, pipe.stream)
         out = ref_layout[0].cpu().numpy().astype(np.complex128)
@@ -114,7 +114,7 @@ class SignalPreprocessor:
         """dechirp.py:215-278: {'peaks': [dict...], 'range_bins_m', 'doppler_bins_hz', 'power_spectrum_db'}."""
         pipe = self._pipe()
         rds_dev = _device.rds_to_device(rds, pipe)
-        _, R, D, A = rds_dev.shape
+        _, R, A, D = rds_dev.shape
         det = pipe.detect(rds_dev, threshold_db=threshold_db, min_range=min_range, max_range=max_range)
         cube_dev, subset = _device.cube_of(rds)
         if cube_dev is not None:

@@ -1,4 +1,5 @@
-// Per-detection angle estimation on the cell-major RDS.
+// Per-detection angle estimation on the RDS rds[F][R][A][D] (rs_common.cuh):
+// the A-channel snapshot of cell (r, d) is A elements at stride D.
 //
 // Replaces AngleEstimator.extract_spatial_signature / music_spectrum / estimate_angle_* /
 // process_targets (angle_estimation.py:67-309).
@@ -124,10 +125,10 @@ __global__ void __launch_bounds__(ANG_THREADS) angles_small_kernel(AngleArgs p) 
         const int mult = (int)(ld >> 16);
         int a, r, d;
         rs_split_key(p.det_key[o], a, r, d);
-        const float2* cell = frame + ((size_t)r * p.D + d) * M;
+        const float2* cell = frame + (size_t)r * M * p.D + d;
         float2 s[AP];
 #pragma unroll
-        for (int m = 0; m < AP; ++m) s[m] = (m < M) ? __ldg(cell + m) : make_float2(0.f, 0.f);
+        for (int m = 0; m < AP; ++m) s[m] = (m < M) ? __ldg(cell + (size_t)m * p.D) : make_float2(0.f, 0.f);
 
         // inter-antenna phase angle(s[1] conj(s[0]))  (velocity_solver.py:136)
         const float pr = s[1].x * s[0].x + s[1].y * s[0].y;
@@ -235,19 +236,9 @@ __global__ void __launch_bounds__(ANG_THREADS) angles_scan_kernel(AngleArgs p, c
                 if (valid[q]) {
                     int a, r, d;
                     rs_split_key(p.det_key[o[q]], a, r, d);
-                    const float2* cell = frame + ((size_t)r * p.D + d) * M;
-                    if (AP == 8 && M == 8) {
-                        const float4* c4 = reinterpret_cast<const float4*>(cell);
+                    const float2* cell = frame + (size_t)r * M * p.D + d;
 #pragma unroll
-                        for (int m = 0; m < 4; ++m) {
-                            const float4 v = __ldg(c4 + m);
-                            s[2 * m] = make_float2(v.x, v.y);
-                            s[2 * m + 1] = make_float2(v.z, v.w);
-                        }
-                    } else {
-#pragma unroll
-                        for (int m = 0; m < AP; ++m) s[m] = (m < M) ? __ldg(cell + m) : make_float2(0.f, 0.f);
-                    }
+                    for (int m = 0; m < AP; ++m) s[m] = (m < M) ? __ldg(cell + (size_t)m * p.D) : make_float2(0.f, 0.f);
                     const float pr = s[1].x * s[0].x + s[1].y * s[0].y;
                     const float pi = s[1].y * s[0].x - s[1].x * s[0].y;
                     yv[q] = atan2f(pi, pr);
@@ -442,19 +433,9 @@ __global__ void __launch_bounds__(ANG_THREADS, MINB) angles_mma_kernel(AngleArgs
                 if (valid) {
                     int a, r, d;
                     rs_split_key(p.det_key[o], a, r, d);
-                    const float2* cell = frame + ((size_t)r * p.D + d) * M;
-                    if (AP == 8 && M == 8) {
-                        const float4* c4 = reinterpret_cast<const float4*>(cell);
+                    const float2* cell = frame + (size_t)r * M * p.D + d;
 #pragma unroll
-                        for (int m = 0; m < 4; ++m) {
-                            const float4 v = __ldg(c4 + m);
-                            s[2 * m] = make_float2(v.x, v.y);
-                            s[2 * m + 1] = make_float2(v.z, v.w);
-                        }
-                    } else {
-#pragma unroll
-                        for (int m = 0; m < AP; ++m) s[m] = (m < M) ? __ldg(cell + m) : make_float2(0.f, 0.f);
-                    }
+                    for (int m = 0; m < AP; ++m) s[m] = (m < M) ? __ldg(cell + (size_t)m * p.D) : make_float2(0.f, 0.f);
                     yv = atan2f(s[1].y * s[0].x - s[1].x * s[0].y, s[1].x * s[0].x + s[1].y * s[0].y);
                 } else {
 #pragma unroll
@@ -612,11 +593,11 @@ __global__ void __launch_bounds__(ANG_THREADS) angles_large_kernel(AngleArgs p) 
         const int mult = (int)(ld >> 16);
         int a, r, d;
         rs_split_key(p.det_key[o], a, r, d);
-        const float2* cell = frame + ((size_t)r * p.D + d) * M;
+        const float2* cell = frame + (size_t)r * M * p.D + d;
         __syncwarp();
         float e = 0.f;
         for (int m = lane; m < M; m += 32) {
-            const float2 x = __ldg(cell + m);
+            const float2 x = __ldg(cell + (size_t)m * p.D);
             s[m] = x;
             e = fmaf(x.x, x.x, fmaf(x.y, x.y, e));
         }
@@ -709,10 +690,10 @@ __global__ void signatures_f64_kernel(const float2* __restrict__ rds, const uint
     if (i >= n) return;
     int a, r, d;
     rs_split_key(keys[i], a, r, d);
-    const float2* cell = rds + (((size_t)frames[i] * R + r) * D + d) * A;
+    const float2* cell = rds + ((size_t)frames[i] * R + r) * A * D + d;
     double e = 0;
     for (int m = lane; m < A; m += 32) {
-        const float2 x = cell[m];
+        const float2 x = cell[(size_t)m * D];
         e += (double)x.x * x.x + (double)x.y * x.y;
     }
 #pragma unroll
@@ -720,7 +701,7 @@ __global__ void signatures_f64_kernel(const float2* __restrict__ rds, const uint
     // angle_estimation.py:86-88: divide by sqrt(power) only when power > 0
     const double sc = e > 0 ? sqrt(e) : 1.0;
     for (int m = lane; m < A; m += 32) {
-        const float2 x = cell[m];
+        const float2 x = cell[(size_t)m * D];
         out[(size_t)i * A + m] = make_double2((double)x.x / sc, (double)x.y / sc);
     }
 }

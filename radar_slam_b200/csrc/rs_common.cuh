@@ -41,6 +41,12 @@ __device__ __forceinline__ void rs_split_key(uint32_t k, int& a, int& r, int& d)
     d = (int)(k & 0xFFFu);
 }
 
+// RDS device layout: rds[F][R][A][D] ("range-major planes"): for every range bin the A antenna rows of D Doppler
+// cells follow each other.  Element (f, r, d, a); the A-channel snapshot of a cell is A elements at stride D.
+__device__ __forceinline__ size_t rs_rds_index(int f, int r, int d, int a, int R, int D, int A) {
+    return (((size_t)f * R + r) * A + a) * D + d;
+}
+
 static inline int rs_smem_optin_limit() {
     int dev = 0, v = 0;
     cudaGetDevice(&dev);

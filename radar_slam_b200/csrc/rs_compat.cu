@@ -5,27 +5,22 @@
 
 namespace {
 
-// 10 log10(|X|^2 + 1e-12) of the cell-major RDS, written in the reference layout [F][A][R][D]
+// 10 log10(|X|^2 + 1e-12) of the RDS rds[F][R][A][D], written in the reference layout [F][A][R][D]
 // (dechirp.py:235-238, 277).
-__global__ void power_db_kernel(const float2* __restrict__ rds, double* __restrict__ out, int A, long long cells) {
-    __shared__ double tile[32][33];
-    const long long f = blockIdx.z;
-    const long long cell0 = (long long)blockIdx.x * 32;
-    const int a0 = blockIdx.y * 32;
-    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-        const long long cell = cell0 + i;
-        const int a = a0 + threadIdx.x;
-        if (cell < cells && a < A) {
-            const float2 x = rds[(f * cells + cell) * A + a];
+__global__ void power_db_kernel(const float2* __restrict__ rds, double* __restrict__ out, int R, int A, int D,
+                                long long rows_total) {
+    // one CTA per Doppler row (f, r, a) -> out row (f, a, r)
+    for (long long row = blockIdx.x; row < rows_total; row += gridDim.x) {
+        const long long f = row / ((long long)R * A);
+        const long long rem = row - f * R * A;
+        const int r = (int)(rem / A), a = (int)(rem - (long long)r * A);
+        const float2* src = rds + row * D;
+        double* dst = out + ((f * A + a) * R + r) * D;
+        for (int d = threadIdx.x; d < D; d += blockDim.x) {
+            const float2 x = src[d];
             const double p = (double)x.x * x.x + (double)x.y * x.y;
-            tile[i][threadIdx.x] = 10.0 * log10(p + 1e-12);
+            dst[d] = 10.0 * log10(p + 1e-12);
         }
-    }
-    __syncthreads();
-    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-        const int a = a0 + i;
-        const long long cell = cell0 + threadIdx.x;
-        if (cell < cells && a < A) out[(f * A + a) * cells + cell] = tile[threadIdx.x][i];
     }
 }
 
@@ -279,9 +274,9 @@ __global__ void robust_confidence_kernel(const double2* __restrict__ sig, const 
 
 extern "C" int rs_power_db_f64(const void* rds, double* out, int F, int A, int C, int S, void* stream) {
     RS_CHECK_ARG(rds && out && F > 0 && F <= 65535 && A > 0 && C > 0 && S > 0, "rs_power_db_f64: bad args");
-    const long long cells = (long long)S * C;
-    dim3 grid((unsigned)((cells + 31) / 32), (unsigned)((A + 31) / 32), (unsigned)F);
-    power_db_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>((const float2*)rds, out, A, cells);
+    const long long rows = (long long)F * S * A;
+    const unsigned grid = (unsigned)(rows < (1ll << 20) ? rows : (1ll << 20));
+    power_db_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>((const float2*)rds, out, S, A, C, rows);
     RS_CHECK_LAUNCH("rs_power_db_f64");
     return RS_OK;
 }

@@ -1,4 +1,4 @@
-// Peak detection on the cell-major RDS.
+// Peak detection on the RDS rds[F][R][A][D] (rs_common.cuh).
 //
 // Replaces SignalPreprocessor.extract_range_doppler_peaks (dechirp.py:215-278).  The reference
 // compares dB values; 10 log10(p + 1e-12) is monotone in p, so the local-maximum test and the
@@ -145,7 +145,7 @@ detect_kernel(const float2* __restrict__ rds, const uint8_t* __restrict__ gate, 
         const int r = r0 - 1 + rr, d = d0 - 1 + dd, a = a0 + ac;
         float p = -1.f;
         if (r >= 0 && r < R && d >= 0 && d < D && a < A) {
-            const float2 x = __ldg(frame + ((size_t)r * D + d) * A + a);
+            const float2 x = __ldg(frame + ((size_t)r * A + a) * D + d);
             p = fmaf(x.x, x.x, x.y * x.y);
         }
         pw[i] = p;
@@ -236,7 +236,8 @@ detect_kernel(const float2* __restrict__ rds, const uint8_t* __restrict__ gate, 
 // ---------------------------------------------------------------------------------------------
 // Fast path: antenna octets (A % 8 == 0), tile = 16 range bins x 128 Doppler bins x 8 antennas.
 // 256 threads; thread = (Doppler bin, half of the tile's rows) and owns ALL 8 antennas of its cells, so
-// the detections of one cell are emitted together.  Loads are float4 (two antennas); the power plane is
+// the detections of one cell are emitted together.  A tile row is one contiguous 8 KB run of the RDS (8 antenna rows
+// of 128 cells); a warp loads 8 antennas x 4 consecutive cells per step and transposes into the power plane, which is
 // [row][doppler + 1][8] floats with the two antenna quads of a cell XOR-swizzled by bit 2 of the Doppler
 // index, which makes both the float2 stores of the load phase and the LDS.128 reads of the walk
 // conflict-free.
@@ -270,47 +271,43 @@ detect_a8_kernel(const float2* __restrict__ rds, const uint8_t* __restrict__ gat
         const int r = r0 - 1 + rr, d = side ? d0 + A8_TD : d0 - 1;
         float p = -1.f;
         if (r >= 0 && r < R && d >= 0 && d < D) {
-            const float2 x = __ldg(frame + ((size_t)r * D + d) * A + a0 + ac);
+            const float2 x = __ldg(frame + ((size_t)r * A + a0 + ac) * D + d);
             p = fmaf(x.x, x.x, x.y * x.y);
         }
         pw[a8_off(rr, side ? A8_TD + 1 : 0, ac >> 2) + (ac & 3)] = p;
     }
-    // ---- interior: each row is 128 cells x 4 float4 (two antennas each); 2 float4 per thread per row.
-    // Row-invariant address parts are hoisted; six rows (12 loads) are in flight per thread before the first use.
+    // ---- interior: a tile row is [8 antennas][128 cells] contiguous; lane = (antenna, cell mod 4), so a warp reads eight
+    // 32-byte sectors per step and its 32 powers land in 32 different banks of the [cell][antenna] plane.
+    // 4 cells per thread per row; row-invariant address parts are hoisted and six rows (24 loads) are in flight.
     {
-        const size_t row_f4 = (size_t)D * A / 2;                                    // float4 per RDS row
-        const float4* src[2];
-        float* dst[2];
+        const int lane = tid & 31, wid = tid >> 5;
+        const int la = lane >> 2, lc = lane & 3;                 // antenna, cell within the group of four
+        const size_t row_el = (size_t)D * A;                     // elements per RDS range row
+        const float2* src = frame + ((size_t)(a0 + la)) * D + d0 + wid * 4 + lc;
+        float* dst[4];
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const int i4 = tid + DET_THREADS * k;
-            const int cell = i4 >> 2, part = i4 & 3;
-            src[k] = reinterpret_cast<const float4*>(frame + ((size_t)d0 + cell) * A + a0) + part;
-            dst[k] = pw + a8_off(0, cell + 1, part >> 1) + (part & 1) * 2;
+        for (int k = 0; k < 4; ++k) {
+            const int cell = wid * 4 + lc + 32 * k;
+            dst[k] = pw + a8_off(0, cell + 1, la >> 2) + (la & 3);
         }
 #pragma unroll
         for (int g = 0; g < 3; ++g) {
             constexpr int NR = (A8_TR + 2) / 3;
-            float4 v[NR][2];
+            float2 v[NR][4];
 #pragma unroll
             for (int q = 0; q < NR; ++q) {
                 const int r = r0 - 1 + g * NR + q;
                 const bool ok = r >= 0 && r < R;
 #pragma unroll
-                for (int k = 0; k < 2; ++k)
-                    v[q][k] = ok ? __ldg(src[k] + (size_t)r * row_f4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int k = 0; k < 4; ++k) v[q][k] = ok ? __ldg(src + (size_t)r * row_el + 32 * k) : make_float2(0.f, 0.f);
             }
 #pragma unroll
             for (int q = 0; q < NR; ++q) {
                 const int rr = g * NR + q, r = r0 - 1 + rr;
                 const bool ok = r >= 0 && r < R;
 #pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    float2 p2;
-                    p2.x = ok ? fmaf(v[q][k].x, v[q][k].x, v[q][k].y * v[q][k].y) : -1.f;
-                    p2.y = ok ? fmaf(v[q][k].z, v[q][k].z, v[q][k].w * v[q][k].w) : -1.f;
-                    *reinterpret_cast<float2*>(dst[k] + rr * A8_W) = p2;
-                }
+                for (int k = 0; k < 4; ++k)
+                    dst[k][rr * A8_W] = ok ? fmaf(v[q][k].x, v[q][k].x, v[q][k].y * v[q][k].y) : -1.f;
             }
         }
     }

@@ -2,7 +2,7 @@
 //
 //   rs_range_fft   : cube[F][A][C][S] * table[S] -> FFT over S -> zero bin 0 (DC removal) ->
 //                    range fftshift -> mid[F][S][A][C]           (dechirp.py:139,108,120,205,208,211)
-//   rs_doppler_fft : mid[F][S][A][C] -> FFT over C -> Doppler fftshift -> rds[F][S][C][A]
+//   rs_doppler_fft : mid[F][S][A][C] -> FFT over C -> Doppler fftshift -> rds[F][S][A][C]  (same row order)
 //
 // Both are shared-memory Stockham autosort kernels: a CTA stages a block of rows, runs the radix
 // passes out of a host-built fp64-accurate twiddle table, and stores with the transpose fused so
@@ -175,7 +175,7 @@ range_fft_kernel(const float2* __restrict__ cube, const float2* __restrict__ tab
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 doppler_fft_kernel(const float2* __restrict__ mid, const float2* __restrict__ tw_g, float2* __restrict__ rds,
-                   FftPlan plan, int A, int C, int NB, long long nrows_total) {
+                   FftPlan plan, int C, int NB, long long nrows_total) {
     extern __shared__ float2 smem[];
     const int ld = C + 1;
     float2* tw = smem;
@@ -195,53 +195,28 @@ doppler_fft_kernel(const float2* __restrict__ mid, const float2* __restrict__ tw
 
     const int half = C / 2;
     for (int i = threadIdx.x; i < nb * C; i += blockDim.x) {
-        const int k = i / nb, b = i - k * nb;
-        const long long gr = row0 + b;
-        const long long fs = gr / A;
-        const int a = (int)(gr - fs * A);
+        const int b = i / C, k = i - b * C;              // lanes along the Doppler axis: coalesced rows
         int p = k + half;
         if (p >= C) p -= C;
-        rds[(fs * C + p) * A + a] = res[b * ld + k];
+        rds[(row0 + b) * C + p] = res[b * ld + k];
     }
 }
 
 // ---------------------------------------------------------------------------------------------
 // layout converters for the legacy adapters
 // ---------------------------------------------------------------------------------------------
-__global__ void cell_to_ref_kernel(const float2* __restrict__ rds, float2* __restrict__ out, int A, long long cells) {
-    // rds [F][cells][A] -> out [F][A][cells]; tile transpose through shared memory
-    __shared__ float2 tile[32][33];
-    const long long f = blockIdx.z;
-    const long long cell0 = (long long)blockIdx.x * 32;
-    const int a0 = blockIdx.y * 32;
-    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-        long long cell = cell0 + i;
-        int a = a0 + threadIdx.x;
-        if (cell < cells && a < A) tile[i][threadIdx.x] = rds[(f * cells + cell) * A + a];
-    }
-    __syncthreads();
-    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-        int a = a0 + i;
-        long long cell = cell0 + threadIdx.x;
-        if (cell < cells && a < A) out[(f * A + a) * cells + cell] = tile[threadIdx.x][i];
-    }
-}
-
-__global__ void ref_to_cell_kernel(const float2* __restrict__ in, float2* __restrict__ rds, int A, long long cells) {
-    __shared__ float2 tile[32][33];
-    const long long f = blockIdx.z;
-    const long long cell0 = (long long)blockIdx.x * 32;
-    const int a0 = blockIdx.y * 32;
-    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-        int a = a0 + i;
-        long long cell = cell0 + threadIdx.x;
-        if (cell < cells && a < A) tile[i][threadIdx.x] = in[(f * A + a) * cells + cell];
-    }
-    __syncthreads();
-    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-        long long cell = cell0 + i;
-        int a = a0 + threadIdx.x;
-        if (cell < cells && a < A) rds[(f * cells + cell) * A + a] = tile[threadIdx.x][i];
+// rds [F][S][A][C] <-> reference layout [F][A][S][C]: a permutation of whole Doppler rows (C contiguous elements)
+__global__ void permute_rows_kernel(const float2* __restrict__ in, float2* __restrict__ out, int n1, int n2, int C,
+                                    long long rows_total) {
+    // in rows are indexed (f, i1, i2) with i1 < n1, i2 < n2; out rows (f, i2, i1)
+    const long long per_f = (long long)n1 * n2;
+    for (long long row = blockIdx.x; row < rows_total; row += gridDim.x) {
+        const long long f = row / per_f;
+        const long long rem = row - f * per_f;
+        const int i1 = (int)(rem / n2), i2 = (int)(rem - (long long)i1 * n2);
+        const float2* src = in + row * C;
+        float2* dst = out + ((f * n2 + i2) * n1 + i1) * C;
+        for (int c = threadIdx.x; c < C; c += blockDim.x) dst[c] = src[c];
     }
 }
 
@@ -262,8 +237,7 @@ static int launch_range_pow2(const float2* cube, const float2* table, const floa
 }
 
 template <int R1, int R2, int NB>
-static int launch_doppler_pow2(const float2* mid, const float2* tw, float2* rds, int A, int lanes_a, long long nrows,
-                               cudaStream_t st) {
+static int launch_doppler_pow2(const float2* mid, const float2* tw, float2* rds, long long nrows, cudaStream_t st) {
     using G = pow2::Geo<R1, R2>;
     const size_t smem = (size_t)(G::N + NB * G::ROWP_DOPP) * sizeof(float2);
     auto kern = pow2::doppler_fft_pow2_kernel<R1, R2, NB>;
@@ -272,7 +246,7 @@ static int launch_doppler_pow2(const float2* mid, const float2* tw, float2* rds,
     if (nblocks >= (1ll << 31)) return 1;
     const int per_sm = (int)((size_t)rs_smem_optin_limit() / smem);
     const long long grid = std::min<long long>(nblocks, (long long)rs_sm_count() * std::max(1, std::min(per_sm, 6)));
-    kern<<<(unsigned)grid, pow2::THREADS, smem, st>>>(mid, tw, rds, A, lanes_a, nrows, (int)nblocks);
+    kern<<<(unsigned)grid, pow2::THREADS, smem, st>>>(mid, tw, rds, nrows, (int)nblocks);
     return 0;
 }
 
@@ -331,20 +305,18 @@ extern "C" int rs_doppler_fft(const void* mid, const void* twiddle_c, void* rds,
     RS_CHECK_ARG(mid && twiddle_c && rds, "rs_doppler_fft: null pointer");
     RS_CHECK_ARG(F > 0 && A > 0 && A <= RS_MAX_ANTENNAS && S > 0 && C > 0 && C <= RS_MAX_DOPPLER_BINS,
                  "rs_doppler_fft: bad dims");
-    {
-        const int lanes_a = (A % 32 == 0) ? 32 : (A == 16 || A == 8 || A == 4) ? A : 0;
-        if (lanes_a && (C == 64 || C == 128 || C == 256)) {
-            const long long nrows = (long long)F * S * A;
-            cudaStream_t st = (cudaStream_t)stream;
-            int rc = 1;
-            if (C == 256) rc = launch_doppler_pow2<16, 16, 32>((const float2*)mid, (const float2*)twiddle_c, (float2*)rds, A, lanes_a, nrows, st);
-            else if (C == 128 && !(getenv("RS_FFT_NB") && atoi(getenv("RS_FFT_NB")) == 64)) rc = /* NB=32 0.91 ms vs NB=64 1.04 ms */ launch_doppler_pow2<16, 8, 32>((const float2*)mid, (const float2*)twiddle_c, (float2*)rds, A, lanes_a, nrows, st);
-            else if (C == 128) rc = launch_doppler_pow2<16, 8, 64>((const float2*)mid, (const float2*)twiddle_c, (float2*)rds, A, lanes_a, nrows, st);
-            else rc = launch_doppler_pow2<8, 8, 64>((const float2*)mid, (const float2*)twiddle_c, (float2*)rds, A, lanes_a, nrows, st);
-            if (rc == 0) {
-                RS_CHECK_LAUNCH("rs_doppler_fft(pow2)");
-                return RS_OK;
-            }
+    if (C == 64 || C == 128 || C == 256) {
+        const long long nrows = (long long)F * S * A;
+        cudaStream_t st = (cudaStream_t)stream;
+        const float2 *m = (const float2*)mid, *tw = (const float2*)twiddle_c;
+        int rc = 1;
+        if (C == 256) rc = launch_doppler_pow2<16, 16, 32>(m, tw, (float2*)rds, nrows, st);
+        else if (C == 128 && !(getenv("RS_FFT_NB") && atoi(getenv("RS_FFT_NB")) == 64)) rc = launch_doppler_pow2<16, 8, 32>(m, tw, (float2*)rds, nrows, st);
+        else if (C == 128) rc = launch_doppler_pow2<16, 8, 64>(m, tw, (float2*)rds, nrows, st);
+        else rc = launch_doppler_pow2<8, 8, 64>(m, tw, (float2*)rds, nrows, st);
+        if (rc == 0) {
+            RS_CHECK_LAUNCH("rs_doppler_fft(pow2)");
+            return RS_OK;
         }
     }
     FftPlan plan;
@@ -362,25 +334,25 @@ extern "C" int rs_doppler_fft(const void* mid, const void* twiddle_c, void* rds,
     const long long blocks = (nrows + NB - 1) / NB;
     RS_CHECK_ARG(blocks < (1ll << 31), "rs_doppler_fft: too many blocks");
     doppler_fft_kernel<<<(unsigned)blocks, 256, need(NB), (cudaStream_t)stream>>>(
-        (const float2*)mid, (const float2*)twiddle_c, (float2*)rds, plan, A, C, NB, nrows);
+        (const float2*)mid, (const float2*)twiddle_c, (float2*)rds, plan, C, NB, nrows);
     RS_CHECK_LAUNCH("rs_doppler_fft");
     return RS_OK;
 }
 
 extern "C" int rs_rds_to_reference_layout(const void* rds, void* out, int F, int A, int C, int S, void* stream) {
     RS_CHECK_ARG(rds && out && F > 0 && A > 0 && C > 0 && S > 0, "rs_rds_to_reference_layout: bad args");
-    const long long cells = (long long)S * C;
-    dim3 grid((unsigned)((cells + 31) / 32), (unsigned)((A + 31) / 32), (unsigned)F);
-    cell_to_ref_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>((const float2*)rds, (float2*)out, A, cells);
+    const long long rows = (long long)F * S * A;
+    const unsigned grid = (unsigned)std::min<long long>(rows, (long long)rs_sm_count() * 16);
+    permute_rows_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>((const float2*)rds, (float2*)out, S, A, C, rows);
     RS_CHECK_LAUNCH("rs_rds_to_reference_layout");
     return RS_OK;
 }
 
 extern "C" int rs_rds_from_reference_layout(const void* rds_ref, void* out, int F, int A, int C, int S, void* stream) {
     RS_CHECK_ARG(rds_ref && out && F > 0 && A > 0 && C > 0 && S > 0, "rs_rds_from_reference_layout: bad args");
-    const long long cells = (long long)S * C;
-    dim3 grid((unsigned)((cells + 31) / 32), (unsigned)((A + 31) / 32), (unsigned)F);
-    ref_to_cell_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>((const float2*)rds_ref, (float2*)out, A, cells);
+    const long long rows = (long long)F * S * A;
+    const unsigned grid = (unsigned)std::min<long long>(rows, (long long)rs_sm_count() * 16);
+    permute_rows_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>((const float2*)rds_ref, (float2*)out, A, S, C, rows);
     RS_CHECK_LAUNCH("rs_rds_from_reference_layout");
     return RS_OK;
 }

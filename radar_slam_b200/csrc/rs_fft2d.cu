@@ -1,0 +1,171 @@
+// Fused dechirp + window + range FFT + Doppler FFT of one (frame, antenna) plane in ONE kernel, the plane kept
+// on chip in the shared memory of a thread-block cluster (dechirp.py:143-213).
+//
+// A 256 x 128 complex64 plane is 256 KB -- more than one SM's shared memory, so the two-kernel path
+// (rs_range_fft -> mid -> rs_doppler_fft) writes and re-reads it through HBM: 32 B per cell for a transform whose
+// input and output are 16 B per cell.  Here NC CTAs of a cluster share the plane through distributed shared memory:
+//   range phase    CTA q reads chirps [q C/NC, (q+1) C/NC) from HBM (coalesced, streamed once), multiplies by
+//                  conj(ref)*window, runs the two register passes of the range FFT (rs_fft_pow2.cuh) and stores
+//                  range bin p of chirp c into M[p mod S/NC][c] of the CTA that OWNS range bins
+//                  [r S/NC, (r+1) S/NC) -- a remote (DSMEM) store for the bins of the peer, lanes along chirps.
+//   cluster.sync   every owner now holds all C chirps of its S/NC range bins.
+//   Doppler phase  in place in M: pass 1 (radix CR1 in registers, inter-pass twiddle) writes each row back through
+//                  a rotation that makes the pass-2 reads conflict free; pass 2 (radix CR2) stores
+//                  rds[f][p][a][.] with the Doppler fftshift -- 128-byte runs.
+// HBM traffic: 8 B in + 8 B out per cell, the algorithmic minimum of the 2-D transform.
+#include <cooperative_groups.h>
+#include <cstdlib>
+#include "rs_common.cuh"
+#include "rs_fft_pow2.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace {
+
+constexpr int F2_THREADS = 512;
+
+template <int SR1, int SR2, int CR1, int CR2, int NC>
+struct Fused {
+    static constexpr int S = SR1 * SR2, C = CR1 * CR2;
+    static constexpr int CB = F2_THREADS / SR2;            // chirps per range batch: one pass-1 item per thread
+    static constexpr int RP = pow2::Geo<SR1, SR2>::ROWP_RANGE;
+    static constexpr int K1P = pow2::Geo<SR1, SR2>::K1P;
+    static constexpr int ROWS = S / NC;                    // range bins owned by one CTA
+    static constexpr int CPC = C / NC;                     // chirps one CTA transforms in the range phase
+    static constexpr int MP = C + 8;                       // pitch of a row of M (complex): 8 (mod 16)
+    static constexpr size_t SMEM = (size_t)(2 * S + C + CB * RP + ROWS * MP) * sizeof(float2);
+    static_assert(CPC % CB == 0, "range batches must tile the CTA's chirps");
+    static_assert(CB * SR1 == F2_THREADS, "one range pass-2 item per thread");
+    static_assert(CR2 == 8 && CR1 == 16, "the in-place rotation below is laid out for a 16 x 8 Doppler split");
+    static_assert((ROWS * CR2) % F2_THREADS == 0 && (ROWS * CR1) % F2_THREADS == 0, "uniform Doppler loops");
+};
+
+template <int SR1, int SR2, int CR1, int CR2, int NC>
+__global__ void __cluster_dims__(NC, 1, 1) __launch_bounds__(F2_THREADS, 1)
+fft2d_cluster_kernel(const float2* __restrict__ cube, const float2* __restrict__ table,
+                     const float2* __restrict__ tw_s_g, const float2* __restrict__ tw_c_g, float2* __restrict__ rds,
+                     int A, int C_total, int chirp0, int dc_removal) {
+    using P = Fused<SR1, SR2, CR1, CR2, NC>;
+    constexpr int S = P::S, C = P::C;
+    extern __shared__ float2 sm[];
+    float2* tabs = sm;                       // [S] conj(ref) * window
+    float2* tw1s = tabs + S;                 // [SR1][SR2] range inter-pass twiddles
+    float2* tw1c = tw1s + S;                 // [CR1][CR2] Doppler inter-pass twiddles
+    float2* Y = tw1c + C;                    // [CB][RP]   range pass-1 -> pass-2 exchange
+    float2* M = Y + P::CB * P::RP;           // [ROWS][MP] this CTA's range bins x all chirps
+    cg::cluster_group cluster = cg::this_cluster();
+    const int q = (int)cluster.block_rank();
+    const int tid = threadIdx.x;
+    for (int i = tid; i < S; i += F2_THREADS) {
+        tabs[i] = table[i];
+        const int k1 = i / SR2, t = i - k1 * SR2;
+        tw1s[i] = tw_s_g[(k1 * t) % S];
+    }
+    for (int i = tid; i < C; i += F2_THREADS) {
+        const int k1 = i / CR2, t = i - k1 * CR2;
+        tw1c[i] = tw_c_g[(k1 * t) % C];
+    }
+    cluster.sync();                          // every CTA of the cluster is resident before the first remote store
+
+    const int plane = blockIdx.x / NC;       // f * A + a
+    const int f = plane / A, a = plane - f * A;
+    const float2* src = cube + ((size_t)plane * C_total + chirp0 + q * P::CPC) * S;
+
+    // ---------------- range phase
+    for (int b0 = 0; b0 < P::CPC; b0 += P::CB) {
+        {
+            const int row = tid / SR2, t = tid - row * SR2;
+            const float2* x = src + (size_t)(b0 + row) * S + t;
+            float2 v[SR1];
+#pragma unroll
+            for (int j = 0; j < SR1; ++j) v[j] = __ldcs(x + SR2 * j);              // streamed once: evict-first
+#pragma unroll
+            for (int j = 0; j < SR1; ++j) v[j] = cmul(v[j], tabs[t + SR2 * j]);
+            pow2::dft<SR1>(v);
+            float2* y = Y + row * P::RP + t;
+#pragma unroll
+            for (int k1 = 0; k1 < SR1; ++k1) y[k1 * P::K1P] = (k1 == 0) ? v[0] : cmul(v[k1], tw1s[k1 * SR2 + t]);
+        }
+        __syncthreads();
+        {
+            const int row = tid % P::CB, k1 = tid / P::CB;                          // lanes along chirps
+            const float2* y = Y + row * P::RP + k1 * P::K1P;
+            float2 u[SR2];
+#pragma unroll
+            for (int n2 = 0; n2 < SR2; ++n2) u[n2] = y[n2];
+            pow2::dft<SR2>(u);
+            const int chirp = q * P::CPC + b0 + row;
+#pragma unroll
+            for (int k2 = 0; k2 < SR2; ++k2) {
+                const int k = k1 + SR1 * k2;
+                const float2 val = (dc_removal && k == 0) ? make_float2(0.f, 0.f) : u[k2];    // mean removal, dechirp.py:120
+                const int p = (k + S / 2) & (S - 1);                                           // range fftshift
+                const int owner = p / P::ROWS, pl = p - owner * P::ROWS;
+                float2* dstM = cluster.map_shared_rank(M, owner);
+                dstM[pl * P::MP + chirp] = val;
+            }
+        }
+        __syncthreads();
+    }
+    cluster.sync();                          // all chirps of this CTA's range bins have arrived
+
+    // ---------------- Doppler phase, in place in M
+    for (int it = tid; it < P::ROWS * CR2; it += F2_THREADS) {
+        const int row = it / CR2, t = it - row * CR2;                               // the CR2 lanes of a row share a warp
+        float2* m = M + row * P::MP;
+        float2 v[CR1];
+#pragma unroll
+        for (int j = 0; j < CR1; ++j) v[j] = m[t + CR2 * j];
+        __syncwarp();                                                               // the row is read before it is rewritten
+        pow2::dft<CR1>(v);
+#pragma unroll
+        for (int k1 = 0; k1 < CR1; ++k1)
+            m[k1 * CR2 + ((t + (k1 >> 1)) & (CR2 - 1))] = (k1 == 0) ? v[0] : cmul(v[k1], tw1c[k1 * CR2 + t]);
+    }
+    __syncthreads();
+    for (int it = tid; it < P::ROWS * CR1; it += F2_THREADS) {
+        const int row = it / CR1, k1 = it - row * CR1;
+        const float2* m = M + row * P::MP + k1 * CR2;
+        float2 u[CR2];
+#pragma unroll
+        for (int n2 = 0; n2 < CR2; ++n2) u[n2] = m[(n2 + (k1 >> 1)) & (CR2 - 1)];
+        pow2::dft<CR2>(u);
+        const int p = q * P::ROWS + row;
+        float2* dst = rds + (((size_t)f * S + p) * A + a) * C;
+#pragma unroll
+        for (int k2 = 0; k2 < CR2; ++k2) __stcs(dst + ((k1 + CR1 * k2 + C / 2) & (C - 1)), u[k2]);   // Doppler fftshift
+    }
+}
+
+}  // namespace
+
+extern "C" int rs_range_fft(const void* cube, const void* table, const void* twiddle_s, void* mid, int F, int A,
+                            int C_total, int chirp0, int C_used, int S, int dc_removal, void* stream);
+extern "C" int rs_doppler_fft(const void* mid, const void* twiddle_c, void* rds, int F, int A, int C, int S,
+                              void* stream);
+
+extern "C" int rs_range_doppler_fft(const void* cube, const void* table, const void* twiddle_s, const void* twiddle_c,
+                                    void* mid_ws, void* rds, int F, int A, int C_total, int chirp0, int C_used, int S,
+                                    int dc_removal, void* stream) {
+    RS_CHECK_ARG(cube && table && twiddle_s && twiddle_c && rds, "rs_range_doppler_fft: null pointer");
+    RS_CHECK_ARG(F > 0 && A > 0 && A <= RS_MAX_ANTENNAS && S > 0 && C_used > 0 && chirp0 >= 0 && chirp0 + C_used <= C_total,
+                 "rs_range_doppler_fft: bad dims");
+    const char* env = getenv("RS_FUSED_FFT");          // 0: force the two-kernel path
+    if (S == 256 && C_used == 128 && !(env && atoi(env) == 0)) {
+        using P = Fused<16, 16, 16, 8, 2>;
+        const long long ctas = (long long)F * A * 2;
+        if (P::SMEM <= (size_t)rs_smem_optin_limit() && ctas < (1ll << 31)) {
+            auto kern = fft2d_cluster_kernel<16, 16, 16, 8, 2>;
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P::SMEM);
+            kern<<<(unsigned)ctas, F2_THREADS, P::SMEM, (cudaStream_t)stream>>>(
+                (const float2*)cube, (const float2*)table, (const float2*)twiddle_s, (const float2*)twiddle_c,
+                (float2*)rds, A, C_total, chirp0, dc_removal);
+            RS_CHECK_LAUNCH("rs_range_doppler_fft(cluster)");
+            return RS_OK;
+        }
+    }
+    RS_CHECK_ARG(mid_ws != nullptr, "rs_range_doppler_fft: this shape needs the mid workspace");
+    int rc = rs_range_fft(cube, table, twiddle_s, mid_ws, F, A, C_total, chirp0, C_used, S, dc_removal, stream);
+    if (rc != RS_OK) return rc;
+    return rs_doppler_fft(mid_ws, twiddle_c, rds, F, A, C_used, S, stream);
+}

@@ -7,7 +7,7 @@
 //         X[k1 + R1 k2] straight to global memory.  The lane -> (row, k1) map of pass 2 is chosen per
 //         kernel so that the TRANSPOSED store of each stage is coalesced:
 //           range stage   lanes = 32 consecutive chirps            -> mid[f][s][a][c..c+31]   (256 B runs)
-//           Doppler stage lanes = (antenna, 4 consecutive k1)      -> rds[f][s][k..k+3][a]    (256 B runs, A = 8)
+//           Doppler stage lanes = 16 consecutive k1 of a row       -> rds[f][s][a][k..k+15]   (128 B runs)
 // One shared-memory round trip per element, no staging copies.
 #pragma once
 #include "rs_common.cuh"
@@ -91,7 +91,7 @@ struct Geo {
     static constexpr int N = R1 * R2;
     static constexpr int K1P = R2 + 1;            // pitch of one k1 line (complex); odd -> conflict-free pass-2 reads
     static constexpr int ROWP_RANGE = R1 * K1P + ((R1 * K1P) % 2 == 0 ? 1 : 0);    // odd: lanes along rows
-    static constexpr int ROWP_DOPP = R1 * K1P + ((18 - (R1 * K1P) % 16) % 16);     // == 2 (mod 16): lanes (a, k1)
+    static constexpr int ROWP_DOPP = ROWP_RANGE;                                    // lanes (row pair, k1)
 };
 
 // ---- pass 1 for `nrows` rows whose element (row, n) is at src[row * row_stride + n] -------------
@@ -166,12 +166,13 @@ range_fft_pow2_kernel(const float2* __restrict__ cube, const float2* __restrict_
 }
 
 // ---------------------------------------------------------------------------------------------
-// Doppler stage: rows of mid are (f, s, a) flattened, C contiguous; CTA = NB rows (NB % A == 0 or A % NB == 0)
+// Doppler stage: rows of mid are (f, s, a) flattened, C contiguous; the RDS keeps that row order (rds[F][S][A][C]),
+// so row g of mid becomes row g of the RDS.  CTA = NB rows.
 // ---------------------------------------------------------------------------------------------
 template <int R1, int R2, int NB>
 __global__ void __launch_bounds__(THREADS)
-doppler_fft_pow2_kernel(const float2* __restrict__ mid, const float2* __restrict__ tw_g, float2* __restrict__ rds, int A,
-                        int lanes_a, long long nrows_total, int nblocks) {
+doppler_fft_pow2_kernel(const float2* __restrict__ mid, const float2* __restrict__ tw_g, float2* __restrict__ rds,
+                        long long nrows_total, int nblocks) {
     using G = Geo<R1, R2>;
     constexpr int C = G::N, RP = G::ROWP_DOPP;
     extern __shared__ float2 sm[];
@@ -182,33 +183,22 @@ doppler_fft_pow2_kernel(const float2* __restrict__ mid, const float2* __restrict
         tw1[i] = tw_g[(k1 * t) % C];
     }
     __syncthreads();
-    const int kl = 32 / lanes_a;                                     // consecutive k1 per warp
     for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
         const long long row0 = (long long)blk * NB;
         const int nb = (int)min((long long)NB, nrows_total - row0);
         pass1<R1, R2, false>(mid + row0 * C, C, nb, RP, nullptr, tw1, Y);
         __syncthreads();
-        // item -> (a_l, k1lo) inside the warp, (row group, k1hi) across warps
-        const int groups = nb / lanes_a;                             // groups of lanes_a consecutive rows (antennas)
-        for (int it = threadIdx.x; it < groups * 32 * (R1 / kl); it += THREADS) {
-            const int lane = it & 31, w = it >> 5;
-            const int a_l = lane % lanes_a, k1lo = lane / lanes_a;
-            const int grp = w % groups, k1 = (w / groups) * kl + k1lo;
-            const int b = grp * lanes_a + a_l;
+        // item = (row, k1): R1 consecutive lanes share a row, so every k2 stores R1 consecutive Doppler bins
+        for (int it = threadIdx.x; it < nb * R1; it += THREADS) {
+            const int b = it / R1, k1 = it - b * R1;
             const float2* y = Y + b * RP + k1 * G::K1P;
             float2 u[R2];
 #pragma unroll
             for (int n2 = 0; n2 < R2; ++n2) u[n2] = y[n2];
             dft<R2>(u);
-            const long long gr = row0 + b;
-            const long long fs = gr / A;
-            const int a = (int)(gr - fs * A);
-            float2* dst = rds + fs * C * A + a;
+            float2* dst = rds + (row0 + b) * C;
 #pragma unroll
-            for (int k2 = 0; k2 < R2; ++k2) {
-                const int p = (k1 + R1 * k2 + C / 2) & (C - 1);        // Doppler fftshift
-                dst[(size_t)p * A] = u[k2];
-            }
+            for (int k2 = 0; k2 < R2; ++k2) dst[(k1 + R1 * k2 + C / 2) & (C - 1)] = u[k2];      // Doppler fftshift
         }
         __syncthreads();
     }

@@ -417,9 +417,12 @@ recheck_angles_kernel(CubeView v, AngleFix q, int32_t* __restrict__ work_idx, in
         const int k = (int)(ldj >> 16);
         int a, r, d;
         rs_split_key(q.det_key[o], a, r, d);
-        const float2* cell = q.rds + (((size_t)f * q.R + r) * q.D + d) * A;
+        const float2* cell = q.rds + ((size_t)f * q.R + r) * A * q.D + d;
         __syncwarp();
-        for (int m = lane; m < A; m += 32) sw[m] = make_double2((double)cell[m].x, (double)cell[m].y);
+        for (int m = lane; m < A; m += 32) {
+            const float2 x = cell[(size_t)m * q.D];
+            sw[m] = make_double2((double)x.x, (double)x.y);
+        }
         __syncwarp();
         double energy = 0;
         for (int m = 0; m < A; ++m) energy += sw[m].x * sw[m].x + sw[m].y * sw[m].y;

@@ -204,7 +204,7 @@ class FramePipeline:
     # ------------------------------------------------------------------ stages
     def range_doppler(self, cube: torch.Tensor, chirp_subset: Optional[Tuple[int, int]] = None,
                       out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """cube complex64 [F, A, C, S] on the device -> cell-major RDS complex64 [F, S, C', A]."""
+        """cube complex64 [F, A, C, S] on the device -> RDS complex64 [F, S, A, C'] (range-major planes)."""
         assert cube.is_cuda and cube.dtype == torch.complex64 and cube.dim() == 4 and cube.is_contiguous()
         F, A, C, S = cube.shape
         c0, c1 = (0, C) if chirp_subset is None else chirp_subset
@@ -214,11 +214,15 @@ class FramePipeline:
             raise ValueError("empty chirp subset")
         tab, tw_s, tw_c = self._fft_tables(S, Cu)[:3]
         mid = self._buf("mid", (F, S, A, Cu), torch.complex64)
-        rds = out if out is not None else torch.empty((F, S, Cu, A), dtype=torch.complex64, device=self.device)
+        rds = out if out is not None else torch.empty((F, S, A, Cu), dtype=torch.complex64, device=self.device)
         st = self.stream
-        self._call("rs_range_fft", cube.data_ptr(), tab.data_ptr(), tw_s.data_ptr(), mid.data_ptr(),
-                   F, A, C, c0, Cu, S, int(self.cfg.dc_removal), st)
-        self._call("rs_doppler_fft", mid.data_ptr(), tw_c.data_ptr(), rds.data_ptr(), F, A, Cu, S, st)
+        if os.environ.get("RS_SPLIT_FFT") == "1":       # the two stages as separate calls (per-stage timing, tests)
+            self._call("rs_range_fft", cube.data_ptr(), tab.data_ptr(), tw_s.data_ptr(), mid.data_ptr(),
+                       F, A, C, c0, Cu, S, int(self.cfg.dc_removal), st)
+            self._call("rs_doppler_fft", mid.data_ptr(), tw_c.data_ptr(), rds.data_ptr(), F, A, Cu, S, st)
+        else:
+            self._call("rs_range_doppler_fft", cube.data_ptr(), tab.data_ptr(), tw_s.data_ptr(), tw_c.data_ptr(),
+                       mid.data_ptr(), rds.data_ptr(), F, A, C, c0, Cu, S, int(self.cfg.dc_removal), st)
         return rds
 
     def seg_cap_for(self, R: int, D: int, A: int) -> Tuple[int, int]:
@@ -229,7 +233,7 @@ class FramePipeline:
     def detect(self, rds: torch.Tensor, threshold_db: Optional[float] = None, min_range: Optional[float] = None,
                max_range: Optional[float] = None, workspace=False) -> Detections:
         assert rds.is_cuda and rds.dtype == torch.complex64 and rds.dim() == 4 and rds.is_contiguous()
-        F, R, D, A = rds.shape
+        F, R, A, D = rds.shape
         c = self.cfg
         thr = tables.power_threshold(c.threshold_db if threshold_db is None else threshold_db)
         gate = self._gate(R, c.min_range if min_range is None else min_range, c.max_range if max_range is None else max_range)
@@ -429,7 +433,7 @@ class FramePipeline:
             if overlap and side_done[ci & 1] is not None:
                 main.wait_event(side_done[ci & 1])                 # workspace set free again
                 side_done[ci & 1] = None
-            rds = self.range_doppler(cube[lo:hi], out=None if keep else self._buf("rds" + tag, (n, S, C, A), torch.complex64))
+            rds = self.range_doppler(cube[lo:hi], out=None if keep else self._buf("rds" + tag, (n, S, A, C), torch.complex64))
             det = self.detect(rds, workspace=False if keep else tag)
             if overlap and pending is not None:
                 # the recheck of the previous chunk (HBM + fp64 bound) starts once this chunk's bandwidth-bound

@@ -36,7 +36,7 @@ def _run(p, cube64, thr, method, res=1.0, search_range=(-90, 90)):
 
 
 def _check_rds_and_keys(rds, det, ref, pk):
-    got = rds[0].permute(2, 0, 1).cpu().numpy()
+    got = rds[0].permute(1, 0, 2).cpu().numpy()
     assert np.abs(got - ref).max() <= 2e-6 * np.abs(ref).max()
     assert int(det.overflow.sum()) == 0
     d = det.frame(0)
@@ -143,7 +143,7 @@ def test_odd_and_non_power_of_two_sizes(S, C, A, win):
     np.random.seed(S + C + A)
     cube = orc.synthesize_frame(p, SCENE[:3]).astype(np.complex64)
     pipe, vel, rds, det, ref, pk = _run(p, cube, 12.0, "music", res=2.0)
-    got = rds[0].permute(2, 0, 1).cpu().numpy()
+    got = rds[0].permute(1, 0, 2).cpu().numpy()
     assert np.abs(got - ref).max() <= 3e-6 * np.abs(ref).max()
     d = det.frame(0)
     assert np.array_equal(d["key"], _keys(pk))
@@ -206,7 +206,7 @@ def test_plateau_overflow_is_reported_and_recoverable():
     cfg = RadarConfig(chirp_duration=6.4e-6, num_chirps=32, num_antennas=8, threshold_db=-20.0)
     pipe = FramePipeline(cfg)
     rds_ref = np.ones((8, 64, 32), dtype=np.complex64)
-    rds = torch.from_numpy(np.ascontiguousarray(rds_ref.transpose(1, 2, 0))[None]).cuda()
+    rds = torch.from_numpy(np.ascontiguousarray(rds_ref.transpose(1, 0, 2))[None]).cuda()      # [1, R, A, D]
     det = pipe.detect(rds)
     assert int(det.overflow.sum()) == 1
     tr, td, nt = _lib.detect_tiling(64, 32, 8)

@@ -49,7 +49,7 @@ def case(request):
 
 
 def test_rds_magnitudes(case):
-    rds = case["rds"][0].permute(2, 0, 1).cpu().numpy().astype(np.complex128)     # [S,C,A] -> [A,S,C]
+    rds = case["rds"][0].permute(1, 0, 2).cpu().numpy().astype(np.complex128)     # [S,A,C] -> [A,S,C]
     ref = case["rds_ref"]
     assert rds.shape == ref.shape
     mx = np.abs(ref).max()
