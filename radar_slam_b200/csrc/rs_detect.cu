@@ -276,38 +276,47 @@ detect_a8_kernel(const float2* __restrict__ rds, const uint8_t* __restrict__ gat
         }
         pw[a8_off(rr, side ? A8_TD + 1 : 0, ac >> 2) + (ac & 3)] = p;
     }
-    // ---- interior: a tile row is [8 antennas][128 cells] contiguous; lane = (antenna, cell mod 4), so a warp reads eight
-    // 32-byte sectors per step and its 32 powers land in 32 different banks of the [cell][antenna] plane.
-    // 4 cells per thread per row; row-invariant address parts are hoisted and six rows (24 loads) are in flight.
+    // ---- interior: a tile row is [8 antennas][128 cells] contiguous.  lane = (antenna a, cell pair j): one float4 load
+    // brings two consecutive cells of antenna a (a warp reads eight 64-byte runs); antenna-neighbour lanes then swap one
+    // power each, so that every lane holds (one cell, antennas 2m and 2m+1) and the plane is filled with conflict-free
+    // 64-bit stores.  2 loads per thread per row; row-invariant address parts hoisted, three rows in flight.
     {
         const int lane = tid & 31, wid = tid >> 5;
-        const int la = lane >> 2, lc = lane & 3;                 // antenna, cell within the group of four
-        const size_t row_el = (size_t)D * A;                     // elements per RDS range row
-        const float2* src = frame + ((size_t)(a0 + la)) * D + d0 + wid * 4 + lc;
-        float* dst[4];
+        const int la = lane >> 2, lj = lane & 3;
+        const size_t row_f4 = (size_t)D * A / 2;                                    // float4 per RDS range row
+        const float4* src[2];
+        float* dst[2];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int cell = wid * 4 + lc + 32 * k;
-            dst[k] = pw + a8_off(0, cell + 1, la >> 2) + (la & 3);
+        for (int k = 0; k < 2; ++k) {
+            const int cb = (wid + 8 * k) * 8 + 2 * lj;                              // first cell of this lane's pair
+            src[k] = reinterpret_cast<const float4*>(frame + ((size_t)(a0 + la)) * D + d0 + cb);
+            const int cell = cb + (la & 1);                                         // even antennas keep the first cell
+            dst[k] = pw + a8_off(0, cell + 1, la >> 2) + (la & 2);
         }
 #pragma unroll
-        for (int g = 0; g < 3; ++g) {
-            constexpr int NR = (A8_TR + 2) / 3;
-            float2 v[NR][4];
+        for (int g = 0; g < 6; ++g) {
+            constexpr int NR = (A8_TR + 2) / 6;
+            float4 v[NR][2];
 #pragma unroll
             for (int q = 0; q < NR; ++q) {
                 const int r = r0 - 1 + g * NR + q;
                 const bool ok = r >= 0 && r < R;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) v[q][k] = ok ? __ldg(src + (size_t)r * row_el + 32 * k) : make_float2(0.f, 0.f);
+                for (int k = 0; k < 2; ++k)
+                    v[q][k] = ok ? __ldg(src[k] + (size_t)r * row_f4) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
 #pragma unroll
             for (int q = 0; q < NR; ++q) {
                 const int rr = g * NR + q, r = r0 - 1 + rr;
                 const bool ok = r >= 0 && r < R;
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    dst[k][rr * A8_W] = ok ? fmaf(v[q][k].x, v[q][k].x, v[q][k].y * v[q][k].y) : -1.f;
+                for (int k = 0; k < 2; ++k) {
+                    const float p0 = ok ? fmaf(v[q][k].x, v[q][k].x, v[q][k].y * v[q][k].y) : -1.f;   // cell cb
+                    const float p1 = ok ? fmaf(v[q][k].z, v[q][k].z, v[q][k].w * v[q][k].w) : -1.f;   // cell cb + 1
+                    const float got = __shfl_xor_sync(0xffffffffu, (la & 1) ? p0 : p1, 4);            // antenna a ^ 1
+                    const float2 pr = (la & 1) ? make_float2(got, p1) : make_float2(p0, got);
+                    *reinterpret_cast<float2*>(dst[k] + rr * A8_W) = pr;
+                }
             }
         }
     }

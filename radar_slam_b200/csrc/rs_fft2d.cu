@@ -22,9 +22,7 @@ namespace cg = cooperative_groups;
 
 namespace {
 
-constexpr int F2_THREADS = 512;
-
-template <int SR1, int SR2, int CR1, int CR2, int NC>
+template <int SR1, int SR2, int CR1, int CR2, int NC, int F2_THREADS>
 struct Fused {
     static constexpr int S = SR1 * SR2, C = CR1 * CR2;
     static constexpr int CB = F2_THREADS / SR2;            // chirps per range batch: one pass-1 item per thread
@@ -40,12 +38,12 @@ struct Fused {
     static_assert((ROWS * CR2) % F2_THREADS == 0 && (ROWS * CR1) % F2_THREADS == 0, "uniform Doppler loops");
 };
 
-template <int SR1, int SR2, int CR1, int CR2, int NC>
-__global__ void __cluster_dims__(NC, 1, 1) __launch_bounds__(F2_THREADS, 1)
+template <int SR1, int SR2, int CR1, int CR2, int NC, int F2_THREADS, int MINB>
+__global__ void __cluster_dims__(NC, 1, 1) __launch_bounds__(F2_THREADS, MINB)
 fft2d_cluster_kernel(const float2* __restrict__ cube, const float2* __restrict__ table,
                      const float2* __restrict__ tw_s_g, const float2* __restrict__ tw_c_g, float2* __restrict__ rds,
                      int A, int C_total, int chirp0, int dc_removal) {
-    using P = Fused<SR1, SR2, CR1, CR2, NC>;
+    using P = Fused<SR1, SR2, CR1, CR2, NC, F2_THREADS>;
     constexpr int S = P::S, C = P::C;
     extern __shared__ float2 sm[];
     float2* tabs = sm;                       // [S] conj(ref) * window
@@ -152,14 +150,27 @@ extern "C" int rs_range_doppler_fft(const void* cube, const void* table, const v
                  "rs_range_doppler_fft: bad dims");
     const char* env = getenv("RS_FUSED_FFT");          // 0: force the two-kernel path
     if (S == 256 && C_used == 128 && !(env && atoi(env) == 0)) {
-        using P = Fused<16, 16, 16, 8, 2>;
-        const long long ctas = (long long)F * A * 2;
-        if (P::SMEM <= (size_t)rs_smem_optin_limit() && ctas < (1ll << 31)) {
-            auto kern = fft2d_cluster_kernel<16, 16, 16, 8, 2>;
-            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P::SMEM);
-            kern<<<(unsigned)ctas, F2_THREADS, P::SMEM, (cudaStream_t)stream>>>(
-                (const float2*)cube, (const float2*)table, (const float2*)twiddle_s, (const float2*)twiddle_c,
-                (float2*)rds, A, C_total, chirp0, dc_removal);
+        const char* nc_env = getenv("RS_FUSED_NC");    // tuning knob: CTAs per cluster (2, 4 or 8)
+        const int nc = nc_env ? atoi(nc_env) : 4;       // measured on B200 (1k frames 256x128x8): 2: 1.63 ms, 4: 1.53, 8: 1.54
+        int launched = 0;
+#define LAUNCH_F2D(NC, THREADS, MINB)                                                                                   \
+    do {                                                                                                                \
+        using P = Fused<16, 16, 16, 8, NC, THREADS>;                                                                    \
+        const long long ctas = (long long)F * A * NC;                                                                   \
+        if (P::SMEM <= (size_t)rs_smem_optin_limit() && ctas < (1ll << 31)) {                                           \
+            auto kern = fft2d_cluster_kernel<16, 16, 16, 8, NC, THREADS, MINB>;                                         \
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P::SMEM);                      \
+            kern<<<(unsigned)ctas, THREADS, P::SMEM, (cudaStream_t)stream>>>(                                           \
+                (const float2*)cube, (const float2*)table, (const float2*)twiddle_s, (const float2*)twiddle_c,          \
+                (float2*)rds, A, C_total, chirp0, dc_removal);                                                          \
+            launched = 1;                                                                                               \
+        }                                                                                                               \
+    } while (0)
+        if (nc == 8) LAUNCH_F2D(8, 256, 3);
+        else if (nc == 4) LAUNCH_F2D(4, 256, 2);
+        else LAUNCH_F2D(2, 512, 1);
+#undef LAUNCH_F2D
+        if (launched) {
             RS_CHECK_LAUNCH("rs_range_doppler_fft(cluster)");
             return RS_OK;
         }
