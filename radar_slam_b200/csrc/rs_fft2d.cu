@@ -35,7 +35,8 @@ struct Fused {
     static_assert(CPC % CB == 0, "range batches must tile the CTA's chirps");
     static_assert(CB * SR1 == F2_THREADS, "one range pass-2 item per thread");
     static_assert(CR2 == 8 && CR1 == 16, "the in-place rotation below is laid out for a 16 x 8 Doppler split");
-    static_assert((ROWS * CR2) % F2_THREADS == 0 && (ROWS * CR1) % F2_THREADS == 0, "uniform Doppler loops");
+    static_assert((ROWS * CR2) % F2_THREADS == 0 && (ROWS * CR1) % F2_THREADS == 0 && F2_THREADS % CR2 == 0,
+                  "uniform Doppler loops");
 };
 
 template <int SR1, int SR2, int CR1, int CR2, int NC, int F2_THREADS, int MINB>
@@ -70,32 +71,39 @@ fft2d_cluster_kernel(const float2* __restrict__ cube, const float2* __restrict__
     const float2* src = cube + ((size_t)plane * C_total + chirp0 + q * P::CPC) * S;
 
     // ---------------- range phase
+    // per-thread constants: pass 1 always handles fast-time column t1, pass 2 always range residue k1r, so the dechirp
+    // table column and the inter-pass twiddles w_S^{k1r n2} (applied on the pass-2 side) live in registers
+    const int row1 = tid / SR2, t1 = tid - row1 * SR2;
+    const int row2 = tid % P::CB, k1r = tid / P::CB;
+    float2 tabv[SR1], twv[SR2];
+#pragma unroll
+    for (int j = 0; j < SR1; ++j) tabv[j] = tabs[t1 + SR2 * j];
+#pragma unroll
+    for (int n2 = 0; n2 < SR2; ++n2) twv[n2] = tw1s[k1r * SR2 + n2];
     for (int b0 = 0; b0 < P::CPC; b0 += P::CB) {
         {
-            const int row = tid / SR2, t = tid - row * SR2;
-            const float2* x = src + (size_t)(b0 + row) * S + t;
+            const float2* x = src + (size_t)(b0 + row1) * S + t1;
             float2 v[SR1];
 #pragma unroll
             for (int j = 0; j < SR1; ++j) v[j] = __ldcs(x + SR2 * j);              // streamed once: evict-first
 #pragma unroll
-            for (int j = 0; j < SR1; ++j) v[j] = cmul(v[j], tabs[t + SR2 * j]);
+            for (int j = 0; j < SR1; ++j) v[j] = cmul(v[j], tabv[j]);
             pow2::dft<SR1>(v);
-            float2* y = Y + row * P::RP + t;
+            float2* y = Y + row1 * P::RP + t1;
 #pragma unroll
-            for (int k1 = 0; k1 < SR1; ++k1) y[k1 * P::K1P] = (k1 == 0) ? v[0] : cmul(v[k1], tw1s[k1 * SR2 + t]);
+            for (int k1 = 0; k1 < SR1; ++k1) y[k1 * P::K1P] = v[k1];
         }
         __syncthreads();
         {
-            const int row = tid % P::CB, k1 = tid / P::CB;                          // lanes along chirps
-            const float2* y = Y + row * P::RP + k1 * P::K1P;
+            const float2* y = Y + row2 * P::RP + k1r * P::K1P;                      // lanes along chirps
             float2 u[SR2];
 #pragma unroll
-            for (int n2 = 0; n2 < SR2; ++n2) u[n2] = y[n2];
+            for (int n2 = 0; n2 < SR2; ++n2) u[n2] = (n2 == 0) ? y[0] : cmul(y[n2], twv[n2]);
             pow2::dft<SR2>(u);
-            const int chirp = q * P::CPC + b0 + row;
+            const int chirp = q * P::CPC + b0 + row2;
 #pragma unroll
             for (int k2 = 0; k2 < SR2; ++k2) {
-                const int k = k1 + SR1 * k2;
+                const int k = k1r + SR1 * k2;
                 const float2 val = (dc_removal && k == 0) ? make_float2(0.f, 0.f) : u[k2];    // mean removal, dechirp.py:120
                 const int p = (k + S / 2) & (S - 1);                                           // range fftshift
                 const int owner = p / P::ROWS, pl = p - owner * P::ROWS;
@@ -108,17 +116,23 @@ fft2d_cluster_kernel(const float2* __restrict__ cube, const float2* __restrict__
     cluster.sync();                          // all chirps of this CTA's range bins have arrived
 
     // ---------------- Doppler phase, in place in M
-    for (int it = tid; it < P::ROWS * CR2; it += F2_THREADS) {
-        const int row = it / CR2, t = it - row * CR2;                               // the CR2 lanes of a row share a warp
-        float2* m = M + row * P::MP;
-        float2 v[CR1];
+    {
+        const int td = tid % CR2;                                                   // this thread's column in every item
+        float2 twd[CR1];
 #pragma unroll
-        for (int j = 0; j < CR1; ++j) v[j] = m[t + CR2 * j];
-        __syncwarp();                                                               // the row is read before it is rewritten
-        pow2::dft<CR1>(v);
+        for (int k1 = 0; k1 < CR1; ++k1) twd[k1] = tw1c[k1 * CR2 + td];
+        for (int it = tid; it < P::ROWS * CR2; it += F2_THREADS) {
+            const int row = it / CR2;                                               // the CR2 lanes of a row share a warp
+            float2* m = M + row * P::MP;
+            float2 v[CR1];
 #pragma unroll
-        for (int k1 = 0; k1 < CR1; ++k1)
-            m[k1 * CR2 + ((t + (k1 >> 1)) & (CR2 - 1))] = (k1 == 0) ? v[0] : cmul(v[k1], tw1c[k1 * CR2 + t]);
+            for (int j = 0; j < CR1; ++j) v[j] = m[td + CR2 * j];
+            __syncwarp();                                                           // the row is read before it is rewritten
+            pow2::dft<CR1>(v);
+#pragma unroll
+            for (int k1 = 0; k1 < CR1; ++k1)
+                m[k1 * CR2 + ((td + (k1 >> 1)) & (CR2 - 1))] = (k1 == 0) ? v[0] : cmul(v[k1], twd[k1]);
+        }
     }
     __syncthreads();
     for (int it = tid; it < P::ROWS * CR1; it += F2_THREADS) {
