@@ -255,7 +255,6 @@ def run_gpu(args):
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
-    clocks = sampler.stop() if rank == 0 else None
 
     # ---- end to end through the public API with HOST buffers (pinned), H2D + D2H inside the timed region
     n_e2e = min(F, args.e2e_frames)
@@ -275,6 +274,7 @@ def run_gpu(args):
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = world * n_e2e * e2e_steps / float(e2e_s.item())
     assert torch.allclose(vel_host.to(dev), vel[:n_e2e], atol=0, rtol=0), "host path and device path disagree"
+    clocks = sampler.stop() if rank == 0 else None      # sampled over both timed regions (device-resident and host-buffer)
 
     if rank != 0:
         if world > 1:
@@ -321,7 +321,7 @@ def run_gpu(args):
     per_launch_bytes = dom["alg_bytes_per_step"] / dom["launches"]
     # measured DRAM traffic of the same kernels from the committed ncu capture (per frame of this shape), if present
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01_v5_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r01_v6_traffic.json")
     if os.path.exists(tpath) and (A, C, S) == (8, 128, 256):
         per_frame = json.load(open(tpath))["dram_bytes_per_frame"]
         for st in stages:

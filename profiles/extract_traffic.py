@@ -1,0 +1,43 @@
+#!/usr/bin/env python
+"""Per-frame DRAM traffic of every hot-path stage from an `ncu --set full` capture (bench.py reports it as
+roofline.traffic):   python profiles/extract_traffic.py gpurun_out/ncu_<tag> <frames per launch> profiles/<tag>_traffic.json"""
+import csv
+import io
+import json
+import subprocess
+import sys
+
+STAGE = {"fft2d_cluster": "rs_range_doppler_fft", "range_fft": "rs_range_fft", "doppler_fft": "rs_doppler_fft",
+         "detect_a8": "rs_detect", "detect_kernel": "rs_detect", "angles_": "rs_angles",
+         "recheck_detect": "rs_recheck_detections_f64", "velocity_from": "rs_velocity_from_partials"}
+RECHECK_PARTS = ("recheck_angles", "recheck_snapshots", "recheck_finish")
+MULT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+
+
+def main():
+    d, frames, out = sys.argv[1], float(sys.argv[2]), sys.argv[3]
+    raw = subprocess.run(["ncu", "-i", f"{d}/prof.ncu-rep", "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units = rows[0], rows[1]
+    ki, rd, wr, gi = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("launch__grid_size")
+    num = lambda x: float(x.replace(",", ""))
+    acc, parts = {}, {}
+    for r in rows[2:]:
+        b = num(r[rd]) * MULT[units[rd]] + num(r[wr]) * MULT[units[wr]]
+        for k, v in STAGE.items():
+            if k in r[ki]:
+                acc.setdefault(v, []).append(b)
+        for k in RECHECK_PARTS:
+            if k in r[ki]:
+                parts.setdefault(k, []).append(b)
+    per_frame = {k: sum(v) / len(v) / frames for k, v in acc.items()}
+    if parts:
+        per_frame["rs_recheck_angles_f64"] = sum(sum(v) / len(v) for v in parts.values()) / frames
+    json.dump({"source": f"{d}/prof.ncu-rep (ncu --set full --clock-control none): dram__bytes_read.sum + dram__bytes_write.sum "
+                         f"per launch of {frames:g} frames, divided by the frames",
+               "dram_bytes_per_frame": per_frame}, open(out, "w"), indent=1)
+    print(json.dumps(per_frame, indent=1))
+
+
+if __name__ == "__main__":
+    main()
