@@ -7,9 +7,9 @@ import json
 import subprocess
 import sys
 
-STAGE = {"fft2d_cluster": "rs_range_doppler_fft", "range_fft": "rs_range_fft", "doppler_fft": "rs_doppler_fft",
-         "detect_a8": "rs_detect", "detect_kernel": "rs_detect", "angles_": "rs_angles",
-         "recheck_detect": "rs_recheck_detections_f64", "velocity_from": "rs_velocity_from_partials"}
+STAGE = {"recheck_detect": "rs_recheck_detections_f64", "fft2d_cluster": "rs_range_doppler_fft", "range_fft": "rs_range_fft",
+         "doppler_fft": "rs_doppler_fft", "detect_a8": "rs_detect", "detect_kernel": "rs_detect", "angles_": "rs_angles",
+         "velocity_from": "rs_velocity_from_partials"}
 RECHECK_PARTS = ("recheck_angles", "recheck_snapshots", "recheck_finish")
 MULT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 
@@ -24,12 +24,14 @@ def main():
     acc, parts = {}, {}
     for r in rows[2:]:
         b = num(r[rd]) * MULT[units[rd]] + num(r[wr]) * MULT[units[wr]]
+        hit = [k for k in RECHECK_PARTS if k in r[ki]]
+        if hit:
+            parts.setdefault(hit[0], []).append(b)
+            continue
         for k, v in STAGE.items():
             if k in r[ki]:
                 acc.setdefault(v, []).append(b)
-        for k in RECHECK_PARTS:
-            if k in r[ki]:
-                parts.setdefault(k, []).append(b)
+                break
     per_frame = {k: sum(v) / len(v) / frames for k, v in acc.items()}
     if parts:
         per_frame["rs_recheck_angles_f64"] = sum(sum(v) / len(v) for v in parts.values()) / frames
