@@ -91,3 +91,28 @@ def test_constructor_signatures_match_reference():
                         (ref.velocity, velocity_solver, ["estimate_velocity_from_angles"])]:
         for fn in fns:
             assert list(inspect.signature(getattr(rm, fn)).parameters) == list(inspect.signature(getattr(mm, fn)).parameters)
+
+
+def test_real_time_shell_signatures_match_reference():
+    """src/core/real_time_processor.py keeps the reference's classes, methods and defaults."""
+    import importlib.util
+    import inspect
+    sys.path.insert(0, ROOT)
+    spec = importlib.util.spec_from_file_location("ref_real_time_processor", os.path.join(REF, "src/core/real_time_processor.py"))
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    from radar_slam_b200.compat import real_time_processor as mine
+    for cls in ("FrameBuffer", "ParallelTargetProcessor", "RealTimeProcessor", "RealTimeVelocityEstimator"):
+        rc, mc = getattr(ref, cls), getattr(mine, cls)
+        for name, fn in inspect.getmembers(rc, predicate=inspect.isfunction):
+            if name.startswith("__") and name != "__init__":
+                continue
+            assert hasattr(mc, name), f"{cls} lacks {name}"
+            rs, ms = inspect.signature(fn), inspect.signature(getattr(mc, name))
+            assert list(rs.parameters) == list(ms.parameters), (cls, name)
+            for k in rs.parameters:
+                assert rs.parameters[k].default == ms.parameters[k].default, (cls, name, k)
+    assert [f.name for f in ref.ProcessingFrame.__dataclass_fields__.values()] == \
+        [f.name for f in mine.ProcessingFrame.__dataclass_fields__.values()]
+    assert list(inspect.signature(ref.create_real_time_estimator).parameters) == \
+        list(inspect.signature(mine.create_real_time_estimator).parameters)
