@@ -245,6 +245,31 @@ int rs_velocity_ls6(const double* pos, const double* ang, const double* y, int n
 int rs_robust_confidence_f64(const void* sig128, const double* angle_deg, const double* positions,
                              double lambda_c, int n, int A, double* out, void* stream);
 
+/* (f3)  ImprovedVelocitySolver (src/algorithms/velocity_solver_improved.py), inter-frame ego-velocity.
+ *   rs_associate_targets: associate_targets_across_frames (:74-129) for `pairs` frame pairs.  cur_xy double
+ *       [pairs][nc_max][2], prev_xy double [pairs][np_max][2] = range (cos az, sin az); n_cur / n_prev int32 [pairs].
+ *       Current targets are visited in order; each takes the nearest still unused previous target closer than
+ *       `threshold` (Euclidean distance in fp64 as scipy cdist, first index on ties).  match_idx int32
+ *       [pairs][nc_max] (-1 = none), match_dist double [pairs][nc_max].
+ *   rs_wrapped_cost: cost_function (:223-266) for nq candidate motions params double [nq][6] = v, w:
+ *       sum_i wrap(y_i - k [v + w x pos_i] . dir(az_i, el_i))^2 + reg_v |v|^2 + reg_w |w|^2, wrap = atan2(sin, cos).
+ *       pos double [n][3], ang double [n][2], y double [n];  cost double [nq].
+ *   rs_wrapped_lattice_search: that cost on the lattice v = (vx_lo + ix h, vy_lo + iy h), ix < nx, iy < ny, for the
+ *       planar model x_i = k (v_x cos az_i + v_y sin az_i) (what :336-355 builds: elevation 0, position = range * dir)
+ *       with phases in cycles: ax = k cos az / 2 pi, by = k sin az / 2 pi, y_cycles = y / 2 pi (double [n], n <= 2048).
+ *       fp32 evaluation with an fp64 re-base every 32 points.  Output: the best lattice point of every tile of
+ *       8 rows x 1024 columns (rs_wrapped_lattice_tiles gives the tile grid): tile_cost float, tile_ix / tile_iy int32
+ *       [tiles_y][tiles_x]. */
+int rs_associate_targets(const double* cur_xy, const int32_t* n_cur, const double* prev_xy, const int32_t* n_prev,
+                         double threshold, int32_t* match_idx, double* match_dist, int pairs, int nc_max, int np_max,
+                         void* stream);
+int rs_wrapped_cost(const double* params, const double* pos, const double* ang, const double* y, int n, int nq,
+                    double k_phase, double reg_v, double reg_w, double* cost, void* stream);
+int rs_wrapped_lattice_tiles(long long nx, long long ny, int* tiles_x, int* tiles_y);
+int rs_wrapped_lattice_search(const double* ax_cycles, const double* by_cycles, const double* y_cycles, int n,
+                              double vx_lo, double vy_lo, double h, long long nx, long long ny, double reg,
+                              float* tile_cost, int32_t* tile_ix, int32_t* tile_iy, void* stream);
+
 /* (f2)  FMCWRadarSimulator.synthesize_frame (scripts/simulate_raw.py:147-221) for F frames on the device:
  *       cube[f][a][c][s] = sum over scatterers of amplitude exp(i(doppler + antenna phase)) delayed_chirp conj(ref_chirp)
  *       (the same [A][S] plane for every chirp, :190-209) + sqrt(noise_power) (N(0,1) + i N(0,1))  (:216-219).

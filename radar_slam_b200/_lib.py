@@ -45,6 +45,10 @@ _SIGNATURES = {
     "rs_process_chirps_f64": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "rs_esprit_f64": (_i, [_vp, _i, _i, _d, _vp, _vp]),
     "rs_velocity_ls6": (_i, [_vp, _vp, _vp, _i, _d, _vp, _vp, _i, _vp, _vp, _vp]),
+    "rs_associate_targets": (_i, [_vp, _vp, _vp, _vp, _d, _vp, _vp, _i, _i, _i, _vp]),
+    "rs_wrapped_cost": (_i, [_vp, _vp, _vp, _vp, _i, _i, _d, _d, _d, _vp, _vp]),
+    "rs_wrapped_lattice_tiles": (_i, [C.c_longlong, C.c_longlong, C.POINTER(_i), C.POINTER(_i)]),
+    "rs_wrapped_lattice_search": (_i, [_vp, _vp, _vp, _i, _d, _d, _d, C.c_longlong, C.c_longlong, _d, _vp, _vp, _vp, _vp]),
     "rs_synthesize_frames": (_i, [_vp, _vp, _i, _d, _d, _d, _d, _vp, _d, C.c_ulonglong, C.c_longlong, _vp, _vp,
                                   _i, _i, _i, _i, _vp]),
     "rs_robust_confidence_f64": (_i, [_vp, _vp, _vp, _d, _i, _i, _vp, _vp]),

@@ -64,7 +64,7 @@ def test_reference_tests_import_this_repo(tmp_path):
     out = r.stdout.split()
     assert out[0] == "radar_slam_b200.compat.robust_angle_estimation" and out[1] == "True"
     assert out[2] == "radar_slam_b200.compat.dechirp"
-    assert out[3] == "src.algorithms.velocity_solver_improved"          # out of scope: the reference's own
+    assert out[3] == "radar_slam_b200.compat.velocity_solver_improved"
 
 
 def test_constructor_signatures_match_reference():
