@@ -217,6 +217,8 @@ def run_gpu(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
+    from radar_slam_b200.sharding import bind_to_gpu_numa_node
+    numa = bind_to_gpu_numa_node(local) if not args.no_numa_bind else {"device": local, "numa_node": "unbound"}
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     cfg = radar_config(args)
@@ -370,7 +372,8 @@ def run_gpu(args):
                    "detections_per_frame": n_det_frame, "detection_overflow": overflow,
                    "undecided_in_fp32_per_frame": flagged, "fp64_recheck": recheck_stats,
                    "cache": "inputs larger than L2 (%.2f GiB cube per GPU)" % (cube.numel() * 8 / 2 ** 30),
-                   "parallelism": f"frames sharded over {world} GPU(s), all-gather of [F,8] velocity rows"},
+                   "parallelism": f"frames sharded over {world} GPU(s), all-gather of [F,8] velocity rows",
+                   "host_binding": numa},
         "roofline": roofline,
         "cpu_baseline": {"value": rate, "unit": "frames/s", "cores": 1, "kind": "port",
                          "sample": f"{n_cpu} frames of the same batch through the oracle port in {dt:.1f}s "
@@ -404,6 +407,7 @@ def main():
     ap.add_argument("--fft-eps", type=float, default=4e-7, help="error bound of the fp32 FFT used by the recheck, in rms units")
     ap.add_argument("--e2e-frames", type=int, default=1000)
     ap.add_argument("--cpu-frames", type=int, default=24)
+    ap.add_argument("--no-numa-bind", action="store_true", help="do not pin each rank to its GPU's NUMA node")
     ap.add_argument("--ref-procs", type=int, default=0)
     ap.add_argument("--ref-frames-per-step", type=int, default=0)
     args = ap.parse_args()
