@@ -34,11 +34,19 @@ METRIC = "frames/s dechirp->range-Doppler->MUSIC->LS ego-velocity"
 WORKLOAD = "configs[1]: 1k-frame synthetic batch per GPU, 256 samples x 128 chirps x 8 channels, MUSIC 1 deg grid, noise_power 0.01, threshold -20 dB"
 
 
+def workload_name(args):
+    if (args.frames, args.samples, args.chirps, args.antennas, args.method, args.grid_res, args.threshold_db) == \
+            (1000, 256, 128, 8, "music", 1.0, -20.0):
+        return WORKLOAD
+    return (f"non-default: {args.frames} frames per GPU, {args.samples} samples x {args.chirps} chirps x {args.antennas} channels, "
+            f"{args.method} ({args.grid_res} deg grid), noise_power 0.01, threshold {args.threshold_db} dB")
+
+
 def radar_config(args):
     from radar_slam_b200 import RadarConfig
     return RadarConfig(fc=77e9, bandwidth=1e9, chirp_duration=args.samples / 10e6, pri=100e-6, num_chirps=args.chirps,
                        sampling_rate=10e6, num_antennas=args.antennas, search_resolution=args.grid_res,
-                       method="music", threshold_db=args.threshold_db, recheck=not args.no_recheck,
+                       method=args.method, threshold_db=args.threshold_db, recheck=not args.no_recheck,
                        fft_eps=args.fft_eps)
 
 
@@ -99,7 +107,7 @@ class ClockSampler:
 
 # ---------------------------------------------------------------------------------- CPU arms
 def _oracle_worker(payload):
-    frames, pdict, res, thr, blas_threads = payload
+    frames, pdict, res, thr, blas_threads, method = payload
     from oracle import radar_oracle as orc
     p = orc.RadarParams(**pdict)
     tim = {}
@@ -107,7 +115,7 @@ def _oracle_worker(payload):
 
     def run():
         for fr in frames:
-            r = orc.process_frame(fr.astype(np.complex128), p, "music", res, thr, timings=tim)
+            r = orc.process_frame(fr.astype(np.complex128), p, method, res, thr, timings=tim)
             out.append((r["velocity"].get("velocity", np.zeros(3))[:2], len(r["peaks"]["antenna"])))
 
     if blas_threads:
@@ -129,11 +137,11 @@ def cpu_oracle_rate(frames: np.ndarray, args, procs: int):
     parts = [x for x in parts if len(x)]
     t0 = time.perf_counter()
     if len(parts) == 1:
-        res = [_oracle_worker((parts[0], pdict, args.grid_res, args.threshold_db, 1 if procs == 1 else 0))]
+        res = [_oracle_worker((parts[0], pdict, args.grid_res, args.threshold_db, 1 if procs == 1 else 0, args.method))]
     else:
         import multiprocessing as mp
         with mp.get_context("fork").Pool(len(parts)) as pool:
-            res = pool.map(_oracle_worker, [(x, pdict, args.grid_res, args.threshold_db, 1) for x in parts])
+            res = pool.map(_oracle_worker, [(x, pdict, args.grid_res, args.threshold_db, 1, args.method) for x in parts])
     dt = time.perf_counter() - t0
     tim = {}
     ndet = []
@@ -178,7 +186,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "frames_per_step": per_step, "detections_per_frame": ndet},
+        "config": {"workload": workload_name(args), "frames_per_step": per_step, "detections_per_frame": ndet},
         "cpu_baseline": {"value": value, "unit": "frames/s", "cores": procs, "kind": "port",
                          "sample": f"{per_step} frames/step of the same workload through oracle.radar_oracle.process_frame "
                                    f"(vectorised fp64 numpy port of the reference; the reference itself is Python and cannot "
@@ -356,18 +364,21 @@ def run_gpu(args):
 
     # ---- CPU baseline: the oracle port on a bounded sample of the SAME frames, one core
     n_cpu = args.cpu_frames
-    sample = cube[:n_cpu].cpu().numpy()
-    rate, dt, tim, ndet_cpu, res = cpu_oracle_rate(sample, args, 1)
-    v_cpu = np.stack([v for v, _ in res[0][0]])
-    v_gpu = vel[:n_cpu, :2].cpu().numpy()
-    parity = float(np.abs(v_cpu - v_gpu).max())
+    if n_cpu > 0:
+        sample = cube[:n_cpu].cpu().numpy()
+        rate, dt, tim, ndet_cpu, res = cpu_oracle_rate(sample, args, 1)
+        v_cpu = np.stack([v for v, _ in res[0][0]])
+        v_gpu = vel[:n_cpu, :2].cpu().numpy()
+        parity = float(np.abs(v_cpu - v_gpu).max())
+    else:                                         # exploratory runs of the big configs: no CPU arm
+        rate, dt, tim, ndet_cpu, parity = None, 0.0, {}, 0.0, None
 
     value = world * F * args.steps / (ms_total / 1e3)
     line = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "frames_per_gpu": F, "samples": S, "chirps": C, "channels": A,
+        "config": {"workload": workload_name(args), "frames_per_gpu": F, "samples": S, "chirps": C, "channels": A,
                    "grid_points": len(pipe._angle_tables(A)["grid"]), "chunk_frames": args.chunk, "host_chunk_frames": args.host_chunk,
                    "detections_per_frame": n_det_frame, "detection_overflow": overflow,
                    "undecided_in_fp32_per_frame": flagged, "fp64_recheck": recheck_stats,
@@ -400,6 +411,7 @@ def main():
     ap.add_argument("--chirps", type=int, default=128)
     ap.add_argument("--antennas", type=int, default=8)
     ap.add_argument("--grid-res", type=float, default=1.0)
+    ap.add_argument("--method", default="music", choices=["music", "beamforming", "esprit"])
     ap.add_argument("--threshold-db", type=float, default=-20.0)
     ap.add_argument("--chunk", type=int, default=500, help="frames per launch set, device-resident path")
     ap.add_argument("--host-chunk", type=int, default=32, help="frames per H2D chunk, host-buffer path")

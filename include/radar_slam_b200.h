@@ -140,6 +140,13 @@ int rs_angles(const void* rds, const float* scan_table, int scan_stride, const v
 int rs_velocity_from_partials(const double* ls_partials, int nseg_per_frame, int F, double k_phase, double bound,
                               double* vel, void* stream);
 
+/* (d'')  the per-segment sums of rs_velocity_from_partials from the detection lists (for what rs_angles does not fuse:
+ *       ESPRIT, A > 16): ls_partials double [F*nseg_per_frame][8], one CTA per segment, deterministic.
+ *       grid_cs NULL or det_aidx < 0 => cos/sin of radians(det_adeg) in fp64. */
+int rs_velocity_partials(const int32_t* det_aidx, const float* det_adeg, const float* det_phase, const uint8_t* det_flags,
+                         const int32_t* det_count, const double* grid_cs, double* ls_partials, int seg_cap,
+                         int nseg_per_frame, int F, void* stream);
+
 /* (d)   replaces VelocitySolver.solve_velocity / two_step_optimization (velocity_solver.py:178-355):
  *       fp64 normal equations of  y = k (v_x cos az + v_y sin az),  k = 4 pi dt / lambda, solved under
  *       the reference's box |v_x|,|v_y| <= bound; success = (n >= 3).  v_z and omega are unobservable

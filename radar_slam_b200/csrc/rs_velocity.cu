@@ -125,6 +125,36 @@ velocity_kernel(const int32_t* __restrict__ det_aidx, const float* __restrict__ 
     }
 }
 
+// The normal-equation sums of ONE segment from its detection list (what rs_angles fuses into its scan for the grid
+// methods at A <= 16): one CTA per segment, fixed reduction order -> deterministic.  ESPRIT and A > 16 go through here,
+// so a frame's millions of detections are summed by all SMs instead of by the one CTA of velocity_kernel.
+__global__ void __launch_bounds__(VEL_THREADS)
+velocity_partials_kernel(const int32_t* __restrict__ det_aidx, const float* __restrict__ det_adeg,
+                         const float* __restrict__ det_phase, const uint8_t* __restrict__ det_flags,
+                         const int32_t* __restrict__ det_count, const double* __restrict__ grid_cs,
+                         double* __restrict__ partials, int seg_cap) {
+    __shared__ double sh[80];
+    const size_t seg = blockIdx.x;
+    const int n = det_count[seg];
+    Sums s{};
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const size_t o = seg * seg_cap + i;
+        if (det_flags[o] & RS_FLAG_DROPPED) continue;
+        double c, sn;
+        const int ai = det_aidx[o];
+        if (grid_cs != nullptr && ai >= 0) { c = grid_cs[2 * ai]; sn = grid_cs[2 * ai + 1]; }
+        else { sincos((double)det_adeg[o] * (3.14159265358979323846 / 180.0), &sn, &c); }
+        const double y = (double)det_phase[o];
+        s.cc += c * c; s.ss += sn * sn; s.cs += c * sn;
+        s.yc += y * c; s.ys += y * sn; s.yy += y * y; s.n += 1.0;
+    }
+    block_reduce(s, sh);
+    if (threadIdx.x == 0) {
+        double* q = partials + seg * 8;
+        q[0] = s.cc; q[1] = s.ss; q[2] = s.cs; q[3] = s.yc; q[4] = s.ys; q[5] = s.yy; q[6] = s.n; q[7] = 0.0;
+    }
+}
+
 // One warp per frame: add the per-segment partial sums written by rs_angles in segment order
 // (lane-strided, then a fixed shuffle tree: deterministic) and solve.
 __global__ void __launch_bounds__(128)
@@ -162,6 +192,18 @@ extern "C" int rs_velocity_from_partials(const double* ls_partials, int nseg_per
     velocity_from_partials_kernel<<<(F + 3) / 4, 128, 0, (cudaStream_t)stream>>>(ls_partials, nseg_per_frame, F, k_phase,
                                                                               bound, vel);
     RS_CHECK_LAUNCH("rs_velocity_from_partials");
+    return RS_OK;
+}
+
+extern "C" int rs_velocity_partials(const int32_t* det_aidx, const float* det_adeg, const float* det_phase,
+                                    const uint8_t* det_flags, const int32_t* det_count, const double* grid_cs,
+                                    double* ls_partials, int seg_cap, int nseg_per_frame, int F, void* stream) {
+    RS_CHECK_ARG(det_aidx && det_adeg && det_phase && det_flags && det_count && ls_partials, "rs_velocity_partials: null pointer");
+    RS_CHECK_ARG(F > 0 && seg_cap > 0 && nseg_per_frame > 0 && (long long)F * nseg_per_frame < (1ll << 31),
+                 "rs_velocity_partials: bad args");
+    velocity_partials_kernel<<<(unsigned)((long long)F * nseg_per_frame), VEL_THREADS, 0, (cudaStream_t)stream>>>(
+        det_aidx, det_adeg, det_phase, det_flags, det_count, grid_cs, ls_partials, seg_cap);
+    RS_CHECK_LAUNCH("rs_velocity_partials");
     return RS_OK;
 }
 

@@ -293,6 +293,15 @@ class FramePipeline:
             self._call("rs_velocity_from_partials", det.ls_partials.data_ptr(), det.ntiles, det.F, k, c.velocity_bound,
                        vel.data_ptr(), self.stream)
             return vel
+        if c.irls_iters == 0:
+            # sums per segment on all SMs, then the same per-frame reduction + solve as the fused path
+            part = self._buf("ls_partials_lists" + det.tag, (det.F * det.ntiles, 8), torch.float64)
+            self._call("rs_velocity_partials", det.aidx.data_ptr(), det.adeg.data_ptr(), det.phase.data_ptr(),
+                       det.flags.data_ptr(), det.count.data_ptr(), t["grid_cs"].data_ptr() if use_grid else 0,
+                       part.data_ptr(), det.seg_cap, det.ntiles, det.F, self.stream)
+            self._call("rs_velocity_from_partials", part.data_ptr(), det.ntiles, det.F, k, c.velocity_bound,
+                       vel.data_ptr(), self.stream)
+            return vel
         self._call(
             "rs_velocity_ls",
             det.aidx.data_ptr(), det.adeg.data_ptr(), det.phase.data_ptr(), det.flags.data_ptr(), det.count.data_ptr(),
