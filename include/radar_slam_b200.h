@@ -125,7 +125,10 @@ int rs_detect(const void* rds, const uint8_t* range_gate, float thr_power, float
  *                     flagged cells of each segment, in arbitrary order (lets the fp64 recheck skip the list scan)
  *       mma_table     optional float [mma_tiles][2][2][A_pad/8][32][2]: TF32 hi/lo B fragments of the (cos, sin) tables
  *                     for the tensor-core scan (8 < 2 A_pad <= 32, symmetric grid); mma_tiles = ceil(ceil(G/2)/8).
- *                     NULL selects the CUDA-core scan. */
+ *                     NULL selects the CUDA-core scan.
+ *       cell_ws       optional workspace of 17 * F*R*D bytes (16-byte aligned) for A > 16: every distinct cell of a frame is
+ *                     evaluated once (mark / evaluate / scatter) instead of once per detection -- with many antennas
+ *                     a cell is flagged on many of them and all share one snapshot.  NULL: one evaluation per leader. */
 #define RS_TIE_LIST_CAP 32
 int rs_angles(const void* rds, const float* scan_table, int scan_stride, const void* steer, const float* grid_deg, int G,
               int method, float tie_eps, double esprit_scale,
@@ -133,7 +136,7 @@ int rs_angles(const void* rds, const float* scan_table, int scan_stride, const v
               int32_t* det_aidx, float* det_adeg, float* det_phase,
               int seg_cap, int nseg_per_frame, int F, int R, int D, int A,
               const double* grid_cs, double* ls_partials, int grid_symmetric, int32_t* det_ntie, int32_t* det_tielist,
-              const float* mma_table, int mma_tiles, void* stream);
+              const float* mma_table, int mma_tiles, void* cell_ws, void* stream);
 
 /* (d')  the velocity solve of rs_velocity_ls from the per-segment sums rs_angles already produced
  *       (no second pass over the detection lists); same output row layout. */

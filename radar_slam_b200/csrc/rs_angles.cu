@@ -576,7 +576,102 @@ __global__ void __launch_bounds__(ANG_THREADS, MINB) angles_mma_kernel(AngleArgs
     }
 }
 
-// warp-per-detection kernel for any A (used for A > 16): lanes scan the grid, snapshot in smem
+// ---- any A (used for A > 16): one warp evaluates one cell, lanes over antennas / grid points, snapshot in smem ----
+struct CellResult {
+    int aidx;
+    float adeg, phase;
+    uint32_t flags;
+};
+
+// Valid on lane 0.  `cell` points at antenna 0 of the cell; antennas are `stride` elements apart.
+__device__ __forceinline__ CellResult large_cell(const AngleArgs& p, const float2* __restrict__ cell, size_t stride,
+                                                 float2* s, int lane) {
+    const int M = p.A;
+    CellResult out{-1, 0.f, 0.f, 0u};
+    __syncwarp();
+    float e = 0.f;
+    for (int m = lane; m < M; m += 32) {
+        const float2 x = __ldg(cell + (size_t)m * stride);
+        s[m] = x;
+        e = fmaf(x.x, x.x, fmaf(x.y, x.y, e));
+    }
+#pragma unroll
+    for (int off = 16; off; off >>= 1) e += __shfl_xor_sync(0xffffffffu, e, off);
+    __syncwarp();
+    out.phase = atan2f(s[1].y * s[0].x - s[1].x * s[0].y, s[1].x * s[0].x + s[1].y * s[0].y);
+    if (p.method == RS_METHOD_ESPRIT) {
+        // warp-cooperative sums in fp64
+        double alpha = 0, gamma = 0, br = 0, bi = 0;
+        for (int m = lane; m < M - 1; m += 32) {
+            const double xr = s[m].x, xi = s[m].y, yr = s[m + 1].x, yi = s[m + 1].y;
+            alpha += xr * xr + xi * xi; gamma += yr * yr + yi * yi;
+            br += xr * yr + xi * yi;    bi += xr * yi - xi * yr;
+        }
+#pragma unroll
+        for (int off = 16; off; off >>= 1) {
+            alpha += __shfl_xor_sync(0xffffffffu, alpha, off); gamma += __shfl_xor_sync(0xffffffffu, gamma, off);
+            br += __shfl_xor_sync(0xffffffffu, br, off);       bi += __shfl_xor_sync(0xffffffffu, bi, off);
+        }
+        const double half = 0.5 * (alpha - gamma);
+        const double lam = 0.5 * (alpha + gamma) + sqrt(half * half + br * br + bi * bi);
+        double v0r, v0i, v1r, v1i;
+        const double na = br * br + bi * bi + (lam - alpha) * (lam - alpha);
+        const double nb = (lam - gamma) * (lam - gamma) + br * br + bi * bi;
+        if (na >= nb) { v0r = br; v0i = bi; v1r = lam - alpha; v1i = 0; }
+        else          { v0r = lam - gamma; v0i = 0; v1r = br; v1i = -bi; }
+        double nr = 0, ni = 0;
+        for (int m = lane; m < M - 2; m += 32) {
+            const double x0r = s[m].x, x0i = s[m].y, x1r = s[m + 1].x, x1i = s[m + 1].y, x2r = s[m + 2].x, x2i = s[m + 2].y;
+            const double ur = v0r * x0r - v0i * x0i + v1r * x1r - v1i * x1i;
+            const double ui = v0r * x0i + v0i * x0r + v1r * x1i + v1i * x1r;
+            const double wr = v0r * x1r - v0i * x1i + v1r * x2r - v1i * x2i;
+            const double wi = v0r * x1i + v0i * x1r + v1r * x2i + v1i * x2r;
+            nr += ur * wr + ui * wi;
+            ni += ur * wi - ui * wr;
+        }
+#pragma unroll
+        for (int off = 16; off; off >>= 1) {
+            nr += __shfl_xor_sync(0xffffffffu, nr, off);
+            ni += __shfl_xor_sync(0xffffffffu, ni, off);
+        }
+        out.adeg = (float)(asin(atan2(ni, nr) * p.esprit_scale) * (180.0 / 3.14159265358979323846));
+        return out;
+    }
+    float best = -1.f, second = -1.f;
+    int bi = 0x7fffffff;
+    for (int g = lane; g < p.G; g += 32) {
+        float ar = 0.f, ai = 0.f;
+        const float2* st = p.steer + g;
+        for (int m = 0; m < M; ++m) {
+            const float2 w = __ldg(st + (size_t)m * p.G);     // a_g[m]; accumulate conj(a) * s
+            const float2 x = s[m];
+            ar = fmaf(w.x, x.x, fmaf(w.y, x.y, ar));
+            ai = fmaf(w.x, x.y, fmaf(-w.y, x.x, ai));
+        }
+        const float v = fmaf(ar, ar, ai * ai);
+        if (v > best) { second = best; best = v; bi = g; }
+        else if (v > second) second = v;
+    }
+    // warp arg-max with first-index tie break; second = best of the rest
+#pragma unroll
+    for (int off = 16; off; off >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, off);
+        const float os = __shfl_xor_sync(0xffffffffu, second, off);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+        if (ob > best || (ob == best && oi < bi)) { second = fmaxf(best, os); best = ob; bi = oi; }
+        else second = fmaxf(second, ob);
+    }
+    if ((best - second) <= p.tie_eps * best) out.flags |= RS_FLAG_TIE;
+    if (p.method == RS_METHOD_MUSIC) {
+        const float full = (float)M * e;
+        if (full - best <= 1e-4f * full) out.flags |= RS_FLAG_GUARD;
+    }
+    out.aidx = bi;
+    out.adeg = p.grid_deg[bi < p.G ? bi : 0];
+    return out;
+}
+
+// warp per detection leader (no workspace)
 __global__ void __launch_bounds__(ANG_THREADS) angles_large_kernel(AngleArgs p) {
     extern __shared__ float2 snap[];   // [warps][A]
     const int seg = blockIdx.x;
@@ -584,100 +679,59 @@ __global__ void __launch_bounds__(ANG_THREADS) angles_large_kernel(AngleArgs p) 
     if (n == 0) return;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const int f = seg / p.nseg_per_frame;
-    const int M = p.A;
-    const float2* frame = p.rds + (size_t)f * p.R * p.D * M;
-    float2* s = snap + wid * M;
+    const float2* frame = p.rds + (size_t)f * p.R * p.D * p.A;
     for (int i = wid; i < n; i += nw) {
         const uint32_t ld = p.det_lead[(size_t)seg * p.seg_cap + i];
         const size_t o = (size_t)seg * p.seg_cap + (ld & 0xFFFFu);
-        const int mult = (int)(ld >> 16);
         int a, r, d;
         rs_split_key(p.det_key[o], a, r, d);
-        const float2* cell = frame + (size_t)r * M * p.D + d;
-        __syncwarp();
-        float e = 0.f;
-        for (int m = lane; m < M; m += 32) {
-            const float2 x = __ldg(cell + (size_t)m * p.D);
-            s[m] = x;
-            e = fmaf(x.x, x.x, fmaf(x.y, x.y, e));
-        }
-#pragma unroll
-        for (int off = 16; off; off >>= 1) e += __shfl_xor_sync(0xffffffffu, e, off);
-        __syncwarp();
-        uint8_t flags = 0;
-        const float phase = atan2f(s[1].y * s[0].x - s[1].x * s[0].y, s[1].x * s[0].x + s[1].y * s[0].y);
-        if (p.method == RS_METHOD_ESPRIT) {
-            // warp-cooperative sums in fp64
-            double alpha = 0, gamma = 0, br = 0, bi = 0;
-            for (int m = lane; m < M - 1; m += 32) {
-                const double xr = s[m].x, xi = s[m].y, yr = s[m + 1].x, yi = s[m + 1].y;
-                alpha += xr * xr + xi * xi; gamma += yr * yr + yi * yi;
-                br += xr * yr + xi * yi;    bi += xr * yi - xi * yr;
-            }
-#pragma unroll
-            for (int off = 16; off; off >>= 1) {
-                alpha += __shfl_xor_sync(0xffffffffu, alpha, off); gamma += __shfl_xor_sync(0xffffffffu, gamma, off);
-                br += __shfl_xor_sync(0xffffffffu, br, off);       bi += __shfl_xor_sync(0xffffffffu, bi, off);
-            }
-            const double half = 0.5 * (alpha - gamma);
-            const double lam = 0.5 * (alpha + gamma) + sqrt(half * half + br * br + bi * bi);
-            double v0r, v0i, v1r, v1i;
-            const double na = br * br + bi * bi + (lam - alpha) * (lam - alpha);
-            const double nb = (lam - gamma) * (lam - gamma) + br * br + bi * bi;
-            if (na >= nb) { v0r = br; v0i = bi; v1r = lam - alpha; v1i = 0; }
-            else          { v0r = lam - gamma; v0i = 0; v1r = br; v1i = -bi; }
-            double nr = 0, ni = 0;
-            for (int m = lane; m < M - 2; m += 32) {
-                const double x0r = s[m].x, x0i = s[m].y, x1r = s[m + 1].x, x1i = s[m + 1].y, x2r = s[m + 2].x, x2i = s[m + 2].y;
-                const double ur = v0r * x0r - v0i * x0i + v1r * x1r - v1i * x1i;
-                const double ui = v0r * x0i + v0i * x0r + v1r * x1i + v1i * x1r;
-                const double wr = v0r * x1r - v0i * x1i + v1r * x2r - v1i * x2i;
-                const double wi = v0r * x1i + v0i * x1r + v1r * x2i + v1i * x2r;
-                nr += ur * wr + ui * wi;
-                ni += ur * wi - ui * wr;
-            }
-#pragma unroll
-            for (int off = 16; off; off >>= 1) {
-                nr += __shfl_xor_sync(0xffffffffu, nr, off);
-                ni += __shfl_xor_sync(0xffffffffu, ni, off);
-            }
-            if (lane == 0)
-                emit(p, seg, i, o, mult, -1, (float)(asin(atan2(ni, nr) * p.esprit_scale) * (180.0 / 3.14159265358979323846)),
-                     phase, 0);
-            continue;
-        }
-        float best = -1.f, second = -1.f;
-        int bi = 0x7fffffff;
-        for (int g = lane; g < p.G; g += 32) {
-            float ar = 0.f, ai = 0.f;
-            const float2* st = p.steer + g;
-            for (int m = 0; m < M; ++m) {
-                const float2 w = __ldg(st + (size_t)m * p.G);     // a_g[m]; accumulate conj(a) * s
-                const float2 x = s[m];
-                ar = fmaf(w.x, x.x, fmaf(w.y, x.y, ar));
-                ai = fmaf(w.x, x.y, fmaf(-w.y, x.x, ai));
-            }
-            const float v = fmaf(ar, ar, ai * ai);
-            if (v > best) { second = best; best = v; bi = g; }
-            else if (v > second) second = v;
-        }
-        // warp arg-max with first-index tie break; second = best of the rest
-#pragma unroll
-        for (int off = 16; off; off >>= 1) {
-            const float ob = __shfl_xor_sync(0xffffffffu, best, off);
-            const float os = __shfl_xor_sync(0xffffffffu, second, off);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
-            if (ob > best || (ob == best && oi < bi)) { second = fmaxf(best, os); best = ob; bi = oi; }
-            else second = fmaxf(second, ob);
-        }
-        if (lane == 0) {
-            if ((best - second) <= p.tie_eps * best) flags |= RS_FLAG_TIE;
-            if (p.method == RS_METHOD_MUSIC) {
-                const float full = (float)M * e;
-                if (full - best <= 1e-4f * full) flags |= RS_FLAG_GUARD;
-            }
-            emit(p, seg, i, o, mult, bi, p.grid_deg[bi], phase, flags);
-        }
+        const CellResult c = large_cell(p, frame + (size_t)r * p.A * p.D + d, (size_t)p.D, snap + wid * p.A, lane);
+        if (lane == 0) emit(p, seg, i, o, (int)(ld >> 16), c.aidx, c.adeg, c.phase, (uint8_t)c.flags);
+    }
+}
+
+// With many antennas a range-Doppler cell is flagged on many of them (17 detections per cell at A = 192), and their
+// snapshot -- hence angle and phase -- is the same.  Three passes evaluate every distinct cell ONCE per frame:
+// mark the cells that carry a detection, evaluate the marked cells (warp per cell), copy the results to the lists.
+__global__ void __launch_bounds__(256) mark_cells_kernel(AngleArgs p, uint8_t* __restrict__ mark) {
+    const int seg = blockIdx.x;
+    const int n = p.det_nlead[seg];
+    const int f = seg / p.nseg_per_frame;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint32_t ld = p.det_lead[(size_t)seg * p.seg_cap + i];
+        int a, r, d;
+        rs_split_key(p.det_key[(size_t)seg * p.seg_cap + (ld & 0xFFFFu)], a, r, d);
+        mark[((size_t)f * p.R + r) * p.D + d] = 1;
+    }
+}
+
+__global__ void __launch_bounds__(ANG_THREADS) eval_cells_kernel(AngleArgs p, const uint8_t* __restrict__ mark,
+                                                                  CellResult* __restrict__ cells, long long ncells) {
+    extern __shared__ float2 snap[];   // [warps][A]
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const long long per_frame = (long long)p.R * p.D;
+    for (long long c = (long long)blockIdx.x * nw + wid; c < ncells; c += (long long)gridDim.x * nw) {
+        if (!mark[c]) continue;
+        const long long f = c / per_frame;
+        const long long rd = c - f * per_frame;
+        const int r = (int)(rd / p.D), d = (int)(rd - (long long)r * p.D);
+        const float2* cell = p.rds + ((size_t)f * p.R + r) * p.A * p.D + d;
+        const CellResult res = large_cell(p, cell, (size_t)p.D, snap + wid * p.A, lane);
+        if (lane == 0) cells[c] = res;
+    }
+}
+
+__global__ void __launch_bounds__(256) scatter_cells_kernel(AngleArgs p, const CellResult* __restrict__ cells) {
+    const int seg = blockIdx.x;
+    const int n = p.det_nlead[seg];
+    const int f = seg / p.nseg_per_frame;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint32_t ld = p.det_lead[(size_t)seg * p.seg_cap + i];
+        const size_t o = (size_t)seg * p.seg_cap + (ld & 0xFFFFu);
+        int a, r, d;
+        rs_split_key(p.det_key[o], a, r, d);
+        const CellResult c = cells[((size_t)f * p.R + r) * p.D + d];
+        emit(p, seg, i, o, (int)(ld >> 16), c.aidx, c.adeg, c.phase, (uint8_t)c.flags);
     }
 }
 
@@ -762,7 +816,7 @@ extern "C" int rs_angles(const void* rds, const float* scan_table, int scan_stri
                          int32_t* det_aidx,
                          float* det_adeg, float* det_phase, int seg_cap, int nseg_per_frame, int F, int R, int D, int A,
                          const double* grid_cs, double* ls_partials, int grid_symmetric, int32_t* det_ntie,
-                         int32_t* det_tielist, const float* mma_table, int mma_tiles, void* stream) {
+                         int32_t* det_tielist, const float* mma_table, int mma_tiles, void* cell_ws, void* stream) {
     RS_CHECK_ARG(rds && det_key && det_lead && det_nlead && det_flags && det_aidx && det_adeg && det_phase,
                  "rs_angles: null pointer");
     RS_CHECK_ARG(ls_partials == nullptr || grid_cs != nullptr, "rs_angles: ls_partials needs grid_cs");
@@ -845,7 +899,20 @@ extern "C" int rs_angles(const void* rds, const float* scan_table, int scan_stri
         RS_CHECK_ARG(ls_partials == nullptr, "rs_angles: ls_partials is not produced for A > 16 (use rs_velocity_ls)");
         RS_CHECK_ARG(!scan || steer, "rs_angles: steer table required for A > 16");
         const size_t smem = (size_t)(ANG_THREADS / 32) * A * sizeof(float2);
-        angles_large_kernel<<<(unsigned)blocks, ANG_THREADS, smem, st>>>(p);
+        if (cell_ws != nullptr) {
+            // workspace: CellResult [F*R*D] followed by the mark bytes [F*R*D]
+            const long long ncells = (long long)F * R * D;
+            CellResult* cells = (CellResult*)cell_ws;
+            uint8_t* mark = (uint8_t*)(cells + ncells);
+            cudaMemsetAsync(mark, 0, (size_t)ncells, st);
+            mark_cells_kernel<<<(unsigned)blocks, 256, 0, st>>>(p, mark);
+            const long long want = (ncells + ANG_THREADS / 32 - 1) / (ANG_THREADS / 32);
+            const long long cap = (long long)rs_sm_count() * 64;
+            eval_cells_kernel<<<(unsigned)(want < cap ? want : cap), ANG_THREADS, smem, st>>>(p, mark, cells, ncells);
+            scatter_cells_kernel<<<(unsigned)blocks, 256, 0, st>>>(p, cells);
+        } else {
+            angles_large_kernel<<<(unsigned)blocks, ANG_THREADS, smem, st>>>(p);
+        }
     }
     RS_CHECK_LAUNCH("rs_angles");
     return RS_OK;

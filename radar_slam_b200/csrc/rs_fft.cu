@@ -265,7 +265,7 @@ extern "C" int rs_range_fft(const void* cube, const void* table, const void* twi
     RS_CHECK_ARG(F > 0 && A > 0 && A <= RS_MAX_ANTENNAS && S > 0 && S <= RS_MAX_RANGE_BINS, "rs_range_fft: bad F/A/S");
     RS_CHECK_ARG(C_used > 0 && chirp0 >= 0 && chirp0 + C_used <= C_total && C_used <= RS_MAX_DOPPLER_BINS,
                  "rs_range_fft: bad chirp subset");
-    if (C_used % 32 == 0 && (S == 64 || S == 128 || S == 256)) {
+    if (C_used % 32 == 0 && (S == 64 || S == 128 || S == 256 || S == 512)) {
         const float2 *cu = (const float2*)cube, *tb = (const float2*)table, *tw = (const float2*)twiddle_s;
         cudaStream_t st = (cudaStream_t)stream;
         int rc = 1;
@@ -273,6 +273,7 @@ extern "C" int rs_range_fft(const void* cube, const void* table, const void* twi
         // measured on B200 (1k frames 256x128x8): CB=16 0.94 ms, CB=32 1.02 ms -- occupancy beats longer store runs
         if (S == 256 && !(cb_env && atoi(cb_env) == 32)) rc = launch_range_pow2<16, 16, 16>(cu, tb, tw, (float2*)mid, F, A, C_total, chirp0, C_used, dc_removal, st);
         else if (S == 256) rc = launch_range_pow2<16, 16, 32>(cu, tb, tw, (float2*)mid, F, A, C_total, chirp0, C_used, dc_removal, st);
+        else if (S == 512) rc = launch_range_pow2<32, 16, 16>(cu, tb, tw, (float2*)mid, F, A, C_total, chirp0, C_used, dc_removal, st);
         else if (S == 128) rc = launch_range_pow2<16, 8, 32>(cu, tb, tw, (float2*)mid, F, A, C_total, chirp0, C_used, dc_removal, st);
         else rc = launch_range_pow2<8, 8, 32>(cu, tb, tw, (float2*)mid, F, A, C_total, chirp0, C_used, dc_removal, st);
         if (rc == 0) {

@@ -1,4 +1,4 @@
-// Two-pass register FFT kernels for power-of-two lengths N = R1 * R2 (R1 >= R2, both in {4, 8, 16}).
+// Two-pass register FFT kernels for power-of-two lengths N = R1 * R2 (R1 >= R2, R1 in {4, 8, 16, 32}, R2 in {4, 8, 16}).
 //
 // Pass 1: a thread owns x[t + R2 j], j < R1 (lanes run along the FFT axis -> coalesced loads),
 //         does the R1-point DFT in registers, applies the inter-pass twiddle w_N^{t k1} and writes
@@ -81,6 +81,24 @@ __device__ __forceinline__ void dft<16>(float2 (&v)[16]) {
         dft<4>(w);
 #pragma unroll
         for (int r = 0; r < 4; ++r) v[q + 4 * r] = w[r];
+    }
+}
+
+// 32 = 2 x 16: X[k] = E[k] + w32^k O[k], X[k + 16] = E[k] - w32^k O[k]
+template <>
+__device__ __forceinline__ void dft<32>(float2 (&v)[32]) {
+    constexpr float WC[16] = {1.00000000000000000000f, 0.98078528040323043058f, 0.92387953251128673848f, 0.83146961230254523567f, 0.70710678118654757274f, 0.55557023301960228867f, 0.38268343236508983729f, 0.19509032201612833135f, 0.00000000000000006123f, -0.19509032201612819257f, -0.38268343236508972627f, -0.55557023301960195560f, -0.70710678118654746172f, -0.83146961230254534669f, -0.92387953251128673848f, -0.98078528040323043058f};
+    constexpr float WS[16] = {-0.00000000000000000000f, -0.19509032201612824808f, -0.38268343236508978178f, -0.55557023301960217765f, -0.70710678118654746172f, -0.83146961230254523567f, -0.92387953251128673848f, -0.98078528040323043058f, -1.00000000000000000000f, -0.98078528040323043058f, -0.92387953251128673848f, -0.83146961230254545772f, -0.70710678118654757274f, -0.55557023301960217765f, -0.38268343236508989280f, -0.19509032201612860891f};
+    float2 e[16], o[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) { e[k] = v[2 * k]; o[k] = v[2 * k + 1]; }
+    dft<16>(e);
+    dft<16>(o);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const float2 t = (k == 0) ? o[0] : make_float2(fmaf(o[k].x, WC[k], -o[k].y * WS[k]), fmaf(o[k].x, WS[k], o[k].y * WC[k]));
+        v[k] = cadd(e[k], t);
+        v[k + 16] = csub(e[k], t);
     }
 }
 

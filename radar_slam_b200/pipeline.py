@@ -277,7 +277,9 @@ class FramePipeline:
             det.nlead.data_ptr(), det.flags.data_ptr(), det.aidx.data_ptr(), det.adeg.data_ptr(), det.phase.data_ptr(),
             det.seg_cap, det.ntiles, det.F, det.R, det.D, det.A,
             t["grid_cs"].data_ptr(), _lib.ptr(det.ls_partials), int(t["symmetric"]), det.ntie.data_ptr(), det.tielist.data_ptr(),
-            _lib.ptr(t["mma"]), t["mma_tiles"], self.stream)
+            _lib.ptr(t["mma"]), t["mma_tiles"],
+            self._buf("cell_ws" + det.tag, (17 * det.F * det.R * det.D + 16,), torch.uint8).data_ptr() if det.A > 16 else 0,
+            self.stream)
         return det
 
     def velocity(self, det: Detections, out: Optional[torch.Tensor] = None, lambda_c: Optional[float] = None,
