@@ -1,0 +1,55 @@
+"""The fused cluster 2-D FFT (rs_range_doppler_fft, csrc/rs_fft2d.cu) against the oracle and against the two-kernel path:
+every cluster size, a chirp subset that still gives a 128-chirp plane, several frames and antennas, DC removal off."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import radar_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _rds(cube, p, env, monkeypatch, subset=None):
+    from radar_slam_b200 import RadarConfig, FramePipeline
+    for k in ("RS_FUSED_FFT", "RS_FUSED_NC", "RS_SPLIT_FFT"):
+        monkeypatch.delenv(k, raising=False)
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    pipe = FramePipeline(RadarConfig(chirp_duration=p.chirp_duration, num_chirps=cube.shape[2], num_antennas=p.num_antennas,
+                                     window_type=p.window_type, dc_removal=p.dc_removal))
+    out = pipe.range_doppler(torch.from_numpy(cube).cuda(), chirp_subset=subset)
+    torch.cuda.synchronize()
+    return out.permute(0, 2, 1, 3).cpu().numpy()                 # [F, S, A, C] -> [F, A, S, C]
+
+
+@pytest.mark.parametrize("A,F,win,dc", [(8, 3, "hann", True), (16, 2, "blackman", True), (3, 2, "hamming", False)])
+def test_cluster_kernel_matches_oracle_and_split_path(monkeypatch, A, F, win, dc):
+    p = orc.RadarParams(chirp_duration=25.6e-6, num_chirps=128, num_antennas=A, window_type=win, dc_removal=dc)
+    scene = np.array([(8.0, 0.0, -10.0, 0.0), (12.0, 0.5, -8.0, 0.0), (25.0, -0.7, 0.0, 0.0)])
+    np.random.seed(21 + A)
+    cube = np.stack([orc.synthesize_frame(p, scene) for _ in range(F)]).astype(np.complex64)
+    ref = np.stack([orc.range_doppler_spectrum(c.astype(np.complex128), p) for c in cube])
+    scale = np.abs(ref).max()
+    split = _rds(cube, p, {"RS_FUSED_FFT": "0"}, monkeypatch)
+    assert np.abs(split - ref).max() <= 2e-6 * scale
+    for nc in ("2", "4", "8"):
+        got = _rds(cube, p, {"RS_FUSED_NC": nc}, monkeypatch)
+        assert got.shape == ref.shape
+        assert np.abs(got - ref).max() <= 2e-6 * scale, nc
+        big = np.abs(ref) > 1e-3 * scale
+        assert (np.abs(np.abs(got[big]) - np.abs(ref[big])) / np.abs(ref[big])).max() < 1e-4       # BASELINE tolerance
+        assert np.abs(got - split).max() <= 1e-6 * scale                                             # same fp32 algorithm
+        if dc:
+            assert np.all(got[:, :, 128, :] == 0)                # the mean-removed bin (range bin 0, shifted to S/2)
+
+
+def test_cluster_kernel_on_a_chirp_subset(monkeypatch):
+    """dechirp.py:184-187: chirps [16, 144) of a 160-chirp frame are a 256 x 128 plane again -> the cluster kernel."""
+    p = orc.RadarParams(chirp_duration=25.6e-6, num_chirps=160, num_antennas=4)
+    np.random.seed(5)
+    cube = orc.synthesize_frame(p, np.array([(10.0, 0.2, -5.0, 0.0)]))[None].astype(np.complex64)
+    ref = orc.range_doppler_spectrum(cube[0].astype(np.complex128), p, chirp_subset=(16, 144))
+    got = _rds(cube, p, {}, monkeypatch, subset=(16, 144))[0]
+    split = _rds(cube, p, {"RS_FUSED_FFT": "0"}, monkeypatch, subset=(16, 144))[0]
+    assert got.shape == ref.shape == (4, 256, 128)
+    assert np.abs(got - ref).max() <= 2e-6 * np.abs(ref).max() and np.abs(got - split).max() <= 1e-6 * np.abs(ref).max()
