@@ -18,10 +18,13 @@
  *   cube   complex64 [F][A][C][S]   raw frame, reference layout frame_signals[A, C, S]
  *                                   (dechirp.py:168-181)
  *   mid    complex64 [F][S][A][C]   range spectrum, range axis already fftshift-ed (private)
- *   rds    complex64 [F][S][C][A]   range-Doppler spectrum, both axes fftshift-ed, CELL-MAJOR:
- *                                   the A-channel snapshot of a cell (the "spatial signature",
- *                                   angle_estimation.py:83) is contiguous.  The reference's
- *                                   rds[a, r, d] (dechirp.py:193-213) is rds_dev[r][d][a].
+ *   rds    complex64 [F][S][A][C]   range-Doppler spectrum, both axes fftshift-ed, RANGE-MAJOR PLANES:
+ *                                   for every range bin the A antenna rows of C Doppler cells follow each
+ *                                   other (the row order of `mid`, so the Doppler FFT keeps rows in place and
+ *                                   a 16-range-bin detection tile row is one contiguous run).  The A-channel
+ *                                   snapshot of a cell (the "spatial signature", angle_estimation.py:83) is A
+ *                                   elements at stride C.  The reference's rds[a, r, d] (dechirp.py:193-213)
+ *                                   is rds_dev[r][a][d].
  *   detections: per (frame, tile) segments of `seg_cap` slots, `det_count[F*ntiles]` valid each
  *       det_key    uint32  (antenna << 24) | (range_bin << 12) | doppler_bin; ascending key order
  *                          is the reference's output order antenna -> range -> doppler
@@ -214,10 +217,10 @@ int rs_music_covariance(const void* cov64, int n, int A, int num_sources, const 
 
 /* helpers for the legacy (list-of-dict) adapters ---------------------------------------------- */
 
-/* rds [F][S][C][A] -> reference layout [F][A][S][C] (complex64) */
+/* rds [F][S][A][C] -> reference layout [F][A][S][C] (complex64): a permutation of whole Doppler rows */
 int rs_rds_to_reference_layout(const void* rds, void* out, int F, int A, int C, int S, void* stream);
 
-/* reference layout [F][A][S][C] complex64 -> cell-major [F][S][C][A] */
+/* reference layout [F][A][S][C] complex64 -> rds [F][S][A][C] */
 int rs_rds_from_reference_layout(const void* rds_ref, void* out, int F, int A, int C, int S, void* stream);
 
 /* unit-energy snapshots (angle_estimation.py:83-88) of n cells: keys as in det_key, frame index per key.
@@ -230,7 +233,7 @@ int rs_signatures_f64(const void* rds, const uint32_t* keys, const int32_t* fram
 int rs_spectra_f64(const void* sig128, const void* steer128, int method, int n, int A, int G,
                    double* out, int32_t* aidx, void* stream);
 
-/* 10 log10(|X|^2 + 1e-12) of the cell-major RDS in the reference layout: out double [F][A][S][C]
+/* 10 log10(|X|^2 + 1e-12) of the RDS in the reference layout: out double [F][A][S][C]
  * (power_spectrum_db of extract_range_doppler_peaks, dechirp.py:235-238, 277). */
 int rs_power_db_f64(const void* rds, double* out, int F, int A, int C, int S, void* stream);
 
