@@ -387,37 +387,49 @@ __device__ int scan_exact_warp(const AngleFix& q, const double2* snap, int A, do
     return bi;
 }
 
-// -------- stage A: one warp per segment walks the flagged leaders in list order
+// -------- stage A: one CTA per 8 segments.  Every warp lists the flagged cells of its own segment (in list order),
+// the CTA's warps then EVALUATE all listed cells round-robin -- the fp64 scans are the expensive part and segments hold
+// anything from zero to a dozen cells -- and finally every warp COMMITS its own segment's results in list order
+// (velocity-sum corrections, stage-B slots), which keeps the outcome independent of who evaluated what.
+struct StageAResult {
+    double dl[5];      // correction of the segment's velocity sums (zero when undecided or unchanged)
+    int undecided, r, d, li;
+};
+
 __global__ void __launch_bounds__(RC_THREADS, 2)
 recheck_angles_kernel(CubeView v, AngleFix q, int32_t* __restrict__ work_idx, int32_t* __restrict__ work_cnt,
                       int32_t* __restrict__ frame_cnt, int4* __restrict__ frame_list, int32_t* __restrict__ stats) {
-    extern __shared__ double2 smd[];
+    extern __shared__ double2 smd[];                        // [RC_WARPS][A] snapshots
+    __shared__ int items[RC_WARPS][RS_TIE_LIST_CAP];        // flagged leader indices per segment, ascending
+    __shared__ int cnt[RC_WARPS], off[RC_WARPS + 1];
+    __shared__ double ds_seg[RC_WARPS];
+    __shared__ StageAResult res[RC_WARPS * RS_TIE_LIST_CAP];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int seg = blockIdx.x * RC_WARPS + wid;
-    if (seg >= q.nseg_total) return;
-    if (lane == 0) work_cnt[seg] = 0;
-    if (q.det_ntie != nullptr && q.det_ntie[seg] == 0) return;
-    const int n = q.det_nlead[seg];
-    if (n == 0) return;
     const int A = v.A;
-    double2* sw = smd + wid * A;         // this warp's snapshot
+    double2* sw = smd + wid * A;
+    const bool seg_ok = seg < q.nseg_total;
     const size_t base = (size_t)seg * q.seg_cap;
-    const int f = seg / q.nseg;
-    // rms(|X|) of the frame from the per-tile power sums; |dS|_2 <= fft_eps * rms * sqrt(A)
-    double psum = 0;
-    for (int sg = lane; sg < q.nseg; sg += 32) psum += (double)q.det_psum[(size_t)f * q.nseg + sg];
-    psum = warp_sum(psum);
-    const double ds_norm = fmax(q.fft_eps * sqrt(psum / ((double)q.R * q.D * A)) * sqrt((double)A), 1e-300);
-    double dl[5] = {0, 0, 0, 0, 0};
-    int nb = 0, lost = 0;
-    // one flagged cell: leader index li, whole warp
-    auto settle = [&](int li) {
-        const uint32_t ldj = q.det_lead[base + li];
-        const size_t o = base + (ldj & 0xFFFFu);
+    const int f = seg_ok ? seg / q.nseg : 0;
+    const int n = seg_ok ? q.det_nlead[seg] : 0;
+    const int ntie = !seg_ok ? 0 : (q.det_ntie != nullptr ? q.det_ntie[seg] : 0x7fffffff);
+    const bool has_work = seg_ok && n > 0 && ntie != 0;
+    const bool listed = has_work && q.det_tielist != nullptr && ntie <= RS_TIE_LIST_CAP;
+
+    auto undecided = [&](int li) {
+        const uint8_t f8 = q.det_flags[base + (q.det_lead[base + li] & 0xFFFFu)];
+        return (f8 & (RS_FLAG_TIE | RS_FLAG_GUARD)) && !(f8 & RS_FLAG_FIXED);
+    };
+    // fp64 scan of leader li of segment sg (whole warp); result valid on lane 0
+    auto evaluate = [&](int sg, int li, double ds_norm, StageAResult& out) {
+        const size_t sbase = (size_t)sg * q.seg_cap;
+        const int sf = sg / q.nseg;
+        const uint32_t ldj = q.det_lead[sbase + li];
+        const size_t o = sbase + (ldj & 0xFFFFu);
         const int k = (int)(ldj >> 16);
         int a, r, d;
         rs_split_key(q.det_key[o], a, r, d);
-        const float2* cell = q.rds + ((size_t)f * q.R + r) * A * q.D + d;
+        const float2* cell = q.rds + ((size_t)sf * q.R + r) * A * q.D + d;
         __syncwarp();
         for (int m = lane; m < A; m += 32) {
             const float2 x = cell[(size_t)m * q.D];
@@ -429,52 +441,91 @@ recheck_angles_kernel(CubeView v, AngleFix q, int32_t* __restrict__ work_idx, in
         // |dS|_2 <= fft_eps * rms * sqrt(A)  (noise-like part)  +  1.5e-7 |s|_2  (part that scales with the cell)
         const ScanRes sr = scan_warp(q, sw, A, energy, ds_norm + 1.5e-7 * sqrt(energy));
         if (lane == 0) {
-            if (!sr.undecided) {
-                apply_angle(q, o, k, sr.idx, dl, stats, 0);
-            } else if (nb < RB_MAX) {
-                const int slot = atomicAdd(frame_cnt + f, 1);
-                if (slot < FB_CAP) {
-                    work_idx[(size_t)seg * RB_MAX + nb] = li;
-                    frame_list[(size_t)f * FB_CAP + slot] = make_int4(seg * RB_MAX + nb, r, d, 0);
-                    ++nb;
-                } else {
-                    ++lost;
-                }
-            } else {
-                ++lost;
-            }
+            for (int j = 0; j < 5; ++j) out.dl[j] = 0;
+            out.undecided = sr.undecided ? 1 : 0;
+            out.r = r; out.d = d; out.li = li;
+            if (!sr.undecided) apply_angle(q, o, k, sr.idx, out.dl, stats, 0);      // this cell's entries only
         }
     };
-    auto undecided = [&](int li) {
-        const uint8_t f8 = q.det_flags[base + (q.det_lead[base + li] & 0xFFFFu)];
-        return (f8 & (RS_FLAG_TIE | RS_FLAG_GUARD)) && !(f8 & RS_FLAG_FIXED);
-    };
-    const int ntie = q.det_ntie != nullptr ? q.det_ntie[seg] : 0x7fffffff;
-    if (q.det_tielist != nullptr && ntie <= RS_TIE_LIST_CAP) {
-        // the list rs_angles wrote (in atomic order): rank-sort it so the items are settled in list order
+
+    // ---- phase 1: this warp's segment: noise level of its frame, ordered list of its flagged cells
+    if (lane == 0) cnt[wid] = 0;
+    if (has_work) {
+        // rms(|X|) of the frame from the per-tile power sums; |dS|_2 <= fft_eps * rms * sqrt(A)
+        double psum = 0;
+        for (int sg = lane; sg < q.nseg; sg += 32) psum += (double)q.det_psum[(size_t)f * q.nseg + sg];
+        psum = warp_sum(psum);
+        if (lane == 0) ds_seg[wid] = fmax(q.fft_eps * sqrt(psum / ((double)q.R * q.D * A)) * sqrt((double)A), 1e-300);
+    }
+    if (listed) {
+        // the list rs_angles wrote (in atomic order): rank-sort it
         int li = lane < ntie ? q.det_tielist[(size_t)seg * RS_TIE_LIST_CAP + lane] : 0x7fffffff;
         const bool live = lane < ntie && li >= 0 && li < n && undecided(li);
         if (!live) li = 0x7fffffff;
         int rank = 0;
         for (int t = 0; t < ntie; ++t) rank += __shfl_sync(0xffffffffu, li, t) < li ? 1 : 0;
-        const int nlive = __popc(__ballot_sync(0xffffffffu, live));
-        for (int rk = 0; rk < nlive; ++rk) {
-            const unsigned who = __ballot_sync(0xffffffffu, live && rank == rk);
-            settle(__shfl_sync(0xffffffffu, li, __ffs(who) - 1));
+        if (live) items[wid][rank] = li;
+        const unsigned lm = __ballot_sync(0xffffffffu, live);
+        if (lane == 0) cnt[wid] = __popc(lm);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int w = 0; w < RC_WARPS; ++w) { off[w] = run; run += cnt[w]; }
+        off[RC_WARPS] = run;
+    }
+    __syncthreads();
+
+    // ---- phase 2: all listed cells of the CTA, round-robin over its warps
+    const int total = off[RC_WARPS];
+    for (int t = wid; t < total; t += RC_WARPS) {
+        int w = 0;
+        while (t >= off[w + 1]) ++w;
+        evaluate(blockIdx.x * RC_WARPS + w, items[w][t - off[w]], ds_seg[w], res[t]);
+    }
+    __syncthreads();
+
+    // ---- phase 3: commit this warp's segment in list order
+    if (!seg_ok) return;
+    double dl[5] = {0, 0, 0, 0, 0};
+    int nb = 0, lost = 0;
+    auto commit = [&](const StageAResult& rr) {             // lane 0
+        if (!rr.undecided) {
+            for (int j = 0; j < 5; ++j) dl[j] += rr.dl[j];
+        } else if (nb < RB_MAX) {
+            const int slot = atomicAdd(frame_cnt + f, 1);
+            if (slot < FB_CAP) {
+                work_idx[(size_t)seg * RB_MAX + nb] = rr.li;
+                frame_list[(size_t)f * FB_CAP + slot] = make_int4(seg * RB_MAX + nb, rr.r, rr.d, 0);
+                ++nb;
+            } else {
+                ++lost;
+            }
+        } else {
+            ++lost;
         }
-    } else {
+    };
+    if (listed) {
+        if (lane == 0)
+            for (int k = 0; k < cnt[wid]; ++k) commit(res[off[wid] + k]);
+    } else if (has_work) {
+        // more flagged cells than the list holds (or no list): this warp scans its leaders and settles them itself
+        StageAResult* mine = &res[wid * RS_TIE_LIST_CAP];    // after the barrier above nobody else uses the array
+        const double ds_norm = ds_seg[wid];
         for (int c0 = 0; c0 < n; c0 += 32) {
             const int i = c0 + lane;
             unsigned mask = __ballot_sync(0xffffffffu, i < n && undecided(i));
             while (mask) {
                 const int j = __ffs(mask) - 1;
                 mask &= mask - 1;
-                settle(c0 + j);
+                evaluate(seg, c0 + j, ds_norm, *mine);
+                if (lane == 0) commit(*mine);
+                __syncwarp();
             }
         }
     }
     if (lane == 0) {
-        if (q.ls_partials) {
+        if (q.ls_partials && has_work) {
             double* ps = q.ls_partials + (size_t)seg * 8;
             for (int j = 0; j < 5; ++j) ps[j] += dl[j];
         }
