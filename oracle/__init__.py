@@ -11,5 +11,7 @@ Parity status: the reference's own tests pin no numeric result on this path
 itself: ``oracle/make_golden.py`` imports the real classes from /root/reference
 (under a matplotlib/h5py stub) and writes ``tests/golden/*.npz``; the restatement in
 ``oracle/radar_oracle.py`` is checked against those fixtures and, when
-/root/reference is present, against the live reference classes.
+/root/reference is present, against the live reference classes.  The inter-frame solver
+(``oracle/interframe_oracle.py``) is pinned the same way through ``tests/golden/interframe_de.npz``, written by
+``oracle/make_interframe_golden.py`` from a run of the reference's own ``ImprovedVelocitySolver``.
 """
