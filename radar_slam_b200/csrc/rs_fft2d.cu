@@ -177,17 +177,15 @@ extern "C" int rs_range_doppler_fft(const void* cube, const void* table, const v
             kern<<<(unsigned)ctas, THREADS, P::SMEM, (cudaStream_t)stream>>>(                                           \
                 (const float2*)cube, (const float2*)table, (const float2*)twiddle_s, (const float2*)twiddle_c,          \
                 (float2*)rds, A, C_total, chirp0, dc_removal);                                                          \
-            launched = 1;                                                                                               \
+            /* a device that cannot co-schedule the cluster rejects the launch: fall back to the two-kernel path */   \
+            if (cudaGetLastError() == cudaSuccess) launched = 1;                                                        \
         }                                                                                                               \
     } while (0)
         if (nc == 8) LAUNCH_F2D(8, 256, 3);
         else if (nc == 4) LAUNCH_F2D(4, 256, 2);
         else LAUNCH_F2D(2, 512, 1);
 #undef LAUNCH_F2D
-        if (launched) {
-            RS_CHECK_LAUNCH("rs_range_doppler_fft(cluster)");
-            return RS_OK;
-        }
+        if (launched) return RS_OK;
     }
     RS_CHECK_ARG(mid_ws != nullptr, "rs_range_doppler_fft: this shape needs the mid workspace");
     int rc = rs_range_fft(cube, table, twiddle_s, mid_ws, F, A, C_total, chirp0, C_used, S, dc_removal, stream);
