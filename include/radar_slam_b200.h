@@ -291,7 +291,7 @@ int rs_wrapped_lattice_search(const double* ax_cycles, const double* by_cycles, 
  *       antenna_pos   double [A] metres;  chirp_rate = bandwidth / chirp_duration;  t = linspace(0, chirp_duration, S)
  *       noise         Philox4x32-10 keyed by seed, counter = (cell pair in frame, first_frame + f): frame k does not
  *                     depend on the batch it is generated in.  Same distribution as the reference, not the same samples.
- *       plane_ws      complex64 [F][A][S] workspace;  cube complex64 [F][A][C][S];  S even. */
+ *       plane_ws      complex64 [F][A][S] workspace;  cube complex64 [F][A][C][S]. */
 int rs_synthesize_frames(const double* scatterers, const int32_t* n_scatterers, int n_max, double fc,
                          double chirp_rate, double chirp_duration, double lambda_c, const double* antenna_pos,
                          double noise_power, unsigned long long seed, long long first_frame, void* plane_ws,

@@ -104,6 +104,31 @@ cube_stream_kernel(const float2* __restrict__ plane, float sigma, uint32_t seed_
     }
 }
 
+// odd S: one cell per thread.  The noise of cell n of a frame is component (n & 1) of the Philox block of pair n >> 1,
+// i.e. the same stream as the vector kernel draws for even S.
+__global__ void __launch_bounds__(SYN_THREADS)
+cube_stream_scalar_kernel(const float2* __restrict__ plane, float sigma, uint32_t seed_lo, uint32_t seed_hi,
+                          long long first_frame, float2* __restrict__ cube, int A, int C, int S, long long cells_total) {
+    const long long cells_per_frame = (long long)A * C * S;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < cells_total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long f = i / cells_per_frame;
+        const long long in = i - f * cells_per_frame;
+        const int s_ = (int)(in % S);
+        const int a = (int)((in / S) / C);
+        float2 out = __ldg(plane + ((size_t)f * A + a) * S + s_);
+        if (sigma > 0.f) {
+            const unsigned long long fa = (unsigned long long)(first_frame + f), pr = (unsigned long long)in >> 1;
+            uint32_t ctr[4] = {(uint32_t)pr, (uint32_t)(pr >> 32), (uint32_t)fa, (uint32_t)(fa >> 32)};
+            philox4x32_10(ctr, seed_lo, seed_hi);
+            const float4 z = normal4(ctr);
+            out.x = fmaf(sigma, (in & 1) ? z.z : z.x, out.x);
+            out.y = fmaf(sigma, (in & 1) ? z.w : z.y, out.y);
+        }
+        __stcs(cube + i, out);
+    }
+}
+
 }  // namespace
 
 extern "C" int rs_synthesize_frames(const double* scatterers, const int32_t* n_scatterers, int n_max, double fc,
@@ -112,14 +137,24 @@ extern "C" int rs_synthesize_frames(const double* scatterers, const int32_t* n_s
                                     long long first_frame, void* plane_ws, void* cube, int F, int A, int C, int S,
                                     void* stream) {
     RS_CHECK_ARG(scatterers && antenna_pos && plane_ws && cube, "rs_synthesize_frames: null pointer");
-    RS_CHECK_ARG(F > 0 && A > 0 && C > 0 && S > 0 && S % 2 == 0 && n_max >= 0 && noise_power >= 0 && first_frame >= 0,
-                 "rs_synthesize_frames: bad dims (S must be even)");
+    RS_CHECK_ARG(F > 0 && A > 0 && C > 0 && S > 0 && n_max >= 0 && noise_power >= 0 && first_frame >= 0,
+                 "rs_synthesize_frames: bad dims");
     RS_CHECK_ARG((long long)F * A < (1ll << 31), "rs_synthesize_frames: too many planes");
     cudaStream_t st = (cudaStream_t)stream;
     scatterer_plane_kernel<<<(unsigned)(F * A), SYN_THREADS, 0, st>>>(scatterers, n_scatterers, n_max, fc, chirp_rate,
                                                                      chirp_duration, lambda_c, antenna_pos, A, S,
                                                                      (float2*)plane_ws);
     RS_CHECK_LAUNCH("rs_synthesize_frames(plane)");
+    if (S % 2 != 0) {
+        const long long cells = (long long)F * A * C * S;
+        const long long want1 = (cells + SYN_THREADS - 1) / SYN_THREADS;
+        const long long cap1 = (long long)rs_sm_count() * 32;
+        cube_stream_scalar_kernel<<<(unsigned)(want1 < cap1 ? want1 : cap1), SYN_THREADS, 0, st>>>(
+            (const float2*)plane_ws, (float)sqrt(noise_power), (uint32_t)seed, (uint32_t)(seed >> 32), first_frame,
+            (float2*)cube, A, C, S, cells);
+        RS_CHECK_LAUNCH("rs_synthesize_frames(stream, odd S)");
+        return RS_OK;
+    }
     const long long pairs = (long long)F * A * C * (S / 2);
     const long long want = (pairs + SYN_THREADS - 1) / SYN_THREADS;
     const long long cap = (long long)rs_sm_count() * 32;

@@ -20,7 +20,7 @@ def _cfg(p):
                        num_chirps=p.num_chirps, sampling_rate=p.sampling_rate, num_antennas=p.num_antennas)
 
 
-@pytest.mark.parametrize("S,C,A", [(256, 16, 8), (400, 4, 3), (512, 2, 16)])
+@pytest.mark.parametrize("S,C,A", [(256, 16, 8), (400, 4, 3), (512, 2, 16), (25, 3, 2)])
 def test_scatterer_term_matches_oracle(S, C, A):
     from radar_slam_b200 import synth
     p = orc.RadarParams(chirp_duration=S / 10e6, num_chirps=C, num_antennas=A, noise_power=0.0)
@@ -52,6 +52,10 @@ def test_noise_is_gaussian_keyed_by_frame():
     assert abs(np.mean(z[:-1, 0] * z[1:, 0])) < 5 / np.sqrt(n)                # neighbouring samples uncorrelated
     assert abs(np.mean(z ** 4) - 3) < 0.05                                     # kurtosis of a normal
     assert 4.5 < np.abs(z).max() < 7                                           # tails present, nothing absurd
+    # an odd number of samples per chirp takes the scalar kernel: same stream, same statistics
+    p_odd = orc.RadarParams(chirp_duration=25.5e-6, num_chirps=64, num_antennas=8)
+    zo = torch.view_as_real(synth.synthesize_frames(_cfg(p_odd), none, 2, seed=7, noise_power=0.01)).double().cpu().numpy().reshape(-1, 2) / 0.1
+    assert p_odd.samples_per_chirp % 2 == 1 and abs(zo.mean()) < 5 / np.sqrt(2 * len(zo)) and abs(zo.var() - 1) < 0.02
     # Kolmogorov-Smirnov against the normal CDF on a subsample
     from scipy import stats
     assert stats.kstest(z[::97, 0], "norm").pvalue > 1e-3
