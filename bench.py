@@ -35,11 +35,12 @@ WORKLOAD = "configs[1]: 1k-frame synthetic batch per GPU, 256 samples x 128 chir
 
 
 def workload_name(args):
-    if (args.frames, args.samples, args.chirps, args.antennas, args.method, args.grid_res, args.threshold_db) == \
-            (1000, 256, 128, 8, "music", 1.0, -20.0):
+    if (args.frames, args.samples, args.chirps, args.antennas, args.method, args.grid_res, args.threshold_db, args.irls) == \
+            (1000, 256, 128, 8, "music", 1.0, -20.0, 0):
         return WORKLOAD
     return (f"non-default: {args.frames} frames per GPU, {args.samples} samples x {args.chirps} chirps x {args.antennas} channels, "
-            f"{args.method} ({args.grid_res} deg grid), noise_power 0.01, threshold {args.threshold_db} dB")
+            f"{args.method} ({args.grid_res} deg grid), noise_power 0.01, threshold {args.threshold_db} dB, "
+            f"{args.irls} Huber iterations")
 
 
 def radar_config(args):
@@ -47,7 +48,7 @@ def radar_config(args):
     return RadarConfig(fc=77e9, bandwidth=1e9, chirp_duration=args.samples / 10e6, pri=100e-6, num_chirps=args.chirps,
                        sampling_rate=10e6, num_antennas=args.antennas, search_resolution=args.grid_res,
                        method=args.method, threshold_db=args.threshold_db, recheck=not args.no_recheck,
-                       fft_eps=args.fft_eps)
+                       fft_eps=args.fft_eps, irls_iters=args.irls, huber_delta=args.huber)
 
 
 def oracle_params(args):
@@ -412,6 +413,8 @@ def main():
     ap.add_argument("--antennas", type=int, default=8)
     ap.add_argument("--grid-res", type=float, default=1.0)
     ap.add_argument("--method", default="music", choices=["music", "beamforming", "esprit"])
+    ap.add_argument("--irls", type=int, default=0, help="Huber reweighting iterations of the velocity solve (configs[3])")
+    ap.add_argument("--huber", type=float, default=1.0)
     ap.add_argument("--threshold-db", type=float, default=-20.0)
     ap.add_argument("--chunk", type=int, default=500, help="frames per launch set, device-resident path")
     ap.add_argument("--host-chunk", type=int, default=32, help="frames per H2D chunk, host-buffer path")
