@@ -4,8 +4,8 @@
 // descending order, keeps E_n = V[:, num_sources:] and evaluates 1 / |a^H E_n E_n^H a| with a 1e-12 guard.
 // In the reference R is always the rank-1 outer product of one snapshot, for which the batched path uses the
 // closed form (rs_angles).  This kernel is the general path for an arbitrary Hermitian R (multi-snapshot or
-// spatially smoothed covariances, num_sources > 1): one warp per matrix, lane j owns column j of R and of V
-// (2 * A complex registers), parallel cyclic Jacobi with the round-robin pair ordering -- the A/2 disjoint
+// spatially smoothed covariances, num_sources > 1): AP lanes per matrix (32 / AP matrices per warp, AP = A padded to a
+// power of two), lane j of a group owns column j of R and of V (2 * A complex registers), parallel cyclic Jacobi with the round-robin pair ordering -- the A/2 disjoint
 // pairs of a round are rotated simultaneously, column updates exchange the two columns of a pair by shuffle,
 // row updates are local to every lane -- then eigenvalue ranking by shuffle and the grid scan with lanes
 // summing |a_g^H v_j|^2 over the noise eigenvectors.
@@ -20,9 +20,12 @@ __global__ void __launch_bounds__(EIG_WARPS * 32)
 music_cov_kernel(const float2* __restrict__ cov, int n, int A, int num_sources, const float2* __restrict__ steer, int G,
                  int sweeps, float* __restrict__ eigvals, float2* __restrict__ eigvecs, float* __restrict__ spectrum,
                  int32_t* __restrict__ aidx) {
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int mat = blockIdx.x * EIG_WARPS + wid;
-    if (mat >= n) return;
+    // lane = column index inside the group of AP lanes that shares one matrix; all shuffles stay inside the group
+    constexpr int GROUPS = 32 / AP;
+    const int lane = (threadIdx.x & 31) % AP, wid = threadIdx.x >> 5;
+    const int mat_raw = (blockIdx.x * EIG_WARPS + wid) * GROUPS + (threadIdx.x & 31) / AP;
+    const bool mat_ok = mat_raw < n;
+    const int mat = mat_ok ? mat_raw : n - 1;        // idle groups recompute the last matrix and write nothing
     const unsigned full = 0xffffffffu;
     // lane j < A holds column j:  r[i] = R[i][j],  v[i] = V[i][j]
     float2 r[AP], v[AP];
@@ -53,10 +56,10 @@ music_cov_kernel(const float2* __restrict__ cov, int n, int A, int num_sources, 
                 if (i == me) mine_diag = r[i].x;
                 if (i == q && me == p) off = make_float2(r[i].x, -r[i].y);       // R_pq = conj(R_qp)
             }
-            const float other_diag = __shfl_sync(full, mine_diag, partner);
+            const float other_diag = __shfl_sync(full, mine_diag, partner, AP);
             float2 bpq;                                                          // R_pq, known to both lanes
-            bpq.x = __shfl_sync(full, off.x, p);
-            bpq.y = __shfl_sync(full, off.y, p);
+            bpq.x = __shfl_sync(full, off.x, p, AP);
+            bpq.y = __shfl_sync(full, off.y, p, AP);
             const float app = (me == p) ? mine_diag : other_diag;
             const float aqq = (me == p) ? other_diag : mine_diag;
             const float babs = sqrtf(bpq.x * bpq.x + bpq.y * bpq.y);
@@ -76,8 +79,8 @@ music_cov_kernel(const float2* __restrict__ cov, int n, int A, int num_sources, 
                                            : make_float2(s * ph.x, s * ph.y);      //  s e^{+i phi}
 #pragma unroll
                 for (int i = 0; i < AP; ++i) {
-                    const float2 orr = make_float2(__shfl_sync(full, r[i].x, partner), __shfl_sync(full, r[i].y, partner));
-                    const float2 ovv = make_float2(__shfl_sync(full, v[i].x, partner), __shfl_sync(full, v[i].y, partner));
+                    const float2 orr = make_float2(__shfl_sync(full, r[i].x, partner, AP), __shfl_sync(full, r[i].y, partner, AP));
+                    const float2 ovv = make_float2(__shfl_sync(full, v[i].x, partner, AP), __shfl_sync(full, v[i].y, partner, AP));
                     r[i] = make_float2(c * r[i].x + (w.x * orr.x - w.y * orr.y), c * r[i].y + (w.x * orr.y + w.y * orr.x));
                     v[i] = make_float2(c * v[i].x + (w.x * ovv.x - w.y * ovv.y), c * v[i].y + (w.x * ovv.y + w.y * ovv.x));
                 }
@@ -87,9 +90,9 @@ music_cov_kernel(const float2* __restrict__ cov, int n, int A, int num_sources, 
 #pragma unroll
             for (int pp = 0; pp < AP; ++pp) {
                 // lane pp broadcasts its (partner, c, s, ph) ; handle each pair once (pp < its partner)
-                const int qq = __shfl_sync(full, partner, pp);
-                const float cc = __shfl_sync(full, c, pp), ss = __shfl_sync(full, s, pp);
-                const float2 pph = make_float2(__shfl_sync(full, ph.x, pp), __shfl_sync(full, ph.y, pp));
+                const int qq = __shfl_sync(full, partner, pp, AP);
+                const float cc = __shfl_sync(full, c, pp, AP), ss = __shfl_sync(full, s, pp, AP);
+                const float2 pph = make_float2(__shfl_sync(full, ph.x, pp, AP), __shfl_sync(full, ph.y, pp, AP));
                 if (pp < qq) {
                     float2 rp = make_float2(0.f, 0.f), rq = make_float2(0.f, 0.f);
 #pragma unroll
@@ -117,10 +120,10 @@ music_cov_kernel(const float2* __restrict__ cov, int n, int A, int num_sources, 
         if (i == lane) lam = r[i].x;
     int rank = 0;
     for (int j = 0; j < A; ++j) {
-        const float lj = __shfl_sync(full, lam, j);
+        const float lj = __shfl_sync(full, lam, j, AP);
         if (lane < A && (lj > lam || (lj == lam && j < lane))) ++rank;
     }
-    if (lane < A) {
+    if (lane < A && mat_ok) {
         if (eigvals) eigvals[(size_t)mat * A + rank] = lam;
         if (eigvecs) {
 #pragma unroll
@@ -147,12 +150,12 @@ music_cov_kernel(const float2* __restrict__ cov, int n, int A, int num_sources, 
         }
         float den = pr * pr + pi * pi;
 #pragma unroll
-        for (int off = 16; off; off >>= 1) den += __shfl_xor_sync(full, den, off);
+        for (int off = AP / 2; off; off >>= 1) den += __shfl_xor_sync(full, den, off, AP);
         const float val = den > 1e-12f ? 1.f / den : 0.f;
-        if (lane == 0 && spectrum) spectrum[(size_t)mat * G + g] = val;
+        if (lane == 0 && spectrum && mat_ok) spectrum[(size_t)mat * G + g] = val;
         if (val > best) { best = val; bi = g; }
     }
-    if (lane == 0 && aidx) aidx[mat] = bi;
+    if (lane == 0 && aidx && mat_ok) aidx[mat] = bi;
 }
 
 }  // namespace
@@ -163,7 +166,9 @@ extern "C" int rs_music_covariance(const void* cov64, int n, int A, int num_sour
     RS_CHECK_ARG(num_sources >= 0 && num_sources < A && sweeps > 0 && sweeps <= 64, "rs_music_covariance: bad num_sources / sweeps");
     RS_CHECK_ARG(steer64 == nullptr || G > 0, "rs_music_covariance: bad grid");
     if (n == 0) return RS_OK;
-    const int blocks = (n + EIG_WARPS - 1) / EIG_WARPS;
+    const int ap = A <= 2 ? 2 : A <= 4 ? 4 : A <= 8 ? 8 : A <= 16 ? 16 : 32;
+    const int per_block = EIG_WARPS * (32 / ap);
+    const int blocks = (n + per_block - 1) / per_block;
     cudaStream_t st = (cudaStream_t)stream;
 #define LAUNCH_EIG(AP)                                                                                                  \
     music_cov_kernel<AP><<<blocks, EIG_WARPS * 32, 0, st>>>((const float2*)cov64, n, A, num_sources, (const float2*)steer64, \
