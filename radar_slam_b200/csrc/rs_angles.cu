@@ -14,6 +14,7 @@
 // ESPRIT (angle_estimation.py:195-221) reduces, for one snapshot, to the principal eigenvector of a
 // 2x2 Hermitian matrix; it is evaluated in fp64 from the fp32 snapshot.
 #include <cstdlib>
+#include <cuda_fp16.h>
 #include "rs_common.cuh"
 
 namespace {
@@ -369,25 +370,33 @@ __global__ void __launch_bounds__(ANG_THREADS) angles_scan_kernel(AngleArgs p, c
 //
 // The lag-form scan is a dense contraction: for the grid pair (g, G-1-g)
 //     E[cell][g] = sum_k Re R_k cos(k phi_g),   O[cell][g] = sum_k Im R_k sin(k phi_g),   P(+-theta) = R_0 + 2 (E +- O),
-// i.e. [cells x K] . [K x pairs] with K = AP lags (k = 1 .. AP-1, zero padded).  It runs on the tensor cores through
-// mma.sync.m16n8k8 TF32 with the 3xTF32 split (x = hi + lo, both TF32: hi*hi + lo*hi + hi*lo), which keeps ~2^-21 relative accuracy per product -- the same order as the fp32 FMA
-// chain; the B fragments (cos / sin tables) are split on the host.  A warp carries 32 cells (two 16-row tiles); lane L
-// computes the lags of cell L, publishes them through shared memory in fragment order, and every lane then tracks
-// (best, runner-up, pair index) for its two accumulator rows and two columns per tile.  The pair maximum is
-// E + |O| and the pair minimum E - |O|, so the tracking costs 6 ALU operations per pair instead of 10 per pair
-// in the CUDA-core scan; which side won is read off the sign of O once, after the scan (|O| ~ 0 means the two sides
-// tie, and a tie is flagged RS_FLAG_TIE anyway).
+// i.e. [cells x lags] . [lags x pairs] with AP - 1 lags, zero padded to AP.  It runs on the tensor cores through
+// mma.sync.m16n8k16 with fp16 operands, fp32 accumulation and a two-way split of both operands (x = hi + lo, both fp16;
+// the lags are divided by R_0 first, so everything lives in [-1, 1]): the products hi*hi + lo*hi + hi*lo keep ~2^-21
+// relative accuracy per product, the same order as an fp32 FMA chain.  The split is packed along K: one k-step holds
+// eight lags as [hi(8) | lo(8)], so  A = [a_hi | a_lo], B = [b_hi ; b_hi]  gives hi*hi + lo*hi in ONE instruction and
+// A = [a_hi | 0], B = [b_lo ; 0]  adds hi*lo -- 2 instructions per matrix, k-step and 8 pairs x 16 cells (the issue
+// limit of mma.sync, 0.46 /clk/SM, is what the tensor part costs).  The B fragments (cos / sin tables) are split and
+// packed on the host.  A warp carries 32 cells (two 16-row tiles); lane L computes the lags of cell L, publishes them
+// through shared memory, every lane builds the A fragments of its rows, and then tracks (best, runner-up, pair index)
+// for its accumulator rows.  The pair maximum is E + |O| and the pair minimum E - |O|, so the tracking costs 5 ALU
+// operations per pair instead of 10 in the CUDA-core scan; which side won is read off the sign of O once, after the
+// scan (|O| ~ 0 means the two sides tie, and a tie is flagged RS_FLAG_TIE anyway).
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t to_tf32(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return r;
-}
-__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+__device__ __forceinline__ void mma_f16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                        uint32_t b1) {
     asm volatile(
-        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
         : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+// (x, y) -> packed fp16 pair of the leading parts (x in the low half) and of the remainders
+__device__ __forceinline__ void split_f16x2(float x, float y, uint32_t& hi, uint32_t& lo) {
+    const __half2 h = __floats2half2_rn(x, y);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(x - hf.x, y - hf.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 __device__ __forceinline__ void track_pair(Track& t, float hi, float lo, int pair) {
     const float m = fminf(t.best, hi);
@@ -398,20 +407,20 @@ __device__ __forceinline__ void track_pair(Track& t, float hi, float lo, int pai
 }
 
 template <int AP, int MINB>
-__global__ void __launch_bounds__(ANG_THREADS, MINB) angles_mma_kernel(AngleArgs p, const float* __restrict__ mma_table,
+__global__ void __launch_bounds__(ANG_THREADS, MINB) angles_mma_kernel(AngleArgs p, const uint32_t* __restrict__ mma_table,
                                                                   int ntiles, const double* __restrict__ grid_cs,
                                                                   double* __restrict__ ls_partials) {
-    constexpr int K = AP, KS = AP / 8, LSTRIDE = 2 * K + 4, TILE_FLOATS = 4 * KS * 64;
-    extern __shared__ float smf[];
-    float* tabs = smf;                              // [ntiles][cos, sin][hi, lo][KS][32 lanes][2]
-    float* Lx = tabs + (size_t)ntiles * TILE_FLOATS; // [warps][32 cells][LSTRIDE]: lags 1..K-1 of E, then of O
+    constexpr int K = AP, KS = AP / 8, LSTRIDE = 2 * K + 8, TILE_WORDS = 2 * KS * 64;
+    extern __shared__ uint32_t smw[];
+    uint32_t* tabs = smw;                                        // [ntiles][cos, sin][KS][32 lanes][b_hi, b_lo]
+    float* Lx = reinterpret_cast<float*>(tabs + (size_t)ntiles * TILE_WORDS);   // [warps][32 cells][LSTRIDE]: E lags / R_0, then O lags / R_0
     __shared__ double red[ANG_THREADS / 32][8];
     const int seg = blockIdx.x;
     const int n = p.det_nlead[seg];
     double acc_ls[7] = {0, 0, 0, 0, 0, 0, 0};
     if (n > 0) {
-        for (int i = threadIdx.x; i < ntiles * TILE_FLOATS / 4; i += blockDim.x)
-            reinterpret_cast<float4*>(tabs)[i] = __ldg(reinterpret_cast<const float4*>(mma_table) + i);
+        for (int i = threadIdx.x; i < ntiles * TILE_WORDS / 4; i += blockDim.x)
+            reinterpret_cast<uint4*>(tabs)[i] = __ldg(reinterpret_cast<const uint4*>(mma_table) + i);
         __syncthreads();
         const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
         const int gq = lane >> 2, tq = lane & 3;
@@ -441,10 +450,13 @@ __global__ void __launch_bounds__(ANG_THREADS, MINB) angles_mma_kernel(AngleArgs
 #pragma unroll
                     for (int m = 0; m < AP; ++m) s[m] = make_float2(0.f, 0.f);
                 }
+#pragma unroll
+                for (int m = 0; m < AP; ++m) rr0 = fmaf(s[m].x, s[m].x, fmaf(s[m].y, s[m].y, rr0));
+                const float inv = rr0 > 0.f ? 1.f / rr0 : 0.f;       // |R_k| <= R_0: the normalised lags lie in [-1, 1]
                 __syncwarp();                       // the previous pass no longer reads this warp's rows
                 float* row = Lw + lane * LSTRIDE;
 #pragma unroll
-                for (int k = 0; k < AP; ++k) {
+                for (int k = 1; k < AP; ++k) {
                     float xr = 0.f, xi = 0.f;
 #pragma unroll
                     for (int m = 0; m + k < AP; ++m) {
@@ -453,52 +465,47 @@ __global__ void __launch_bounds__(ANG_THREADS, MINB) angles_mma_kernel(AngleArgs
                         xi = fmaf(s[m + k].y, s[m].x, xi);
                         xi = fmaf(-s[m + k].x, s[m].y, xi);
                     }
-                    if (k == 0) rr0 = xr;
-                    else { row[k - 1] = xr; row[K + k - 1] = xi; }
+                    row[k - 1] = xr * inv;
+                    row[K + k - 1] = xi * inv;
                 }
                 row[K - 1] = 0.f;
                 row[2 * K - 1] = 0.f;
                 __syncwarp();
             }
-            float my_best = NEG, my_second = NEG;
-            int my_pair = 0;
-#pragma unroll 1
+            // A fragments of both 16-cell tiles: rows gq, gq + 8 of tile t; columns 2 tq, 2 tq + 1 of k-step s
+            uint32_t aE[2][KS][4], aO[2][KS][4];
+#pragma unroll
             for (int t = 0; t < 2; ++t) {
-                // A fragments of this 16-cell tile: rows gq, gq+8; columns tq + 8s, tq + 4 + 8s
-                uint32_t aEh[KS][4], aEl[KS][4], aOh[KS][4], aOl[KS][4];
-                const float* r0 = Lw + (16 * t + gq) * LSTRIDE;
+                const float* r0 = Lw + (16 * t + gq) * LSTRIDE + 2 * tq;
                 const float* r1 = r0 + 8 * LSTRIDE;
 #pragma unroll
                 for (int s_ = 0; s_ < KS; ++s_) {
-                    const int c0 = tq + 8 * s_, c1 = c0 + 4;
-                    const float vE[4] = {r0[c0], r1[c0], r0[c1], r1[c1]};
-                    const float vO[4] = {r0[K + c0], r1[K + c0], r0[K + c1], r1[K + c1]};
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        aEh[s_][q] = to_tf32(vE[q]);
-                        aEl[s_][q] = to_tf32(vE[q] - __uint_as_float(aEh[s_][q]));
-                        aOh[s_][q] = to_tf32(vO[q]);
-                        aOl[s_][q] = to_tf32(vO[q] - __uint_as_float(aOh[s_][q]));
-                    }
+                    const float2 e0 = *reinterpret_cast<const float2*>(r0 + 8 * s_), e1 = *reinterpret_cast<const float2*>(r1 + 8 * s_);
+                    const float2 o0 = *reinterpret_cast<const float2*>(r0 + K + 8 * s_), o1 = *reinterpret_cast<const float2*>(r1 + K + 8 * s_);
+                    split_f16x2(e0.x, e0.y, aE[t][s_][0], aE[t][s_][2]);
+                    split_f16x2(e1.x, e1.y, aE[t][s_][1], aE[t][s_][3]);
+                    split_f16x2(o0.x, o0.y, aO[t][s_][0], aO[t][s_][2]);
+                    split_f16x2(o1.x, o1.y, aO[t][s_][1], aO[t][s_][3]);
                 }
-                Track tr[2] = {Track{NEG, NEG, 0}, Track{NEG, NEG, 0}};
-                const float2* tb = reinterpret_cast<const float2*>(tabs) + lane;
-                for (int j = 0; j < ntiles; ++j, tb += TILE_FLOATS / 2) {
-                    // one accumulator per matrix: the large product first, then the two small ones (E and O chains alternate)
+            }
+            Track tr[2][2] = {{Track{NEG, NEG, 0}, Track{NEG, NEG, 0}}, {Track{NEG, NEG, 0}, Track{NEG, NEG, 0}}};
+            const uint2* tb = reinterpret_cast<const uint2*>(tabs) + lane;
+            for (int j = 0; j < ntiles; ++j, tb += TILE_WORDS / 2) {
+                uint2 bE[KS], bO[KS];                                // (b_hi, b_lo) of this lane's rows 2 tq, 2 tq + 1
+#pragma unroll
+                for (int s_ = 0; s_ < KS; ++s_) { bE[s_] = tb[s_ * 32]; bO[s_] = tb[(KS + s_) * 32]; }
+                const int pb = 8 * j + 2 * tq;
+                const bool masked = j == ntiles - 1;
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {
                     float cE[4] = {0.f, 0.f, 0.f, 0.f}, cO[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                     for (int s_ = 0; s_ < KS; ++s_) {
-                        const float2 bEh = tb[(0 * KS + s_) * 32], bEl = tb[(1 * KS + s_) * 32];
-                        const float2 bOh = tb[(2 * KS + s_) * 32], bOl = tb[(3 * KS + s_) * 32];
-                        mma_tf32(cE, aEh[s_], __float_as_uint(bEh.x), __float_as_uint(bEh.y));
-                        mma_tf32(cO, aOh[s_], __float_as_uint(bOh.x), __float_as_uint(bOh.y));
-                        mma_tf32(cE, aEl[s_], __float_as_uint(bEh.x), __float_as_uint(bEh.y));
-                        mma_tf32(cO, aOl[s_], __float_as_uint(bOh.x), __float_as_uint(bOh.y));
-                        mma_tf32(cE, aEh[s_], __float_as_uint(bEl.x), __float_as_uint(bEl.y));
-                        mma_tf32(cO, aOh[s_], __float_as_uint(bOl.x), __float_as_uint(bOl.y));
+                        mma_f16(cE, aE[t][s_][0], aE[t][s_][1], aE[t][s_][2], aE[t][s_][3], bE[s_].x, bE[s_].x);   // hi hi + lo hi
+                        mma_f16(cO, aO[t][s_][0], aO[t][s_][1], aO[t][s_][2], aO[t][s_][3], bO[s_].x, bO[s_].x);
+                        mma_f16(cE, aE[t][s_][0], aE[t][s_][1], 0u, 0u, bE[s_].y, 0u);                              // hi lo
+                        mma_f16(cO, aO[t][s_][0], aO[t][s_][1], 0u, 0u, bO[s_].y, 0u);
                     }
-                    const int pb = 8 * j + 2 * tq;
-                    const bool masked = j == ntiles - 1;
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         const float e = cE[q], od = fabsf(cO[q]);
@@ -508,28 +515,33 @@ __global__ void __launch_bounds__(ANG_THREADS, MINB) angles_mma_kernel(AngleArgs
                             if (pair > last_pair) { hi = NEG; lo = NEG; }
                             else if (odd && pair == half) lo = NEG;        // the middle angle has no partner
                         }
-                        track_pair(tr[q >> 1], hi, lo, pair);
+                        track_pair(tr[t][q >> 1], hi, lo, pair);
                     }
                 }
+            }
+            float my_best = NEG, my_second = NEG;
+            int my_pair = 0;
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
                 // the four lanes of a quad hold different columns of the same rows: merge them
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
 #pragma unroll
                     for (int off = 1; off <= 2; off <<= 1) {
-                        const float ob = __shfl_xor_sync(0xffffffffu, tr[h].best, off);
-                        const float os = __shfl_xor_sync(0xffffffffu, tr[h].second, off);
-                        const int oi = __shfl_xor_sync(0xffffffffu, tr[h].idx, off);
-                        tr[h].second = fmaxf(fmaxf(tr[h].second, os), fminf(tr[h].best, ob));
-                        if (ob > tr[h].best || (ob == tr[h].best && oi < tr[h].idx)) { tr[h].best = ob; tr[h].idx = oi; }
+                        const float ob = __shfl_xor_sync(0xffffffffu, tr[t][h].best, off);
+                        const float os = __shfl_xor_sync(0xffffffffu, tr[t][h].second, off);
+                        const int oi = __shfl_xor_sync(0xffffffffu, tr[t][h].idx, off);
+                        tr[t][h].second = fmaxf(fmaxf(tr[t][h].second, os), fminf(tr[t][h].best, ob));
+                        if (ob > tr[t][h].best || (ob == tr[t][h].best && oi < tr[t][h].idx)) { tr[t][h].best = ob; tr[t][h].idx = oi; }
                     }
                 }
                 // row (t, h, gq) is cell 16 t + 8 h + gq of the warp: hand the result to the lane that owns the cell
                 const int src = 4 * (lane & 7);
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    const float vb = __shfl_sync(0xffffffffu, tr[h].best, src);
-                    const float vs = __shfl_sync(0xffffffffu, tr[h].second, src);
-                    const int vi = __shfl_sync(0xffffffffu, tr[h].idx, src);
+                    const float vb = __shfl_sync(0xffffffffu, tr[t][h].best, src);
+                    const float vs = __shfl_sync(0xffffffffu, tr[t][h].second, src);
+                    const int vi = __shfl_sync(0xffffffffu, tr[t][h].idx, src);
                     if ((lane >> 4) == t && ((lane >> 3) & 1) == h) { my_best = vb; my_second = vs; my_pair = vi; }
                 }
             }
@@ -541,12 +553,13 @@ __global__ void __launch_bounds__(ANG_THREADS, MINB) angles_mma_kernel(AngleArgs
 #pragma unroll
                 for (int k = 1; k < AP; ++k) od = fmaf(row[k - 1], __ldg(trow + 2 * (k - 1) + 1), od);
                 const int bi = (odd && my_pair == half) ? half : (od >= 0.f ? my_pair : G - 1 - my_pair);
-                const float pbest = rr0 + 2.f * my_best;
+                // my_best, my_second are (P - R_0) / (2 R_0) of the best and second-best grid point
+                const float pnorm = 1.f + 2.f * my_best;
                 uint8_t flags = 0;
-                if (2.f * (my_best - my_second) <= p.tie_eps * fabsf(pbest)) flags |= RS_FLAG_TIE;
+                if (2.f * (my_best - my_second) <= p.tie_eps * fabsf(pnorm)) flags |= RS_FLAG_TIE;
                 if (p.method == RS_METHOD_MUSIC) {
-                    const float full = (float)M * rr0;
-                    if (full - pbest <= 1e-4f * full) flags |= RS_FLAG_GUARD;
+                    const float full = (float)M;
+                    if (full - pnorm <= 1e-4f * full) flags |= RS_FLAG_GUARD;
                 }
                 const int live = emit(p, seg, i, o, mult, bi, p.grid_deg[bi], yv, flags);
                 if (ls_partials != nullptr) {
@@ -867,17 +880,17 @@ extern "C" int rs_angles(const void* rds, const float* scan_table, int scan_stri
             const char* mma_env = getenv("RS_ANGLES_MMA");  // 0: force the CUDA-core scan
             if (mma_table != nullptr && grid_symmetric && (ap == 8 || ap == 16) && !(mma_env && atoi(mma_env) == 0)) {
                 RS_CHECK_ARG(mma_tiles == ((G + 1) / 2 + 7) / 8, "rs_angles: mma_tiles must be ceil(ceil(G/2)/8)");
-                const size_t sm = ((size_t)mma_tiles * 4 * (ap / 8) * 64 + (size_t)(ANG_THREADS / 32) * 32 * (2 * ap + 4)) *
+                const size_t sm = ((size_t)mma_tiles * 2 * (ap / 8) * 64 + (size_t)(ANG_THREADS / 32) * 32 * (2 * ap + 8)) *
                                   sizeof(float);
                 if (sm <= (size_t)rs_smem_optin_limit()) {
                     // occupancy beats per-warp ILP here (measured): 64 registers / 8 CTAs per SM at A <= 8
                     if (ap == 8) {
                         cudaFuncSetAttribute(angles_mma_kernel<8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-                        angles_mma_kernel<8, 8><<<(unsigned)blocks, ANG_THREADS, sm, st>>>(p, mma_table, mma_tiles, grid_cs,
+                        angles_mma_kernel<8, 8><<<(unsigned)blocks, ANG_THREADS, sm, st>>>(p, (const uint32_t*)mma_table, mma_tiles, grid_cs,
                                                                                         ls_partials);
                     } else {
                         cudaFuncSetAttribute(angles_mma_kernel<16, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-                        angles_mma_kernel<16, 5><<<(unsigned)blocks, ANG_THREADS, sm, st>>>(p, mma_table, mma_tiles,
+                        angles_mma_kernel<16, 5><<<(unsigned)blocks, ANG_THREADS, sm, st>>>(p, (const uint32_t*)mma_table, mma_tiles,
                                                                                          grid_cs, ls_partials);
                     }
                     RS_CHECK_LAUNCH("rs_angles(mma)");

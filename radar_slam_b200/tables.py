@@ -88,12 +88,22 @@ def tf32_split(x32: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
     return hi, lo
 
 
+def f16_split(x32: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+    """x (float32, |x| <= 1) -> (hi, lo) fp16 with x = hi + lo up to 2^-22 |x| (+ 3e-8 where lo is subnormal)."""
+    x32 = np.asarray(x32, dtype=np.float32)
+    hi = x32.astype(np.float16)
+    lo = (x32 - hi.astype(np.float32)).astype(np.float16)
+    return hi, lo
+
+
 def scan_mma_table(scan: np.ndarray, G: int, A: int) -> Tuple[np.ndarray, int]:
-    """B-operand fragments of the tensor-core angle scan (mma.sync m16n8k8 TF32, 3xTF32 split) for a grid that is
-    symmetric about 0: grid pairs (g, G-1-g), g < ceil(G/2), share cos(k phi_g) and differ in the sign of sin(k phi_g).
-    Layout float32 [ntiles][matrix: cos, sin][part: hi, lo][kstep][lane 32][2]: lane holds B[k = lane%4 + 4r + 8s]
-    [n = lane/4] of tile j, i.e. the table value for lag k+1 and pair 8j + n (0 beyond the last lag / pair).
-    `scan` is the float32 [G][stride] table of scan_table()."""
+    """B-operand fragments of the tensor-core angle scan (mma.sync m16n8k16 fp16, operands split hi + lo and packed along
+    K as [hi(8) | lo(8)] per k-step) for a grid that is symmetric about 0: grid pairs (g, G-1-g), g < ceil(G/2), share
+    cos(k phi_g) and differ in the sign of sin(k phi_g).
+    Layout uint32 [ntiles][matrix: cos, sin][kstep][lane 32][2] = (packed b_hi, packed b_lo): a word holds the table values
+    of lags 8 s + 2 (lane % 4) + 1 (low half) and + 2 (high half) for pair 8 j + lane / 4 (0 beyond the last lag / pair).
+    Returned as a float32 view of those words (the C ABI passes it as const float*).  `scan` is the float32
+    [G][stride] table of scan_table()."""
     ap = padded_antennas(A)
     assert ap in (8, 16)
     npairs = (G + 1) // 2
@@ -105,17 +115,17 @@ def scan_mma_table(scan: np.ndarray, G: int, A: int) -> Tuple[np.ndarray, int]:
         if lag <= ap - 1:
             T[0, k, :npairs] = scan[:npairs, 2 * (lag - 1)]
             T[1, k, :npairs] = scan[:npairs, 2 * (lag - 1) + 1]
-    hi, lo = tf32_split(T)
-    parts = np.stack([hi, lo], axis=1)                   # [matrix][part][K][pairs]
-    out = np.zeros((nt, 2, 2, KS, 32, 2), dtype=np.float32)
+    hi, lo = f16_split(T)
+    hi16, lo16 = hi.view(np.uint16).astype(np.uint32), lo.view(np.uint16).astype(np.uint32)
+    out = np.zeros((nt, 2, KS, 32, 2), dtype=np.uint32)
     lane = np.arange(32)
     for j in range(nt):
+        n = 8 * j + lane // 4
         for s_ in range(KS):
-            for r in range(2):
-                k = (lane % 4) + 4 * r + 8 * s_
-                n = 8 * j + lane // 4
-                out[j, :, :, s_, :, r] = parts[:, :, k, n]
-    return out.reshape(-1), nt
+            k0 = 8 * s_ + 2 * (lane % 4)
+            out[j, :, s_, :, 0] = hi16[:, k0, n] | (hi16[:, k0 + 1, n] << 16)
+            out[j, :, s_, :, 1] = lo16[:, k0, n] | (lo16[:, k0 + 1, n] << 16)
+    return out.reshape(-1).view(np.float32), nt
 
 
 def grid_cos_sin(grid_deg: np.ndarray) -> np.ndarray:
