@@ -126,9 +126,10 @@ int rs_detect(const void* rds, const uint8_t* range_gate, float thr_power, float
  *       det_ntie      optional int32 [F*nseg_per_frame]: cells flagged TIE / GUARD per segment
  *       det_tielist   optional int32 [F*nseg_per_frame][RS_TIE_LIST_CAP]: leader indices of the first RS_TIE_LIST_CAP
  *                     flagged cells of each segment, in arbitrary order (lets the fp64 recheck skip the list scan)
- *       mma_table     optional float [mma_tiles][2][2][A_pad/8][32][2]: TF32 hi/lo B fragments of the (cos, sin) tables
- *                     for the tensor-core scan (8 < 2 A_pad <= 32, symmetric grid); mma_tiles = ceil(ceil(G/2)/8).
- *                     NULL selects the CUDA-core scan.
+ *       mma_table     optional, 32-bit words [mma_tiles][2][A_pad/8][32][2] (passed as const float*): fp16 hi / lo B
+ *                     fragments of the (cos, sin) tables for the tensor-core scan, packed for mma.sync.m16n8k16
+ *                     (radar_slam_b200/tables.py: scan_mma_table); 8 < 2 A_pad <= 32, symmetric grid;
+ *                     mma_tiles = ceil(ceil(G/2)/8).  NULL selects the CUDA-core scan.
  *       cell_ws       optional workspace of 17 * F*R*D bytes (16-byte aligned) for A > 16: every distinct cell of a frame is
  *                     evaluated once (mark / evaluate / scatter) instead of once per detection -- with many antennas
  *                     a cell is flagged on many of them and all share one snapshot.  NULL: one evaluation per leader. */
