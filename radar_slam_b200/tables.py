@@ -77,17 +77,6 @@ def scan_table(grid_deg: np.ndarray, spacing: float, lambda_c: float, A: int) ->
     return tab.astype(np.float32), stride
 
 
-def tf32_split(x32: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
-    """x (float32) -> (hi, lo), both exactly representable in TF32 (10 explicit mantissa bits, rounded like
-    cvt.rna.tf32.f32: nearest, ties away from zero), with x = hi + lo up to 2^-22 |x|."""
-    def rna(v):
-        b = np.ascontiguousarray(v, dtype=np.float32).view(np.uint32).astype(np.uint64)
-        return ((b + 0x1000) & 0xFFFFE000).astype(np.uint32).view(np.float32)
-    hi = rna(x32)
-    lo = rna((x32.astype(np.float32) - hi).astype(np.float32))
-    return hi, lo
-
-
 def f16_split(x32: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
     """x (float32, |x| <= 1) -> (hi, lo) fp16 with x = hi + lo up to 2^-22 |x| (+ 3e-8 where lo is subnormal)."""
     x32 = np.asarray(x32, dtype=np.float32)
