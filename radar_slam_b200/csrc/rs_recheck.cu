@@ -55,19 +55,20 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 __device__ __forceinline__ int unshift(int pos, int n) { return (pos - n / 2 + n) % n; }      // undo np.fft.fftshift
 
-// Y[i] = sum_c x[c][s] u[i][c]  for one fast-time column (col = plane + s); eight loads in flight
+// Y[i] = sum_c x[c][s] u[i][c]  for one fast-time column (col = plane + s); LD loads in flight
 template <int NB>
 __device__ __forceinline__ void column_dft(const float2* __restrict__ col, int S, int C, const double2* __restrict__ u,
                                            double2 (&Y)[NB]) {
+    constexpr int LD = NB <= 2 ? 16 : 8;          // few cells: the column walk is latency bound, keep more loads in flight
 #pragma unroll
     for (int i = 0; i < NB; ++i) Y[i] = make_double2(0, 0);
     int c = 0;
-    for (; c + 8 <= C; c += 8) {
-        float2 x[8];
+    for (; c + LD <= C; c += LD) {
+        float2 x[LD];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) x[j] = __ldg(col + (size_t)(c + j) * S);
+        for (int j = 0; j < LD; ++j) x[j] = __ldg(col + (size_t)(c + j) * S);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < LD; ++j) {
             const double xr = (double)x[j].x, xi = (double)x[j].y;
 #pragma unroll
             for (int i = 0; i < NB; ++i) {
