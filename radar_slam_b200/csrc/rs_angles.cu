@@ -13,6 +13,7 @@
 //
 // ESPRIT (angle_estimation.py:195-221) reduces, for one snapshot, to the principal eigenvector of a
 // 2x2 Hermitian matrix; it is evaluated in fp64 from the fp32 snapshot.
+#include <type_traits>
 #include <cstdlib>
 #include <cuda_fp16.h>
 #include "rs_common.cuh"
@@ -379,9 +380,9 @@ __global__ void __launch_bounds__(ANG_THREADS) angles_scan_kernel(AngleArgs p, c
 // limit of mma.sync, 0.46 /clk/SM, is what the tensor part costs).  The B fragments (cos / sin tables) are split and
 // packed on the host.  A warp carries 32 cells (two 16-row tiles); lane L computes the lags of cell L, publishes them
 // through shared memory, every lane builds the A fragments of its rows, and then tracks (best, runner-up, pair index)
-// for its accumulator rows.  The pair maximum is E + |O| and the pair minimum E - |O|, so the tracking costs 5 ALU
-// operations per pair instead of 10 in the CUDA-core scan; which side won is read off the sign of O once, after the
-// scan (|O| ~ 0 means the two sides tie, and a tie is flagged RS_FLAG_TIE anyway).
+// for its accumulator rows.  The pair maximum is E + |O| and the pair minimum E - |O|; the scan tracks the maxima only
+// (6 ALU operations per pair and cell); which side won is read off the sign of O once, after the scan, where the
+// losing side also enters the runner-up (|O| ~ 0 means the two sides tie, and a tie is flagged RS_FLAG_TIE anyway).
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mma_f16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
                                         uint32_t b1) {
@@ -389,6 +390,13 @@ __device__ __forceinline__ void mma_f16(float (&c)[4], uint32_t a0, uint32_t a1,
         "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
         : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
         : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+// the k = 8 form: its A fragment is the first half (a0, a1) of the k = 16 fragment, its B fragment one word
+__device__ __forceinline__ void mma_f16_k8(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t b0) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a0), "r"(a1), "r"(b0));
 }
 // (x, y) -> packed fp16 pair of the leading parts (x in the low half) and of the remainders
 __device__ __forceinline__ void split_f16x2(float x, float y, uint32_t& hi, uint32_t& lo) {
@@ -398,11 +406,14 @@ __device__ __forceinline__ void split_f16x2(float x, float y, uint32_t& hi, uint
     hi = *reinterpret_cast<const uint32_t*>(&h);
     lo = *reinterpret_cast<const uint32_t*>(&l);
 }
-__device__ __forceinline__ void track_pair(Track& t, float hi, float lo, int pair) {
+// Only the pair maxima are tracked in the scan: the minimum E - |O| of a pair can be the runner-up only for the winning
+// pair itself (elsewhere its own maximum is a better candidate), and that one is added after the scan from the odd part
+// of the winner.
+__device__ __forceinline__ void track_max(Track& t, float hi, int pair) {
     const float m = fminf(t.best, hi);
     const bool up = hi > t.best;
     t.best = fmaxf(t.best, hi);
-    t.second = fmaxf(t.second, fmaxf(lo, m));
+    t.second = fmaxf(t.second, m);
     t.idx = up ? pair : t.idx;
 }
 
@@ -410,17 +421,25 @@ template <int AP, int MINB>
 __global__ void __launch_bounds__(ANG_THREADS, MINB) angles_mma_kernel(AngleArgs p, const uint32_t* __restrict__ mma_table,
                                                                   int ntiles, const double* __restrict__ grid_cs,
                                                                   double* __restrict__ ls_partials) {
-    constexpr int K = AP, KS = AP / 8, LSTRIDE = 2 * K + 8, TILE_WORDS = 2 * KS * 64;
+    constexpr int K = AP, KS = AP / 8, LSTRIDE = 2 * K + 8, TILE_WORDS = KS * 192;
     extern __shared__ uint32_t smw[];
-    uint32_t* tabs = smw;                                        // [ntiles][cos, sin][KS][32 lanes][b_hi, b_lo]
+    // per tile: [KS][32 lanes] (cos_hi, cos_hi, sin_hi, sin_hi), then [KS][32 lanes] (cos_lo, sin_lo) -- every B operand of
+    // the loop below is an aligned register pair / single register of one LDS.128 or LDS.64 result
+    uint32_t* tabs = smw;
     float* Lx = reinterpret_cast<float*>(tabs + (size_t)ntiles * TILE_WORDS);   // [warps][32 cells][LSTRIDE]: E lags / R_0, then O lags / R_0
     __shared__ double red[ANG_THREADS / 32][8];
     const int seg = blockIdx.x;
     const int n = p.det_nlead[seg];
     double acc_ls[7] = {0, 0, 0, 0, 0, 0, 0};
     if (n > 0) {
-        for (int i = threadIdx.x; i < ntiles * TILE_WORDS / 4; i += blockDim.x)
-            reinterpret_cast<uint4*>(tabs)[i] = __ldg(reinterpret_cast<const uint4*>(mma_table) + i);
+        for (int i = threadIdx.x; i < ntiles * KS * 32; i += blockDim.x) {
+            const int j = i / (KS * 32), sl = i - j * (KS * 32);          // mma_table: [ntiles][cos, sin][KS][32][hi, lo]
+            const uint2 c = __ldg(reinterpret_cast<const uint2*>(mma_table) + (size_t)(2 * j) * KS * 32 + sl);
+            const uint2 sn = __ldg(reinterpret_cast<const uint2*>(mma_table) + (size_t)(2 * j + 1) * KS * 32 + sl);
+            uint32_t* tile = tabs + (size_t)j * TILE_WORDS;
+            reinterpret_cast<uint4*>(tile)[sl] = make_uint4(c.x, c.x, sn.x, sn.x);
+            reinterpret_cast<uint2*>(tile + KS * 128)[sl] = make_uint2(c.y, sn.y);
+        }
         __syncthreads();
         const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
         const int gq = lane >> 2, tq = lane & 3;
@@ -489,36 +508,39 @@ __global__ void __launch_bounds__(ANG_THREADS, MINB) angles_mma_kernel(AngleArgs
                 }
             }
             Track tr[2][2] = {{Track{NEG, NEG, 0}, Track{NEG, NEG, 0}}, {Track{NEG, NEG, 0}, Track{NEG, NEG, 0}}};
-            const uint2* tb = reinterpret_cast<const uint2*>(tabs) + lane;
-            for (int j = 0; j < ntiles; ++j, tb += TILE_WORDS / 2) {
-                uint2 bE[KS], bO[KS];                                // (b_hi, b_lo) of this lane's rows 2 tq, 2 tq + 1
+            const uint32_t* tb = tabs + 4 * lane;
+            // one tile = 8 grid pairs x 32 cells; only the last tile can hold pairs beyond the grid, so it is peeled
+            auto scan_tile = [&](const int j, auto masked_c) {
+                constexpr bool MASKED = decltype(masked_c)::value;
+                uint4 bh[KS];                                        // (cos_hi, cos_hi, sin_hi, sin_hi) of this lane's rows 2 tq, 2 tq + 1
+                uint2 bl[KS];                                        // (cos_lo, sin_lo)
 #pragma unroll
-                for (int s_ = 0; s_ < KS; ++s_) { bE[s_] = tb[s_ * 32]; bO[s_] = tb[(KS + s_) * 32]; }
+                for (int s_ = 0; s_ < KS; ++s_) {
+                    bh[s_] = *reinterpret_cast<const uint4*>(tb + s_ * 128);
+                    bl[s_] = *reinterpret_cast<const uint2*>(tb + KS * 128 - 2 * lane + s_ * 64);
+                }
                 const int pb = 8 * j + 2 * tq;
-                const bool masked = j == ntiles - 1;
 #pragma unroll
                 for (int t = 0; t < 2; ++t) {
                     float cE[4] = {0.f, 0.f, 0.f, 0.f}, cO[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                     for (int s_ = 0; s_ < KS; ++s_) {
-                        mma_f16(cE, aE[t][s_][0], aE[t][s_][1], aE[t][s_][2], aE[t][s_][3], bE[s_].x, bE[s_].x);   // hi hi + lo hi
-                        mma_f16(cO, aO[t][s_][0], aO[t][s_][1], aO[t][s_][2], aO[t][s_][3], bO[s_].x, bO[s_].x);
-                        mma_f16(cE, aE[t][s_][0], aE[t][s_][1], 0u, 0u, bE[s_].y, 0u);                              // hi lo
-                        mma_f16(cO, aO[t][s_][0], aO[t][s_][1], 0u, 0u, bO[s_].y, 0u);
+                        mma_f16(cE, aE[t][s_][0], aE[t][s_][1], aE[t][s_][2], aE[t][s_][3], bh[s_].x, bh[s_].y);   // hi hi + lo hi
+                        mma_f16(cO, aO[t][s_][0], aO[t][s_][1], aO[t][s_][2], aO[t][s_][3], bh[s_].z, bh[s_].w);
+                        mma_f16_k8(cE, aE[t][s_][0], aE[t][s_][1], bl[s_].x);                                      // hi lo
+                        mma_f16_k8(cO, aO[t][s_][0], aO[t][s_][1], bl[s_].y);
                     }
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        const float e = cE[q], od = fabsf(cO[q]);
-                        float hi = e + od, lo = e - od;
+                        float hi = cE[q] + fabsf(cO[q]);
                         const int pair = pb + (q & 1);
-                        if (masked) {
-                            if (pair > last_pair) { hi = NEG; lo = NEG; }
-                            else if (odd && pair == half) lo = NEG;        // the middle angle has no partner
-                        }
-                        track_pair(tr[t][q >> 1], hi, lo, pair);
+                        if (MASKED && pair > last_pair) hi = NEG;
+                        track_max(tr[t][q >> 1], hi, pair);
                     }
                 }
-            }
+            };
+            for (int j = 0; j < ntiles - 1; ++j, tb += TILE_WORDS) scan_tile(j, std::false_type{});
+            scan_tile(ntiles - 1, std::true_type{});
             float my_best = NEG, my_second = NEG;
             int my_pair = 0;
 #pragma unroll
@@ -552,7 +574,9 @@ __global__ void __launch_bounds__(ANG_THREADS, MINB) angles_mma_kernel(AngleArgs
                 float od = 0.f;
 #pragma unroll
                 for (int k = 1; k < AP; ++k) od = fmaf(row[k - 1], __ldg(trow + 2 * (k - 1) + 1), od);
-                const int bi = (odd && my_pair == half) ? half : (od >= 0.f ? my_pair : G - 1 - my_pair);
+                const bool middle = odd && my_pair == half;             // the middle angle has no partner
+                const int bi = middle ? half : (od >= 0.f ? my_pair : G - 1 - my_pair);
+                if (!middle) my_second = fmaxf(my_second, my_best - 2.f * fabsf(od));   // the losing side of the winning pair
                 // my_best, my_second are (P - R_0) / (2 R_0) of the best and second-best grid point
                 const float pnorm = 1.f + 2.f * my_best;
                 uint8_t flags = 0;
@@ -880,7 +904,7 @@ extern "C" int rs_angles(const void* rds, const float* scan_table, int scan_stri
             const char* mma_env = getenv("RS_ANGLES_MMA");  // 0: force the CUDA-core scan
             if (mma_table != nullptr && grid_symmetric && (ap == 8 || ap == 16) && !(mma_env && atoi(mma_env) == 0)) {
                 RS_CHECK_ARG(mma_tiles == ((G + 1) / 2 + 7) / 8, "rs_angles: mma_tiles must be ceil(ceil(G/2)/8)");
-                const size_t sm = ((size_t)mma_tiles * 2 * (ap / 8) * 64 + (size_t)(ANG_THREADS / 32) * 32 * (2 * ap + 8)) *
+                const size_t sm = ((size_t)mma_tiles * (ap / 8) * 192 + (size_t)(ANG_THREADS / 32) * 32 * (2 * ap + 8)) *
                                   sizeof(float);
                 if (sm <= (size_t)rs_smem_optin_limit()) {
                     // occupancy beats per-warp ILP here (measured): 64 registers / 8 CTAs per SM at A <= 8
