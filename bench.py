@@ -352,16 +352,24 @@ def run_gpu(args):
             "frac_hbm_2d": 16 * F * A * C * S / ms_fft / 1e6 / peak,
             "note": "the whole 2-D transform (dechirp, window, range FFT, Doppler FFT, both shifts) against its 16 B/cell "
                     "(cube in, RDS out); one cluster kernel when the plane fits distributed shared memory"}
-    if dom["kernel"] == "rs_angles":
+    ang = next((st for st in stages if st["kernel"] == "rs_angles"), None)
+    if ang is not None:
+        # the angle stage is not HBM bound: report its arithmetic rate next to its (contractual) HBM fraction
         G = len(pipe._angle_tables(A)["grid"])
         ap = 2 if A <= 2 else 4 if A <= 4 else 8 if A <= 8 else 16
         cells = float(det.nlead[: det.F * det.ntiles].sum().item()) / det.F * F
         flops = cells * (G * 2 * (ap - 1) + 8 * ap * ap)
-        roofline["note"] = ("dominant kernel is the per-cell MUSIC grid scan: a [cells x lags] . [lags x grid pairs] contraction "
-                            "on the tensor cores (mma.sync 3xTF32) whose argmax / runner-up tracking is ALU-issue bound, not "
-                            "HBM bound; its HBM fraction is reported for the contract, its arithmetic rate below")
-        roofline["distinct_cells_per_step"] = cells
-        roofline["scan_tflops_fp32_equivalent"] = flops / dom["ms_per_step"] / 1e9
+        roofline["angle_scan"] = {
+            "distinct_cells_per_step": cells, "scan_tflops_fp32_equivalent": flops / ang["ms_per_step"] / 1e9,
+            "note": "per-cell MUSIC grid scan = [cells x lags] . [lags x grid pairs] on the tensor cores (mma.sync m16n8k16 + "
+                    "m16n8k8, fp16 operands split hi + lo, fp32 accumulation); its argmax / runner-up tracking is ALU-issue "
+                    "bound, not HBM bound"}
+    if dom["kernel"] == "rs_range_doppler_fft":
+        roofline["note"] = ("dominant kernel is the fused cluster 2-D FFT: HBM traffic at the algorithmic minimum (16 B/cell, plane "
+                            "held in distributed shared memory between the passes), bounded by shared-memory bandwidth and the "
+                            "cluster barrier rather than by HBM")
+    elif dom["kernel"] == "rs_angles":
+        roofline["note"] = "dominant kernel is the per-cell MUSIC grid scan (see angle_scan): ALU-issue bound, not HBM bound"
 
     # ---- CPU baseline: the oracle port on a bounded sample of the SAME frames, one core
     n_cpu = args.cpu_frames
@@ -416,7 +424,7 @@ def main():
     ap.add_argument("--irls", type=int, default=0, help="Huber reweighting iterations of the velocity solve (configs[3])")
     ap.add_argument("--huber", type=float, default=1.0)
     ap.add_argument("--threshold-db", type=float, default=-20.0)
-    ap.add_argument("--chunk", type=int, default=500, help="frames per launch set, device-resident path")
+    ap.add_argument("--chunk", type=int, default=1000, help="frames per launch set, device-resident path")
     ap.add_argument("--host-chunk", type=int, default=32, help="frames per H2D chunk, host-buffer path")
     ap.add_argument("--no-recheck", action="store_true", help="skip the fp64 recheck of flagged decisions (fp32 path only)")
     ap.add_argument("--fft-eps", type=float, default=4e-7, help="error bound of the fp32 FFT used by the recheck, in rms units")

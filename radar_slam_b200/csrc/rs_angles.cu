@@ -541,32 +541,42 @@ __global__ void __launch_bounds__(ANG_THREADS, MINB) angles_mma_kernel(AngleArgs
             };
             for (int j = 0; j < ntiles - 1; ++j, tb += TILE_WORDS) scan_tile(j, std::false_type{});
             scan_tile(ntiles - 1, std::true_type{});
-            float my_best = NEG, my_second = NEG;
-            int my_pair = 0;
-#pragma unroll
-            for (int t = 0; t < 2; ++t) {
-                // the four lanes of a quad hold different columns of the same rows: merge them
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-#pragma unroll
-                    for (int off = 1; off <= 2; off <<= 1) {
-                        const float ob = __shfl_xor_sync(0xffffffffu, tr[t][h].best, off);
-                        const float os = __shfl_xor_sync(0xffffffffu, tr[t][h].second, off);
-                        const int oi = __shfl_xor_sync(0xffffffffu, tr[t][h].idx, off);
-                        tr[t][h].second = fmaxf(fmaxf(tr[t][h].second, os), fminf(tr[t][h].best, ob));
-                        if (ob > tr[t][h].best || (ob == tr[t][h].best && oi < tr[t][h].idx)) { tr[t][h].best = ob; tr[t][h].idx = oi; }
-                    }
-                }
-                // row (t, h, gq) is cell 16 t + 8 h + gq of the warp: hand the result to the lane that owns the cell
-                const int src = 4 * (lane & 7);
+            // The four lanes of a quad hold different columns of the same four rows (t, h).  Transposing reduction: lanes
+            // tq and tq ^ 1 split the tiles (the even lane keeps t = 0 and hands its t = 1 trackers over), then lanes tq
+            // and tq ^ 2 split h: lane tq ends with the merged tracker of row (t, h) = (tq & 1, tq >> 1) -- 3 merges
+            // and 9 shuffles per lane instead of 8 and 24.
+            auto merge = [](Track& k, float ob, float os, int oi) {
+                k.second = fmaxf(fmaxf(k.second, os), fminf(k.best, ob));
+                if (ob > k.best || (ob == k.best && oi < k.idx)) { k.best = ob; k.idx = oi; }
+            };
+            Track kh[2];
+            {
+                const bool up1 = (tq & 1) != 0;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    const float vb = __shfl_sync(0xffffffffu, tr[t][h].best, src);
-                    const float vs = __shfl_sync(0xffffffffu, tr[t][h].second, src);
-                    const int vi = __shfl_sync(0xffffffffu, tr[t][h].idx, src);
-                    if ((lane >> 4) == t && ((lane >> 3) & 1) == h) { my_best = vb; my_second = vs; my_pair = vi; }
+                    Track keep = up1 ? tr[1][h] : tr[0][h];
+                    const Track send = up1 ? tr[0][h] : tr[1][h];
+                    const float ob = __shfl_xor_sync(0xffffffffu, send.best, 1);
+                    const float os = __shfl_xor_sync(0xffffffffu, send.second, 1);
+                    const int oi = __shfl_xor_sync(0xffffffffu, send.idx, 1);
+                    merge(keep, ob, os, oi);
+                    kh[h] = keep;
                 }
             }
+            const bool up2 = (tq & 2) != 0;
+            Track mine = up2 ? kh[1] : kh[0];
+            {
+                const Track send = up2 ? kh[0] : kh[1];
+                const float ob = __shfl_xor_sync(0xffffffffu, send.best, 2);
+                const float os = __shfl_xor_sync(0xffffffffu, send.second, 2);
+                const int oi = __shfl_xor_sync(0xffffffffu, send.idx, 2);
+                merge(mine, ob, os, oi);
+            }
+            // row (t, h, gq) is cell 16 t + 8 h + gq of the warp: fetch it from lane 4 gq + t + 2 h
+            const int src = 4 * (lane & 7) + (lane >> 4) + 2 * ((lane >> 3) & 1);
+            float my_best = __shfl_sync(0xffffffffu, mine.best, src);
+            float my_second = __shfl_sync(0xffffffffu, mine.second, src);
+            const int my_pair = __shfl_sync(0xffffffffu, mine.idx, src);
             if (valid) {
                 // which side of the pair won: sign of the odd part, re-evaluated with the fp32 table
                 const float* row = Lw + lane * LSTRIDE + K;
