@@ -55,6 +55,15 @@ fft2d_cluster_kernel(const float2* __restrict__ cube, const float2* __restrict__
     cg::cluster_group cluster = cg::this_cluster();
     const int q = (int)cluster.block_rank();
     const int tid = threadIdx.x;
+    const int plane = blockIdx.x / NC;       // f * A + a
+    const int f = plane / A, a = plane - f * A;
+    const float2* src = cube + ((size_t)plane * C_total + chirp0 + q * P::CPC) * S;
+    const int row1 = tid / SR2, t1 = tid - row1 * SR2;
+    const int row2 = tid % P::CB, k1r = tid / P::CB;
+
+    // "Every CTA of the cluster is resident" is all the first cluster barrier has to establish (no data is handed
+    // over), so it is split: a relaxed arrive here, the wait right before the first remote store.
+    asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
     for (int i = tid; i < S; i += F2_THREADS) {
         tabs[i] = table[i];
         const int k1 = i / SR2, t = i - k1 * SR2;
@@ -64,17 +73,11 @@ fft2d_cluster_kernel(const float2* __restrict__ cube, const float2* __restrict__
         const int k1 = i / CR2, t = i - k1 * CR2;
         tw1c[i] = tw_c_g[(k1 * t) % C];
     }
-    cluster.sync();                          // every CTA of the cluster is resident before the first remote store
-
-    const int plane = blockIdx.x / NC;       // f * A + a
-    const int f = plane / A, a = plane - f * A;
-    const float2* src = cube + ((size_t)plane * C_total + chirp0 + q * P::CPC) * S;
+    __syncthreads();
 
     // ---------------- range phase
     // per-thread constants: pass 1 always handles fast-time column t1, pass 2 always range residue k1r, so the dechirp
     // table column and the inter-pass twiddles w_S^{k1r n2} (applied on the pass-2 side) live in registers
-    const int row1 = tid / SR2, t1 = tid - row1 * SR2;
-    const int row2 = tid % P::CB, k1r = tid / P::CB;
     float2 tabv[SR1], twv[SR2];
 #pragma unroll
     for (int j = 0; j < SR1; ++j) tabv[j] = tabs[t1 + SR2 * j];
@@ -100,6 +103,7 @@ fft2d_cluster_kernel(const float2* __restrict__ cube, const float2* __restrict__
 #pragma unroll
             for (int n2 = 0; n2 < SR2; ++n2) u[n2] = (n2 == 0) ? y[0] : cmul(y[n2], twv[n2]);
             pow2::dft<SR2>(u);
+            if (b0 == 0) asm volatile("barrier.cluster.wait.aligned;" ::: "memory");   // the peers' M exists
             const int chirp = q * P::CPC + b0 + row2;
 #pragma unroll
             for (int k2 = 0; k2 < SR2; ++k2) {
