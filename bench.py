@@ -332,8 +332,12 @@ def run_gpu(args):
     per_launch_bytes = dom["alg_bytes_per_step"] / dom["launches"]
     # measured DRAM traffic of the same kernels from the committed ncu capture (per frame of this shape), if present
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01_v8_traffic.json")
-    if os.path.exists(tpath) and (A, C, S) == (8, 128, 256):
+    import glob
+    import re
+    tfiles = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_v*_traffic.json")),
+                    key=lambda q: [int(x) for x in re.findall(r"\d+", os.path.basename(q))])
+    tpath = tfiles[-1] if tfiles else ""                 # the newest committed capture
+    if tpath and (A, C, S) == (8, 128, 256):
         per_frame = json.load(open(tpath))["dram_bytes_per_frame"]
         for st in stages:
             if st["kernel"] in per_frame:

@@ -26,7 +26,9 @@ def main():
         b = num(r[rd]) * MULT[units[rd]] + num(r[wr]) * MULT[units[wr]]
         hit = [k for k in RECHECK_PARTS if k in r[ki]]
         if hit:
-            parts.setdefault(hit[0], []).append(b)
+            nm = r[ki]
+            nm = nm[: nm.index(">(") + 1] if ">(" in nm else nm.split("(")[0]
+            parts.setdefault(nm, []).append(b)                       # template instantiations are separate launches of one call
             continue
         for k, v in STAGE.items():
             if k in r[ki]:
