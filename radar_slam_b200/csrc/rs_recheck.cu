@@ -397,7 +397,7 @@ struct StageAResult {
     int undecided, r, d, li;
 };
 
-__global__ void __launch_bounds__(RC_THREADS, 2)
+__global__ void __launch_bounds__(RC_THREADS, 4)
 recheck_angles_kernel(CubeView v, AngleFix q, int32_t* __restrict__ work_idx, int32_t* __restrict__ work_cnt,
                       int32_t* __restrict__ frame_cnt, int4* __restrict__ frame_list, int32_t* __restrict__ stats) {
     extern __shared__ double2 smd[];                        // [RC_WARPS][A] snapshots
