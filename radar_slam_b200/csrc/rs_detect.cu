@@ -293,26 +293,33 @@ detect_a8_kernel(const float2* __restrict__ rds, const uint8_t* __restrict__ gat
             const int cell = cb + (la & 1);                                         // even antennas keep the first cell
             dst[k] = pw + a8_off(0, cell + 1, la >> 2) + (la & 2);
         }
-#pragma unroll
-        for (int g = 0; g < 6; ++g) {
-            constexpr int NR = (A8_TR + 2) / 6;
-            float4 v[NR][2];
+        // The six row groups are software pipelined through two register buffers: the loads of group g + 1 are in
+        // flight while group g is squared and stored, so the CTA waits for HBM once instead of six times.
+        constexpr int NR = (A8_TR + 2) / 6;
+        float4 v[2][NR][2];
+        auto fetch = [&](int g, float4 (&w)[NR][2]) {
 #pragma unroll
             for (int q = 0; q < NR; ++q) {
                 const int r = r0 - 1 + g * NR + q;
                 const bool ok = r >= 0 && r < R;
 #pragma unroll
                 for (int k = 0; k < 2; ++k)
-                    v[q][k] = ok ? __ldg(src[k] + (size_t)r * row_f4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    w[q][k] = ok ? __ldg(src[k] + (size_t)r * row_f4) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
+        };
+        fetch(0, v[0]);
+#pragma unroll
+        for (int g = 0; g < 6; ++g) {
+            if (g + 1 < 6) fetch(g + 1, v[(g + 1) & 1]);
 #pragma unroll
             for (int q = 0; q < NR; ++q) {
                 const int rr = g * NR + q, r = r0 - 1 + rr;
                 const bool ok = r >= 0 && r < R;
 #pragma unroll
                 for (int k = 0; k < 2; ++k) {
-                    const float p0 = ok ? fmaf(v[q][k].x, v[q][k].x, v[q][k].y * v[q][k].y) : -1.f;   // cell cb
-                    const float p1 = ok ? fmaf(v[q][k].z, v[q][k].z, v[q][k].w * v[q][k].w) : -1.f;   // cell cb + 1
+                    const float4 x = v[g & 1][q][k];
+                    const float p0 = ok ? fmaf(x.x, x.x, x.y * x.y) : -1.f;   // cell cb
+                    const float p1 = ok ? fmaf(x.z, x.z, x.w * x.w) : -1.f;   // cell cb + 1
                     const float got = __shfl_xor_sync(0xffffffffu, (la & 1) ? p0 : p1, 4);            // antenna a ^ 1
                     const float2 pr = (la & 1) ? make_float2(got, p1) : make_float2(p0, got);
                     *reinterpret_cast<float2*>(dst[k] + rr * A8_W) = pr;
