@@ -61,6 +61,14 @@ fft2d_cluster_kernel(const float2* __restrict__ cube, const float2* __restrict__
     const int row1 = tid / SR2, t1 = tid - row1 * SR2;
     const int row2 = tid % P::CB, k1r = tid / P::CB;
 
+    // The raw chirps are software pipelined: batch b + 1 is requested right after pass 1 of batch b has consumed its
+    // registers (batch 0 before anything else), so its HBM latency runs under pass 2 / the table staging.
+    float2 v[SR1];
+    {
+        const float2* x = src + (size_t)row1 * S + t1;
+#pragma unroll
+        for (int j = 0; j < SR1; ++j) v[j] = __ldcs(x + SR2 * j);                  // streamed once: evict-first
+    }
     // "Every CTA of the cluster is resident" is all the first cluster barrier has to establish (no data is handed
     // over), so it is split: a relaxed arrive here, the wait right before the first remote store.
     asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
@@ -76,19 +84,15 @@ fft2d_cluster_kernel(const float2* __restrict__ cube, const float2* __restrict__
     __syncthreads();
 
     // ---------------- range phase
-    // per-thread constants: pass 1 always handles fast-time column t1, pass 2 always range residue k1r, so the dechirp
-    // table column and the inter-pass twiddles w_S^{k1r n2} (applied on the pass-2 side) live in registers
-    float2 tabv[SR1], twv[SR2];
+    // per-thread constants: pass 1 always handles fast-time column t1, so the dechirp table column lives in registers;
+    // the inter-pass twiddles w_S^{k1r n2} of pass 2 are read from shared memory (two distinct addresses per warp:
+    // broadcasts), which leaves the registers for the chirps in flight
+    float2 tabv[SR1];
 #pragma unroll
     for (int j = 0; j < SR1; ++j) tabv[j] = tabs[t1 + SR2 * j];
-#pragma unroll
-    for (int n2 = 0; n2 < SR2; ++n2) twv[n2] = tw1s[k1r * SR2 + n2];
+    const float2* twr = tw1s + k1r * SR2;
     for (int b0 = 0; b0 < P::CPC; b0 += P::CB) {
         {
-            const float2* x = src + (size_t)(b0 + row1) * S + t1;
-            float2 v[SR1];
-#pragma unroll
-            for (int j = 0; j < SR1; ++j) v[j] = __ldcs(x + SR2 * j);              // streamed once: evict-first
 #pragma unroll
             for (int j = 0; j < SR1; ++j) v[j] = cmul(v[j], tabv[j]);
             pow2::dft<SR1>(v);
@@ -96,12 +100,17 @@ fft2d_cluster_kernel(const float2* __restrict__ cube, const float2* __restrict__
 #pragma unroll
             for (int k1 = 0; k1 < SR1; ++k1) y[k1 * P::K1P] = v[k1];
         }
+        if (b0 + P::CB < P::CPC) {
+            const float2* x = src + (size_t)(b0 + P::CB + row1) * S + t1;
+#pragma unroll
+            for (int j = 0; j < SR1; ++j) v[j] = __ldcs(x + SR2 * j);
+        }
         __syncthreads();
         {
             const float2* y = Y + row2 * P::RP + k1r * P::K1P;                      // lanes along chirps
             float2 u[SR2];
 #pragma unroll
-            for (int n2 = 0; n2 < SR2; ++n2) u[n2] = (n2 == 0) ? y[0] : cmul(y[n2], twv[n2]);
+            for (int n2 = 0; n2 < SR2; ++n2) u[n2] = (n2 == 0) ? y[0] : cmul(y[n2], twr[n2]);
             pow2::dft<SR2>(u);
             if (b0 == 0) asm volatile("barrier.cluster.wait.aligned;" ::: "memory");   // the peers' M exists
             const int chirp = q * P::CPC + b0 + row2;
@@ -117,7 +126,9 @@ fft2d_cluster_kernel(const float2* __restrict__ cube, const float2* __restrict__
         }
         __syncthreads();
     }
-    cluster.sync();                          // all chirps of this CTA's range bins have arrived
+    // all chirps of this CTA's range bins have arrived
+
+    cluster.sync();                          // all chirps of this CTA's range bins have arrived (release / acquire)
 
     // ---------------- Doppler phase, in place in M
     {
