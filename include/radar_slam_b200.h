@@ -92,6 +92,10 @@ int rs_range_doppler_fft(const void* cube, const void* table, const void* twiddl
                          void* mid_ws, void* rds, int F, int A, int C_total, int chirp0, int C_used, int S,
                          int dc_removal, void* stream);
 
+/*       Clusters of the persistent fused kernel that can be co-resident on the current device (0: the device cannot
+ *       run it and rs_range_doppler_fft uses the other paths; < 0: CUDA error).  Diagnostic for bench / tests. */
+int rs_fft2d_ws_max_clusters(void);
+
 /* (b)   replaces extract_range_doppler_peaks (dechirp.py:215-278): |X|^2, 3x3 local maximum per
  *       antenna plane (scipy maximum_filter 'reflect' == ignore out-of-range neighbours, ties
  *       count), strict threshold, range gate, per-tile compaction by ballot/prefix sums.

@@ -19,7 +19,7 @@ import torch
 from .. import tables
 from . import _device
 from .angle_estimation import _peaks_list
-from .lazy import column_of
+from .lazy import column_of, records_of
 
 logger = logging.getLogger(__name__)
 
@@ -225,6 +225,9 @@ def extract_angles_robust(rds_path: str, peak_info_path: str, output_path: str, 
     """robust_angle_estimation.py:508-570."""
     rds = np.load(rds_path)
     peak_info = dict(np.load(peak_info_path, allow_pickle=True))
+    # 'peaks' comes back as the reference's 1-D object array of dicts or as the 0-d object array np.savez makes of a
+    # LazyRecords (this package's own dechirp stage): unwrap before anything asks for its length
+    peak_info['peaks'] = records_of(peak_info['peaks'])
     logger.info(f"Loaded RDS: {rds.shape}")
     logger.info(f"Found {len(peak_info['peaks'])} peaks")
     if radar_params is None:

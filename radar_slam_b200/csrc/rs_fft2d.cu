@@ -171,6 +171,10 @@ extern "C" int rs_range_fft(const void* cube, const void* table, const void* twi
 extern "C" int rs_doppler_fft(const void* mid, const void* twiddle_c, void* rds, int F, int A, int C, int S,
                               void* stream);
 
+// K12 v2 (rs_fft2d_ws.cu): persistent warp-specialised cluster kernel fed by TMA.  1 = launched, 0 = not applicable here.
+int rs_fft2d_ws_launch(const void* cube, const void* table, const void* twiddle_s, const void* twiddle_c, void* rds, int F,
+                       int A, int C_total, int chirp0, int dc_removal, int store_tma, int xfer, cudaStream_t stream);
+
 extern "C" int rs_range_doppler_fft(const void* cube, const void* table, const void* twiddle_s, const void* twiddle_c,
                                     void* mid_ws, void* rds, int F, int A, int C_total, int chirp0, int C_used, int S,
                                     int dc_removal, void* stream) {
@@ -179,6 +183,22 @@ extern "C" int rs_range_doppler_fft(const void* cube, const void* table, const v
                  "rs_range_doppler_fft: bad dims");
     const char* env = getenv("RS_FUSED_FFT");          // 0: force the two-kernel path
     if (S == 256 && C_used == 128 && !(env && atoi(env) == 0)) {
+        // RS_K12 = ws (default): the warp-specialised TMA kernel; v1: round 1's phase-serial cluster kernel below.
+        // RS_K12_STORE = tma: Doppler rows leave through bulk (TMA) stores instead of st.global from registers.
+        const char* k12 = getenv("RS_K12");
+        if (!(k12 && k12[0] == 'v')) {
+            const char* st = getenv("RS_K12_STORE");
+            const char* xf = getenv("RS_K12_XFER");            // 0: st.shared::cluster + release arrive, 1 / 2: st.async
+            const int r = rs_fft2d_ws_launch(cube, table, twiddle_s, twiddle_c, rds, F, A, C_total, chirp0, dc_removal,
+                                             st && st[0] == 't', xf ? atoi(xf) : 0, (cudaStream_t)stream);
+            if (r == 1) return RS_OK;
+            const char* strict = getenv("RS_K12_STRICT");        // tests: no silent fall-back to the round-1 kernel
+            if (strict && atoi(strict) == 1) {
+                rs_set_error("rs_range_doppler_fft: the warp-specialised kernel could not be launched (%s)",
+                             cudaGetErrorString(cudaGetLastError()));
+                return RS_ECUDA;
+            }
+        }
         const char* nc_env = getenv("RS_FUSED_NC");    // tuning knob: CTAs per cluster (2, 4 or 8)
         const int nc = nc_env ? atoi(nc_env) : 4;       // measured on B200 (1k frames 256x128x8): 2: 1.63 ms, 4: 1.53, 8: 1.54
         int launched = 0;

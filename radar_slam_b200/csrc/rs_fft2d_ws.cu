@@ -1,0 +1,408 @@
+// K12 v2: the fused dechirp + window + range FFT + Doppler FFT of 256 x 128 planes as a PERSISTENT, WARP-SPECIALISED
+// 4-CTA cluster kernel fed by TMA (dechirp.py:143-213).
+//
+// Round 1's cluster kernel (rs_fft2d.cu) ran the two phases of a plane one after the other in every CTA: raw chirps
+// only flowed from HBM during the range phase, RDS rows only during the Doppler phase, and a cluster barrier stood
+// between them (0.50 of the HBM peak; long-scoreboard / barrier / MEMBAR stalls).  Here the two phases of
+// CONSECUTIVE planes run side by side on every SM:
+//
+//   producer        one thread of the range group streams the CTA's 32 chirps of plane n+1 with cp.async.bulk.tensor
+//                   (TMA, evict-first) into a two-slot ring of 16-chirp stages (32 KB each), full/empty mbarriers
+//   range group     8 warps: stage -> registers (conj(ref)*window column held in registers) -> radix-16 pass 1,
+//                   written back IN PLACE in the stage through a per-chirp rotation -> radix-16 pass 2 -> range bin p
+//                   of chirp c goes to M[n&1][p mod 64][c] of the CTA that owns range bins [64r, 64r+64)
+//                   (st.shared::cluster, 128-byte runs along chirps), then one release-arrive per warp on the four
+//                   owners' "plane full" mbarriers
+//   Doppler group   8 warps: wait for "plane full" of buffer n&1, each warp owns 8 range rows: radix-16 pass 1 in
+//                   place (rotation keeps pass 2 conflict free), radix-8 pass 2, Doppler fftshift, rows stored either
+//                   straight from registers (default) or written back to the row and shipped with a bulk (TMA) store
+//                   (RS_K12_STORE=tma), then one release-arrive per warp on the four CTAs' "buffer empty" mbarriers
+//
+// The plane quarter M is double buffered (2 x 68 KB), so the range group of plane n+1 never waits for the Doppler
+// group of plane n, a slow CTA of the cluster is absorbed by the buffer instead of a barrier, and loads and stores
+// are in flight all the time.  No __syncthreads and no barrier.cluster inside the plane loop: one 256-thread named
+// barrier per stage in the range group, __syncwarp in the Doppler group, mbarriers across CTAs.
+// HBM traffic stays at the algorithmic minimum, 8 B in + 8 B out per cell.
+#include <cuda.h>
+#include <cstdlib>
+#include <mutex>
+#include "rs_common.cuh"
+#include "rs_fft_pow2.cuh"
+
+namespace ws {
+
+constexpr int S = 256, C = 128, NC = 4;
+constexpr int CB = 16;                  // chirps per stage
+constexpr int CPC = C / NC;             // chirps one CTA transforms per plane
+constexpr int NSTAGE = CPC / CB;        // stages per plane == ring slots
+constexpr int ROWS = S / NC;            // range bins owned by one CTA
+constexpr int MP = C + 8;               // row pitch of M (complex): 8 (mod 16)
+constexpr int R_THREADS = 256, D_THREADS = 256;
+constexpr int THREADS = R_THREADS + D_THREADS;       // 16 warps x 128 registers fill the register file
+constexpr uint32_t STAGE_BYTES = CB * S * sizeof(float2);
+static_assert(NSTAGE == 2, "the ring is indexed by the stage of the plane");
+
+struct __align__(128) Smem {
+    float2 stage[NSTAGE][CB * S];       // TMA destination, range passes run in place
+    float2 M[2][ROWS * MP];             // this CTA's range bins x all chirps, double buffered over planes
+    float2 tw1s[S];                     // range inter-pass twiddles w_S^{k1 n2}
+    float2 tw1c[C];                     // Doppler inter-pass twiddles
+    unsigned long long full_ld[NSTAGE], empty_ld[NSTAGE], full_M[2], empty_M[2];
+    unsigned long long full_Mw[2][D_THREADS / 32];   // XFER 2: one transaction barrier per Doppler warp (its 8 rows)
+};
+
+__device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long* b, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* b, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {     // release at cluster scope
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+template <bool CLUSTER>
+__device__ __forceinline__ bool mbar_try(unsigned long long* b, uint32_t parity) {
+    uint32_t ok;
+    if (CLUSTER)
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(s32(b)), "r"(parity) : "memory");
+    else
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(s32(b)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol error must end as a trapped launch (RS_ECUDA), never as a hung GPU.
+template <bool CLUSTER>
+__device__ __forceinline__ void mbar_wait(unsigned long long* b, uint32_t parity) {
+    if (mbar_try<CLUSTER>(b, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try<CLUSTER>(b, parity)) {
+        if (clock64() - t0 > 4000000000ll) __trap();
+    }
+}
+// "I no longer read it" needs no cluster-scope release (nothing the peer must see was written): the default
+// release.cta arrive is what costs no MEMBAR.ALL.GPU
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// remote store that completes bytes on the destination CTA's transaction barrier: hand-over without any fence
+__device__ __forceinline__ void st_async(uint32_t addr, float2 v, uint32_t mbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];"
+                 ::"r"(addr), "f"(v.x), "f"(v.y), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void st_cluster(uint32_t addr, float2 v) {
+    asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(v.x), "f"(v.y) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int x, int y, unsigned long long* bar,
+                                            unsigned long long policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%2, %3}], [%4], %5;"
+        ::"r"(s32(dst)), "l"(map), "r"(x), "r"(y), "r"(s32(bar)), "l"(policy) : "memory");
+}
+// one finished Doppler row (1 KB, 16-byte aligned in M) -> its place in the RDS
+__device__ __forceinline__ void bulk_store_row(float2* dst, const float2* src) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 ::"l"(dst), "r"(s32(src)), "n"(C * sizeof(float2)) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+constexpr unsigned long long EVICT_FIRST = 0x12F0000000000000ull;       // createpolicy fractional evict_first, 1.0
+
+// XFER: how range bins reach their owner: 0 = st.shared::cluster + release.cluster arrive per warp,
+//       1 = st.async completing bytes on one barrier per buffer, 2 = st.async, one barrier per Doppler warp
+template <bool STORE_TMA, int XFER>
+__global__ void __cluster_dims__(NC, 1, 1) __launch_bounds__(THREADS, 1)
+fft2d_ws_kernel(const __grid_constant__ CUtensorMap map_cube, const float2* __restrict__ table, const float2* __restrict__ tw_s_g, const float2* __restrict__ tw_c_g,
+                float2* __restrict__ rds, int A, int C_total, int chirp0, int dc_removal, int nplanes) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+    const int tid = threadIdx.x;
+    uint32_t q;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(q));
+    const int cid = blockIdx.x / NC, ncl = gridDim.x / NC;
+
+    for (int i = tid; i < S; i += THREADS) {
+        const int k1 = i >> 4, t = i & 15;
+        sm.tw1s[i] = tw_s_g[(k1 * t) & (S - 1)];
+    }
+    for (int i = tid; i < C; i += THREADS) {
+        const int k1 = i >> 3, t = i & 7;
+        sm.tw1c[i] = tw_c_g[(k1 * t) & (C - 1)];
+    }
+    if (tid == 0) {
+        for (int s = 0; s < NSTAGE; ++s) {
+            mbar_init(&sm.full_ld[s], 1);
+            mbar_init(&sm.empty_ld[s], R_THREADS / 32);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&sm.full_M[b], XFER == 0 ? NC * (R_THREADS / 32) : 1);
+            mbar_init(&sm.empty_M[b], NC * (D_THREADS / 32));
+            for (int w = 0; w < D_THREADS / 32; ++w) mbar_init(&sm.full_Mw[b][w], 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    cluster_sync_all();                       // every CTA's barriers exist before the first remote arrive / store
+
+    const int warp = tid >> 5, lane = tid & 31;
+    if (warp < R_THREADS / 32) {
+        // =============================================================== range group
+        const int row1 = tid >> 4, t1 = tid & 15;            // pass 1: chirp of the stage, fast-time column
+        const int row2 = tid & 15, k1r = tid >> 4;            // pass 2: lanes along chirps
+        float2 tabv[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) tabv[j] = table[t1 + 16 * j];
+        const float2* twr = sm.tw1s + k1r * 16;
+        // remote bases of M[0] row k1r, this thread's chirp column, in the four owners
+        uint32_t mbase[NC];
+#pragma unroll
+        for (int o = 0; o < NC; ++o) mbase[o] = mapa(s32(&sm.M[0][0]), o) + (uint32_t)((k1r * MP + q * CPC + row2) * sizeof(float2));
+        uint32_t bbase[NC];                                   // the owners' transaction barrier for row k1r (+ 16 pl16)
+#pragma unroll
+        for (int o = 0; o < NC; ++o)
+            bbase[o] = XFER == 2 ? mapa(s32(&sm.full_Mw[0][k1r >> 3]), o) : mapa(s32(&sm.full_M[0]), o);
+        // thread 0 doubles as the TMA producer: the first plane's stages now, stage s of the next plane as soon as the
+        // eight warps have taken stage s of this one into registers
+        if (tid == 0 && cid < nplanes) {
+#pragma unroll 1
+            for (int s = 0; s < NSTAGE; ++s) {
+                mbar_expect_tx(&sm.full_ld[s], STAGE_BYTES);
+                tma_load_2d(sm.stage[s], &map_cube, 0, cid * C_total + chirp0 + (int)q * CPC + s * CB, &sm.full_ld[s], EVICT_FIRST);
+            }
+        }
+        int it = 0;
+        for (int plane = cid; plane < nplanes; plane += ncl, ++it) {
+            const int b = it & 1;
+            const uint32_t boff = (uint32_t)(b * ROWS * MP * sizeof(float2));
+#pragma unroll 1
+            for (int s = 0; s < NSTAGE; ++s) {
+                float2* st = sm.stage[s];
+                mbar_wait<false>(&sm.full_ld[s], it & 1);
+                {
+                    float2 v[16];
+                    const float2* x = st + row1 * S + t1;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = x[16 * j];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = cmul(v[j], tabv[j]);
+                    pow2::dft<16>(v);
+                    __syncwarp();                                       // the chirp is read before it is rewritten
+                    float2* y = st + row1 * S + ((t1 + row1) & 15);
+#pragma unroll
+                    for (int k1 = 0; k1 < 16; ++k1) y[16 * k1] = v[k1];
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(R_THREADS) : "memory");
+                float2 u[16];
+                {
+                    const float2* y = st + row2 * S + 16 * k1r;
+#pragma unroll
+                    for (int n2 = 0; n2 < 16; ++n2) u[n2] = y[(n2 + row2) & 15];
+                }
+                // the stage is consumed: order the generic accesses before the next TMA write, then release the slot
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm.empty_ld[s]);
+                if (tid == 0 && plane + ncl < nplanes) {
+                    mbar_wait<false>(&sm.empty_ld[s], it & 1);
+                    mbar_expect_tx(&sm.full_ld[s], STAGE_BYTES);
+                    tma_load_2d(st, &map_cube, 0, (plane + ncl) * C_total + chirp0 + (int)q * CPC + s * CB, &sm.full_ld[s], EVICT_FIRST);
+                }
+#pragma unroll
+                for (int n2 = 1; n2 < 16; ++n2) u[n2] = cmul(u[n2], twr[n2]);
+                pow2::dft<16>(u);
+                if (s == 0) mbar_wait<false>(&sm.empty_M[b], ((it >> 1) & 1) ^ 1);    // the owners' Doppler groups left buffer b
+                const uint32_t coff = boff + (uint32_t)(s * CB * sizeof(float2));
+#pragma unroll
+                for (int k2 = 0; k2 < 16; ++k2) {
+                    // k = k1r + 16 k2, range fftshift p = (k + S/2) mod S = k1r + 16 ((k2 + 8) mod 16)
+                    const int k2s = (k2 + 8) & 15;
+                    const int owner = k2s >> 2, pl16 = k2s & 3;                       // p = 64 owner + 16 pl16 + k1r
+                    float2 val = u[k2];
+                    if (k2 == 0 && dc_removal && k1r == 0) val = make_float2(0.f, 0.f);   // mean removal, dechirp.py:120
+                    const uint32_t dst = mbase[owner] + coff + (uint32_t)(pl16 * 16 * MP * sizeof(float2));
+                    if (XFER == 0) st_cluster(dst, val);
+                    else if (XFER == 1) st_async(dst, val, bbase[owner] + (uint32_t)(b * 8));
+                    else st_async(dst, val, bbase[owner] + (uint32_t)((b * (D_THREADS / 32) + 2 * pl16) * 8));
+                }
+            }
+            if (XFER == 0) {
+                __syncwarp();
+                if (lane < NC) mbar_arrive_cluster(mapa(s32(&sm.full_M[b]), lane));
+            }
+        }
+    } else {
+        // =============================================================== Doppler group
+        const int w = warp - R_THREADS / 32;
+        const int td = lane & 7;
+        float2 twd[16];
+#pragma unroll
+        for (int k1 = 0; k1 < 16; ++k1) twd[k1] = sm.tw1c[k1 * 8 + td];
+        const int k1p = lane & 15;
+        int it = 0;
+        for (int plane = cid; plane < nplanes; plane += ncl, ++it) {
+            const int b = it & 1;
+            const int f = plane / A, a = plane - f * A;
+            float2* Mb = sm.M[b];
+            if (XFER == 1) {
+                if (w == 0 && lane == 0) mbar_expect_tx(&sm.full_M[b], ROWS * C * sizeof(float2));
+                mbar_wait<false>(&sm.full_M[b], (it >> 1) & 1);
+            } else if (XFER == 2) {
+                if (lane == 0) mbar_expect_tx(&sm.full_Mw[b][w], 8 * C * sizeof(float2));
+                mbar_wait<false>(&sm.full_Mw[b][w], (it >> 1) & 1);
+            } else {
+                mbar_wait<false>(&sm.full_M[b], (it >> 1) & 1);
+            }
+            // pass 1, in place: radix 16 over chirps td + 8 j
+#pragma unroll 1
+            for (int i = 0; i < 2; ++i) {
+                float2* m = Mb + (8 * w + 4 * i + (lane >> 3)) * MP;
+                float2 v[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = m[td + 8 * j];
+                __syncwarp();
+                pow2::dft<16>(v);
+#pragma unroll
+                for (int k1 = 0; k1 < 16; ++k1)
+                    m[k1 * 8 + ((td + (k1 >> 1)) & 7)] = (k1 == 0) ? v[0] : cmul(v[k1], twd[k1]);
+            }
+            __syncwarp();
+            // pass 2: radix 8, Doppler fftshift
+#pragma unroll 1
+            for (int i = 0; i < 4; ++i) {
+                const int row = 8 * w + 2 * i + (lane >> 4);
+                float2* m = Mb + row * MP;
+                float2 u[8];
+#pragma unroll
+                for (int n2 = 0; n2 < 8; ++n2) u[n2] = m[k1p * 8 + ((n2 + (k1p >> 1)) & 7)];
+                pow2::dft<8>(u);
+                const int p = q * ROWS + row;
+                float2* dst = rds + (((size_t)f * S + p) * A + a) * C;
+                if (!STORE_TMA) {
+#pragma unroll
+                    for (int k2 = 0; k2 < 8; ++k2) __stcs(dst + ((k1p + 16 * k2 + C / 2) & (C - 1)), u[k2]);
+                } else {
+                    __syncwarp();                                       // both rows are read before they are rewritten
+#pragma unroll
+                    for (int k2 = 0; k2 < 8; ++k2) m[(k1p + 16 * k2 + C / 2) & (C - 1)] = u[k2];
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (k1p == 0) bulk_store_row(dst, m);
+                }
+            }
+            if (STORE_TMA) {
+                if (k1p == 0) asm volatile("cp.async.bulk.commit_group;\n cp.async.bulk.wait_group.read 0;" ::: "memory");
+            }
+            __syncwarp();
+            if (lane < NC) mbar_arrive_remote(mapa(s32(&sm.empty_M[b]), lane));
+        }
+        if (STORE_TMA && k1p == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+    cluster_sync_all();                       // no CTA leaves while a peer may still store to it or arrive on it
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    });
+    return fn;
+}
+
+}  // namespace ws
+
+// Returns 1 when the kernel was launched, 0 when this device / shape cannot take it (the caller falls back), < 0 on error.
+int rs_fft2d_ws_launch(const void* cube, const void* table, const void* twiddle_s, const void* twiddle_c, void* rds, int F,
+                       int A, int C_total, int chirp0, int dc_removal, int store_tma, int xfer, cudaStream_t stream) {
+    using namespace ws;
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) return 0;
+    if (((uintptr_t)cube & 15) || ((uintptr_t)rds & 15)) return 0;
+    const long long rows_in = (long long)F * A * C_total;
+    if (rows_in >= (1ll << 31) || (long long)F * S >= (1ll << 31)) return 0;
+    if (sizeof(Smem) > (size_t)rs_smem_optin_limit()) return 0;
+
+    CUtensorMap map_cube;
+    {
+        cuuint64_t gdim[2] = {(cuuint64_t)S, (cuuint64_t)rows_in};
+        cuuint64_t gstr[1] = {(cuuint64_t)S * sizeof(float2)};
+        cuuint32_t box[2] = {(cuuint32_t)S, (cuuint32_t)CB};
+        cuuint32_t estr[2] = {1, 1};
+        if (enc(&map_cube, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, const_cast<void*>(cube), gdim, gstr, box, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return 0;
+    }
+    typedef void (*Kern)(const CUtensorMap, const float2*, const float2*, const float2*, float2*, int, int, int, int, int);
+    static const Kern kerns[2][3] = {{fft2d_ws_kernel<false, 0>, fft2d_ws_kernel<false, 1>, fft2d_ws_kernel<false, 2>},
+                                     {fft2d_ws_kernel<true, 0>, fft2d_ws_kernel<true, 1>, fft2d_ws_kernel<true, 2>}};
+    if (xfer < 0 || xfer > 2) xfer = 0;
+    Kern kern = kerns[store_tma ? 1 : 0][xfer];
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    static int max_clusters[2][3] = {{-1, -1, -1}, {-1, -1, -1}};
+    int& mc = max_clusters[store_tma ? 1 : 0][xfer];
+    if (mc < 0) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(NC * 64);
+        cfg.blockDim = dim3(THREADS);
+        cfg.dynamicSmemBytes = sizeof(Smem);
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) {
+            cudaGetLastError();
+            n = 0;
+        }
+        mc = n;
+    }
+    int ncl = mc;
+    const char* env = getenv("RS_K12_CLUSTERS");           // tuning knob
+    if (env && atoi(env) > 0) ncl = atoi(env);
+    if (ncl <= 0) return 0;
+    const int nplanes = F * A;
+    if (ncl > nplanes) ncl = nplanes;
+    kern<<<ncl * NC, THREADS, sizeof(Smem), stream>>>(map_cube, (const float2*)table, (const float2*)twiddle_s,
+                                                       (const float2*)twiddle_c, (float2*)rds, A, C_total, chirp0, dc_removal,
+                                                       nplanes);
+    if (cudaGetLastError() != cudaSuccess) return 0;
+    return 1;
+}
+
+extern "C" int rs_fft2d_ws_max_clusters(void) {
+    using namespace ws;
+    auto kern = fft2d_ws_kernel<false, 0>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(NC * 64);
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = sizeof(Smem);
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    return n;
+}

@@ -1,4 +1,4 @@
-"""The fused cluster 2-D FFT (rs_range_doppler_fft, csrc/rs_fft2d.cu) against the oracle and against the two-kernel path:
+"""The fused cluster 2-D FFT (rs_range_doppler_fft, csrc/rs_fft2d.cu and csrc/rs_fft2d_ws.cu) against the oracle and against the two-kernel path:
 every cluster size, a chirp subset that still gives a 128-chirp plane, several frames and antennas, DC removal off."""
 import numpy as np
 import pytest
@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 
 def _rds(cube, p, env, monkeypatch, subset=None):
     from radar_slam_b200 import RadarConfig, FramePipeline
-    for k in ("RS_FUSED_FFT", "RS_FUSED_NC", "RS_SPLIT_FFT"):
+    for k in ("RS_FUSED_FFT", "RS_FUSED_NC", "RS_SPLIT_FFT", "RS_K12", "RS_K12_STORE", "RS_K12_CLUSTERS", "RS_K12_STRICT", "RS_K12_XFER"):
         monkeypatch.delenv(k, raising=False)
     for k, v in env.items():
         monkeypatch.setenv(k, v)
@@ -32,8 +32,16 @@ def test_cluster_kernel_matches_oracle_and_split_path(monkeypatch, A, F, win, dc
     scale = np.abs(ref).max()
     split = _rds(cube, p, {"RS_FUSED_FFT": "0"}, monkeypatch)
     assert np.abs(split - ref).max() <= 2e-6 * scale
-    for nc in ("2", "4", "8"):
-        got = _rds(cube, p, {"RS_FUSED_NC": nc}, monkeypatch)
+    variants = [{"RS_K12": "v1", "RS_FUSED_NC": nc} for nc in ("2", "4", "8")]
+    # the persistent warp-specialised TMA kernel: default, bulk-store rows, and so few clusters that every cluster
+    # walks many planes (both M buffers and both ring slots wrap several times)
+    ws = {"RS_K12": "ws", "RS_K12_STRICT": "1"}                  # strict: fail instead of falling back to v1
+    variants += [ws, dict(ws, RS_K12_STORE="tma"), dict(ws, RS_K12_CLUSTERS="1"),
+                 dict(ws, RS_K12_STORE="tma", RS_K12_CLUSTERS="2"), dict(ws, RS_K12_XFER="1", RS_K12_CLUSTERS="3"),
+                 dict(ws, RS_K12_XFER="2"), dict(ws, RS_K12_XFER="2", RS_K12_STORE="tma", RS_K12_CLUSTERS="1")]
+    for env in variants:
+        nc = str(env)
+        got = _rds(cube, p, env, monkeypatch)
         assert got.shape == ref.shape
         assert np.abs(got - ref).max() <= 2e-6 * scale, nc
         big = np.abs(ref) > 1e-3 * scale
