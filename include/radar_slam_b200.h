@@ -247,6 +247,30 @@ int rs_power_db_f64(const void* rds, double* out, int F, int A, int C, int S, vo
 int rs_process_chirps_f64(const void* in128, const void* ref128, const double* window, int rows, int S,
                           int dc_removal, void* out128, void* stream);
 
+/* ---- fp64 frame path of the legacy class API (one frame per call; csrc/rs_legacy_f64.cu) ----------------------------
+ * The reference computes RDS, peak mask and spectra in float64 from whatever arrays the caller holds; these entry points
+ * do the same on the device so that the legacy methods are exact also for an RDS that was np.load-ed from a stage file.
+ *
+ * SignalPreprocessor.generate_range_doppler_spectrum (dechirp.py:168-213) in fp64: (x conj(ref)) w - mean per chirp,
+ * FFT over fast time, FFT over slow time, fftshift on both axes.
+ *   cube128 complex128 [A][C_total][S], ref128 complex128 [S] (the reference chirp, NOT conjugated), window double [S],
+ *   twiddle_*128 complex128 [S] / [C_used] = exp(-2 pi i k / n);  rds128 complex128 [A][S][C_used] (reference layout). */
+int rs_range_doppler_f64(const void* cube128, const void* ref128, const double* window, const void* twiddle_s128,
+                         const void* twiddle_c128, void* rds128, int A, int C_total, int chirp0, int C_used, int S,
+                         int dc_removal, void* stream);
+
+/* extract_range_doppler_peaks (dechirp.py:215-278) in fp64 on a complex128 RDS [A][R][D]: power_db = 10 log10(|X|^2 +
+ * 1e-12) (written to power_db [A][R][D]), 3x3 'reflect' local maximum on the dB values (ties count), strict threshold,
+ * range gate.  keys (det_key packing) come out in the reference's order antenna -> range -> doppler; *total is the
+ * number of detections (may exceed cap: then only the first cap keys were written).  row_count int32 [A*R] and
+ * row_offset int64 [A*R] are workspace. */
+int rs_detect_f64(const void* rds128, const uint8_t* gate, double threshold_db, double* power_db, int* row_count,
+                  long long* row_offset, uint32_t* keys, long long cap, long long* total, int A, int R, int D, void* stream);
+
+/* unit-energy snapshots (angle_estimation.py:83-88) of n cells of a complex128 RDS [A][R][D]: out complex128 [n][A]. */
+int rs_signatures_c128(const void* rds128, const int* range_bin, const int* doppler_bin, int n, void* out128, int A, int R,
+                       int D, void* stream);
+
 /* AngleEstimator.estimate_angle_esprit for n snapshots in fp64 (angle_estimation.py:178-225): out double [n] deg. */
 int rs_esprit_f64(const void* sig128, int n, int A, double esprit_scale, double* out, void* stream);
 

@@ -18,12 +18,16 @@ sys.path.insert(0, ROOT)
 
 VARIANTS = {
     "v1": {"RS_K12": "v1"},
-    "ws": {"RS_K12": "ws", "RS_K12_STORE": "direct"},
+    "ws": {"RS_K12": "ws"},                                           # library default
     "ws-tma": {"RS_K12": "ws", "RS_K12_STORE": "tma"},
-    "ws-x1": {"RS_K12": "ws", "RS_K12_XFER": "1"},
-    "ws-x2": {"RS_K12": "ws", "RS_K12_XFER": "2"},
-    "ws-tma-x1": {"RS_K12": "ws", "RS_K12_STORE": "tma", "RS_K12_XFER": "1"},
-    "ws-tma-x2": {"RS_K12": "ws", "RS_K12_STORE": "tma", "RS_K12_XFER": "2"},
+    "ws0": {"RS_K12": "ws", "RS_K12_VARIANT": "0", "RS_K12_STORE": "direct"},
+    "ws0-tma": {"RS_K12": "ws", "RS_K12_VARIANT": "0", "RS_K12_STORE": "tma"},
+    "ws1": {"RS_K12": "ws", "RS_K12_VARIANT": "1", "RS_K12_STORE": "direct"},
+    "ws1-tma": {"RS_K12": "ws", "RS_K12_VARIANT": "1", "RS_K12_STORE": "tma"},
+    "ws2": {"RS_K12": "ws", "RS_K12_VARIANT": "2", "RS_K12_STORE": "direct"},
+    "ws2-tma": {"RS_K12": "ws", "RS_K12_VARIANT": "2", "RS_K12_STORE": "tma"},
+    "ws3": {"RS_K12": "ws", "RS_K12_VARIANT": "3", "RS_K12_STORE": "direct"},
+    "ws3-tma": {"RS_K12": "ws", "RS_K12_VARIANT": "3", "RS_K12_STORE": "tma"},
     "split": {"RS_FUSED_FFT": "0"},
 }
 
@@ -49,7 +53,7 @@ def main():
     ref = None
     nbytes = 16 * cube.numel()
     for name in args.variants.split(","):
-        for k in ("RS_K12", "RS_K12_STORE", "RS_K12_XFER", "RS_FUSED_FFT", "RS_FUSED_NC", "RS_K12_CLUSTERS"):
+        for k in ("RS_K12", "RS_K12_STORE", "RS_K12_VARIANT", "RS_FUSED_FFT", "RS_FUSED_NC", "RS_K12_CLUSTERS"):
             os.environ.pop(k, None)
         base, _, ncl = name.partition("@")
         os.environ.update(VARIANTS[base])

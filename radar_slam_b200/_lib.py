@@ -45,6 +45,9 @@ _SIGNATURES = {
     "rs_spectra_f64": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "rs_power_db_f64": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "rs_process_chirps_f64": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "rs_range_doppler_f64": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "rs_detect_f64": (_i, [_vp, _vp, _d, _vp, _vp, _vp, _vp, C.c_longlong, _vp, _i, _i, _i, _vp]),
+    "rs_signatures_c128": (_i, [_vp, _vp, _vp, _i, _vp, _i, _i, _i, _vp]),
     "rs_esprit_f64": (_i, [_vp, _i, _i, _d, _vp, _vp]),
     "rs_velocity_ls6": (_i, [_vp, _vp, _vp, _i, _d, _vp, _vp, _i, _vp, _vp, _vp]),
     "rs_associate_targets": (_i, [_vp, _vp, _vp, _vp, _d, _vp, _vp, _i, _i, _i, _vp]),

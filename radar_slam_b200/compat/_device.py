@@ -1,7 +1,6 @@
-"""Shared device plumbing of the legacy adapters: pipeline cache, RDS upload cache, small ctypes helpers."""
+"""Shared device plumbing of the legacy adapters: pipeline cache, fp64 upload / detect / snapshot helpers."""
 from __future__ import annotations
 
-import weakref
 from collections import OrderedDict
 from dataclasses import replace
 from typing import Optional, Tuple
@@ -13,7 +12,6 @@ from .. import _lib
 from ..pipeline import FramePipeline, RadarConfig
 
 _pipes: "OrderedDict[tuple, FramePipeline]" = OrderedDict()
-_rds_cache: "OrderedDict[int, tuple]" = OrderedDict()
 
 
 def pipeline(**kw) -> FramePipeline:
@@ -29,41 +27,38 @@ def pipeline(**kw) -> FramePipeline:
     return p
 
 
-def _sample(arr: np.ndarray) -> complex:
-    flat = arr.reshape(-1)
-    step = max(1, flat.size // 61)
-    return complex(flat[::step].sum())
-
-
-def remember_rds(arr: np.ndarray, dev: torch.Tensor, cube: Optional[torch.Tensor] = None,
-                 chirp_subset: Optional[Tuple[int, int]] = None) -> None:
-    """Remember the device copy ([1,S,A,C]) of an RDS array handed to the caller, and the raw cube it
-    came from when known (lets the peak extractor settle fp32-undecidable cells in fp64)."""
-    try:
-        ref = weakref.ref(arr)
-    except TypeError:
-        return
-    _rds_cache[id(arr)] = (ref, _sample(arr), dev, cube, chirp_subset)
-    while len(_rds_cache) > 2:
-        _rds_cache.popitem(last=False)
-
-
 def rds_to_device(rds: np.ndarray, pipe: FramePipeline) -> torch.Tensor:
-    """Reference-layout RDS [A, R, D] (any complex dtype, host) -> complex64 [1, R, A, D] on the
-    device.  Re-uses the device copy when `rds` is the very array this library returned."""
-    ent = _rds_cache.get(id(rds))
-    if ent is not None and ent[0]() is rds and ent[1] == _sample(rds):
-        return ent[2]
+    """Reference-layout RDS [A, R, D] (host, any complex dtype) -> complex128 [A, R, D] on the device.
+
+    Always a fresh upload of exactly the array the caller passed: the legacy API works on whatever RDS it is
+    handed (edited in place, np.load-ed from a stage file, ...), one frame per call, so there is nothing to cache."""
     rds = np.asarray(rds)
     if rds.ndim != 3:
         raise ValueError("rds must be [num_antennas, range_bins, doppler_bins]")
-    A, R, D = rds.shape
-    host = torch.from_numpy(np.ascontiguousarray(rds, dtype=np.complex64))
-    ref_layout = host.to(pipe.device).view(1, A, R, D)
-    out = torch.empty((1, R, A, D), dtype=torch.complex64, device=pipe.device)
-    pipe._call("rs_rds_from_reference_layout", ref_layout.data_ptr(), out.data_ptr(), 1, A, D, R, pipe.stream)
-    remember_rds(rds, out)
-    return out
+    return torch.from_numpy(np.ascontiguousarray(rds, dtype=np.complex128)).to(pipe.device)
+
+
+def detect_f64(pipe: FramePipeline, rds128: torch.Tensor, gate: np.ndarray, threshold_db: float):
+    """extract_range_doppler_peaks (dechirp.py:235-263) in fp64 on the device.
+    -> (antenna, range_bin, doppler_bin int64 arrays in the reference's order, power_db float64 [A, R, D])."""
+    A, R, D = rds128.shape
+    dev = pipe.device
+    power_db = torch.empty((A, R, D), dtype=torch.float64, device=dev)
+    row_count = torch.empty((A * R,), dtype=torch.int32, device=dev)
+    row_off = torch.empty((A * R,), dtype=torch.int64, device=dev)
+    total = torch.zeros((1,), dtype=torch.int64, device=dev)
+    gate_dev = torch.from_numpy(np.ascontiguousarray(gate, dtype=np.uint8)).to(dev)
+    cap = max(1024, (A * R * D) // 8)
+    while True:
+        keys = torch.empty((cap,), dtype=torch.int32, device=dev)
+        pipe._call("rs_detect_f64", rds128.data_ptr(), gate_dev.data_ptr(), float(threshold_db), power_db.data_ptr(),
+                   row_count.data_ptr(), row_off.data_ptr(), keys.data_ptr(), cap, total.data_ptr(), A, R, D, pipe.stream)
+        n = int(total.item())
+        if n <= cap:
+            break
+        cap = n                                   # plateau-heavy input: every cell can be a peak
+    k = keys[:n].cpu().numpy().view(np.uint32).astype(np.int64)
+    return k >> 24, (k >> 12) & 0xFFF, k & 0xFFF, power_db.cpu().numpy()
 
 
 def keys_tensor(antenna, range_bin, doppler_bin, device) -> torch.Tensor:
@@ -74,15 +69,15 @@ def keys_tensor(antenna, range_bin, doppler_bin, device) -> torch.Tensor:
     return torch.from_numpy(key.astype(np.uint32).view(np.int32)).to(device)
 
 
-def signatures(pipe: FramePipeline, rds_dev: torch.Tensor, range_bin, doppler_bin) -> torch.Tensor:
-    """Unit-energy snapshots complex128 [n, A] for cells of frame 0 (angle_estimation.py:83-88)."""
-    _, R, A, D = rds_dev.shape
+def signatures(pipe: FramePipeline, rds128: torch.Tensor, range_bin, doppler_bin) -> torch.Tensor:
+    """Unit-energy snapshots complex128 [n, A] of cells of a complex128 RDS [A, R, D] (angle_estimation.py:83-88)."""
+    A, R, D = rds128.shape
     n = len(range_bin)
-    keys = keys_tensor(np.zeros(n, dtype=np.int64), range_bin, doppler_bin, pipe.device)
-    frames = torch.zeros(n, dtype=torch.int32, device=pipe.device)
+    rb = torch.from_numpy(np.ascontiguousarray(range_bin, dtype=np.int32)).to(pipe.device)
+    db = torch.from_numpy(np.ascontiguousarray(doppler_bin, dtype=np.int32)).to(pipe.device)
     out = torch.empty((n, A), dtype=torch.complex128, device=pipe.device)
-    pipe._call("rs_signatures_f64", rds_dev.data_ptr(), keys.data_ptr(), frames.data_ptr(), n, out.data_ptr(),
-               1, R, D, A, pipe.stream)
+    pipe._call("rs_signatures_c128", rds128.data_ptr(), rb.data_ptr(), db.data_ptr(), n, out.data_ptr(), A, R, D,
+               pipe.stream)
     return out
 
 
@@ -102,11 +97,3 @@ def esprit(pipe: FramePipeline, sig128: torch.Tensor, scale: float) -> torch.Ten
     out = torch.empty((n,), dtype=torch.float64, device=pipe.device)
     pipe._call("rs_esprit_f64", sig128.data_ptr(), n, A, float(scale), out.data_ptr(), pipe.stream)
     return out
-
-
-def cube_of(rds: np.ndarray):
-    """(device cube, chirp_subset) the RDS array was computed from in this process, or (None, None)."""
-    ent = _rds_cache.get(id(rds))
-    if ent is not None and ent[0]() is rds and ent[1] == _sample(rds) and ent[3] is not None:
-        return ent[3], ent[4]
-    return None, None

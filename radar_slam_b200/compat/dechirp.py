@@ -2,7 +2,8 @@
 
 Same constructor, attributes, method names, argument meaning, return types and error behaviour
 (dechirp.py:21-355); the frame-level work -- dechirp*window, DC removal, 2-D FFT + fftshift, dB power,
-3x3 local maxima, threshold and range gate -- runs in libradarslam_b200.so on the GPU in complex64.
+3x3 local maxima, threshold and range gate -- runs in libradarslam_b200.so on the GPU, in fp64 like the
+reference (csrc/rs_legacy_f64.cu); the batched complex64 path with its fp64 recheck is radar_slam_b200.FramePipeline.
 matplotlib is imported lazily so the module loads where it is not installed.
 """
 from __future__ import annotations
@@ -86,7 +87,7 @@ class SignalPreprocessor:
     def generate_range_doppler_spectrum(self, frame_signals: np.ndarray,
                                         chirp_subset: Optional[Tuple[int, int]] = None) -> np.ndarray:
         """[num_antennas, num_chirps, samples] complex -> RDS [num_antennas, range_bins, doppler_bins]
-        complex128 holding complex64-precision values (dechirp.py:168-213)."""
+        complex128, computed in fp64 (dechirp.py:168-213)."""
         frame_signals = np.asarray(frame_signals)
         num_antennas, num_chirps, samples_per_chirp = frame_signals.shape
         if samples_per_chirp != self.samples_per_chirp:
@@ -100,40 +101,32 @@ class SignalPreprocessor:
                 raise ValueError("could not broadcast input array: chirp_subset outside the frame")
             chirp_subset = (start, end)
         pipe = self._pipe()
-        cube = torch.from_numpy(np.ascontiguousarray(frame_signals, dtype=np.complex64)[None]).to(pipe.device)
-        rds_dev = pipe.range_doppler(cube, chirp_subset)
-        _, S, A, Cu = rds_dev.shape
-        ref_layout = torch.empty((1, A, S, Cu), dtype=torch.complex64, device=pipe.device)
-        pipe._call("rs_rds_to_reference_layout", rds_dev.data_ptr(), ref_layout.data_ptr(), 1, A, Cu, S, pipe.stream)
-        out = ref_layout[0].cpu().numpy().astype(np.complex128)
-        _device.remember_rds(out, rds_dev, cube, chirp_subset)
-        return out
+        c0, c1 = chirp_subset if chirp_subset is not None else (0, num_chirps)
+        Cu, S = c1 - c0, samples_per_chirp
+        # the reference works in complex128 (dechirp.py:193-211): so does this method -- fp64 kernels on the very
+        # array the caller passed, one frame per call (the batched complex64 path is FramePipeline)
+        cube = torch.from_numpy(np.ascontiguousarray(frame_signals, dtype=np.complex128)).to(pipe.device)
+        ref = torch.from_numpy(self.generate_reference_chirp().astype(np.complex128)).to(pipe.device)
+        win = torch.from_numpy(np.ascontiguousarray(tables.window(self.window_type, S), dtype=np.float64)).to(pipe.device)
+        tw_s = torch.from_numpy(tables.twiddles128(S)).to(pipe.device)
+        tw_c = torch.from_numpy(tables.twiddles128(Cu)).to(pipe.device)
+        rds = torch.empty((num_antennas, S, Cu), dtype=torch.complex128, device=pipe.device)
+        pipe._call("rs_range_doppler_f64", cube.data_ptr(), ref.data_ptr(), win.data_ptr(), tw_s.data_ptr(),
+                   tw_c.data_ptr(), rds.data_ptr(), num_antennas, num_chirps, c0, Cu, S, int(bool(self.dc_removal)),
+                   pipe.stream)
+        return rds.cpu().numpy()
 
     def extract_range_doppler_peaks(self, rds: np.ndarray, threshold_db: float = -20.0, min_range: float = 1.0,
                                     max_range: float = 200.0) -> Dict:
-        """dechirp.py:215-278: {'peaks': [dict...], 'range_bins_m', 'doppler_bins_hz', 'power_spectrum_db'}."""
+        """dechirp.py:215-278: {'peaks': [dict...], 'range_bins_m', 'doppler_bins_hz', 'power_spectrum_db'},
+        decided in fp64 on the array passed in (wherever it came from)."""
         pipe = self._pipe()
         rds_dev = _device.rds_to_device(rds, pipe)
-        _, R, A, D = rds_dev.shape
-        det = pipe.detect(rds_dev, threshold_db=threshold_db, min_range=min_range, max_range=max_range)
-        cube_dev, subset = _device.cube_of(rds)
-        if cube_dev is not None:
-            # the RDS was computed here from a known cube: cells fp32 cannot decide are settled in fp64
-            pipe.recheck_detections(cube_dev, det, subset)
-        if int(det.overflow.sum().item()):
-            # plateau-heavy input: rerun with segments that can hold every cell of a tile
-            from ..pipeline import FramePipeline
-            from .. import _lib
-            tr, td, _ = _lib.detect_tiling(R, D, A)
-            big = FramePipeline(pipe.cfg, device=str(pipe.device), seg_cap=tr * td * min(A, 8))
-            det = big.detect(rds_dev, threshold_db=threshold_db, min_range=min_range, max_range=max_range)
-        power_db_dev = torch.empty((1, A, R, D), dtype=torch.float64, device=pipe.device)
-        pipe._call("rs_power_db_f64", rds_dev.data_ptr(), power_db_dev.data_ptr(), 1, A, D, R, pipe.stream)
-        d = det.frame(0)
-        power_db = power_db_dev[0].cpu().numpy()
+        A, R, D = rds_dev.shape
+        gate = tables.range_gate(self.range_resolution, R, min_range, max_range)
+        ant, rb, db, power_db = _device.detect_f64(pipe, rds_dev, gate, threshold_db)
         range_bins_m = tables.range_axis(self.range_resolution, R)
         doppler_bins_hz = tables.doppler_axis(self.sampling_rate, D)
-        ant, rb, db = d["antenna"], d["range_bin"], d["doppler_bin"]
         rm, dh, pw = range_bins_m[rb], doppler_bins_hz[db], power_db[ant, rb, db]
         # dechirp.py:265-272: one dict per peak; kept as columns and materialised on access (compat/lazy.py)
         peaks = LazyRecords({'antenna': ant, 'range_bin': rb, 'doppler_bin': db, 'range_m': rm, 'doppler_hz': dh,

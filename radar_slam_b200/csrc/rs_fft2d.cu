@@ -173,7 +173,7 @@ extern "C" int rs_doppler_fft(const void* mid, const void* twiddle_c, void* rds,
 
 // K12 v2 (rs_fft2d_ws.cu): persistent warp-specialised cluster kernel fed by TMA.  1 = launched, 0 = not applicable here.
 int rs_fft2d_ws_launch(const void* cube, const void* table, const void* twiddle_s, const void* twiddle_c, void* rds, int F,
-                       int A, int C_total, int chirp0, int dc_removal, int store_tma, int xfer, cudaStream_t stream);
+                       int A, int C_total, int chirp0, int dc_removal, int store_tma, int variant, cudaStream_t stream);
 
 extern "C" int rs_range_doppler_fft(const void* cube, const void* table, const void* twiddle_s, const void* twiddle_c,
                                     void* mid_ws, void* rds, int F, int A, int C_total, int chirp0, int C_used, int S,
@@ -188,9 +188,11 @@ extern "C" int rs_range_doppler_fft(const void* cube, const void* table, const v
         const char* k12 = getenv("RS_K12");
         if (!(k12 && k12[0] == 'v')) {
             const char* st = getenv("RS_K12_STORE");
-            const char* xf = getenv("RS_K12_XFER");            // 0: st.shared::cluster + release arrive, 1 / 2: st.async
+            // RS_K12_VARIANT: 0 = st.shared::cluster + release arrives, scalar butterflies; 1 = st.async hand-over;
+            // 2 (default) = + f32x2 butterflies; 3 = + two independent range subgroups
+            const char* vr = getenv("RS_K12_VARIANT");
             const int r = rs_fft2d_ws_launch(cube, table, twiddle_s, twiddle_c, rds, F, A, C_total, chirp0, dc_removal,
-                                             st && st[0] == 't', xf ? atoi(xf) : 0, (cudaStream_t)stream);
+                                             st && st[0] == 't', vr ? atoi(vr) : 2, (cudaStream_t)stream);
             if (r == 1) return RS_OK;
             const char* strict = getenv("RS_K12_STRICT");        // tests: no silent fall-back to the round-1 kernel
             if (strict && atoi(strict) == 1) {

@@ -48,7 +48,6 @@ struct __align__(128) Smem {
     float2 tw1s[S];                     // range inter-pass twiddles w_S^{k1 n2}
     float2 tw1c[C];                     // Doppler inter-pass twiddles
     unsigned long long full_ld[NSTAGE], empty_ld[NSTAGE], full_M[2], empty_M[2];
-    unsigned long long full_Mw[2][D_THREADS / 32];   // XFER 2: one transaction barrier per Doppler warp (its 8 rows)
 };
 
 __device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -70,25 +69,24 @@ __device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {     // release at cluster scope
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
-template <bool CLUSTER>
 __device__ __forceinline__ bool mbar_try(unsigned long long* b, uint32_t parity) {
     uint32_t ok;
-    if (CLUSTER)
-        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-                     : "=r"(ok) : "r"(s32(b)), "r"(parity) : "memory");
-    else
-        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-                     : "=r"(ok) : "r"(s32(b)), "r"(parity) : "memory");
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(s32(b)), "r"(parity) : "memory");
     return ok != 0;
 }
-// Bounded wait: a protocol error must end as a trapped launch (RS_ECUDA), never as a hung GPU.
-template <bool CLUSTER>
+// Bounded wait: a protocol error must end as a trapped launch (RS_ECUDA), never as a hung GPU.  Waits are acquire.cta:
+// what they guard lives in THIS CTA's shared memory (written by TMA, st.async or a peer's st.shared::cluster), so the
+// L1 invalidation an acquire.cluster would add (CCTL.IVALL) buys nothing.
 __device__ __forceinline__ void mbar_wait(unsigned long long* b, uint32_t parity) {
-    if (mbar_try<CLUSTER>(b, parity)) return;
+    if (mbar_try(b, parity)) return;
     const long long t0 = clock64();
-    while (!mbar_try<CLUSTER>(b, parity)) {
+    while (!mbar_try(b, parity)) {
         if (clock64() - t0 > 4000000000ll) __trap();
     }
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 // "I no longer read it" needs no cluster-scope release (nothing the peer must see was written): the default
 // release.cta arrive is what costs no MEMBAR.ALL.GPU
@@ -121,9 +119,10 @@ __device__ __forceinline__ void cluster_sync_all() {
 
 constexpr unsigned long long EVICT_FIRST = 0x12F0000000000000ull;       // createpolicy fractional evict_first, 1.0
 
-// XFER: how range bins reach their owner: 0 = st.shared::cluster + release.cluster arrive per warp,
-//       1 = st.async completing bytes on one barrier per buffer, 2 = st.async, one barrier per Doppler warp
-template <bool STORE_TMA, int XFER>
+// XFER: how range bins reach their owner: 0 = st.shared::cluster + one release.cluster arrive per warp,
+//       1 = st.async completing bytes on the owner's transaction barrier (no fence anywhere).
+// PACKED: butterflies with f32x2 adds (FADD2).
+template <bool STORE_TMA, int XFER, bool PACKED, int RG>
 __global__ void __cluster_dims__(NC, 1, 1) __launch_bounds__(THREADS, 1)
 fft2d_ws_kernel(const __grid_constant__ CUtensorMap map_cube, const float2* __restrict__ table, const float2* __restrict__ tw_s_g, const float2* __restrict__ tw_c_g,
                 float2* __restrict__ rds, int A, int C_total, int chirp0, int dc_removal, int nplanes) {
@@ -145,12 +144,11 @@ fft2d_ws_kernel(const __grid_constant__ CUtensorMap map_cube, const float2* __re
     if (tid == 0) {
         for (int s = 0; s < NSTAGE; ++s) {
             mbar_init(&sm.full_ld[s], 1);
-            mbar_init(&sm.empty_ld[s], R_THREADS / 32);
+            mbar_init(&sm.empty_ld[s], R_THREADS / RG / 32);
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&sm.full_M[b], XFER == 0 ? NC * (R_THREADS / 32) : 1);
             mbar_init(&sm.empty_M[b], NC * (D_THREADS / 32));
-            for (int w = 0; w < D_THREADS / 32; ++w) mbar_init(&sm.full_Mw[b][w], 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -160,27 +158,30 @@ fft2d_ws_kernel(const __grid_constant__ CUtensorMap map_cube, const float2* __re
     const int warp = tid >> 5, lane = tid & 31;
     if (warp < R_THREADS / 32) {
         // =============================================================== range group
-        const int row1 = tid >> 4, t1 = tid & 15;            // pass 1: chirp of the stage, fast-time column
-        const int row2 = tid & 15, k1r = tid >> 4;            // pass 2: lanes along chirps
+        // RG subgroups of 8 / RG warps; a subgroup owns the stages s = g (mod RG) of every plane (its own TMA requests,
+        // its own named barrier), so with RG = 2 the halves drift apart and fill each other's latencies
+        constexpr int RGT = R_THREADS / RG;                   // threads of a subgroup
+        constexpr int NI = CB * 16 / RGT;                     // items per thread and pass
+        constexpr int HS = RGT / 16;                          // item stride of the slow index
+        const int g = tid / RGT, tg = tid - g * RGT;
+        const int t1 = tg & 15, hi = tg >> 4;                 // pass 1: fast-time column, chirp hi (+ HS i) of the stage
+        const int row2 = tg & 15;                             // pass 2: lanes along chirps, k1 = hi (+ HS i)
         float2 tabv[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) tabv[j] = table[t1 + 16 * j];
-        const float2* twr = sm.tw1s + k1r * 16;
-        // remote bases of M[0] row k1r, this thread's chirp column, in the four owners
-        uint32_t mbase[NC];
+        // remote bases of row `hi` of M[0], this thread's chirp column of stage 0, in the four owners
+        uint32_t mbase[NC], bbase[NC];
 #pragma unroll
-        for (int o = 0; o < NC; ++o) mbase[o] = mapa(s32(&sm.M[0][0]), o) + (uint32_t)((k1r * MP + q * CPC + row2) * sizeof(float2));
-        uint32_t bbase[NC];                                   // the owners' transaction barrier for row k1r (+ 16 pl16)
-#pragma unroll
-        for (int o = 0; o < NC; ++o)
-            bbase[o] = XFER == 2 ? mapa(s32(&sm.full_Mw[0][k1r >> 3]), o) : mapa(s32(&sm.full_M[0]), o);
-        // thread 0 doubles as the TMA producer: the first plane's stages now, stage s of the next plane as soon as the
-        // eight warps have taken stage s of this one into registers
-        if (tid == 0 && cid < nplanes) {
+        for (int o = 0; o < NC; ++o) {
+            mbase[o] = mapa(s32(&sm.M[0][0]), o) + (uint32_t)((hi * MP + q * CPC + row2) * sizeof(float2));
+            bbase[o] = mapa(s32(&sm.full_M[0]), o);
+        }
+        const int chirp_row0 = chirp0 + (int)q * CPC;
+        if (tg == 0 && cid < nplanes) {
 #pragma unroll 1
-            for (int s = 0; s < NSTAGE; ++s) {
+            for (int s = g; s < NSTAGE; s += RG) {
                 mbar_expect_tx(&sm.full_ld[s], STAGE_BYTES);
-                tma_load_2d(sm.stage[s], &map_cube, 0, cid * C_total + chirp0 + (int)q * CPC + s * CB, &sm.full_ld[s], EVICT_FIRST);
+                tma_load_2d(sm.stage[s], &map_cube, 0, cid * C_total + chirp_row0 + s * CB, &sm.full_ld[s], EVICT_FIRST);
             }
         }
         int it = 0;
@@ -188,54 +189,63 @@ fft2d_ws_kernel(const __grid_constant__ CUtensorMap map_cube, const float2* __re
             const int b = it & 1;
             const uint32_t boff = (uint32_t)(b * ROWS * MP * sizeof(float2));
 #pragma unroll 1
-            for (int s = 0; s < NSTAGE; ++s) {
+            for (int s = g; s < NSTAGE; s += RG) {
                 float2* st = sm.stage[s];
-                mbar_wait<false>(&sm.full_ld[s], it & 1);
-                {
+                mbar_wait(&sm.full_ld[s], it & 1);
+#pragma unroll 1
+                for (int i = 0; i < NI; ++i) {
+                    const int row1 = hi + HS * i;
                     float2 v[16];
                     const float2* x = st + row1 * S + t1;
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[j] = x[16 * j];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[j] = cmul(v[j], tabv[j]);
-                    pow2::dft<16>(v);
+                    if (PACKED) pow2::dftp<16>(v); else pow2::dft<16>(v);
                     __syncwarp();                                       // the chirp is read before it is rewritten
                     float2* y = st + row1 * S + ((t1 + row1) & 15);
 #pragma unroll
                     for (int k1 = 0; k1 < 16; ++k1) y[16 * k1] = v[k1];
                 }
-                asm volatile("bar.sync 1, %0;" ::"n"(R_THREADS) : "memory");
-                float2 u[16];
-                {
-                    const float2* y = st + row2 * S + 16 * k1r;
+                named_bar_sync(1 + g, RGT);
+#pragma unroll 1
+                for (int i = 0; i < NI; ++i) {
+                    const int k1r = hi + HS * i;
+                    float2 u[16];
+                    {
+                        const float2* y = st + row2 * S + 16 * k1r;
 #pragma unroll
-                    for (int n2 = 0; n2 < 16; ++n2) u[n2] = y[(n2 + row2) & 15];
-                }
-                // the stage is consumed: order the generic accesses before the next TMA write, then release the slot
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&sm.empty_ld[s]);
-                if (tid == 0 && plane + ncl < nplanes) {
-                    mbar_wait<false>(&sm.empty_ld[s], it & 1);
-                    mbar_expect_tx(&sm.full_ld[s], STAGE_BYTES);
-                    tma_load_2d(st, &map_cube, 0, (plane + ncl) * C_total + chirp0 + (int)q * CPC + s * CB, &sm.full_ld[s], EVICT_FIRST);
-                }
+                        for (int n2 = 0; n2 < 16; ++n2) u[n2] = y[(n2 + row2) & 15];
+                    }
+                    if (i == NI - 1) {
+                        // the stage is consumed: order the generic accesses before the next TMA write, release the slot,
+                        // and thread 0 of the subgroup requests the same stage of the next plane once all its warps did
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&sm.empty_ld[s]);
+                        if (tg == 0 && plane + ncl < nplanes) {
+                            mbar_wait(&sm.empty_ld[s], it & 1);
+                            mbar_expect_tx(&sm.full_ld[s], STAGE_BYTES);
+                            tma_load_2d(st, &map_cube, 0, (plane + ncl) * C_total + chirp_row0 + s * CB, &sm.full_ld[s], EVICT_FIRST);
+                        }
+                    }
+                    const float2* twr = sm.tw1s + k1r * 16;
 #pragma unroll
-                for (int n2 = 1; n2 < 16; ++n2) u[n2] = cmul(u[n2], twr[n2]);
-                pow2::dft<16>(u);
-                if (s == 0) mbar_wait<false>(&sm.empty_M[b], ((it >> 1) & 1) ^ 1);    // the owners' Doppler groups left buffer b
-                const uint32_t coff = boff + (uint32_t)(s * CB * sizeof(float2));
+                    for (int n2 = 1; n2 < 16; ++n2) u[n2] = cmul(u[n2], twr[n2]);
+                    if (PACKED) pow2::dftp<16>(u); else pow2::dft<16>(u);
+                    if (s == g && i == 0) mbar_wait(&sm.empty_M[b], ((it >> 1) & 1) ^ 1);   // the owners' Doppler groups left buffer b
+                    const uint32_t roff = boff + (uint32_t)((i * HS * MP + s * CB) * sizeof(float2));
 #pragma unroll
-                for (int k2 = 0; k2 < 16; ++k2) {
-                    // k = k1r + 16 k2, range fftshift p = (k + S/2) mod S = k1r + 16 ((k2 + 8) mod 16)
-                    const int k2s = (k2 + 8) & 15;
-                    const int owner = k2s >> 2, pl16 = k2s & 3;                       // p = 64 owner + 16 pl16 + k1r
-                    float2 val = u[k2];
-                    if (k2 == 0 && dc_removal && k1r == 0) val = make_float2(0.f, 0.f);   // mean removal, dechirp.py:120
-                    const uint32_t dst = mbase[owner] + coff + (uint32_t)(pl16 * 16 * MP * sizeof(float2));
-                    if (XFER == 0) st_cluster(dst, val);
-                    else if (XFER == 1) st_async(dst, val, bbase[owner] + (uint32_t)(b * 8));
-                    else st_async(dst, val, bbase[owner] + (uint32_t)((b * (D_THREADS / 32) + 2 * pl16) * 8));
+                    for (int k2 = 0; k2 < 16; ++k2) {
+                        // k = k1r + 16 k2, range fftshift p = (k + S/2) mod S = k1r + 16 ((k2 + 8) mod 16)
+                        const int k2s = (k2 + 8) & 15;
+                        const int owner = k2s >> 2, pl16 = k2s & 3;                   // p = 64 owner + 16 pl16 + k1r
+                        float2 val = u[k2];
+                        if (k2 == 0 && dc_removal && k1r == 0) val = make_float2(0.f, 0.f);   // mean removal, dechirp.py:120
+                        const uint32_t dst = mbase[owner] + roff + (uint32_t)(pl16 * 16 * MP * sizeof(float2));
+                        if (XFER == 0) st_cluster(dst, val);
+                        else st_async(dst, val, bbase[owner] + (uint32_t)(b * 8));
+                    }
                 }
             }
             if (XFER == 0) {
@@ -256,15 +266,8 @@ fft2d_ws_kernel(const __grid_constant__ CUtensorMap map_cube, const float2* __re
             const int b = it & 1;
             const int f = plane / A, a = plane - f * A;
             float2* Mb = sm.M[b];
-            if (XFER == 1) {
-                if (w == 0 && lane == 0) mbar_expect_tx(&sm.full_M[b], ROWS * C * sizeof(float2));
-                mbar_wait<false>(&sm.full_M[b], (it >> 1) & 1);
-            } else if (XFER == 2) {
-                if (lane == 0) mbar_expect_tx(&sm.full_Mw[b][w], 8 * C * sizeof(float2));
-                mbar_wait<false>(&sm.full_Mw[b][w], (it >> 1) & 1);
-            } else {
-                mbar_wait<false>(&sm.full_M[b], (it >> 1) & 1);
-            }
+            if (XFER == 1 && w == 0 && lane == 0) mbar_expect_tx(&sm.full_M[b], ROWS * C * sizeof(float2));
+            mbar_wait(&sm.full_M[b], (it >> 1) & 1);
             // pass 1, in place: radix 16 over chirps td + 8 j
 #pragma unroll 1
             for (int i = 0; i < 2; ++i) {
@@ -273,7 +276,7 @@ fft2d_ws_kernel(const __grid_constant__ CUtensorMap map_cube, const float2* __re
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = m[td + 8 * j];
                 __syncwarp();
-                pow2::dft<16>(v);
+                if (PACKED) pow2::dftp<16>(v); else pow2::dft<16>(v);
 #pragma unroll
                 for (int k1 = 0; k1 < 16; ++k1)
                     m[k1 * 8 + ((td + (k1 >> 1)) & 7)] = (k1 == 0) ? v[0] : cmul(v[k1], twd[k1]);
@@ -287,7 +290,7 @@ fft2d_ws_kernel(const __grid_constant__ CUtensorMap map_cube, const float2* __re
                 float2 u[8];
 #pragma unroll
                 for (int n2 = 0; n2 < 8; ++n2) u[n2] = m[k1p * 8 + ((n2 + (k1p >> 1)) & 7)];
-                pow2::dft<8>(u);
+                if (PACKED) pow2::dftp<8>(u); else pow2::dft<8>(u);
                 const int p = q * ROWS + row;
                 float2* dst = rds + (((size_t)f * S + p) * A + a) * C;
                 if (!STORE_TMA) {
@@ -335,7 +338,7 @@ static EncodeTiledFn encode_fn() {
 
 // Returns 1 when the kernel was launched, 0 when this device / shape cannot take it (the caller falls back), < 0 on error.
 int rs_fft2d_ws_launch(const void* cube, const void* table, const void* twiddle_s, const void* twiddle_c, void* rds, int F,
-                       int A, int C_total, int chirp0, int dc_removal, int store_tma, int xfer, cudaStream_t stream) {
+                       int A, int C_total, int chirp0, int dc_removal, int store_tma, int variant, cudaStream_t stream) {
     using namespace ws;
     EncodeTiledFn enc = encode_fn();
     if (!enc) return 0;
@@ -356,16 +359,19 @@ int rs_fft2d_ws_launch(const void* cube, const void* table, const void* twiddle_
             return 0;
     }
     typedef void (*Kern)(const CUtensorMap, const float2*, const float2*, const float2*, float2*, int, int, int, int, int);
-    static const Kern kerns[2][3] = {{fft2d_ws_kernel<false, 0>, fft2d_ws_kernel<false, 1>, fft2d_ws_kernel<false, 2>},
-                                     {fft2d_ws_kernel<true, 0>, fft2d_ws_kernel<true, 1>, fft2d_ws_kernel<true, 2>}};
-    if (xfer < 0 || xfer > 2) xfer = 0;
-    Kern kern = kerns[store_tma ? 1 : 0][xfer];
+    // the measured variants: [bulk store][variant]: 0 = release-arrive hand-over, scalar, 1 subgroup (the first version),
+    // 1 = st.async, scalar, 1 subgroup; 2 = st.async, packed, 1 subgroup; 3 = st.async, packed, 2 subgroups
+    static const Kern kerns[2][4] = {
+        {fft2d_ws_kernel<false, 0, false, 1>, fft2d_ws_kernel<false, 1, false, 1>, fft2d_ws_kernel<false, 1, true, 1>, fft2d_ws_kernel<false, 1, true, 2>},
+        {fft2d_ws_kernel<true, 0, false, 1>, fft2d_ws_kernel<true, 1, false, 1>, fft2d_ws_kernel<true, 1, true, 1>, fft2d_ws_kernel<true, 1, true, 2>}};
+    if (variant < 0 || variant > 3) variant = 2;
+    Kern kern = kerns[store_tma ? 1 : 0][variant];
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)) != cudaSuccess) {
         cudaGetLastError();
         return 0;
     }
-    static int max_clusters[2][3] = {{-1, -1, -1}, {-1, -1, -1}};
-    int& mc = max_clusters[store_tma ? 1 : 0][xfer];
+    static int max_clusters[2][4] = {{-1, -1, -1, -1}, {-1, -1, -1, -1}};
+    int& mc = max_clusters[store_tma ? 1 : 0][variant];
     if (mc < 0) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(NC * 64);
@@ -393,7 +399,7 @@ int rs_fft2d_ws_launch(const void* cube, const void* table, const void* twiddle_
 
 extern "C" int rs_fft2d_ws_max_clusters(void) {
     using namespace ws;
-    auto kern = fft2d_ws_kernel<false, 0>;
+    auto kern = fft2d_ws_kernel<false, 1, true, 1>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(NC * 64);

@@ -235,12 +235,11 @@ __global__ void signatures_c128_kernel(const double2* __restrict__ rds, const in
         const double m = hypot(x.x, x.y);                            // np.abs(s) ** 2, angle_estimation.py:86
         p += m * m;
     }
-    const double inv = p > 0 ? 1.0 / sqrt(p) : 1.0;
+    const double nrm = sqrt(p);
     for (int a = 0; a < A; ++a) {
         const double2 x = rds[(size_t)a * R * D + cell];
-        out[(size_t)i * A + a] = p > 0 ? make_double2(x.x / sqrt(p), x.y / sqrt(p)) : x;
+        out[(size_t)i * A + a] = p > 0 ? make_double2(x.x / nrm, x.y / nrm) : x;
     }
-    (void)inv;
 }
 
 }  // namespace

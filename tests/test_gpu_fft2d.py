@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 
 def _rds(cube, p, env, monkeypatch, subset=None):
     from radar_slam_b200 import RadarConfig, FramePipeline
-    for k in ("RS_FUSED_FFT", "RS_FUSED_NC", "RS_SPLIT_FFT", "RS_K12", "RS_K12_STORE", "RS_K12_CLUSTERS", "RS_K12_STRICT", "RS_K12_XFER"):
+    for k in ("RS_FUSED_FFT", "RS_FUSED_NC", "RS_SPLIT_FFT", "RS_K12", "RS_K12_STORE", "RS_K12_CLUSTERS", "RS_K12_STRICT", "RS_K12_VARIANT"):
         monkeypatch.delenv(k, raising=False)
     for k, v in env.items():
         monkeypatch.setenv(k, v)
@@ -37,8 +37,9 @@ def test_cluster_kernel_matches_oracle_and_split_path(monkeypatch, A, F, win, dc
     # walks many planes (both M buffers and both ring slots wrap several times)
     ws = {"RS_K12": "ws", "RS_K12_STRICT": "1"}                  # strict: fail instead of falling back to v1
     variants += [ws, dict(ws, RS_K12_STORE="tma"), dict(ws, RS_K12_CLUSTERS="1"),
-                 dict(ws, RS_K12_STORE="tma", RS_K12_CLUSTERS="2"), dict(ws, RS_K12_XFER="1", RS_K12_CLUSTERS="3"),
-                 dict(ws, RS_K12_XFER="2"), dict(ws, RS_K12_XFER="2", RS_K12_STORE="tma", RS_K12_CLUSTERS="1")]
+                 dict(ws, RS_K12_STORE="tma", RS_K12_CLUSTERS="2"), dict(ws, RS_K12_VARIANT="0", RS_K12_CLUSTERS="3"),
+                 dict(ws, RS_K12_VARIANT="1"), dict(ws, RS_K12_VARIANT="3", RS_K12_STORE="tma", RS_K12_CLUSTERS="1"),
+                 dict(ws, RS_K12_VARIANT="3")]
     for env in variants:
         nc = str(env)
         got = _rds(cube, p, env, monkeypatch)
