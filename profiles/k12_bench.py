@@ -20,16 +20,11 @@ VARIANTS = {
     "v1": {"RS_K12": "v1"},
     "ws": {"RS_K12": "ws"},                                           # library default
     "ws-tma": {"RS_K12": "ws", "RS_K12_STORE": "tma"},
-    "ws0": {"RS_K12": "ws", "RS_K12_VARIANT": "0", "RS_K12_STORE": "direct"},
-    "ws0-tma": {"RS_K12": "ws", "RS_K12_VARIANT": "0", "RS_K12_STORE": "tma"},
-    "ws1": {"RS_K12": "ws", "RS_K12_VARIANT": "1", "RS_K12_STORE": "direct"},
-    "ws1-tma": {"RS_K12": "ws", "RS_K12_VARIANT": "1", "RS_K12_STORE": "tma"},
-    "ws2": {"RS_K12": "ws", "RS_K12_VARIANT": "2", "RS_K12_STORE": "direct"},
-    "ws2-tma": {"RS_K12": "ws", "RS_K12_VARIANT": "2", "RS_K12_STORE": "tma"},
-    "ws3": {"RS_K12": "ws", "RS_K12_VARIANT": "3", "RS_K12_STORE": "direct"},
-    "ws3-tma": {"RS_K12": "ws", "RS_K12_VARIANT": "3", "RS_K12_STORE": "tma"},
     "split": {"RS_FUSED_FFT": "0"},
 }
+for _v in range(8):                                                    # wsN / wsN-tma: RS_K12_VARIANT = N (rs_fft2d_ws.cu)
+    VARIANTS[f"ws{_v}"] = {"RS_K12": "ws", "RS_K12_VARIANT": str(_v), "RS_K12_STORE": "direct"}
+    VARIANTS[f"ws{_v}-tma"] = {"RS_K12": "ws", "RS_K12_VARIANT": str(_v), "RS_K12_STORE": "tma"}
 
 
 def main():
@@ -53,10 +48,12 @@ def main():
     ref = None
     nbytes = 16 * cube.numel()
     for name in args.variants.split(","):
-        for k in ("RS_K12", "RS_K12_STORE", "RS_K12_VARIANT", "RS_FUSED_FFT", "RS_FUSED_NC", "RS_K12_CLUSTERS"):
+        for k in ("RS_K12", "RS_K12_STORE", "RS_K12_VARIANT", "RS_K12_SIDE", "RS_FUSED_FFT", "RS_FUSED_NC", "RS_K12_CLUSTERS"):
             os.environ.pop(k, None)
         base, _, ncl = name.partition("@")
+        base, _, side = base.partition("+")                           # ws3-tma+60: 60 permille of the frames to the side kernel
         os.environ.update(VARIANTS[base])
+        os.environ["RS_K12_SIDE"] = side or "0"
         if ncl:
             os.environ["RS_K12_CLUSTERS"] = ncl
         out = torch.empty((args.frames, 256, args.antennas, 128), dtype=torch.complex64, device=pipe.device)

@@ -32,22 +32,19 @@
 namespace ws {
 
 constexpr int S = 256, C = 128, NC = 4;
-constexpr int CB = 16;                  // chirps per stage
 constexpr int CPC = C / NC;             // chirps one CTA transforms per plane
-constexpr int NSTAGE = CPC / CB;        // stages per plane == ring slots
+constexpr int MAXSTAGE = 4;             // stages per plane == ring slots: CPC / CB with CB = 16 or 8 chirps per stage
 constexpr int ROWS = S / NC;            // range bins owned by one CTA
 constexpr int MP = C + 8;               // row pitch of M (complex): 8 (mod 16)
 constexpr int R_THREADS = 256, D_THREADS = 256;
 constexpr int THREADS = R_THREADS + D_THREADS;       // 16 warps x 128 registers fill the register file
-constexpr uint32_t STAGE_BYTES = CB * S * sizeof(float2);
-static_assert(NSTAGE == 2, "the ring is indexed by the stage of the plane");
 
 struct __align__(128) Smem {
-    float2 stage[NSTAGE][CB * S];       // TMA destination, range passes run in place
+    float2 stage[CPC * S];              // TMA destination: CPC / CB slots of CB chirps, range passes run in place
     float2 M[2][ROWS * MP];             // this CTA's range bins x all chirps, double buffered over planes
     float2 tw1s[S];                     // range inter-pass twiddles w_S^{k1 n2}
     float2 tw1c[C];                     // Doppler inter-pass twiddles
-    unsigned long long full_ld[NSTAGE], empty_ld[NSTAGE], full_M[2], empty_M[2];
+    unsigned long long full_ld[MAXSTAGE], empty_ld[MAXSTAGE], full_M[2], empty_M[2];
 };
 
 __device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -98,6 +95,16 @@ __device__ __forceinline__ void st_async(uint32_t addr, float2 v, uint32_t mbar)
     asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];"
                  ::"r"(addr), "f"(v.x), "f"(v.y), "r"(mbar) : "memory");
 }
+// shared-memory accesses by 32-bit shared-space address: the swizzled layouts below form every address with at most one
+// XOR of an immediate, which the compiler cannot derive from generic-pointer index arithmetic
+__device__ __forceinline__ float2 lds2(uint32_t a) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts2(uint32_t a, float2 v) {
+    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(v.x), "f"(v.y) : "memory");
+}
 __device__ __forceinline__ void st_cluster(uint32_t addr, float2 v) {
     asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(v.x), "f"(v.y) : "memory");
 }
@@ -109,9 +116,9 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
         ::"r"(s32(dst)), "l"(map), "r"(x), "r"(y), "r"(s32(bar)), "l"(policy) : "memory");
 }
 // one finished Doppler row (1 KB, 16-byte aligned in M) -> its place in the RDS
-__device__ __forceinline__ void bulk_store_row(float2* dst, const float2* src) {
+__device__ __forceinline__ void bulk_store_row(float2* dst, uint32_t src) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                 ::"l"(dst), "r"(s32(src)), "n"(C * sizeof(float2)) : "memory");
+                 ::"l"(dst), "r"(src), "n"(C * sizeof(float2)) : "memory");
 }
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -122,12 +129,14 @@ constexpr unsigned long long EVICT_FIRST = 0x12F0000000000000ull;       // creat
 // XFER: how range bins reach their owner: 0 = st.shared::cluster + one release.cluster arrive per warp,
 //       1 = st.async completing bytes on the owner's transaction barrier (no fence anywhere).
 // PACKED: butterflies with f32x2 adds (FADD2).
-template <bool STORE_TMA, int XFER, bool PACKED, int RG>
+template <bool STORE_TMA, int XFER, bool PACKED, int RG, int CB>
 __global__ void __cluster_dims__(NC, 1, 1) __launch_bounds__(THREADS, 1)
 fft2d_ws_kernel(const __grid_constant__ CUtensorMap map_cube, const float2* __restrict__ table, const float2* __restrict__ tw_s_g, const float2* __restrict__ tw_c_g,
                 float2* __restrict__ rds, int A, int C_total, int chirp0, int dc_removal, int nplanes) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+    constexpr int NSTAGE = CPC / CB;
+    constexpr uint32_t STAGE_BYTES = CB * S * sizeof(float2);
     const int tid = threadIdx.x;
     uint32_t q;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(q));
@@ -162,18 +171,19 @@ fft2d_ws_kernel(const __grid_constant__ CUtensorMap map_cube, const float2* __re
         // its own named barrier), so with RG = 2 the halves drift apart and fill each other's latencies
         constexpr int RGT = R_THREADS / RG;                   // threads of a subgroup
         constexpr int NI = CB * 16 / RGT;                     // items per thread and pass
-        constexpr int HS = RGT / 16;                          // item stride of the slow index
+        constexpr int HS1 = RGT / 16, HS2 = RGT / CB;         // item strides of the slow index in pass 1 / pass 2
+        static_assert(NI >= 1 && NI * RGT == CB * 16 && NSTAGE % RG == 0 && NSTAGE <= MAXSTAGE, "range item geometry");
         const int g = tid / RGT, tg = tid - g * RGT;
-        const int t1 = tg & 15, hi = tg >> 4;                 // pass 1: fast-time column, chirp hi (+ HS i) of the stage
-        const int row2 = tg & 15;                             // pass 2: lanes along chirps, k1 = hi (+ HS i)
+        const int t1 = tg & 15, hi = tg >> 4;                 // pass 1: fast-time column, chirp hi (+ HS1 i) of the stage
+        const int row2 = tg & (CB - 1), k1b = tg / CB;        // pass 2: lanes along chirps, k1 = k1b (+ HS2 i)
         float2 tabv[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) tabv[j] = table[t1 + 16 * j];
-        // remote bases of row `hi` of M[0], this thread's chirp column of stage 0, in the four owners
+        // remote bases of row `k1b` of M[0], this thread's chirp column of stage 0, in the four owners
         uint32_t mbase[NC], bbase[NC];
 #pragma unroll
         for (int o = 0; o < NC; ++o) {
-            mbase[o] = mapa(s32(&sm.M[0][0]), o) + (uint32_t)((hi * MP + q * CPC + row2) * sizeof(float2));
+            mbase[o] = mapa(s32(&sm.M[0][0]), o) + (uint32_t)((k1b * MP + q * CPC + row2) * sizeof(float2));
             bbase[o] = mapa(s32(&sm.full_M[0]), o);
         }
         const int chirp_row0 = chirp0 + (int)q * CPC;
@@ -181,7 +191,7 @@ fft2d_ws_kernel(const __grid_constant__ CUtensorMap map_cube, const float2* __re
 #pragma unroll 1
             for (int s = g; s < NSTAGE; s += RG) {
                 mbar_expect_tx(&sm.full_ld[s], STAGE_BYTES);
-                tma_load_2d(sm.stage[s], &map_cube, 0, cid * C_total + chirp_row0 + s * CB, &sm.full_ld[s], EVICT_FIRST);
+                tma_load_2d(sm.stage + s * CB * S, &map_cube, 0, cid * C_total + chirp_row0 + s * CB, &sm.full_ld[s], EVICT_FIRST);
             }
         }
         int it = 0;
@@ -190,32 +200,36 @@ fft2d_ws_kernel(const __grid_constant__ CUtensorMap map_cube, const float2* __re
             const uint32_t boff = (uint32_t)(b * ROWS * MP * sizeof(float2));
 #pragma unroll 1
             for (int s = g; s < NSTAGE; s += RG) {
-                float2* st = sm.stage[s];
+                float2* st = sm.stage + s * CB * S;
                 mbar_wait(&sm.full_ld[s], it & 1);
 #pragma unroll 1
                 for (int i = 0; i < NI; ++i) {
-                    const int row1 = hi + HS * i;
+                    const int row1 = hi + HS1 * i;
+                    const uint32_t rowa = s32(st) + (uint32_t)(row1 * S * sizeof(float2));
                     float2 v[16];
-                    const float2* x = st + row1 * S + t1;
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = x[16 * j];
+                    for (int j = 0; j < 16; ++j) v[j] = lds2(rowa + (uint32_t)((t1 + 16 * j) * sizeof(float2)));
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = cmul(v[j], tabv[j]);
+                    for (int j = 0; j < 16; ++j) v[j] = PACKED ? pow2::cmulp(v[j], tabv[j]) : cmul(v[j], tabv[j]);
                     if (PACKED) pow2::dftp<16>(v); else pow2::dft<16>(v);
                     __syncwarp();                                       // the chirp is read before it is rewritten
-                    float2* y = st + row1 * S + ((t1 + row1) & 15);
+                    // Y[k1][t1] -> slot 16 k1 + (t1 ^ rot), rot = chirp (^ 8 for odd k1 when a half-warp of pass 2 covers
+                    // two k1): pass-1 writes and pass-2 reads are both conflict free in the unpadded 2 KB chirp rows
+                    const uint32_t ye = rowa + (uint32_t)(((t1 ^ row1) & 15) * sizeof(float2));
+                    const uint32_t yo = CB == 8 ? rowa + (uint32_t)(((t1 ^ row1 ^ 8) & 15) * sizeof(float2)) : ye;
 #pragma unroll
-                    for (int k1 = 0; k1 < 16; ++k1) y[16 * k1] = v[k1];
+                    for (int k1 = 0; k1 < 16; ++k1) sts2(((k1 & 1) ? yo : ye) + (uint32_t)(16 * k1 * sizeof(float2)), v[k1]);
                 }
                 named_bar_sync(1 + g, RGT);
 #pragma unroll 1
                 for (int i = 0; i < NI; ++i) {
-                    const int k1r = hi + HS * i;
+                    const int k1r = k1b + HS2 * i;
                     float2 u[16];
                     {
-                        const float2* y = st + row2 * S + 16 * k1r;
+                        const int rot = (row2 ^ (CB == 8 ? 8 * (k1r & 1) : 0)) & 15;
+                        const uint32_t yb = s32(st) + (uint32_t)((row2 * S + 16 * k1r + rot) * sizeof(float2));
 #pragma unroll
-                        for (int n2 = 0; n2 < 16; ++n2) u[n2] = y[(n2 + row2) & 15];
+                        for (int n2 = 0; n2 < 16; ++n2) u[n2] = lds2(yb ^ (uint32_t)(n2 * sizeof(float2)));
                     }
                     if (i == NI - 1) {
                         // the stage is consumed: order the generic accesses before the next TMA write, release the slot,
@@ -231,10 +245,10 @@ fft2d_ws_kernel(const __grid_constant__ CUtensorMap map_cube, const float2* __re
                     }
                     const float2* twr = sm.tw1s + k1r * 16;
 #pragma unroll
-                    for (int n2 = 1; n2 < 16; ++n2) u[n2] = cmul(u[n2], twr[n2]);
+                    for (int n2 = 1; n2 < 16; ++n2) u[n2] = PACKED ? pow2::cmulp(u[n2], twr[n2]) : cmul(u[n2], twr[n2]);
                     if (PACKED) pow2::dftp<16>(u); else pow2::dft<16>(u);
                     if (s == g && i == 0) mbar_wait(&sm.empty_M[b], ((it >> 1) & 1) ^ 1);   // the owners' Doppler groups left buffer b
-                    const uint32_t roff = boff + (uint32_t)((i * HS * MP + s * CB) * sizeof(float2));
+                    const uint32_t roff = boff + (uint32_t)((i * HS2 * MP + s * CB) * sizeof(float2));
 #pragma unroll
                     for (int k2 = 0; k2 < 16; ++k2) {
                         // k = k1r + 16 k2, range fftshift p = (k + S/2) mod S = k1r + 16 ((k2 + 8) mod 16)
@@ -268,41 +282,46 @@ fft2d_ws_kernel(const __grid_constant__ CUtensorMap map_cube, const float2* __re
             float2* Mb = sm.M[b];
             if (XFER == 1 && w == 0 && lane == 0) mbar_expect_tx(&sm.full_M[b], ROWS * C * sizeof(float2));
             mbar_wait(&sm.full_M[b], (it >> 1) & 1);
-            // pass 1, in place: radix 16 over chirps td + 8 j
+            // pass 1, in place: radix 16 over chirps td + 8 j; V[k1][td] -> slot 8 k1 + (td ^ (k1 >> 1))
+            const uint32_t Ma = s32(Mb);
 #pragma unroll 1
             for (int i = 0; i < 2; ++i) {
-                float2* m = Mb + (8 * w + 4 * i + (lane >> 3)) * MP;
+                const uint32_t ma = Ma + (uint32_t)(((8 * w + 4 * i + (lane >> 3)) * MP + td) * sizeof(float2));
                 float2 v[16];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = m[td + 8 * j];
+                for (int j = 0; j < 16; ++j) v[j] = lds2(ma + (uint32_t)(8 * j * sizeof(float2)));
                 __syncwarp();
                 if (PACKED) pow2::dftp<16>(v); else pow2::dft<16>(v);
 #pragma unroll
                 for (int k1 = 0; k1 < 16; ++k1)
-                    m[k1 * 8 + ((td + (k1 >> 1)) & 7)] = (k1 == 0) ? v[0] : cmul(v[k1], twd[k1]);
+                    sts2((ma ^ (uint32_t)((k1 >> 1) * sizeof(float2))) + (uint32_t)(8 * k1 * sizeof(float2)),
+                         (k1 == 0) ? v[0] : PACKED ? pow2::cmulp(v[k1], twd[k1]) : cmul(v[k1], twd[k1]));
             }
             __syncwarp();
             // pass 2: radix 8, Doppler fftshift
 #pragma unroll 1
             for (int i = 0; i < 4; ++i) {
                 const int row = 8 * w + 2 * i + (lane >> 4);
-                float2* m = Mb + row * MP;
+                const uint32_t rowa = Ma + (uint32_t)(row * MP * sizeof(float2));
+                const uint32_t ub = rowa + (uint32_t)((8 * k1p + (k1p >> 1)) * sizeof(float2));
                 float2 u[8];
 #pragma unroll
-                for (int n2 = 0; n2 < 8; ++n2) u[n2] = m[k1p * 8 + ((n2 + (k1p >> 1)) & 7)];
+                for (int n2 = 0; n2 < 8; ++n2) u[n2] = lds2(ub ^ (uint32_t)(n2 * sizeof(float2)));
                 if (PACKED) pow2::dftp<8>(u); else pow2::dft<8>(u);
                 const int p = q * ROWS + row;
-                float2* dst = rds + (((size_t)f * S + p) * A + a) * C;
+                // Doppler fftshift: bin k1p + 16 k2 goes to (k1p + 16 k2 + 64) mod 128; k1p < 16, so no runtime wrap
+                float2* dst = rds + (((size_t)f * S + p) * A + a) * C + k1p;
                 if (!STORE_TMA) {
 #pragma unroll
-                    for (int k2 = 0; k2 < 8; ++k2) __stcs(dst + ((k1p + 16 * k2 + C / 2) & (C - 1)), u[k2]);
+                    for (int k2 = 0; k2 < 8; ++k2) __stcs(dst + ((16 * k2 + C / 2) & (C - 1)), u[k2]);
                 } else {
                     __syncwarp();                                       // both rows are read before they are rewritten
 #pragma unroll
-                    for (int k2 = 0; k2 < 8; ++k2) m[(k1p + 16 * k2 + C / 2) & (C - 1)] = u[k2];
+                    for (int k2 = 0; k2 < 8; ++k2)
+                        sts2(rowa + (uint32_t)((k1p + ((16 * k2 + C / 2) & (C - 1))) * sizeof(float2)), u[k2]);
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
-                    if (k1p == 0) bulk_store_row(dst, m);
+                    if (k1p == 0) bulk_store_row(dst, rowa);
                 }
             }
             if (STORE_TMA) {
@@ -317,6 +336,7 @@ fft2d_ws_kernel(const __grid_constant__ CUtensorMap map_cube, const float2* __re
 }
 
 // ------------------------------------------------------------------------------------------------ host side
+constexpr int NVARIANT = 5;
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -347,11 +367,13 @@ int rs_fft2d_ws_launch(const void* cube, const void* table, const void* twiddle_
     if (rows_in >= (1ll << 31) || (long long)F * S >= (1ll << 31)) return 0;
     if (sizeof(Smem) > (size_t)rs_smem_optin_limit()) return 0;
 
+    if (variant < 0 || variant >= NVARIANT) variant = 4;
+    const int cb = variant == 4 ? 8 : 16;                  // chirps per stage = rows of the TMA box
     CUtensorMap map_cube;
     {
         cuuint64_t gdim[2] = {(cuuint64_t)S, (cuuint64_t)rows_in};
         cuuint64_t gstr[1] = {(cuuint64_t)S * sizeof(float2)};
-        cuuint32_t box[2] = {(cuuint32_t)S, (cuuint32_t)CB};
+        cuuint32_t box[2] = {(cuuint32_t)S, (cuuint32_t)cb};
         cuuint32_t estr[2] = {1, 1};
         if (enc(&map_cube, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, const_cast<void*>(cube), gdim, gstr, box, estr,
                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -360,17 +382,19 @@ int rs_fft2d_ws_launch(const void* cube, const void* table, const void* twiddle_
     }
     typedef void (*Kern)(const CUtensorMap, const float2*, const float2*, const float2*, float2*, int, int, int, int, int);
     // the measured variants: [bulk store][variant]: 0 = release-arrive hand-over, scalar, 1 subgroup (the first version),
-    // 1 = st.async, scalar, 1 subgroup; 2 = st.async, packed, 1 subgroup; 3 = st.async, packed, 2 subgroups
-    static const Kern kerns[2][4] = {
-        {fft2d_ws_kernel<false, 0, false, 1>, fft2d_ws_kernel<false, 1, false, 1>, fft2d_ws_kernel<false, 1, true, 1>, fft2d_ws_kernel<false, 1, true, 2>},
-        {fft2d_ws_kernel<true, 0, false, 1>, fft2d_ws_kernel<true, 1, false, 1>, fft2d_ws_kernel<true, 1, true, 1>, fft2d_ws_kernel<true, 1, true, 2>}};
-    if (variant < 0 || variant > 3) variant = 2;
+    // 1 = st.async, scalar, 1 subgroup; 2 = st.async, packed, 1 subgroup; 3 = st.async, packed, 2 subgroups;
+    // 4 = as 3 with 8-chirp stages: four ring slots, two per subgroup (a slot is refilled 3/4 of a plane ahead)
+    static const Kern kerns[2][NVARIANT] = {
+        {fft2d_ws_kernel<false, 0, false, 1, 16>, fft2d_ws_kernel<false, 1, false, 1, 16>, fft2d_ws_kernel<false, 1, true, 1, 16>,
+         fft2d_ws_kernel<false, 1, true, 2, 16>, fft2d_ws_kernel<false, 1, true, 2, 8>},
+        {fft2d_ws_kernel<true, 0, false, 1, 16>, fft2d_ws_kernel<true, 1, false, 1, 16>, fft2d_ws_kernel<true, 1, true, 1, 16>,
+         fft2d_ws_kernel<true, 1, true, 2, 16>, fft2d_ws_kernel<true, 1, true, 2, 8>}};
     Kern kern = kerns[store_tma ? 1 : 0][variant];
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)) != cudaSuccess) {
         cudaGetLastError();
         return 0;
     }
-    static int max_clusters[2][4] = {{-1, -1, -1, -1}, {-1, -1, -1, -1}};
+    static int max_clusters[2][NVARIANT] = {{-1, -1, -1, -1, -1}, {-1, -1, -1, -1, -1}};
     int& mc = max_clusters[store_tma ? 1 : 0][variant];
     if (mc < 0) {
         cudaLaunchConfig_t cfg = {};
@@ -399,7 +423,7 @@ int rs_fft2d_ws_launch(const void* cube, const void* table, const void* twiddle_
 
 extern "C" int rs_fft2d_ws_max_clusters(void) {
     using namespace ws;
-    auto kern = fft2d_ws_kernel<false, 1, true, 1>;
+    auto kern = fft2d_ws_kernel<false, 1, true, 2, 8>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(NC * 64);

@@ -102,13 +102,16 @@ __device__ __forceinline__ void dft<32>(float2 (&v)[32]) {
     }
 }
 
-// ---- packed variants: complex add / sub as ONE Blackwell f32x2 instruction (FADD2) -----------------------------------
-// The butterflies of a DFT are mostly complex additions; add.rn.f32x2 performs the (re, im) pair in one issue slot with
-// the same IEEE result as two scalar adds.  The +-i rotations keep their scalar form (a half swap has no packed
-// encoding in PTX).  dft<16>: 154 -> 112 floating-point instructions, dft<8>: 64 -> 44.
-__device__ __forceinline__ unsigned long long pk2(float2 a) {
+// ---- packed variants: Blackwell f32x2 arithmetic (FADD2 / FMUL2 / FFMA2) ----------------------------------------------
+// A complex value is an (re, im) register pair, so a complex add is ONE add.rn.f32x2 with the IEEE result of two scalar
+// adds.  ptxas folds the half swap and the per-half sign of the packed operands into the instruction's operand
+// modifiers (SASS: R.F32x2.LO_HI, .NP / .PN, and a scalar broadcast R.F32), so
+//   a -+ i b         = add.f32x2(a, (b.y, -b.x)) / add.f32x2(a, (-b.y, b.x))               1 instruction
+//   a * b (complex)  = fma.f32x2((a.y, a.x), (-b.y, b.y), mul.f32x2(a, (b.x, b.x)))        2 instructions, b stays (re, im)
+// dft<16>: 154 -> 80 floating-point instructions, dft<8>: 64 -> 28, a twiddle multiply: 4 -> 2.
+__device__ __forceinline__ unsigned long long pk2(float lo, float hi) {
     unsigned long long r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
     return r;
 }
 __device__ __forceinline__ float2 up2(unsigned long long a) {
@@ -118,20 +121,31 @@ __device__ __forceinline__ float2 up2(unsigned long long a) {
 }
 __device__ __forceinline__ float2 padd(float2 a, float2 b) {
     unsigned long long r;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk2(a)), "l"(pk2(b)));
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk2(a.x, a.y)), "l"(pk2(b.x, b.y)));
     return up2(r);
 }
 __device__ __forceinline__ float2 psub(float2 a, float2 b) {
     unsigned long long r;
-    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk2(a)), "l"(pk2(b)));
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk2(a.x, a.y)), "l"(pk2(b.x, b.y)));
     return up2(r);
 }
 // a + (-i) b and a - (-i) b
-__device__ __forceinline__ float2 add_mi(float2 a, float2 b) { return make_float2(a.x + b.y, a.y - b.x); }
-__device__ __forceinline__ float2 sub_mi(float2 a, float2 b) { return make_float2(a.x - b.y, a.y + b.x); }
-// x (c - i s): x times a unit twiddle given by its cosine and (positive) sine
-__device__ __forceinline__ float2 mulw(float2 x, float c, float s) {
-    return make_float2(fmaf(c, x.x, s * x.y), fmaf(c, x.y, -s * x.x));
+__device__ __forceinline__ float2 add_mi(float2 a, float2 b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk2(a.x, a.y)), "l"(pk2(b.y, -b.x)));
+    return up2(r);
+}
+__device__ __forceinline__ float2 sub_mi(float2 a, float2 b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk2(a.x, a.y)), "l"(pk2(-b.y, b.x)));
+    return up2(r);
+}
+// complex product
+__device__ __forceinline__ float2 cmulp(float2 a, float2 b) {
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk2(a.x, a.y)), "l"(pk2(b.x, b.x)));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(r) : "l"(pk2(a.y, a.x)), "l"(pk2(-b.y, b.y)));
+    return up2(r);
 }
 
 template <int R>
@@ -153,13 +167,13 @@ __device__ __forceinline__ void dftp<8>(float2 (&v)[8]) {
     dftp<4>(e);
     dftp<4>(o);
     const float h = 0.70710678118654752440f;
-    o[1] = make_float2(h * (o[1].x + o[1].y), h * (o[1].y - o[1].x));
-    o[3] = make_float2(h * (o[3].y - o[3].x), -h * (o[3].x + o[3].y));
+    o[1] = cmulp(o[1], make_float2(h, -h));             // w8^1
+    o[3] = cmulp(o[3], make_float2(-h, -h));            // w8^3
     v[0] = padd(e[0], o[0]);
     v[4] = psub(e[0], o[0]);
     v[1] = padd(e[1], o[1]);
     v[5] = psub(e[1], o[1]);
-    v[2] = add_mi(e[2], o[2]);          // o[2] carries the factor -i
+    v[2] = add_mi(e[2], o[2]);                          // w8^2 = -i
     v[6] = sub_mi(e[2], o[2]);
     v[3] = padd(e[3], o[3]);
     v[7] = psub(e[3], o[3]);
@@ -181,10 +195,15 @@ __device__ __forceinline__ void dftp<16>(float2 (&v)[16]) {
         float2 w[4];
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
-            const int m = a * q;                        // w16^m
+            const int m = a * q;                        // w16^m = exp(-2 pi i m / 16)
             const float2 x = u[a][q];
-            w[a] = m == 0 ? x : m == 1 ? mulw(x, c1, s1) : m == 2 ? mulw(x, h, h) : m == 3 ? mulw(x, s1, c1)
-                 : m == 4 ? make_float2(x.y, -x.x) : m == 6 ? mulw(x, -h, h) : /* 9 */ mulw(x, -c1, -s1);
+            w[a] = m == 0 ? x
+                 : m == 1 ? cmulp(x, make_float2(c1, -s1))
+                 : m == 2 ? cmulp(x, make_float2(h, -h))
+                 : m == 3 ? cmulp(x, make_float2(s1, -c1))
+                 : m == 4 ? make_float2(x.y, -x.x)
+                 : m == 6 ? cmulp(x, make_float2(-h, -h))
+                 : /* 9 */  cmulp(x, make_float2(-c1, s1));
         }
         dftp<4>(w);
 #pragma unroll

@@ -63,13 +63,13 @@ def test_signal_preprocessor_attributes():
 def test_rds_and_peak_dict(legacy):
     rds, ref, info, pk = legacy["rds"], legacy["rds_ref"], legacy["info"], legacy["pk"]
     assert rds.dtype == np.complex128 and rds.shape == ref.shape
-    assert np.abs(rds - ref).max() <= 2e-6 * np.abs(ref).max()
+    assert np.abs(rds - ref).max() <= 1e-12 * np.abs(ref).max()                   # the legacy API computes in fp64
     assert set(info) == {"peaks", "range_bins_m", "doppler_bins_hz", "power_spectrum_db"}
     assert np.array_equal(info["range_bins_m"], pk["range_bins_m"])
     assert np.array_equal(info["doppler_bins_hz"], pk["doppler_bins_hz"])
     assert info["power_spectrum_db"].shape == ref.shape
     loud = pk["power_spectrum_db"] > -60
-    assert np.abs(info["power_spectrum_db"][loud] - pk["power_spectrum_db"][loud]).max() < 1e-3
+    assert np.abs(info["power_spectrum_db"][loud] - pk["power_spectrum_db"][loud]).max() < 1e-9
     peaks = info["peaks"]
     assert [q["antenna"] for q in peaks] == pk["antenna"].tolist()                # bit-exact, reference order
     assert [int(q["range_bin"]) for q in peaks] == pk["range_bin"].tolist()
@@ -77,7 +77,7 @@ def test_rds_and_peak_dict(legacy):
     assert set(peaks[0]) == {"antenna", "range_bin", "doppler_bin", "range_m", "doppler_hz", "power_db"}
     assert np.array_equal([q["range_m"] for q in peaks], pk["range_m"])
     assert np.array_equal([q["doppler_hz"] for q in peaks], pk["doppler_hz"])
-    assert np.abs(np.array([q["power_db"] for q in peaks]) - pk["power_db"]).max() < 1e-4
+    assert np.abs(np.array([q["power_db"] for q in peaks]) - pk["power_db"]).max() < 1e-9
 
 
 def test_chirp_subset(legacy):
@@ -86,7 +86,7 @@ def test_chirp_subset(legacy):
     got = pre.generate_range_doppler_spectrum(cube, chirp_subset=sub)
     want = orc.range_doppler_spectrum(cube, p, sub)
     assert got.shape == want.shape
-    assert np.abs(got - want).max() <= 2e-6 * np.abs(want).max()
+    assert np.abs(got - want).max() <= 1e-12 * np.abs(want).max()
 
 
 def test_rds_reupload_roundtrip(legacy):
@@ -97,8 +97,29 @@ def test_rds_reupload_roundtrip(legacy):
     buf.seek(0)
     rds2 = np.load(buf)
     info2 = legacy["pre"].extract_range_doppler_peaks(rds2, threshold_db=legacy["cfg"]["thr"])
-    assert [(q["antenna"], q["range_bin"], q["doppler_bin"]) for q in info2["peaks"]] == \
-           [(q["antenna"], q["range_bin"], q["doppler_bin"]) for q in legacy["info"]["peaks"]]
+    pk = legacy["pk"]
+    assert np.array_equal(info2["peaks"].column("antenna"), pk["antenna"])         # exact, with no cube to go back to
+    assert np.array_equal(info2["peaks"].column("range_bin"), pk["range_bin"])
+    assert np.array_equal(info2["peaks"].column("doppler_bin"), pk["doppler_bin"])
+    # ... and on the ORACLE's own fp64 RDS (an array this library has never seen)
+    info3 = legacy["pre"].extract_range_doppler_peaks(legacy["rds_ref"].copy(), threshold_db=legacy["cfg"]["thr"])
+    assert np.array_equal(info3["peaks"].column("antenna"), pk["antenna"])
+    assert np.array_equal(info3["peaks"].column("range_bin"), pk["range_bin"])
+    assert np.array_equal(info3["peaks"].column("doppler_bin"), pk["doppler_bin"])
+    assert np.abs(info3["power_spectrum_db"] - pk["power_spectrum_db"]).max() < 1e-9
+
+
+def test_rds_edited_in_place_is_honoured(legacy):
+    """The reference always works on the array it is handed: a zero-Doppler notch written into the RDS after it was
+    returned must be seen by the peak extractor and the angle stage (no stale device copy)."""
+    p, cfg = legacy["p"], legacy["cfg"]
+    rds = legacy["pre"].generate_range_doppler_spectrum(legacy["cube"])
+    rds[:, :, rds.shape[2] // 2] = 0
+    want = orc.extract_peaks(rds, p, threshold_db=cfg["thr"])
+    got = legacy["pre"].extract_range_doppler_peaks(rds, threshold_db=cfg["thr"])
+    assert np.array_equal(got["peaks"].column("range_bin"), want["range_bin"])
+    assert np.array_equal(got["peaks"].column("doppler_bin"), want["doppler_bin"])
+    assert not np.any(got["peaks"].column("doppler_bin") == rds.shape[2] // 2)
 
 
 @pytest.mark.parametrize("method,name", [("music", "music_deg"), ("esprit", "esprit_deg"), ("beamforming", "beam_deg")])
@@ -116,20 +137,18 @@ def test_process_targets_vs_reference_outputs(legacy, method, name):
                                "range_bin", "doppler_bin", "spatial_signature", "spectrum"}
     got = np.array([t["azimuth_deg"] for t in targets])
     diff = np.abs(got - g[name])
+    assert diff.max() < 0.05, diff.max()                  # BASELINE tolerance, every target, no tie-band exception
     if method == "esprit":
-        assert diff.max() < 0.05
         assert targets[0]["spectrum"] is None
     else:
-        # fp64 scan on fp32-accurate snapshots: a flip needs a top-2 gap at the snapshot's rounding level
-        assert np.all(g["music_top2_gap"][diff >= 0.05] < 1e-5), diff.max()
-        assert (diff >= 0.05).mean() < 2e-3
+        assert diff.max() == 0.0                          # grid methods: the reference's grid point itself
         assert targets[0]["spectrum"].shape == est.azimuth_grid.shape
-    np.testing.assert_allclose(np.array([t["spatial_signature"] for t in targets[:8]]), g["sig_first8"], atol=2e-6)
+    np.testing.assert_allclose(np.array([t["spatial_signature"] for t in targets[:8]]), g["sig_first8"], atol=1e-12)
     assert np.allclose([t["azimuth_rad"] for t in targets], np.radians(got))
     if method == "music":
         den_got = 1.0 / np.array([t["spectrum"] for t in targets[:2]])
         den_ref = 1.0 / g["music_spec_first2"]
-        assert np.abs(den_got - den_ref).max() < 1e-4 * p.num_antennas
+        assert np.abs(den_got - den_ref).max() < 1e-9 * p.num_antennas
 
 
 def test_process_targets_unknown_method_and_single_calls(legacy):
@@ -171,7 +190,7 @@ def test_velocity_solver_vs_reference_de(legacy):
                         "predicted_phases", "observed_phases", "num_targets", "step1_result", "step2_result"}
     assert np.abs(res["velocity"][:2] - g["vel_velocity"][:2]).max() < 1e-3       # BASELINE tolerance
     assert res["cost"] <= float(g["vel_cost"]) * (1 + 1e-6) + 1e-9
-    np.testing.assert_allclose(res["observed_phases"], g["vel_observed"], atol=5e-6)
+    np.testing.assert_allclose(res["observed_phases"], g["vel_observed"], atol=1e-9)
     assert solver.solve_velocity(None, targets[:2]) == {"success": False, "message": "Insufficient targets"}
     np.testing.assert_allclose(res["residuals"], res["observed_phases"] - res["predicted_phases"])
     assert abs(res["rmse"] - np.sqrt(np.mean(res["residuals"] ** 2))) < 1e-15
@@ -241,8 +260,9 @@ def test_reference_style_single_target():
     assert rds.shape == (8, 400, 64)
     info = pre.extract_range_doppler_peaks(rds, threshold_db=-30.0)
     assert any(45 <= q["range_m"] <= 55 for q in info["peaks"])
-    want = orc.extract_peaks(orc.range_doppler_spectrum(raw.astype(np.complex64).astype(np.complex128), p), p, -30.0)
-    assert len(info["peaks"]) == len(want["antenna"])
+    want = orc.extract_peaks(orc.range_doppler_spectrum(raw, p), p, -30.0)
+    assert np.array_equal(info["peaks"].column("range_bin"), want["range_bin"])
+    assert np.array_equal(info["peaks"].column("doppler_bin"), want["doppler_bin"])
 
 
 def test_pipeline_script_flow_with_stage_files(tmp_path):
@@ -269,10 +289,10 @@ def test_pipeline_script_flow_with_stage_files(tmp_path):
     res = VelocitySolver(fc=77e9, lambda_c=77e9 / 3e8, num_antennas=8).solve_velocity(rds_l, loaded, dt=0.1)   # :246
     assert res["success"] and np.all(np.abs(res["velocity"][:2]) <= 50.0)
     np.savez(tmp_path / "v.npz", **res)
-    pk = orc.extract_peaks(orc.range_doppler_spectrum(raw.astype(np.complex64).astype(np.complex128), p), p, 18.0)
+    pk = orc.extract_peaks(orc.range_doppler_spectrum(raw, p), p, 18.0)
     grid = orc.azimuth_grid((-90, 90), 0.5)
     steer = orc.steering_matrix(grid, p.antenna_positions, p.lambda_c)
-    sigs = orc.spatial_signatures(orc.range_doppler_spectrum(raw.astype(np.complex64).astype(np.complex128), p),
+    sigs = orc.spatial_signatures(orc.range_doppler_spectrum(raw, p),
                                   pk["range_bin"], pk["doppler_bin"])
     _, ang = orc.argmax_angles(orc.music_spectra(sigs, steer), grid)
     want = orc.solve_velocity(pk["range_m"], np.radians(ang), sigs, 77e9 / 3e8, 0.1)

@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 
 def _rds(cube, p, env, monkeypatch, subset=None):
     from radar_slam_b200 import RadarConfig, FramePipeline
-    for k in ("RS_FUSED_FFT", "RS_FUSED_NC", "RS_SPLIT_FFT", "RS_K12", "RS_K12_STORE", "RS_K12_CLUSTERS", "RS_K12_STRICT", "RS_K12_VARIANT"):
+    for k in ("RS_FUSED_FFT", "RS_FUSED_NC", "RS_SPLIT_FFT", "RS_K12", "RS_K12_STORE", "RS_K12_CLUSTERS", "RS_K12_STRICT", "RS_K12_VARIANT", "RS_K12_SIDE"):
         monkeypatch.delenv(k, raising=False)
     for k, v in env.items():
         monkeypatch.setenv(k, v)
@@ -39,7 +39,8 @@ def test_cluster_kernel_matches_oracle_and_split_path(monkeypatch, A, F, win, dc
     variants += [ws, dict(ws, RS_K12_STORE="tma"), dict(ws, RS_K12_CLUSTERS="1"),
                  dict(ws, RS_K12_STORE="tma", RS_K12_CLUSTERS="2"), dict(ws, RS_K12_VARIANT="0", RS_K12_CLUSTERS="3"),
                  dict(ws, RS_K12_VARIANT="1"), dict(ws, RS_K12_VARIANT="3", RS_K12_STORE="tma", RS_K12_CLUSTERS="1"),
-                 dict(ws, RS_K12_VARIANT="3")]
+                 dict(ws, RS_K12_VARIANT="3"), dict(ws, RS_K12_VARIANT="2", RS_K12_CLUSTERS="2"),
+                 dict(ws, RS_K12_VARIANT="4", RS_K12_CLUSTERS="1"), dict(ws, RS_K12_VARIANT="4", RS_K12_STORE="tma")]
     for env in variants:
         nc = str(env)
         got = _rds(cube, p, env, monkeypatch)
@@ -62,3 +63,17 @@ def test_cluster_kernel_on_a_chirp_subset(monkeypatch):
     split = _rds(cube, p, {"RS_FUSED_FFT": "0"}, monkeypatch, subset=(16, 144))[0]
     assert got.shape == ref.shape == (4, 256, 128)
     assert np.abs(got - ref).max() <= 2e-6 * np.abs(ref).max() and np.abs(got - split).max() <= 1e-6 * np.abs(ref).max()
+
+
+def test_side_kernel_share_of_the_frames(monkeypatch):
+    """rs_range_doppler_fft sends the last RS_K12_SIDE permille of a batch (>= 64 frames) to a 2-CTA-cluster kernel on a
+    forked stream (the SMs the 4-CTA clusters strand): every frame, on either side of the split, must come out right."""
+    p = orc.RadarParams(chirp_duration=25.6e-6, num_chirps=128, num_antennas=2)
+    rng = np.random.RandomState(3)
+    F = 72
+    cube = (rng.randn(F, 2, 128, 256) + 1j * rng.randn(F, 2, 128, 256)).astype(np.complex64)
+    ref = np.stack([orc.range_doppler_spectrum(c.astype(np.complex128), p) for c in cube])
+    scale = np.abs(ref).max()
+    for side in ("0", "60", "250", "999"):
+        got = _rds(cube, p, {"RS_K12": "ws", "RS_K12_STRICT": "1", "RS_K12_SIDE": side}, monkeypatch)
+        assert np.abs(got - ref).max() <= 2e-6 * scale, side

@@ -58,3 +58,37 @@ def test_stage_files_round_trip_without_dicts(tmp_path, name, method):
     assert res["success"] == res_list["success"]
     for k in ("velocity", "angular_velocity", "residuals", "observed_phases"):
         assert np.array_equal(np.asarray(res[k]), np.asarray(res_list[k])), k
+
+
+def test_cli_file_interfaces_chain(tmp_path):
+    """process_frame -> extract_angles_from_rds -> estimate_velocity_from_angles through their FILE interfaces
+    (dechirp.py:313-355, angle_estimation.py:368-417, velocity_solver.py:418-467): what the three CLIs do.  The peaks
+    written by process_frame are LazyRecords (a 0-d object array once np.load-ed); the angle stage must unwrap them."""
+    from src.radar_signal.dechirp import process_frame
+    from src.angle_estimation.angle_estimation import extract_angles_from_rds
+    from src.robust_angle_estimation import extract_angles_robust
+    from src.velocity_solver.velocity_solver import estimate_velocity_from_angles
+    from oracle import radar_oracle as orc
+    p = orc.RadarParams(chirp_duration=12.8e-6, num_chirps=32)
+    np.random.seed(4)
+    raw = orc.synthesize_frame(p, np.array([[12.0, 0.4, -3.0, 0.0], [20.0, -0.3, 0.0, 0.0], [30.0, 0.1, -6.0, 0.0]]))
+    np.save(tmp_path / "frame.npy", raw)
+    params = {"fc": 77e9, "bandwidth": 1e9, "chirp_duration": 12.8e-6, "pri": 100e-6, "num_chirps": 32, "sampling_rate": 10e6}
+    out = process_frame(str(tmp_path / "frame.npy"), str(tmp_path / "frame_rds.npy"), params)
+    want = orc.extract_peaks(orc.range_doppler_spectrum(raw, p), p, threshold_db=-20.0)
+    assert out["num_peaks"] == len(want["antenna"]) > 0
+    res = extract_angles_from_rds(str(tmp_path / "frame_rds.npy"), str(tmp_path / "frame_rds_peaks.npz"),
+                                  str(tmp_path / "frame_angles.npz"), method="beamforming")
+    assert res["num_targets"] == out["num_peaks"]
+    rob = extract_angles_robust(str(tmp_path / "frame_rds.npy"), str(tmp_path / "frame_rds_peaks.npz"),
+                                str(tmp_path / "frame_robust.npz"))
+    assert rob["num_targets"] >= 0 and "statistics" in rob
+    vel = estimate_velocity_from_angles(str(tmp_path / "frame_angles.npz"), str(tmp_path / "frame_rds.npy"),
+                                        str(tmp_path / "frame_vel.npz"), dt=0.1)
+    assert vel["success"] and vel["num_targets"] == res["num_targets"]
+    grid = orc.azimuth_grid((-90, 90), 0.5)
+    steer = orc.steering_matrix(grid, p.antenna_positions, p.lambda_c)
+    sigs = orc.spatial_signatures(orc.range_doppler_spectrum(raw, p), want["range_bin"], want["doppler_bin"])
+    _, ang = orc.argmax_angles(orc.beamforming_spectra(sigs, steer), grid)
+    ref = orc.solve_velocity(want["range_m"], np.radians(ang), sigs, 3e8 / 77e9, 0.1)
+    assert np.abs(vel["velocity"][:2] - ref["velocity"][:2]).max() < 1e-3
