@@ -1,17 +1,24 @@
 #!/usr/bin/env python
 """Benchmark of the radar-slam per-frame hot path on B200 (contract in the task statement).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--frames F] [--chunk B] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload auto|configs1|configs4] [--impl reference]
 
-A "step" is one pass of the hot path (dechirp -> range FFT -> Doppler FFT -> peak detection ->
-MUSIC -> least-squares ego-velocity) over one batch of F synthetic frames per GPU.  Workload at any
-N: BASELINE.json configs[1] -- 1k frames of 256 samples x 128 chirps x 8 channels per GPU, MUSIC on
-a 1 degree grid, reference-default noise and threshold -- weak scaling, frames sharded by rank with
-no data-path collective except the all-gather of the per-frame velocity rows.
+A "step" is one pass of the hot path (dechirp -> range FFT -> Doppler FFT -> peak detection -> MUSIC -> least-squares
+ego-velocity) over one batch of synthetic frames.
 
-The JSON line carries: value (frames/s, inputs resident in HBM), e2e (same metric through
-FramePipeline.process_host with pinned HOST buffers), roofline of the dominant kernel and of every
-stage, cpu_baseline (the oracle port timed on this box's host cores), clocks, gpu_launches.
+  N = 1 (headline)   BASELINE.json configs[1]: 1k frames of 256 samples x 128 chirps x 8 channels, MUSIC on a 1 degree
+                     grid, reference-default noise and threshold, the 1.95 GiB cube resident in HBM (>> L2).
+                     The same line carries `configs4_n1`: the N > 1 workload measured on this one GPU.
+  N > 1              BASELINE.json configs[4]: ONE 65 536-frame sequence of 256 x 128 x 16 cubes, STRONG-scaled: rank r
+                     owns the contiguous frame block frame_block(r, N, 65536), walks it in chunks through a resident pool
+                     of synthetic frames (inputs resident in HBM when the timed region starts; pool >> L2), the solve
+                     writes into the rank's slot of the all-gather buffer and one NCCL all_gather_into_tensor of the
+                     [65536, 8] velocity rows ends the step.  `configs1_weak` carries the round-1 weak-scaling figure.
+
+The JSON line carries: value (frames/s, inputs resident in HBM), e2e (the same through FramePipeline.process_host with
+pinned HOST buffers, H2D + D2H + the all-gather inside the timed region, next to a copy-only ceiling measured with the
+same buffers), roofline of the dominant kernel and of every stage, cpu_baseline (the oracle port timed on this box's
+host cores), a >= 1 s sustained run, clocks, gpu_launches.
 `--impl reference` times the reference algorithm's CPU port (oracle/) on all host cores.
 """
 from __future__ import annotations
@@ -32,6 +39,12 @@ sys.path.insert(0, ROOT)
 
 METRIC = "frames/s dechirp->range-Doppler->MUSIC->LS ego-velocity"
 WORKLOAD = "configs[1]: 1k-frame synthetic batch per GPU, 256 samples x 128 chirps x 8 channels, MUSIC 1 deg grid, noise_power 0.01, threshold -20 dB"
+WORKLOAD4 = ("configs[4]: one 65536-frame synthetic sequence, 256 samples x 128 chirps x 16 channels, frame-sharded by contiguous "
+             "block, MUSIC 1 deg grid, noise_power 0.01, threshold -20 dB, NCCL all-gather of the velocity rows")
+# kernels behind one C-ABI call (for gpu_launches): the 2-D transform is the persistent cluster kernel + the side kernel
+KERNELS_PER_CALL = {"rs_range_doppler_fft": 2, "rs_detect": 1, "rs_angles": 1, "rs_recheck_detections_f64": 1,
+                    "rs_recheck_angles_f64": 3, "rs_velocity_from_partials": 1, "rs_velocity_partials": 1, "rs_velocity_ls": 1,
+                    "rs_range_fft": 1, "rs_doppler_fft": 1}
 
 
 def workload_name(args):
@@ -129,20 +142,25 @@ def _oracle_worker(payload):
     return out, tim
 
 
-def cpu_oracle_rate(frames: np.ndarray, args, procs: int):
-    """Frames/s of the oracle port (vectorised numpy restatement of the reference) on `procs` processes."""
+def cpu_oracle_rate(frames: np.ndarray, args, procs: int, pool=None):
+    """Frames/s of the oracle port (vectorised numpy restatement of the reference) on `procs` processes.
+    `pool`: a multiprocessing pool to reuse (the reference arm keeps one alive over all its steps)."""
     from dataclasses import asdict
     p = oracle_params(args)
     pdict = asdict(p)
     parts = [frames[i::procs] for i in range(procs)]
     parts = [x for x in parts if len(x)]
     t0 = time.perf_counter()
-    if len(parts) == 1:
+    if len(parts) == 1 and pool is None:
         res = [_oracle_worker((parts[0], pdict, args.grid_res, args.threshold_db, 1 if procs == 1 else 0, args.method))]
     else:
         import multiprocessing as mp
-        with mp.get_context("fork").Pool(len(parts)) as pool:
-            res = pool.map(_oracle_worker, [(x, pdict, args.grid_res, args.threshold_db, 1, args.method) for x in parts])
+        payload = [(x, pdict, args.grid_res, args.threshold_db, 1, args.method) for x in parts]
+        if pool is not None:
+            res = pool.map(_oracle_worker, payload)
+        else:
+            with mp.get_context("fork").Pool(len(parts)) as own:
+                res = own.map(_oracle_worker, payload)
     dt = time.perf_counter() - t0
     tim = {}
     ndet = []
@@ -171,31 +189,45 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    import multiprocessing as mp
+    wl = resolve_workload(args, int(os.environ.get("WORLD_SIZE", "1")))
+    if wl == "configs4":
+        args.antennas = 16
     cores = os.cpu_count() or 1
     procs = max(1, min(cores, args.ref_procs or cores))
-    per_step = max(procs, args.ref_frames_per_step or procs)
+    per_step = args.ref_frames_per_step or 2 * procs          # fixed sample per step: ~1-3 s of CPU work per step
     frames = host_frames(args, per_step, 4242)
-    for _ in range(args.warmup):
-        cpu_oracle_rate(frames[:procs], args, procs)
-    t0 = time.perf_counter()
-    ndet = 0.0
-    for _ in range(args.steps):
-        _, _, _, ndet, _ = cpu_oracle_rate(frames, args, procs)
-    dt = time.perf_counter() - t0
+    # one worker pool for the whole run: forking a pool inside the timed loop cost up to 60 % of a step in round 1
+    with mp.get_context("fork").Pool(procs) as pool:
+        for _ in range(args.warmup):
+            cpu_oracle_rate(frames[:procs], args, procs, pool)
+        t0 = time.perf_counter()
+        ndet = 0.0
+        for _ in range(args.steps):
+            _, _, _, ndet, _ = cpu_oracle_rate(frames, args, procs, pool)
+        dt = time.perf_counter() - t0
     value = per_step * args.steps / dt
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args), "frames_per_step": per_step, "detections_per_frame": ndet},
+        "scaling": "strong" if wl == "configs4" else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD4 if wl == "configs4" else workload_name(args), "samples": args.samples,
+                   "chirps": args.chirps, "channels": args.antennas, "frames_per_step": per_step,
+                   "detections_per_frame": ndet},
         "cpu_baseline": {"value": value, "unit": "frames/s", "cores": procs, "kind": "port",
                          "sample": f"{per_step} frames/step of the same workload through oracle.radar_oracle.process_frame "
                                    f"(vectorised fp64 numpy port of the reference; the reference itself is Python and cannot "
-                                   f"travel to this box), {procs} processes"},
+                                   f"travel to this box), {procs} worker processes kept alive over all steps"},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def resolve_workload(args, world: int) -> str:
+    if args.workload != "auto":
+        return args.workload
+    return "configs1" if world == 1 else "configs4"
 
 
 # ---------------------------------------------------------------------------------- GPU arm
@@ -216,6 +248,119 @@ def stage_bytes(name, F, A, C, S, n_det):
     return 0
 
 
+def _barrier(world, dev):
+    import torch
+    import torch.distributed as dist
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+
+
+def _max_over_ranks(x: float, world, dev) -> float:
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([x], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def _time_steps(step, steps, warmup, world, dev):
+    """W untimed warm-up steps, then exactly `steps` steps between barrier + synchronize on both sides; CUDA events on the
+    launching stream, max over ranks.  Returns total milliseconds."""
+    import torch
+    for _ in range(warmup):
+        step()
+    _barrier(world, dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    _barrier(world, dev)
+    return _max_over_ranks(e0.elapsed_time(e1), world, dev)
+
+
+def _e2e(pipe, host, vel_slot, gather, chunk, steps, world, dev, frames_this_rank):
+    """End to end through FramePipeline.process_host with pinned host buffers: H2D of every chunk, kernels, the all-gather
+    of the velocity rows and the D2H of the result inside the timed region; then the same buffers / chunking / streams
+    with the kernels left out (copy-only ceiling of this platform), all ranks concurrently.  Wall clock, max over ranks."""
+    import torch
+    vel_host = torch.empty((frames_this_rank, 8), dtype=torch.float64, pin_memory=True)
+
+    def run(copy_only):
+        pipe.process_host(host, chunk_frames=chunk, vel_dev=vel_slot, vel_host=vel_host, copy_only=copy_only)
+        if not copy_only:
+            gather.gather()
+            torch.cuda.synchronize(dev)
+
+    out = {}
+    for name, copy_only in (("e2e", False), ("ceiling", True)):
+        for _ in range(2):
+            run(copy_only)
+        _barrier(world, dev)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            run(copy_only)
+        torch.cuda.synchronize(dev)
+        out[name] = _max_over_ranks(time.perf_counter() - t0, world, dev) / steps
+    return out, vel_host
+
+
+def measure_configs4(args, world, rank, dev, steps, warmup):
+    """BASELINE configs[4]: one 65 536-frame 256 x 128 x 16 sequence, strong-scaled by contiguous frame block."""
+    import copy
+    import torch
+    from radar_slam_b200 import FramePipeline, synth
+    from radar_slam_b200.sharding import VelocityGather, frame_block
+    a4 = copy.copy(args)
+    a4.antennas, a4.samples, a4.chirps = 16, 256, 128
+    cfg = radar_config(a4)
+    pipe = FramePipeline(cfg, device=str(dev))
+    total = args.total_frames
+    lo, hi = frame_block(rank, world, total)
+    block = hi - lo
+    P = min(block, args.pool_frames)
+    A, C, S = 16, 128, 256
+    # resident pool of this rank's first P frames of the sequence (frame k depends only on (seed, k)); the block is walked
+    # through the pool chunk by chunk, so the inputs are in HBM when the timed region starts and far exceed the L2
+    pool = synth.synth_cubes(cfg, P, seed=1234, first_frame=lo, device=dev)
+    gather = VelocityGather(total, dev)
+    vel = gather.slot()
+
+    def step():
+        for c0 in range(0, block, P):
+            n = min(P, block - c0)
+            pipe.process(pool[:n], chunk_frames=args.chunk, vel_out=vel[c0:c0 + n])
+        gather.gather()
+
+    pipe.launches = 0
+    ms_total = _time_steps(step, steps, warmup, world, dev)
+    calls = pipe.launches // (steps + warmup)
+    # ---- end to end on a bounded sample of the block (PCIe bound: a whole block would take seconds per step)
+    n_e2e = min(block, args.e2e_frames4)
+    host = torch.empty((n_e2e, A, C, S), dtype=torch.complex64, pin_memory=True)
+    host.copy_(pool[:min(P, n_e2e)].repeat(((n_e2e + P - 1) // P), 1, 1, 1)[:n_e2e] if n_e2e > P else pool[:n_e2e])
+    torch.cuda.synchronize(dev)
+    t, _ = _e2e(pipe, host, vel, gather, args.host_chunk, max(1, min(steps, 3)), world, dev, n_e2e)
+    bytes_step = n_e2e * A * C * S * 8
+    res = {
+        "workload": WORKLOAD4, "total_frames": total, "frames_this_rank": block, "resident_pool_frames": P,
+        "value": total * steps / (ms_total / 1e3), "unit": "frames/s", "ms_per_step": ms_total / steps, "scaling": "strong",
+        "stage_calls_per_step": calls,
+        "e2e": {"value": world * n_e2e / t["e2e"], "unit": "frames/s", "frames_per_step_per_gpu": n_e2e,
+                "h2d_bytes_per_step": bytes_step, "d2h_bytes_per_step": n_e2e * 64,
+                "h2d_ceiling_gbs_per_gpu": bytes_step / t["ceiling"] / 1e9,
+                "ceiling_frames_per_s": world * n_e2e / t["ceiling"],
+                "frac_of_ceiling": t["ceiling"] / t["e2e"],
+                "note": "ceiling = the same pinned buffers, chunking and streams with the kernels left out, all ranks "
+                        "concurrently; the all-gather is inside the end-to-end region"},
+    }
+    del pool, host
+    torch.cuda.empty_cache()
+    return res
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -230,12 +375,57 @@ def run_gpu(args):
     numa = bind_to_gpu_numa_node(local) if not args.no_numa_bind else {"device": local, "numa_node": "unbound"}
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    wl = resolve_workload(args, world)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+
+    c4 = None
+    if wl == "configs4" or (world == 1 and not args.no_configs4 and args.workload == "auto"):
+        steps4 = args.steps if wl == "configs4" else max(2, min(args.steps, 3))
+        c4 = measure_configs4(args, world, rank, dev, steps4, args.warmup if wl == "configs4" else 3)
+    c1 = measure_configs1(args, world, rank, dev, numa, detailed=(wl == "configs1"))
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank == 0:
+        if wl == "configs1":
+            line = c1
+            if c4 is not None:
+                line["configs4_n1" if world == 1 else "configs4"] = c4
+        else:
+            line = {
+                "metric": METRIC, "value": c4["value"], "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": c4["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": WORKLOAD4, "total_frames": c4["total_frames"], "samples": 256, "chirps": 128,
+                           "channels": 16, "frames_this_rank": c4["frames_this_rank"],
+                           "resident_pool_frames": c4["resident_pool_frames"], "chunk_frames": args.chunk,
+                           "cache": "inputs larger than L2 (resident pool of %.2f GiB per GPU, walked block by block)"
+                                    % (c4["resident_pool_frames"] * 16 * 128 * 256 * 8 / 2 ** 30),
+                           "parallelism": f"one {c4['total_frames']}-frame sequence, contiguous frame blocks over {world} GPU(s), "
+                                          f"all-gather of [F,8] velocity rows",
+                           "host_binding": numa},
+                "roofline": c1["roofline"], "cpu_baseline": c1["cpu_baseline"], "e2e": c4["e2e"],
+                "gpu_launches": int(c4["stage_calls_per_step"] * args.steps * 10 / 6),   # 10 kernels behind the 6 stage calls
+                "configs1_weak": {k: c1[k] for k in ("value", "ms_per_step", "scaling", "e2e", "config")},
+            }
+        line["clocks"] = clocks
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def measure_configs1(args, world, rank, dev, numa, detailed=True):
+    """BASELINE configs[1] per GPU (weak scaling at N > 1); with `detailed` also the per-stage roofline, the CPU baseline
+    and the sustained run.  Returns the JSON line (dict) on every rank."""
+    import torch
+    from radar_slam_b200 import FramePipeline, synth
+    from radar_slam_b200.sharding import VelocityGather
     cfg = radar_config(args)
     pipe = FramePipeline(cfg, device=str(dev))
     F, A, C, S = args.frames, args.antennas, args.chirps, args.samples
 
     cube = synth.synth_cubes(cfg, F, seed=1234, first_frame=rank * F, device=dev)
-    from radar_slam_b200.sharding import VelocityGather
     gather = VelocityGather(world * F, dev)       # all-gather target; this rank's slot is the solve's output
     vel = gather.slot()
 
@@ -243,65 +433,69 @@ def run_gpu(args):
         pipe.process(cube, chunk_frames=args.chunk, vel_out=vel)
         gather.gather()                           # NCCL all_gather_into_tensor of the [F, 8] rows (no-op at N=1)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    for _ in range(args.warmup):
-        step()
-    barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     pipe.launches = 0
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    e1.record()
-    barrier()
-    launches = pipe.launches
-    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = float(ms.item())
+    pipe.call_counts = {}
+    ms_total = _time_steps(step, args.steps, args.warmup, world, dev)
+    launches = sum(KERNELS_PER_CALL.get(k, 1) * v for k, v in pipe.call_counts.items()) * args.steps // (args.steps + args.warmup)
 
-    # ---- end to end through the public API with HOST buffers (pinned), H2D + D2H inside the timed region
+    # ---- sustained: the same step for >= 1 s (thermally / power settled), reported next to the K-step figure
+    sustained = None
+    if detailed and args.sustain_s > 0:
+        n_sus = max(args.steps, int(args.sustain_s * 1e3 / (ms_total / args.steps)) + 1)
+        ms_sus = _time_steps(step, n_sus, 0, world, dev)
+        sustained = {"steps": n_sus, "seconds": ms_sus / 1e3, "value": world * F * n_sus / (ms_sus / 1e3), "unit": "frames/s"}
+
+    # ---- end to end through the public API with HOST buffers (pinned): H2D + kernels + all-gather + D2H in the timed region
     n_e2e = min(F, args.e2e_frames)
     host = torch.empty((n_e2e, A, C, S), dtype=torch.complex64, pin_memory=True)
     host.copy_(cube[:n_e2e])
     torch.cuda.synchronize(dev)
-    for _ in range(max(1, min(args.warmup, 2))):
-        pipe.process_host(host, chunk_frames=args.host_chunk)
-    barrier()
-    t0 = time.perf_counter()
     e2e_steps = max(1, min(args.steps, 3))
-    for _ in range(e2e_steps):
-        vel_host = pipe.process_host(host, chunk_frames=args.host_chunk)          # returns after the D2H completed
-    torch.cuda.synchronize(dev)
-    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_value = world * n_e2e * e2e_steps / float(e2e_s.item())
-    assert torch.allclose(vel_host.to(dev), vel[:n_e2e], atol=0, rtol=0), "host path and device path disagree"
-    clocks = sampler.stop() if rank == 0 else None      # sampled over both timed regions (device-resident and host-buffer)
-
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-
-    # ---- per-stage device times (CUDA events on the launching stream) for the roofline
-    pipe.profile = []
-    os.environ["RS_NO_OVERLAP"] = "1"             # stage times one after the other (the timed run above overlaps the recheck)
+    t_e2e, vel_host = _e2e(pipe, host, vel, gather, args.host_chunk, e2e_steps, world, dev, n_e2e)
+    e2e_value = world * n_e2e / t_e2e["e2e"]
     pipe.process(cube, chunk_frames=args.chunk, vel_out=vel)
+    pipe.process_host(host, chunk_frames=args.host_chunk, vel_dev=gather.buf.new_empty((n_e2e, 8)), vel_host=vel_host)
     torch.cuda.synchronize(dev)
-    os.environ.pop("RS_NO_OVERLAP")
+    assert torch.equal(vel_host.to(dev), vel[:n_e2e]), "host path and device path disagree"
+    bytes_step = n_e2e * A * C * S * 8
+    e2e = {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": bytes_step, "d2h_bytes_per_step": n_e2e * 64,
+           "frames_per_step": n_e2e, "h2d_ceiling_gbs_per_gpu": bytes_step / t_e2e["ceiling"] / 1e9,
+           "ceiling_frames_per_s": world * n_e2e / t_e2e["ceiling"], "frac_of_ceiling": t_e2e["ceiling"] / t_e2e["e2e"],
+           "note": "ceiling = the same pinned buffers, chunking and streams with the kernels left out, all ranks concurrently; "
+                   "the all-gather is inside the end-to-end region"}
+
+    value = world * F * args.steps / (ms_total / 1e3)
+    line = {
+        "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args), "frames_per_gpu": F, "samples": S, "chirps": C, "channels": A,
+                   "chunk_frames": args.chunk, "host_chunk_frames": args.host_chunk,
+                   "cache": "inputs larger than L2 (%.2f GiB cube per GPU)" % (cube.numel() * 8 / 2 ** 30),
+                   "parallelism": f"frames sharded over {world} GPU(s), all-gather of [F,8] velocity rows",
+                   "host_binding": numa},
+        "e2e": e2e, "gpu_launches": launches,
+    }
+    if sustained is not None:
+        line["sustained"] = sustained
+    if not detailed or rank != 0:
+        line.setdefault("roofline", None)
+        line.setdefault("cpu_baseline", None)
+        return line
+
+    # ---- per-stage device times (CUDA events on the launching stream) for the roofline: averaged over several passes
+    os.environ["RS_NO_OVERLAP"] = "1"             # stage times one after the other (the timed run above overlaps the recheck)
     stage_ms, stage_n = {}, {}
-    for name, a, b in pipe.profile:
-        stage_ms[name] = stage_ms.get(name, 0.0) + a.elapsed_time(b)
-        stage_n[name] = stage_n.get(name, 0) + 1
+    passes = max(1, args.profile_passes)
+    for _ in range(passes):
+        pipe.profile = []
+        pipe.process(cube, chunk_frames=args.chunk, vel_out=vel)
+        torch.cuda.synchronize(dev)
+        for name, a, b in pipe.profile:
+            stage_ms[name] = stage_ms.get(name, 0.0) + a.elapsed_time(b) / passes
+            stage_n[name] = stage_n.get(name, 0) + 1
+    stage_n = {k: v // passes for k, v in stage_n.items()}
+    os.environ.pop("RS_NO_OVERLAP")
     pipe.profile = None
     # detections per frame (for the algorithmic bytes of the list-driven stages)
     rds = pipe.range_doppler(cube[: min(F, 64)])
@@ -369,11 +563,13 @@ def run_gpu(args):
                     "m16n8k8, fp16 operands split hi + lo, fp32 accumulation); its argmax / runner-up tracking is ALU-issue "
                     "bound, not HBM bound"}
     if dom["kernel"] == "rs_range_doppler_fft":
-        roofline["note"] = ("dominant kernel is the fused cluster 2-D FFT: HBM traffic at the algorithmic minimum (16 B/cell, plane "
-                            "held in distributed shared memory between the passes), bounded by shared-memory bandwidth and the "
-                            "cluster barrier rather than by HBM")
+        roofline["note"] = ("dominant kernel is the fused 2-D FFT (persistent warp-specialised 4-CTA clusters fed by TMA + the side "
+                            "kernel on the stranded SMs): HBM traffic at the algorithmic minimum (16 B/cell, plane held in "
+                            "distributed shared memory between the passes)")
     elif dom["kernel"] == "rs_angles":
-        roofline["note"] = "dominant kernel is the per-cell MUSIC grid scan (see angle_scan): ALU-issue bound, not HBM bound"
+        roofline["note"] = ("dominant kernel by time is the per-cell MUSIC grid scan (see angle_scan): ALU-issue bound, not HBM "
+                            "bound -- its HBM fraction is reported because the contract asks for one; the HBM-bound stages are "
+                            "in fft_stages / stages")
 
     # ---- CPU baseline: the oracle port on a bounded sample of the SAME frames, one core
     n_cpu = args.cpu_frames
@@ -386,31 +582,16 @@ def run_gpu(args):
     else:                                         # exploratory runs of the big configs: no CPU arm
         rate, dt, tim, ndet_cpu, parity = None, 0.0, {}, 0.0, None
 
-    value = world * F * args.steps / (ms_total / 1e3)
-    line = {
-        "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args), "frames_per_gpu": F, "samples": S, "chirps": C, "channels": A,
-                   "grid_points": len(pipe._angle_tables(A)["grid"]), "chunk_frames": args.chunk, "host_chunk_frames": args.host_chunk,
-                   "detections_per_frame": n_det_frame, "detection_overflow": overflow,
-                   "undecided_in_fp32_per_frame": flagged, "fp64_recheck": recheck_stats,
-                   "cache": "inputs larger than L2 (%.2f GiB cube per GPU)" % (cube.numel() * 8 / 2 ** 30),
-                   "parallelism": f"frames sharded over {world} GPU(s), all-gather of [F,8] velocity rows",
-                   "host_binding": numa},
-        "roofline": roofline,
-        "cpu_baseline": {"value": rate, "unit": "frames/s", "cores": 1, "kind": "port",
-                         "sample": f"{n_cpu} frames of the same batch through the oracle port in {dt:.1f}s "
-                                   f"(stage seconds {json.dumps({k: round(v, 2) for k, v in tim.items()})}); "
-                                   f"{ndet_cpu:.0f} detections/frame",
-                         "max_abs_velocity_diff_vs_gpu": parity},
-        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": n_e2e * A * C * S * 8,
-                "d2h_bytes_per_step": n_e2e * 64, "frames_per_step": n_e2e},
-        "gpu_launches": launches, "clocks": clocks,
-    }
-    print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    line["config"].update({"grid_points": len(pipe._angle_tables(A)["grid"]), "detections_per_frame": n_det_frame,
+                           "detection_overflow": overflow, "undecided_in_fp32_per_frame": flagged,
+                           "fp64_recheck": recheck_stats, "profile_passes": passes})
+    line["roofline"] = roofline
+    line["cpu_baseline"] = {"value": rate, "unit": "frames/s", "cores": 1, "kind": "port",
+                            "sample": f"{n_cpu} frames of the same batch through the oracle port in {dt:.1f}s "
+                                      f"(stage seconds {json.dumps({k: round(v, 2) for k, v in tim.items()})}); "
+                                      f"{ndet_cpu:.0f} detections/frame",
+                            "max_abs_velocity_diff_vs_gpu": parity}
+    return line
 
 
 def main():
@@ -435,6 +616,14 @@ def main():
     ap.add_argument("--e2e-frames", type=int, default=1000)
     ap.add_argument("--cpu-frames", type=int, default=24)
     ap.add_argument("--no-numa-bind", action="store_true", help="do not pin each rank to its GPU's NUMA node")
+    ap.add_argument("--workload", default="auto", choices=["auto", "configs1", "configs4"],
+                    help="auto: configs[1] at N = 1 (plus configs[4] on one GPU as `configs4_n1`), configs[4] strong-scaled at N > 1")
+    ap.add_argument("--total-frames", type=int, default=65536, help="length of the configs[4] sequence")
+    ap.add_argument("--pool-frames", type=int, default=512, help="configs[4]: resident synthetic frames per GPU (2 GiB at 512)")
+    ap.add_argument("--e2e-frames4", type=int, default=1024, help="configs[4]: frames per GPU of the end-to-end sample")
+    ap.add_argument("--no-configs4", action="store_true", help="N = 1: skip the configs[4] side measurement")
+    ap.add_argument("--sustain-s", type=float, default=1.0, help="length of the sustained run (0: off)")
+    ap.add_argument("--profile-passes", type=int, default=5, help="passes averaged for the per-stage times")
     ap.add_argument("--ref-procs", type=int, default=0)
     ap.add_argument("--ref-frames-per-step", type=int, default=0)
     args = ap.parse_args()

@@ -39,7 +39,9 @@ struct Fused {
                   "uniform Doppler loops");
 };
 
-template <int SR1, int SR2, int CR1, int CR2, int NC, int F2_THREADS, int MINB>
+// PACKED: the f32x2 arithmetic of rs_fft_pow2.cuh -- the same operations in the same order as the warp-specialised kernel
+// (rs_fft2d_ws.cu), so a batch split between the two kernels is bit-identical to either of them alone
+template <int SR1, int SR2, int CR1, int CR2, int NC, int F2_THREADS, int MINB, bool PACKED = false>
 __global__ void __cluster_dims__(NC, 1, 1) __launch_bounds__(F2_THREADS, MINB)
 fft2d_cluster_kernel(const float2* __restrict__ cube, const float2* __restrict__ table,
                      const float2* __restrict__ tw_s_g, const float2* __restrict__ tw_c_g, float2* __restrict__ rds,
@@ -94,8 +96,8 @@ fft2d_cluster_kernel(const float2* __restrict__ cube, const float2* __restrict__
     for (int b0 = 0; b0 < P::CPC; b0 += P::CB) {
         {
 #pragma unroll
-            for (int j = 0; j < SR1; ++j) v[j] = cmul(v[j], tabv[j]);
-            pow2::dft<SR1>(v);
+            for (int j = 0; j < SR1; ++j) v[j] = PACKED ? pow2::cmulp(v[j], tabv[j]) : cmul(v[j], tabv[j]);
+            if (PACKED) pow2::dftp<SR1>(v); else pow2::dft<SR1>(v);
             float2* y = Y + row1 * P::RP + t1;
 #pragma unroll
             for (int k1 = 0; k1 < SR1; ++k1) y[k1 * P::K1P] = v[k1];
@@ -110,8 +112,8 @@ fft2d_cluster_kernel(const float2* __restrict__ cube, const float2* __restrict__
             const float2* y = Y + row2 * P::RP + k1r * P::K1P;                      // lanes along chirps
             float2 u[SR2];
 #pragma unroll
-            for (int n2 = 0; n2 < SR2; ++n2) u[n2] = (n2 == 0) ? y[0] : cmul(y[n2], twr[n2]);
-            pow2::dft<SR2>(u);
+            for (int n2 = 0; n2 < SR2; ++n2) u[n2] = (n2 == 0) ? y[0] : PACKED ? pow2::cmulp(y[n2], twr[n2]) : cmul(y[n2], twr[n2]);
+            if (PACKED) pow2::dftp<SR2>(u); else pow2::dft<SR2>(u);
             if (b0 == 0) asm volatile("barrier.cluster.wait.aligned;" ::: "memory");   // the peers' M exists
             const int chirp = q * P::CPC + b0 + row2;
 #pragma unroll
@@ -143,10 +145,10 @@ fft2d_cluster_kernel(const float2* __restrict__ cube, const float2* __restrict__
 #pragma unroll
             for (int j = 0; j < CR1; ++j) v[j] = m[td + CR2 * j];
             __syncwarp();                                                           // the row is read before it is rewritten
-            pow2::dft<CR1>(v);
+            if (PACKED) pow2::dftp<CR1>(v); else pow2::dft<CR1>(v);
 #pragma unroll
             for (int k1 = 0; k1 < CR1; ++k1)
-                m[k1 * CR2 + ((td + (k1 >> 1)) & (CR2 - 1))] = (k1 == 0) ? v[0] : cmul(v[k1], twd[k1]);
+                m[k1 * CR2 + ((td + (k1 >> 1)) & (CR2 - 1))] = (k1 == 0) ? v[0] : PACKED ? pow2::cmulp(v[k1], twd[k1]) : cmul(v[k1], twd[k1]);
         }
     }
     __syncthreads();
@@ -156,7 +158,7 @@ fft2d_cluster_kernel(const float2* __restrict__ cube, const float2* __restrict__
         float2 u[CR2];
 #pragma unroll
         for (int n2 = 0; n2 < CR2; ++n2) u[n2] = m[(n2 + (k1 >> 1)) & (CR2 - 1)];
-        pow2::dft<CR2>(u);
+        if (PACKED) pow2::dftp<CR2>(u); else pow2::dft<CR2>(u);
         const int p = q * P::ROWS + row;
         float2* dst = rds + (((size_t)f * S + p) * A + a) * C;
 #pragma unroll
@@ -233,7 +235,7 @@ extern "C" int rs_range_doppler_fft(const void* cube, const void* table, const v
                                              dc_removal, st && st[0] == 't', vr ? atoi(vr) : -1, main_st);
             if (r == 1 && F_side) {
                 using P = Fused<16, 16, 16, 8, 2, 512>;
-                auto kern = fft2d_cluster_kernel<16, 16, 16, 8, 2, 512, 1>;
+                auto kern = fft2d_cluster_kernel<16, 16, 16, 8, 2, 512, 1, true>;       // packed: bit-identical to the main kernel
                 cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P::SMEM);
                 const float2* cube_s = (const float2*)cube + (size_t)F_main * A * C_total * S;
                 float2* rds_s = (float2*)rds + (size_t)F_main * S * A * C_used;

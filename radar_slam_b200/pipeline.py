@@ -135,11 +135,23 @@ class FramePipeline:
         self.seg_cap_override = seg_cap
         self._tab: Dict = {}
         self._ws: Dict = {}
-        self.launches = 0          # kernels of libradarslam_b200 launched since the last reset
+        self.launches = 0          # C-ABI stage calls since the last reset
+        self.call_counts = None    # set to {} to count calls per entry point (bench.py: kernels launched)
         self.profile = None        # set to a list to collect (stage, start_event, end_event) per launch
+        self.nvtx = os.environ.get("RS_NVTX") == "1"
 
     def _call(self, name: str, *args) -> None:
         fn = getattr(self.lib, name)
+        if self.call_counts is not None:
+            self.call_counts[name] = self.call_counts.get(name, 0) + 1
+        if self.nvtx:                      # RS_NVTX=1: one NVTX range per stage call (nsys / ncu --nvtx timelines)
+            torch.cuda.nvtx.range_push(name)
+            try:
+                _lib.check(fn(*args), name)
+            finally:
+                torch.cuda.nvtx.range_pop()
+            self.launches += 1
+            return
         if self.profile is None:
             _lib.check(fn(*args), name)
         else:
@@ -470,13 +482,19 @@ class FramePipeline:
             main.wait_stream(side)
         return (vel, last[0], last[1]) if keep else vel
 
-    def process_host(self, cube_host: torch.Tensor, chunk_frames: int = 32) -> torch.Tensor:
+    def process_host(self, cube_host: torch.Tensor, chunk_frames: int = 32, vel_dev: Optional[torch.Tensor] = None,
+                     vel_host: Optional[torch.Tensor] = None, copy_only: bool = False) -> torch.Tensor:
         """End-to-end with HOST buffers: pinned cube[F,A,C,S] -> pinned vel[F,8]; H2D and D2H copies run on
-        a second stream and overlap the kernels of the neighbouring chunk."""
+        a second stream and overlap the kernels of the neighbouring chunk.
+        vel_dev: device rows to write (e.g. this rank's slot of the all-gather buffer); vel_host: pinned result buffer;
+        copy_only: the same buffers, chunking and stream protocol with the kernels left out -- the platform's ceiling
+        for this path (bench.py reports the end-to-end rate as a fraction of it)."""
         assert not cube_host.is_cuda and cube_host.dtype == torch.complex64
         F, A, C, S = cube_host.shape
-        vel_dev = torch.empty((F, 8), dtype=torch.float64, device=self.device)
-        vel_host = torch.empty((F, 8), dtype=torch.float64, pin_memory=True)
+        if vel_dev is None:
+            vel_dev = self._buf("host_vel_dev", (F, 8), torch.float64)
+        if vel_host is None:
+            vel_host = torch.empty((F, 8), dtype=torch.float64, pin_memory=True)
         copy_stream = self._ws.setdefault("copy_stream", torch.cuda.Stream(self.device))
         main = torch.cuda.current_stream(self.device)
         stage = [self._buf(f"stage{i}", (chunk_frames, A, C, S), torch.complex64) for i in range(2)]
@@ -491,8 +509,9 @@ class FramePipeline:
                 stage[b][: hi - lo].copy_(cube_host[lo:hi], non_blocking=True)
                 ev_h2d[b].record(copy_stream)
             main.wait_event(ev_h2d[b])
-            self.process(stage[b][: hi - lo], chunk_frames=chunk_frames, vel_out=vel_dev[lo:hi])
+            if not copy_only:
+                self.process(stage[b][: hi - lo], chunk_frames=chunk_frames, vel_out=vel_dev[lo:hi])
             ev_free[b].record(main)
-        vel_host.copy_(vel_dev, non_blocking=True)
+        vel_host.copy_(vel_dev[:F], non_blocking=True)
         main.synchronize()
         return vel_host
