@@ -136,7 +136,10 @@ int rs_detect(const void* rds, const uint8_t* range_gate, float thr_power, float
  *                     mma_tiles = ceil(ceil(G/2)/8).  NULL selects the CUDA-core scan.
  *       cell_ws       optional workspace of 17 * F*R*D bytes (16-byte aligned) for A > 16: every distinct cell of a frame is
  *                     evaluated once (mark / evaluate / scatter) instead of once per detection -- with many antennas
- *                     a cell is flagged on many of them and all share one snapshot.  NULL: one evaluation per leader. */
+ *                     a cell is flagged on many of them and all share one snapshot.  NULL: one evaluation per leader.
+ *       tc_table      optional, bytes [tc_halves][cos, sin][KC][32 x 16 fp16]: the same tables as UMMA B operands (K-major,
+ *                     no swizzle) for the tcgen05 / TMEM scan (radar_slam_b200/tables.py: scan_tc_table), tc_halves =
+ *                     ceil(ceil(G/2)/32); used instead of the mma.sync scan when RS_ANGLES_TC=1 (measured variant). */
 #define RS_TIE_LIST_CAP 32
 int rs_angles(const void* rds, const float* scan_table, int scan_stride, const void* steer, const float* grid_deg, int G,
               int method, float tie_eps, double esprit_scale,
@@ -144,7 +147,7 @@ int rs_angles(const void* rds, const float* scan_table, int scan_stride, const v
               int32_t* det_aidx, float* det_adeg, float* det_phase,
               int seg_cap, int nseg_per_frame, int F, int R, int D, int A,
               const double* grid_cs, double* ls_partials, int grid_symmetric, int32_t* det_ntie, int32_t* det_tielist,
-              const float* mma_table, int mma_tiles, void* cell_ws, void* stream);
+              const float* mma_table, int mma_tiles, void* cell_ws, const void* tc_table, int tc_halves, void* stream);
 
 /* (d')  the velocity solve of rs_velocity_ls from the per-segment sums rs_angles already produced
  *       (no second pass over the detection lists); same output row layout. */

@@ -46,6 +46,7 @@ struct AngleArgs {
 
 // write one cell's result to all of its detections (same snapshot on every antenna that flagged the cell)
 // returns how many of them are live (not RS_FLAG_DROPPED): the weight of the cell in the velocity sums
+template <bool BATCH = false>
 __device__ __forceinline__ int emit(const AngleArgs& p, int seg, int lead_i, size_t o, int k, int aidx, float adeg,
                                     float phase, uint8_t extra_flags) {
     int live = 0;
@@ -53,7 +54,26 @@ __device__ __forceinline__ int emit(const AngleArgs& p, int seg, int lead_i, siz
         const int slot = atomicAdd(p.det_ntie + seg, 1);
         if (p.det_tielist && slot < RS_TIE_LIST_CAP) p.det_tielist[(size_t)seg * RS_TIE_LIST_CAP + slot] = lead_i;
     }
-    for (int e = 0; e < k; ++e) {
+    // BATCH (the tcgen05 kernel: few resident warps, registers to spare): the flags of up to eight entries are fetched
+    // together -- one latency instead of k; longer groups finish in the loop below
+    int e0 = 0;
+    if (BATCH) {
+        uint8_t fl8[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) fl8[e] = e < k ? p.det_flags[o + e] : (uint8_t)RS_FLAG_DROPPED;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            if (e < k) {
+                p.det_aidx[o + e] = aidx;
+                p.det_adeg[o + e] = adeg;
+                p.det_phase[o + e] = phase;
+                live += (fl8[e] & RS_FLAG_DROPPED) ? 0 : 1;
+                if (extra_flags) p.det_flags[o + e] = fl8[e] | extra_flags;
+            }
+        }
+        e0 = 8;
+    }
+    for (int e = e0; e < k; ++e) {
         p.det_aidx[o + e] = aidx;
         p.det_adeg[o + e] = adeg;
         p.det_phase[o + e] = phase;
@@ -623,6 +643,320 @@ __global__ void __launch_bounds__(ANG_THREADS, MINB) angles_mma_kernel(AngleArgs
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// tcgen05 scan (RS_ANGLES_TC=1): the same contraction on the 5th-generation tensor cores.
+//
+// One CTA = 128 threads = 128 cells = the 128 TMEM lanes of a UMMA tile.  Every thread gathers its cell's snapshot,
+// forms the normalised lags and writes its ROW of the A operand ([Re R_k] for the even part, [Im R_k] for the odd
+// part, fp16 hi / lo split packed along K exactly as in the mma.sync kernel) into shared memory in the canonical
+// K-major no-swizzle UMMA layout (8 x 16-byte core matrices).  One elected thread issues
+//     tcgen05.mma.cta_group::1.kind::f16   D[128 x 48] (+)= A[128 x 16] . B[16 x 48]
+// per 16-wide K chunk for the cos table (E) and the sin table (O) of one "job" of 32 grid pairs into one of two 64-column TMEM
+// buffers, commits to that buffer's mbarrier, and after the wait each thread reads ITS OWN cell's 32 + 32 accumulators with
+// tcgen05.ld.32x32b -- a whole row per thread, so the pair maximum E + |O| is tracked without any cross-lane merge
+// (the mma.sync fragment layout spreads a row over a quad: 3 merges and 12 shuffles per cell there).  Two jobs are in
+// flight: the tensor core fills one buffer while the threads track the other, and the next tile's snapshot loads are
+// issued before the tracking starts, so their latency is hidden too.  The B operand (cos / sin tables, split hi / lo,
+// already in UMMA layout) is built on the host (tables.scan_tc_table).
+// 128 TMEM columns per CTA: four CTAs per SM keep 16 warps resident for the ALU-bound tracking.
+// ---------------------------------------------------------------------------------------------
+namespace tc5 {
+
+constexpr int NPH = 32;                    // grid pairs per job (UMMA N); two jobs in flight in 2 x 64 TMEM columns
+constexpr int TMEM_COLS = 128;
+
+__device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// K-major, no swizzle: element (row, k) of a [rows x 16] fp16 chunk sits at (row / 8) * 256 + (k / 8) * 128 + (row % 8) * 16
+// + (k % 8) * 2: leading (K) byte offset 128, stride (M / N) byte offset 256, descriptor version 1 (Blackwell)
+__device__ __forceinline__ unsigned long long smem_desc(uint32_t addr) {
+    return (unsigned long long)((addr & 0x3FFFFu) >> 4) | ((unsigned long long)(128 >> 4) << 16) |
+           ((unsigned long long)(256 >> 4) << 32) | (1ull << 46);
+}
+// kind::f16: D fp32 (bit 4), A / B fp16 K-major, N >> 3 at bit 17, M >> 4 at bit 24
+constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(NPH >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+
+__device__ __forceinline__ void umma(uint32_t tmem_d, unsigned long long da, unsigned long long db, uint32_t accumulate) {
+    asm volatile(
+        "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(IDESC), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                   "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+}
+
+__device__ __forceinline__ void ld8(uint32_t taddr, float (&v)[8]) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]);
+}
+
+}  // namespace tc5
+
+template <int AP>
+__global__ void __launch_bounds__(ANG_THREADS, 4) angles_tc5_kernel(AngleArgs p, const uint4* __restrict__ tc_table, int njobs,
+                                                                 const double* __restrict__ grid_cs,
+                                                                 double* __restrict__ ls_partials) {
+    using namespace tc5;
+    constexpr int K = AP;                              // lag slots per part (AP - 1 lags + one zero)
+    constexpr int KC = AP == 8 ? 2 : 3;                // 16-wide K chunks per matrix: AP 8: [hi|lo][hi|0]; AP 16: [hi][lo][hi]
+    constexpr int B_CHUNK = NPH * 32;                  // bytes of one [32 x 16] fp16 chunk
+    constexpr int A_CHUNK = 128 * 32;                  // bytes of one [128 x 16] fp16 chunk
+    constexpr int A_CHUNKS = 2;                        // stored A chunks per matrix (AP 16 re-uses [hi] for the third)
+    constexpr int LSTRIDE = K + 1;
+    extern __shared__ __align__(128) unsigned char smraw[];
+    unsigned char* Bt = smraw;                                                   // [njobs][E, O][KC][B_CHUNK]
+    unsigned char* At = Bt + (size_t)njobs * 2 * KC * B_CHUNK;                   // [E, O][A_CHUNKS][A_CHUNK]
+    float* Lx = reinterpret_cast<float*>(At + 2 * A_CHUNKS * A_CHUNK);           // [128][LSTRIDE] odd lags / R_0 (fp32)
+    __shared__ unsigned long long mbar[2];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ double red[ANG_THREADS / 32][8];
+    const int seg = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int n = p.det_nlead[seg];
+    double acc_ls[7] = {0, 0, 0, 0, 0, 0, 0};
+    if (n > 0) {
+        if (wid == 0) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(&tmem_base_s)), "n"(TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+        if (tid == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(&mbar[0])) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(&mbar[1])) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        {
+            const int n16 = njobs * 2 * KC * B_CHUNK / 16;
+            uint4* dst = reinterpret_cast<uint4*>(Bt);
+            for (int i = tid; i < n16; i += ANG_THREADS) dst[i] = __ldg(tc_table + i);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tmem_base = tmem_base_s;
+        const uint32_t trow = tmem_base + ((uint32_t)(wid * 32) << 16);          // this warp's 32 TMEM lanes
+        uint32_t phase[2] = {0u, 0u};
+        const int f = seg / p.nseg_per_frame;
+        const float2* frame = p.rds + (size_t)f * p.R * p.D * p.A;
+        const int M = p.A, G = p.G;
+        const int half = G / 2, odd = G & 1, last_pair = (G + 1) / 2 - 1;
+        const float NEG = -3.0e38f;
+        // this thread's row of a chunk: (tid / 8) * 256 + (tid % 8) * 16, k 0..7 at +0, k 8..15 at +128
+        const uint32_t arow = (uint32_t)((tid >> 3) * 256 + (tid & 7) * 16);
+        float* row = Lx + tid * LSTRIDE;
+        const uint32_t a_base = s32(At), b_base = s32(Bt);
+        // job j = grid pairs [32 j, 32 j + 32) of the current tile -> TMEM buffer j & 1 (E at +0, O at +32 of its 64 columns)
+        auto issue_job = [&](int jb) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t d0 = tmem_base + (uint32_t)((jb & 1) * 2 * NPH);
+#pragma unroll
+            for (int part = 0; part < 2; ++part) {
+#pragma unroll
+                for (int c = 0; c < KC; ++c) {
+                    const int ac = (AP == 16 && c == 2) ? 0 : c;                     // AP 16: the third chunk multiplies hi again
+                    umma(d0 + (uint32_t)(part * NPH), smem_desc(a_base + (uint32_t)((part * A_CHUNKS + ac) * A_CHUNK)),
+                         smem_desc(b_base + (uint32_t)(((jb * 2 + part) * KC + c) * B_CHUNK)), c > 0 ? 1u : 0u);
+                }
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(&mbar[jb & 1])) : "memory");
+        };
+        // The chain leader -> key -> snapshot is three dependent global loads.  It is software pipelined over the tiles:
+        // while tile t is scanned, the snapshot of tile t + 1 is in flight (its key arrived during tile t - 1) and so is the
+        // leader of tile t + 2; its key is requested after the scan.
+        float2 s[AP];
+        const size_t segbase = (size_t)seg * p.seg_cap;
+        auto lead_of = [&](int i) -> uint32_t { return i < n ? p.det_lead[segbase + i] : (1u << 16); };
+        auto key_of = [&](int i, uint32_t l) -> uint32_t { return i < n ? p.det_key[segbase + (l & 0xFFFFu)] : 0u; };
+        auto snapshot = [&](int i, uint32_t key) {
+            if (i < n) {
+                int a, r, d;
+                rs_split_key(key, a, r, d);
+                const float2* cell = frame + (size_t)r * M * p.D + d;
+#pragma unroll
+                for (int m = 0; m < AP; ++m) s[m] = (m < M) ? __ldg(cell + (size_t)m * p.D) : make_float2(0.f, 0.f);
+            } else {
+#pragma unroll
+                for (int m = 0; m < AP; ++m) s[m] = make_float2(0.f, 0.f);
+            }
+        };
+        uint32_t ld = lead_of(tid), ld1 = lead_of(ANG_THREADS + tid), ld2 = 1u << 16;
+        uint32_t key1 = 0u;
+        snapshot(tid, key_of(tid, ld));
+        key1 = key_of(ANG_THREADS + tid, ld1);
+        for (int base = 0; base < n; base += ANG_THREADS) {
+            const int i = base + tid;
+            const bool valid = i < n;
+            const size_t o = (size_t)seg * p.seg_cap + (ld & 0xFFFFu);
+            const int mult = (int)(ld >> 16);
+            float yv = 0.f;
+            {
+                float rr0 = 0.f;
+                if (valid) yv = atan2f(s[1].y * s[0].x - s[1].x * s[0].y, s[1].x * s[0].x + s[1].y * s[0].y);
+#pragma unroll
+                for (int m = 0; m < AP; ++m) rr0 = fmaf(s[m].x, s[m].x, fmaf(s[m].y, s[m].y, rr0));
+                const float inv = rr0 > 0.f ? 1.f / rr0 : 0.f;       // |R_k| <= R_0: the normalised lags lie in [-1, 1]
+                float le[K], lo_[K];
+#pragma unroll
+                for (int k = 1; k < AP; ++k) {
+                    float xr = 0.f, xi = 0.f;
+#pragma unroll
+                    for (int m = 0; m + k < AP; ++m) {
+                        xr = fmaf(s[m + k].x, s[m].x, xr);
+                        xr = fmaf(s[m + k].y, s[m].y, xr);
+                        xi = fmaf(s[m + k].y, s[m].x, xi);
+                        xi = fmaf(-s[m + k].x, s[m].y, xi);
+                    }
+                    le[k - 1] = xr * inv;
+                    lo_[k - 1] = xi * inv;
+                    row[k - 1] = xi * inv;                            // the odd lags are needed again after the scan
+                }
+                le[K - 1] = 0.f;
+                lo_[K - 1] = 0.f;
+                // fp16 hi / lo split, packed along K, into this thread's rows of the E and O operands
+#pragma unroll
+                for (int part = 0; part < 2; ++part) {
+                    uint32_t hi[K / 2], lw[K / 2];
+#pragma unroll
+                    for (int j = 0; j < K / 2; ++j) {
+                        if (part == 0) split_f16x2(le[2 * j], le[2 * j + 1], hi[j], lw[j]);
+                        else split_f16x2(lo_[2 * j], lo_[2 * j + 1], hi[j], lw[j]);
+                    }
+                    unsigned char* A0 = At + part * A_CHUNKS * A_CHUNK + arow;
+                    if (AP == 8) {
+                        // chunk 0 = [hi(8) | lo(8)], chunk 1 = [hi(8) | 0]
+                        *reinterpret_cast<uint4*>(A0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                        *reinterpret_cast<uint4*>(A0 + 128) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                        *reinterpret_cast<uint4*>(A0 + A_CHUNK) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                        *reinterpret_cast<uint4*>(A0 + A_CHUNK + 128) = make_uint4(0u, 0u, 0u, 0u);
+                    } else {
+                        // chunk 0 = hi(16), chunk 1 = lo(16)
+                        constexpr int H = K / 2;
+                        *reinterpret_cast<uint4*>(A0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                        *reinterpret_cast<uint4*>(A0 + 128) = make_uint4(hi[4 % H], hi[5 % H], hi[6 % H], hi[7 % H]);
+                        *reinterpret_cast<uint4*>(A0 + A_CHUNK) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                        *reinterpret_cast<uint4*>(A0 + A_CHUNK + 128) = make_uint4(lw[4 % H], lw[5 % H], lw[6 % H], lw[7 % H]);
+                    }
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic writes of A -> the tensor core's async reads
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncthreads();                                             // A complete; both TMEM buffers drained by the last tile
+            if (tid == 0) {
+                issue_job(0);
+                if (njobs > 1) issue_job(1);
+            }
+            // the next tile's snapshot is requested now and consumed after this tile's scan: its latency hides under the tracking
+            snapshot(base + ANG_THREADS + tid, key1);
+            ld2 = lead_of(base + 2 * ANG_THREADS + tid);
+            Track tr[4] = {Track{NEG, NEG, 0}, Track{NEG, NEG, 0}, Track{NEG, NEG, 0}, Track{NEG, NEG, 0}};
+            for (int jb = 0; jb < njobs; ++jb) {
+                const int b = jb & 1;
+                {
+                    uint32_t ok = 0;
+                    const long long t0 = clock64();
+                    while (!ok) {
+                        asm volatile("{\n .reg .pred q;\n mbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\n selp.u32 %0, 1, 0, q;\n}"
+                                     : "=r"(ok) : "r"(s32(&mbar[b])), "r"(phase[b]) : "memory");
+                        if (!ok && clock64() - t0 > 4000000000ll) __trap();
+                    }
+                    phase[b] ^= 1u;
+                }
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t tb = trow + (uint32_t)(b * 2 * NPH);
+                // TMEM reads (64 B / clk / SM) are the scarce resource of this kernel: groups of 8 pairs, the loads of group
+                // g + 1 in flight while group g is tracked
+                float e[2][8], od[2][8];
+                ld8(tb, e[0]);
+                ld8(tb + (uint32_t)NPH, od[0]);
+#pragma unroll
+                for (int g = 0; g < NPH / 8; ++g) {
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (g + 1 < NPH / 8) {
+                        ld8(tb + (uint32_t)(8 * (g + 1)), e[(g + 1) & 1]);
+                        ld8(tb + (uint32_t)(NPH + 8 * (g + 1)), od[(g + 1) & 1]);
+                    }
+                    const int pb = jb * NPH + 8 * g;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float hi = e[g & 1][j] + fabsf(od[g & 1][j]);
+                        if (pb + j > last_pair) hi = NEG;
+                        track_max(tr[j & 3], hi, pb + j);
+                    }
+                }
+                if (jb + 2 < njobs) {
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncthreads();                                     // every thread has read buffer b
+                    if (tid == 0) issue_job(jb + 2);
+                }
+            }
+            // the four interleaved trackers of this cell
+            auto merge = [](Track& k, const Track& t) {
+                k.second = fmaxf(fmaxf(k.second, t.second), fminf(k.best, t.best));
+                if (t.best > k.best || (t.best == k.best && t.idx < k.idx)) { k.best = t.best; k.idx = t.idx; }
+            };
+            merge(tr[0], tr[1]);
+            merge(tr[2], tr[3]);
+            merge(tr[0], tr[2]);
+            float my_best = tr[0].best, my_second = tr[0].second;
+            const int my_pair = tr[0].idx;
+            if (valid) {
+                // which side of the pair won: sign of the odd part, re-evaluated with the fp32 table
+                const float* trow_t = p.scan_table + (size_t)my_pair * p.scan_stride;
+                float od = 0.f;
+#pragma unroll
+                for (int k = 1; k < AP; ++k) od = fmaf(row[k - 1], __ldg(trow_t + 2 * (k - 1) + 1), od);
+                const bool middle = odd && my_pair == half;             // the middle angle has no partner
+                const int bi = middle ? half : (od >= 0.f ? my_pair : G - 1 - my_pair);
+                if (!middle) my_second = fmaxf(my_second, my_best - 2.f * fabsf(od));   // the losing side of the winning pair
+                const float pnorm = 1.f + 2.f * my_best;
+                uint8_t flags = 0;
+                if (2.f * (my_best - my_second) <= p.tie_eps * fabsf(pnorm)) flags |= RS_FLAG_TIE;
+                if (p.method == RS_METHOD_MUSIC) {
+                    const float full = (float)M;
+                    if (full - pnorm <= 1e-4f * full) flags |= RS_FLAG_GUARD;
+                }
+                const int live = emit<true>(p, seg, i, o, mult, bi, p.grid_deg[bi], yv, flags);
+                if (ls_partials != nullptr) {
+                    const double c = grid_cs[2 * bi], sn = grid_cs[2 * bi + 1], y = (double)yv, w = (double)live;
+                    acc_ls[0] += w * c * c; acc_ls[1] += w * sn * sn; acc_ls[2] += w * c * sn;
+                    acc_ls[3] += w * y * c; acc_ls[4] += w * y * sn; acc_ls[5] += w * y * y; acc_ls[6] += w;
+                }
+            }
+            ld = ld1;
+            ld1 = ld2;
+            key1 = key_of(base + 2 * ANG_THREADS + tid, ld1);
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (wid == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    }
+    if (ls_partials == nullptr) return;
+#pragma unroll
+    for (int q = 0; q < 7; ++q) {
+#pragma unroll
+        for (int off = 16; off; off >>= 1) acc_ls[q] += __shfl_xor_sync(0xffffffffu, acc_ls[q], off);
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < 7; ++q) red[wid][q] = acc_ls[q];
+    }
+    __syncthreads();
+    if (threadIdx.x < 7) {
+        double t = 0;
+        for (int w = 0; w < ANG_THREADS / 32; ++w) t += red[w][threadIdx.x];
+        ls_partials[(size_t)seg * 8 + threadIdx.x] = t;
+    }
+}
+
 // ---- any A (used for A > 16): one warp evaluates one cell, lanes over antennas / grid points, snapshot in smem ----
 struct CellResult {
     int aidx;
@@ -863,7 +1197,8 @@ extern "C" int rs_angles(const void* rds, const float* scan_table, int scan_stri
                          int32_t* det_aidx,
                          float* det_adeg, float* det_phase, int seg_cap, int nseg_per_frame, int F, int R, int D, int A,
                          const double* grid_cs, double* ls_partials, int grid_symmetric, int32_t* det_ntie,
-                         int32_t* det_tielist, const float* mma_table, int mma_tiles, void* cell_ws, void* stream) {
+                         int32_t* det_tielist, const float* mma_table, int mma_tiles, void* cell_ws, const void* tc_table,
+                         int tc_halves, void* stream) {
     RS_CHECK_ARG(rds && det_key && det_lead && det_nlead && det_flags && det_aidx && det_adeg && det_phase,
                  "rs_angles: null pointer");
     RS_CHECK_ARG(ls_partials == nullptr || grid_cs != nullptr, "rs_angles: ls_partials needs grid_cs");
@@ -911,6 +1246,30 @@ extern "C" int rs_angles(const void* rds, const float* scan_table, int scan_stri
             angles_scan_kernel<AP, ND, false><<<(unsigned)blocks, ANG_THREADS, smem, st>>>(p, grid_cs, ls_partials);     \
         }                                                                                                                \
     } while (0)
+            // RS_ANGLES_TC: 1 / 0 force the tcgen05 / TMEM scan on / off.  Default: on for 9..16 antennas, where it beats the
+            // mma.sync scan (1.46 vs 1.67 ms per 300 frames of 256 x 128 x 16), off for 5..8 (1.56 vs 1.27 ms per 1000 frames of
+            // 256 x 128 x 8: there the TMEM read-out of 2 x 91 fp32 accumulators per cell at 64 B/clk/SM is what bounds it)
+            const char* tc_env = getenv("RS_ANGLES_TC");
+            const bool use_tc = tc_env ? atoi(tc_env) == 1 : ap == 16;
+            if (tc_table != nullptr && tc_halves > 0 && grid_symmetric && (ap == 8 || ap == 16) && use_tc) {
+                RS_CHECK_ARG(tc_halves == ((G + 1) / 2 + tc5::NPH - 1) / tc5::NPH, "rs_angles: tc_halves must be ceil(ceil(G/2)/32)");
+                const int kc = ap == 8 ? 2 : 3;
+                size_t sm = (size_t)tc_halves * 2 * kc * tc5::NPH * 32 + 2 * 2 * 128 * 32 + (size_t)128 * (ap + 1) * sizeof(float);
+                // at most four CTAs (4 x 128 TMEM columns) may be resident on an SM: pad the request so that a fifth never fits
+                const size_t floor4 = (size_t)rs_smem_optin_limit() / 5 + 1024;
+                if (sm < floor4) sm = floor4;
+                if (sm <= (size_t)rs_smem_optin_limit()) {
+                    if (ap == 8) {
+                        cudaFuncSetAttribute(angles_tc5_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+                        angles_tc5_kernel<8><<<(unsigned)blocks, ANG_THREADS, sm, st>>>(p, (const uint4*)tc_table, tc_halves, grid_cs, ls_partials);
+                    } else {
+                        cudaFuncSetAttribute(angles_tc5_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+                        angles_tc5_kernel<16><<<(unsigned)blocks, ANG_THREADS, sm, st>>>(p, (const uint4*)tc_table, tc_halves, grid_cs, ls_partials);
+                    }
+                    RS_CHECK_LAUNCH("rs_angles(tcgen05)");
+                    return RS_OK;
+                }
+            }
             const char* mma_env = getenv("RS_ANGLES_MMA");  // 0: force the CUDA-core scan
             if (mma_table != nullptr && grid_symmetric && (ap == 8 || ap == 16) && !(mma_env && atoi(mma_env) == 0)) {
                 RS_CHECK_ARG(mma_tiles == ((G + 1) / 2 + 7) / 8, "rs_angles: mma_tiles must be ceil(ceil(G/2)/8)");

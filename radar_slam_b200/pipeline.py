@@ -186,12 +186,14 @@ class FramePipeline:
             steer = tables.steering(grid, pos, c.lambda_c)
             symmetric = bool(np.array_equal(grid[::-1], -grid))
             mma, mma_tiles = (tables.scan_mma_table(scan, len(grid), A) if symmetric and 4 < A <= 16 else (None, 0))
+            tc, tc_halves = (tables.scan_tc_table(scan, len(grid), A) if symmetric and 4 < A <= 16 else (None, 0))
             self._tab[key] = {
                 "grid": grid, "G": len(grid), "stride": stride,
                 "scan": self._dev(scan), "grid_f32": self._dev(grid.astype(np.float32)),
                 "steer64": self._dev(steer.astype(np.complex64)) if A > 16 else None,
                 "steer128": self._dev(steer), "grid_cs": self._dev(tables.grid_cos_sin(grid)),
                 "symmetric": symmetric, "mma": self._dev(mma) if mma is not None else None, "mma_tiles": mma_tiles,
+                "tc": self._dev(tc) if tc is not None else None, "tc_halves": tc_halves,
             }
         return self._tab[key]
 
@@ -291,7 +293,7 @@ class FramePipeline:
             t["grid_cs"].data_ptr(), _lib.ptr(det.ls_partials), int(t["symmetric"]), det.ntie.data_ptr(), det.tielist.data_ptr(),
             _lib.ptr(t["mma"]), t["mma_tiles"],
             self._buf("cell_ws" + det.tag, (17 * det.F * det.R * det.D + 16,), torch.uint8).data_ptr() if det.A > 16 else 0,
-            self.stream)
+            _lib.ptr(t["tc"]), t["tc_halves"], self.stream)
         return det
 
     def velocity(self, det: Detections, out: Optional[torch.Tensor] = None, lambda_c: Optional[float] = None,

@@ -117,6 +117,41 @@ def scan_mma_table(scan: np.ndarray, G: int, A: int) -> Tuple[np.ndarray, int]:
     return out.reshape(-1).view(np.float32), nt
 
 
+def scan_tc_table(scan: np.ndarray, G: int, A: int, pairs_per_half: int = 32) -> Tuple[np.ndarray, int]:
+    """B operands of the tcgen05 angle scan (csrc/rs_angles.cu, angles_tc5_kernel) for a grid symmetric about 0.
+    Grid pairs (g, G-1-g) are cut into jobs of 32 (the UMMA N).  Per job: the cos table then the sin table, each as KC
+    chunks of [32 pairs x 16 K-slots] fp16 in the canonical K-major no-swizzle UMMA layout -- element (n, k) at byte
+    (n // 8) * 256 + (k // 8) * 128 + (n % 8) * 16 + (k % 8) * 2.  K packing of the hi / lo split (x = hi + lo, both fp16):
+        A <= 8 : chunk 0 = [hi(8) | hi(8)] (against A = [a_hi | a_lo]), chunk 1 = [lo(8) | 0] (against [a_hi | 0])
+        A <= 16: chunk 0 = hi(16) (against a_hi), chunk 1 = hi(16) (against a_lo), chunk 2 = lo(16) (against a_hi)
+    K-slot j holds lag j + 1; the last slot is zero.  Returns (uint8 bytes, number of halves)."""
+    ap = padded_antennas(A)
+    assert ap in (8, 16)
+    npairs = (G + 1) // 2
+    nh = (npairs + pairs_per_half - 1) // pairs_per_half
+    kc = 2 if ap == 8 else 3
+    T = np.zeros((2, ap, nh * pairs_per_half), dtype=np.float32)         # [cos / sin][slot][pair]
+    for k in range(ap - 1):
+        T[0, k, :npairs] = scan[:npairs, 2 * k]
+        T[1, k, :npairs] = scan[:npairs, 2 * k + 1]
+    hi, lo = f16_split(T)
+    out = np.zeros((nh, 2, kc, pairs_per_half * 16), dtype=np.float16)
+    n = np.arange(pairs_per_half)
+    for h in range(nh):
+        cols = h * pairs_per_half + n
+        for part in range(2):
+            if ap == 8:
+                chunks = [np.concatenate([hi[part, :, cols].T, hi[part, :, cols].T], axis=0),       # [16 slots][48]
+                          np.concatenate([lo[part, :, cols].T, np.zeros((8, pairs_per_half), np.float16)], axis=0)]
+            else:
+                chunks = [hi[part, :, cols].T, hi[part, :, cols].T, lo[part, :, cols].T]
+            for c, ch in enumerate(chunks):
+                for k in range(16):
+                    off = (n // 8) * 128 + (k // 8) * 64 + (n % 8) * 8 + (k % 8)                      # in fp16 elements
+                    out[h, part, c, off] = ch[k]
+    return out.reshape(-1).view(np.uint8), nh
+
+
 def grid_cos_sin(grid_deg: np.ndarray) -> np.ndarray:
     """(cos, sin) of np.radians(grid) -- what velocity_solver.py:94-97 evaluates per target. f64 [G][2]."""
     az = np.radians(grid_deg)

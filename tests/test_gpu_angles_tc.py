@@ -1,0 +1,55 @@
+"""The tcgen05 / TMEM angle scan (csrc/rs_angles.cu: angles_tc5_kernel, RS_ANGLES_TC) against the oracle and against the
+mma.sync scan: same flag contract (every disagreement with the oracle's argmax carries RS_FLAG_TIE / RS_FLAG_GUARD),
+identical results after the fp64 recheck."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import radar_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(cube, A, method, tc, recheck, monkeypatch, res=1.0, thr=-20.0):
+    from radar_slam_b200 import RadarConfig, FramePipeline
+    monkeypatch.setenv("RS_ANGLES_TC", tc)
+    cfg = RadarConfig(chirp_duration=25.6e-6, num_chirps=128, num_antennas=A, search_resolution=res, method=method,
+                      threshold_db=thr, recheck=recheck)
+    pipe = FramePipeline(cfg)
+    vel, rds, det = pipe.process(torch.from_numpy(cube).cuda(), keep=True)
+    torch.cuda.synchronize()
+    return pipe, vel.cpu().numpy(), [det.frame(f) for f in range(cube.shape[0])]
+
+
+@pytest.mark.parametrize("A,method,res", [(8, "music", 1.0), (16, "music", 1.0), (8, "beamforming", 0.5), (6, "music", 2.0)])
+def test_tcgen05_scan_matches_oracle_and_mma(monkeypatch, A, method, res):
+    p = orc.RadarParams(chirp_duration=25.6e-6, num_chirps=128, num_antennas=A)
+    scene = np.array([(8.0, 0.0, -10.0, 0.0), (12.0, 0.5, -8.0, 0.0), (25.0, -0.7, 0.0, 0.0), (17.0, 1.2, -4.0, 0.0)])
+    np.random.seed(40 + A)
+    cube = np.stack([orc.synthesize_frame(p, scene) for _ in range(2)]).astype(np.complex64)
+    grid = orc.azimuth_grid((-90, 90), res)
+    steer = orc.steering_matrix(grid, p.antenna_positions, p.lambda_c)
+    # fp32 kernels only: flag contract
+    _, _, tc = _run(cube, A, method, "1", False, monkeypatch, res)
+    _, _, mma = _run(cube, A, method, "0", False, monkeypatch, res)
+    for f in range(2):
+        ref = orc.range_doppler_spectrum(cube[f].astype(np.complex128), p)
+        assert np.array_equal(tc[f]["key"], mma[f]["key"])
+        rb, db = tc[f]["range_bin"], tc[f]["doppler_bin"]
+        sigs = orc.spatial_signatures(ref, rb, db)
+        idx, _ = orc.argmax_angles(orc.beamforming_spectra(sigs, steer) if method == "beamforming"
+                                   else orc.music_spectra(sigs, steer), grid)
+        for got in (tc[f], mma[f]):
+            bad = got["aidx"] != idx
+            assert np.all(got["flags"][bad] & 5), "unflagged angle mismatch"
+            assert bad.mean() < 0.02
+        # the two scans evaluate the same products (fp16 hi / lo split, fp32 accumulation): they agree outside flagged cells
+        diff = tc[f]["aidx"] != mma[f]["aidx"]
+        assert np.all((tc[f]["flags"][diff] | mma[f]["flags"][diff]) & 5)
+        assert np.allclose(tc[f]["phase"], mma[f]["phase"])
+    # with the fp64 recheck both are exact, hence identical, and so are the velocities
+    _, v_tc, tc = _run(cube, A, method, "1", True, monkeypatch, res)
+    _, v_mma, mma = _run(cube, A, method, "0", True, monkeypatch, res)
+    for f in range(2):
+        assert np.array_equal(tc[f]["aidx"], mma[f]["aidx"])
+    assert np.abs(v_tc[:, :2] - v_mma[:, :2]).max() < 1e-9
