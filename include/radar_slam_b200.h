@@ -150,9 +150,11 @@ int rs_angles(const void* rds, const float* scan_table, int scan_stride, const v
               const float* mma_table, int mma_tiles, void* cell_ws, const void* tc_table, int tc_halves, void* stream);
 
 /* (d')  the velocity solve of rs_velocity_ls from the per-segment sums rs_angles already produced
- *       (no second pass over the detection lists); same output row layout. */
+ *       (no second pass over the detection lists); same output row layout.  det_overflow (int32 [F], may be NULL): frames
+ *       whose detection segments overflowed in rs_detect report success = 0 (their row holds the solution of the
+ *       truncated list). */
 int rs_velocity_from_partials(const double* ls_partials, int nseg_per_frame, int F, double k_phase, double bound,
-                              double* vel, void* stream);
+                              const int32_t* det_overflow, double* vel, void* stream);
 
 /* (d'')  the per-segment sums of rs_velocity_from_partials from the detection lists (for what rs_angles does not fuse:
  *       ESPRIT, A > 16): ls_partials double [F*nseg_per_frame][8], one CTA per segment, deterministic.
@@ -289,6 +291,21 @@ int rs_velocity_ls6(const double* pos, const double* ang, const double* y, int n
  * clipped to [0, 1].  positions double [A] (metres). */
 int rs_robust_confidence_f64(const void* sig128, const double* angle_deg, const double* positions,
                              double lambda_c, int n, int A, double* out, void* stream);
+
+/* (f3)  AdvancedVelocityOptimizer.compute_regularized_cost_function (advanced_velocity_optimization.py:153-223) for nq
+ *       candidate motions params double [nq][6]: wrapped residual sum of squares + the five regularisers (speed above
+ *       0.8 max_velocity, rotation rate above 0.8 max_angular_velocity, change against previous_motion (double [6], may be
+ *       NULL), the large-speed / large-rate product, vertical velocity), fp64.  cost double [nq]. */
+int rs_regularized_cost(const double* params, const double* pos, const double* ang, const double* y, int n, int nq,
+                        double k_phase, double max_velocity, double max_angular_velocity, double weight,
+                        const double* previous_motion, double* cost, void* stream);
+
+/* (f3)  Gauss-Newton polish of nq starting points v_xy double [nq][2] inside their basins of
+ *       sum_i wrap(y_i - k (v_x cos az_i + v_y sin az_i))^2 + reg |v - centre|^2, clipped to the box; v_xy is updated in
+ *       place, cost double [nq] receives the value of that function at the result. */
+int rs_wrapped_gn_polish(const double* cos_az, const double* sin_az, const double* y, int n, double k_phase, double reg,
+                         double centre_x, double centre_y, double lo_x, double hi_x, double lo_y, double hi_y, double* v_xy,
+                         double* cost, int nq, int iters, void* stream);
 
 /* (f3)  ImprovedVelocitySolver (src/algorithms/velocity_solver_improved.py), inter-frame ego-velocity.
  *   rs_associate_targets: associate_targets_across_frames (:74-129) for `pairs` frame pairs.  cur_xy double

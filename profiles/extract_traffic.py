@@ -7,10 +7,11 @@ import json
 import subprocess
 import sys
 
-STAGE = {"recheck_detect": "rs_recheck_detections_f64", "fft2d_cluster": "rs_range_doppler_fft", "range_fft": "rs_range_fft",
+STAGE = {"recheck_detect": "rs_recheck_detections_f64", "range_fft": "rs_range_fft",
          "doppler_fft": "rs_doppler_fft", "detect_a8": "rs_detect", "detect_kernel": "rs_detect", "angles_": "rs_angles",
          "velocity_from": "rs_velocity_from_partials"}
 RECHECK_PARTS = ("recheck_angles", "recheck_snapshots", "recheck_finish")
+K12_PARTS = ("fft2d_ws", "fft2d_cluster")        # one rs_range_doppler_fft call = persistent cluster kernel + side kernel
 MULT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 
 
@@ -21,9 +22,13 @@ def main():
     hdr, units = rows[0], rows[1]
     ki, rd, wr, gi = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("launch__grid_size")
     num = lambda x: float(x.replace(",", ""))
-    acc, parts = {}, {}
+    acc, parts, k12 = {}, {}, {}
     for r in rows[2:]:
         b = num(r[rd]) * MULT[units[rd]] + num(r[wr]) * MULT[units[wr]]
+        hit12 = [k for k in K12_PARTS if k in r[ki]]
+        if hit12:
+            k12.setdefault(hit12[0], []).append(b)
+            continue
         hit = [k for k in RECHECK_PARTS if k in r[ki]]
         if hit:
             nm = r[ki]
@@ -35,6 +40,8 @@ def main():
                 acc.setdefault(v, []).append(b)
                 break
     per_frame = {k: sum(v) / len(v) / frames for k, v in acc.items()}
+    if k12:
+        per_frame["rs_range_doppler_fft"] = sum(sum(v) / len(v) for v in k12.values()) / frames
     if parts:
         per_frame["rs_recheck_angles_f64"] = sum(sum(v) / len(v) for v in parts.values()) / frames
     json.dump({"source": f"{d}/prof.ncu-rep (ncu --set full --clock-control none): dram__bytes_read.sum + dram__bytes_write.sum "

@@ -31,7 +31,7 @@ _SIGNATURES = {
     "rs_angles": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _f, _d, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                        _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _i, _vp]),
     "rs_velocity_partials": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
-    "rs_velocity_from_partials": (_i, [_vp, _i, _i, _d, _d, _vp, _vp]),
+    "rs_velocity_from_partials": (_i, [_vp, _i, _i, _d, _d, _vp, _vp, _vp]),
     "rs_music_covariance": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "rs_recheck_detections_f64": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _d, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i,
                                        _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -52,6 +52,8 @@ _SIGNATURES = {
     "rs_velocity_ls6": (_i, [_vp, _vp, _vp, _i, _d, _vp, _vp, _i, _vp, _vp, _vp]),
     "rs_associate_targets": (_i, [_vp, _vp, _vp, _vp, _d, _vp, _vp, _i, _i, _i, _vp]),
     "rs_wrapped_cost": (_i, [_vp, _vp, _vp, _vp, _i, _i, _d, _d, _d, _vp, _vp]),
+    "rs_regularized_cost": (_i, [_vp, _vp, _vp, _vp, _i, _i, _d, _d, _d, _d, _vp, _vp, _vp]),
+    "rs_wrapped_gn_polish": (_i, [_vp, _vp, _vp, _i, _d, _d, _d, _d, _d, _d, _d, _d, _vp, _vp, _i, _i, _vp]),
     "rs_wrapped_lattice_tiles": (_i, [C.c_longlong, C.c_longlong, C.POINTER(_i), C.POINTER(_i)]),
     "rs_wrapped_lattice_search": (_i, [_vp, _vp, _vp, _i, _d, _d, _d, C.c_longlong, C.c_longlong, _d, _vp, _vp, _vp, _vp]),
     "rs_synthesize_frames": (_i, [_vp, _vp, _i, _d, _d, _d, _d, _vp, _d, C.c_ulonglong, C.c_longlong, _vp, _vp,

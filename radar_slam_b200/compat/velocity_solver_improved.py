@@ -7,8 +7,8 @@ residual to (-pi, pi] while the model's phase slope is 4 pi dt / lambda (322 rad
 cost has a local minimum every ~2 cm/s per target direction over a +-50 m/s box, and `differential_evolution(seed=42)`
 (velocity_solver_improved.py:389-420) returns whichever of them its population happens to reach (scipy-version
 dependent).  two_step_optimization here searches the whole box on a lattice finer than a basin
-(rs_wrapped_lattice_search, ~1e9 points on the GPU), polishes the best tiles in fp64 inside their basins and returns the
-global minimiser; its cost is <= the cost of the reference's answer (tests/test_gpu_interframe.py checks that against a
+(rs_wrapped_lattice_search, ~1e9 points on the GPU), polishes the best tiles in fp64 inside their basins
+(rs_wrapped_gn_polish, Gauss-Newton on the device) and returns the global minimiser; its cost is <= the cost of the reference's answer (tests/test_gpu_interframe.py checks that against a
 committed run of the reference's own class).  v_z and w do not enter the reference's planar model (elevation 0,
 position = range * direction) and are returned as 0, which is where the regulariser puts them.
 """
@@ -25,6 +25,40 @@ from . import _device
 from .lazy import LazyRecords, column_of, records_of
 
 logger = logging.getLogger(__name__)
+
+
+def wrapped_global_search(dev, c: np.ndarray, s: np.ndarray, y: np.ndarray, k: float, bounds, reg_lattice: float,
+                          reg_polish: float, centre, points_per_period: float = 6.0, polish_candidates: int = 48):
+    """Global search of  sum_i wrap(y_i - k (v_x c_i + v_y s_i))^2 (+ reg |v - centre|^2)  over a (v_x, v_y) box, all on the
+    device: rs_wrapped_lattice_search evaluates the cost on a lattice finer than a basin (step 2 pi / (k points_per_period))
+    and keeps the best point of every tile; the `polish_candidates` best tiles are refined inside their basins by
+    rs_wrapped_gn_polish (fp64 Gauss-Newton).  Returns (candidates [K, 2], their polished costs [K], lattice points)."""
+    lib = _lib.load()
+    (x_lo, x_hi), (y_lo, y_hi) = bounds
+    x_lo, x_hi, y_lo, y_hi = float(x_lo), float(x_hi), float(y_lo), float(y_hi)
+    h = 2 * np.pi / abs(k) / points_per_period
+    nx, ny = int(np.floor((x_hi - x_lo) / h)) + 1, int(np.floor((y_hi - y_lo) / h)) + 1
+    tx, ty = _lib.C.c_int(), _lib.C.c_int()
+    _lib.check(lib.rs_wrapped_lattice_tiles(nx, ny, _lib.C.byref(tx), _lib.C.byref(ty)), "rs_wrapped_lattice_tiles")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(dev)      # noqa: E731
+    st = torch.cuda.current_stream(dev).cuda_stream
+    ax, by, yc = t(k * c / (2 * np.pi)), t(k * s / (2 * np.pi)), t(y / (2 * np.pi))
+    ntile = tx.value * ty.value
+    tc = torch.empty(ntile, dtype=torch.float32, device=dev)
+    tix = torch.empty(ntile, dtype=torch.int32, device=dev)
+    tiy = torch.empty(ntile, dtype=torch.int32, device=dev)
+    _lib.check(lib.rs_wrapped_lattice_search(ax.data_ptr(), by.data_ptr(), yc.data_ptr(), len(y), x_lo, y_lo, h, nx, ny,
+                                             float(reg_lattice), tc.data_ptr(), tix.data_ptr(), tiy.data_ptr(), st),
+               "rs_wrapped_lattice_search")
+    kbest = min(polish_candidates, ntile)
+    _, idx = torch.topk(tc, kbest, largest=False)
+    v = torch.stack([x_lo + tix[idx].double() * h, y_lo + tiy[idx].double() * h], dim=1).contiguous()
+    cost = torch.empty(kbest, dtype=torch.float64, device=dev)
+    cd, sd, yd = t(c), t(s), t(y)
+    _lib.check(lib.rs_wrapped_gn_polish(cd.data_ptr(), sd.data_ptr(), yd.data_ptr(), len(y), float(k), float(reg_polish),
+                                        float(centre[0]), float(centre[1]), x_lo, x_hi, y_lo, y_hi, v.data_ptr(),
+                                        cost.data_ptr(), kbest, 20, st), "rs_wrapped_gn_polish")
+    return v.cpu().numpy(), cost.cpu().numpy(), int(nx) * int(ny)
 
 
 class _Result(dict):
@@ -137,45 +171,12 @@ class ImprovedVelocitySolver:
     # ---- the optimiser
     def _global_search(self, c: np.ndarray, s: np.ndarray, y: np.ndarray, k: float):
         """Global minimiser of sum wrap(y - k (vx c + vy s))^2 + 0.01 (vx^2 + vy^2) over the velocity box."""
-        dev = self._device()
-        lib = _lib.load()
-        (x_lo, x_hi), (y_lo, y_hi) = self.velocity_bounds
-        h = 2 * np.pi / abs(k) / self.lattice_points_per_period
-        nx, ny = int(np.floor((x_hi - x_lo) / h)) + 1, int(np.floor((y_hi - y_lo) / h)) + 1
-        tx, ty = _lib.C.c_int(), _lib.C.c_int()
-        _lib.check(lib.rs_wrapped_lattice_tiles(nx, ny, _lib.C.byref(tx), _lib.C.byref(ty)), "rs_wrapped_lattice_tiles")
-        t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(dev)      # noqa: E731
-        ax, by, yc = t(k * c / (2 * np.pi)), t(k * s / (2 * np.pi)), t(y / (2 * np.pi))
-        ntile = tx.value * ty.value
-        tc = torch.empty(ntile, dtype=torch.float32, device=dev)
-        tix = torch.empty(ntile, dtype=torch.int32, device=dev)
-        tiy = torch.empty(ntile, dtype=torch.int32, device=dev)
-        _lib.check(lib.rs_wrapped_lattice_search(ax.data_ptr(), by.data_ptr(), yc.data_ptr(), len(y), x_lo, y_lo, h, nx, ny,
-                                                 0.01, tc.data_ptr(), tix.data_ptr(), tiy.data_ptr(),
-                                                 torch.cuda.current_stream(dev).cuda_stream), "rs_wrapped_lattice_search")
-        kbest = min(self.polish_candidates, ntile)
-        vals, idx = torch.topk(tc, kbest, largest=False)
-        ix, iy = tix[idx].cpu().numpy().astype(float), tiy[idx].cpu().numpy().astype(float)
-        cand = np.stack([x_lo + ix * h, y_lo + iy * h], axis=1)
-        # fp64 Gauss-Newton inside each candidate's basin (the wrapped residual is linear in v there)
-        lo, hi = np.array([x_lo, y_lo]), np.array([x_hi, y_hi])
-        G = k * np.stack([c, s], axis=1)                                         # [N, 2]
-        H = G.T @ G + 0.01 * np.eye(2)
-        best_v, best_f = None, np.inf
-        for v in cand:
-            for _ in range(20):
-                r = y - G @ v
-                r = np.arctan2(np.sin(r), np.cos(r))
-                step = np.linalg.solve(H, G.T @ r - 0.01 * v)
-                v = np.clip(v + step, lo, hi)
-                if np.abs(step).max() < 1e-13:
-                    break
-            r = y - G @ v
-            r = np.arctan2(np.sin(r), np.cos(r))
-            f = float(np.sum(r ** 2) + 0.01 * np.sum(v ** 2))
-            if f < best_f:
-                best_f, best_v = f, v
-        return best_v, best_f, int(nx) * int(ny)
+        cand, cost, npts = wrapped_global_search(self._device(), c, s, y, k, self.velocity_bounds, reg_lattice=0.01,
+                                                 reg_polish=0.01, centre=(0.0, 0.0),
+                                                 points_per_period=self.lattice_points_per_period,
+                                                 polish_candidates=self.polish_candidates)
+        b = int(np.argmin(cost))
+        return cand[b], float(cost[b]), npts
 
     def two_step_optimization(self, target_associations: List[Dict], dt: float,
                               initial_guess: Optional[np.ndarray] = None) -> Dict:

@@ -1170,6 +1170,9 @@ __global__ void spectra_f64_kernel(const double2* __restrict__ sig, const double
             v = den > 1e-12 ? 1.0 / den : 0.0;
         }
         out[(size_t)i * G + g] = v;
+        // np.argmax (angle_estimation.py:173): a NaN is the maximum, the first NaN wins -- encoded as +inf here, where
+        // the lowest index already wins ties
+        if (v != v) v = INFINITY;
         if (v > best) { best = v; bi = g; }
     }
     red_v[threadIdx.x] = best;
@@ -1186,7 +1189,7 @@ __global__ void spectra_f64_kernel(const double2* __restrict__ sig, const double
         }
         __syncthreads();
     }
-    if (threadIdx.x == 0) aidx[i] = red_i[0];
+    if (threadIdx.x == 0) aidx[i] = red_i[0] < G ? red_i[0] : 0;
 }
 
 }  // namespace

@@ -101,6 +101,99 @@ wrapped_cost_kernel(const double* __restrict__ params, const double* __restrict_
         cost[q] = acc + reg_v * (vx * vx + vy * vy + vz * vz) + reg_w * (wx * wx + wy * wy + wz * wz);   // :255-260
 }
 
+// ---- AdvancedVelocityOptimizer.compute_regularized_cost_function (advanced_velocity_optimization.py:153-223) ----------
+// wrapped residual sum + five regularisers, fp64, one warp per candidate motion
+__global__ void __launch_bounds__(IF_THREADS)
+regularized_cost_kernel(const double* __restrict__ params, const double* __restrict__ pos, const double* __restrict__ ang,
+                        const double* __restrict__ y, double k_phase, double max_v, double max_w, double weight,
+                        const double* __restrict__ previous, double* __restrict__ cost, int n, int nq) {
+    const int q = blockIdx.x * (IF_THREADS / 32) + (threadIdx.x >> 5);
+    if (q >= nq) return;
+    const int lane = threadIdx.x & 31;
+    const double* m = params + (size_t)q * 6;
+    const double vx = m[0], vy = m[1], vz = m[2], wx = m[3], wy = m[4], wz = m[5];
+    double acc = 0;
+    for (int i = lane; i < n; i += 32) {
+        const double px = pos[3 * i], py = pos[3 * i + 1], pz = pos[3 * i + 2];
+        const double az = ang[2 * i], el = ang[2 * i + 1];
+        const double dx = cos(el) * cos(az), dy = cos(el) * sin(az), dz = sin(el);       // :239-243
+        const double rx = vx + (wy * pz - wz * py), ry = vy + (wz * px - wx * pz), rz = vz + (wx * py - wy * px);   // :246-247
+        const double pred = k_phase * (rx * dx + ry * dy + rz * dz);                      // :253
+        const double r = y[i] - pred;
+        const double wr = atan2(sin(r), cos(r));                                          // :185
+        acc += wr * wr;
+    }
+#pragma unroll
+    for (int off = 16; off; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (lane == 0) {
+        double reg = 0;
+        const double vm = sqrt(vx * vx + vy * vy + vz * vz), wm = sqrt(wx * wx + wy * wy + wz * wz);
+        if (vm > max_v * 0.8) reg += weight * (vm - max_v * 0.8) * (vm - max_v * 0.8);     // 1. speed           :194-196
+        if (wm > max_w * 0.8) reg += weight * (wm - max_w * 0.8) * (wm - max_w * 0.8);     // 2. rotation rate   :199-201
+        if (previous != nullptr) {                                                        // 3. temporal        :204-207
+            double t = 0;
+            for (int j = 0; j < 6; ++j) t += (m[j] - previous[j]) * (m[j] - previous[j]);
+            reg += weight * 0.1 * t;
+        }
+        if (vm > 20 && wm > 5) reg += weight * 0.01 * (vm - 20) * (wm - 5);               // 4. combination     :211-213
+        reg += weight * 10.0 * vz * vz;                                                   // 5. vertical motion :216-217
+        cost[q] = acc + reg;
+    }
+}
+
+// ---- Gauss-Newton polish inside a basin of the wrapped cost -------------------------------------------------------------
+// minimise  sum_i wrap(y_i - k (v_x c_i + v_y s_i))^2 + reg |v - centre|^2  from a batch of starting points: inside a
+// basin the wrapped residual is linear in v, so the normal matrix H = G^T G + reg I is constant.  One warp per start.
+__global__ void __launch_bounds__(IF_THREADS)
+gn_polish_kernel(const double* __restrict__ c, const double* __restrict__ s, const double* __restrict__ y, int n, double k,
+                 double reg, double cx, double cy, double lo_x, double hi_x, double lo_y, double hi_y,
+                 double* __restrict__ v, double* __restrict__ cost, int nq, int iters) {
+    const int q = blockIdx.x * (IF_THREADS / 32) + (threadIdx.x >> 5);
+    if (q >= nq) return;
+    const int lane = threadIdx.x & 31;
+    double hxx = 0, hxy = 0, hyy = 0;
+    for (int i = lane; i < n; i += 32) {
+        const double gx = k * c[i], gy = k * s[i];
+        hxx += gx * gx; hxy += gx * gy; hyy += gy * gy;
+    }
+#pragma unroll
+    for (int off = 16; off; off >>= 1) {
+        hxx += __shfl_xor_sync(0xffffffffu, hxx, off);
+        hxy += __shfl_xor_sync(0xffffffffu, hxy, off);
+        hyy += __shfl_xor_sync(0xffffffffu, hyy, off);
+    }
+    hxx += reg; hyy += reg;
+    double det = hxx * hyy - hxy * hxy;
+    if (!(fabs(det) > 1e-300)) det = 1e-300;
+    double vx = v[2 * q], vy = v[2 * q + 1];
+    double f = 0;
+    for (int it = 0; it <= iters; ++it) {
+        double gx = 0, gy = 0;
+        f = 0;
+        for (int i = lane; i < n; i += 32) {
+            const double r0 = y[i] - k * (vx * c[i] + vy * s[i]);
+            const double r = atan2(sin(r0), cos(r0));
+            gx += k * c[i] * r; gy += k * s[i] * r;
+            f += r * r;
+        }
+#pragma unroll
+        for (int off = 16; off; off >>= 1) {
+            gx += __shfl_xor_sync(0xffffffffu, gx, off);
+            gy += __shfl_xor_sync(0xffffffffu, gy, off);
+            f += __shfl_xor_sync(0xffffffffu, f, off);
+        }
+        f += reg * ((vx - cx) * (vx - cx) + (vy - cy) * (vy - cy));
+        if (it == iters) break;
+        gx -= reg * (vx - cx);
+        gy -= reg * (vy - cy);
+        const double sx = (hyy * gx - hxy * gy) / det, sy = (hxx * gy - hxy * gx) / det;
+        vx = fmin(hi_x, fmax(lo_x, vx + sx));
+        vy = fmin(hi_y, fmax(lo_y, vy + sy));
+        if (fmax(fabs(sx), fabs(sy)) < 1e-13) iters = it + 1;       // converged: one more pass evaluates the cost
+    }
+    if (lane == 0) { v[2 * q] = vx; v[2 * q + 1] = vy; cost[q] = f; }
+}
+
 // ---- lattice search ----------------------------------------------------------------------------------------------
 constexpr int LS_L = 32;          // consecutive v_x points per thread
 constexpr int LS_ROWS = 8;        // v_y rows per CTA (one warp each)
@@ -192,6 +285,28 @@ extern "C" int rs_wrapped_cost(const double* params, const double* pos, const do
     wrapped_cost_kernel<<<(nq + wpb - 1) / wpb, IF_THREADS, 0, (cudaStream_t)stream>>>(params, pos, ang, y, k_phase, reg_v,
                                                                                       reg_w, cost, n, nq);
     RS_CHECK_LAUNCH("rs_wrapped_cost");
+    return RS_OK;
+}
+
+extern "C" int rs_regularized_cost(const double* params, const double* pos, const double* ang, const double* y, int n, int nq,
+                                   double k_phase, double max_velocity, double max_angular_velocity, double weight,
+                                   const double* previous_motion, double* cost, void* stream) {
+    RS_CHECK_ARG(params && pos && ang && y && cost && n >= 0 && nq > 0, "rs_regularized_cost: bad args");
+    const int wpb = IF_THREADS / 32;
+    regularized_cost_kernel<<<(nq + wpb - 1) / wpb, IF_THREADS, 0, (cudaStream_t)stream>>>(
+        params, pos, ang, y, k_phase, max_velocity, max_angular_velocity, weight, previous_motion, cost, n, nq);
+    RS_CHECK_LAUNCH("rs_regularized_cost");
+    return RS_OK;
+}
+
+extern "C" int rs_wrapped_gn_polish(const double* cos_az, const double* sin_az, const double* y, int n, double k_phase,
+                                    double reg, double centre_x, double centre_y, double lo_x, double hi_x, double lo_y,
+                                    double hi_y, double* v_xy, double* cost, int nq, int iters, void* stream) {
+    RS_CHECK_ARG(cos_az && sin_az && y && v_xy && cost && n > 0 && nq > 0 && iters >= 0 && reg >= 0, "rs_wrapped_gn_polish: bad args");
+    const int wpb = IF_THREADS / 32;
+    gn_polish_kernel<<<(nq + wpb - 1) / wpb, IF_THREADS, 0, (cudaStream_t)stream>>>(
+        cos_az, sin_az, y, n, k_phase, reg, centre_x, centre_y, lo_x, hi_x, lo_y, hi_y, v_xy, cost, nq, iters);
+    RS_CHECK_LAUNCH("rs_wrapped_gn_polish");
     return RS_OK;
 }
 

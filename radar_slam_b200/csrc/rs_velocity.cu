@@ -159,7 +159,7 @@ velocity_partials_kernel(const int32_t* __restrict__ det_aidx, const float* __re
 // (lane-strided, then a fixed shuffle tree: deterministic) and solve.
 __global__ void __launch_bounds__(128)
 velocity_from_partials_kernel(const double* __restrict__ partials, int nseg, int F, double kph, double bound,
-                              double* __restrict__ vel) {
+                              const int32_t* __restrict__ overflow, double* __restrict__ vel) {
     const int lane = threadIdx.x & 31;
     const int f = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (f >= F) return;
@@ -180,17 +180,20 @@ velocity_from_partials_kernel(const double* __restrict__ partials, int nseg, int
         if (ok) box_ls(kph * kph * s[0], kph * kph * s[1], kph * kph * s[2], kph * s[3], kph * s[4], bound, &vx, &vy);
         double* o = vel + (size_t)f * 8;
         o[0] = vx; o[1] = vy; o[2] = 0.0; o[3] = 0.0; o[4] = 0.0; o[5] = 0.0;
-        o[6] = ok ? 1.0 : 0.0; o[7] = s[6];
+        // a frame whose detection segments overflowed (rs_detect: det_overflow) was solved from a truncated list: the row
+        // carries the best-effort solution but reports failure, so no caller can mistake it for the full answer
+        const bool complete = overflow == nullptr || overflow[f] == 0;
+        o[6] = (ok && complete) ? 1.0 : 0.0; o[7] = s[6];
     }
 }
 
 }  // namespace
 
 extern "C" int rs_velocity_from_partials(const double* ls_partials, int nseg_per_frame, int F, double k_phase,
-                                         double bound, double* vel, void* stream) {
+                                         double bound, const int32_t* det_overflow, double* vel, void* stream) {
     RS_CHECK_ARG(ls_partials && vel && nseg_per_frame > 0 && F > 0 && bound > 0, "rs_velocity_from_partials: bad args");
     velocity_from_partials_kernel<<<(F + 3) / 4, 128, 0, (cudaStream_t)stream>>>(ls_partials, nseg_per_frame, F, k_phase,
-                                                                              bound, vel);
+                                                                              bound, det_overflow, vel);
     RS_CHECK_LAUNCH("rs_velocity_from_partials");
     return RS_OK;
 }

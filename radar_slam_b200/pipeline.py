@@ -254,6 +254,8 @@ class FramePipeline:
         cap, ntiles = self.seg_cap_for(R, D, A)
         n = F * ntiles * cap
         tag = workspace if isinstance(workspace, str) else ""      # "0" / "1": double-buffered workspaces
+        if workspace:
+            self._ws["_nframes" + tag] = F                          # status(): how much of the overflow buffer is current
         alloc = (lambda nm, shp, dt: self._buf(nm + tag, shp, dt)) if workspace else \
             (lambda nm, shp, dt: torch.empty(shp, dtype=dt, device=self.device))
         det = Detections(
@@ -307,7 +309,7 @@ class FramePipeline:
         assert vel.is_contiguous() and vel.dtype == torch.float64
         if det.ls_partials is not None and use_grid and c.irls_iters == 0:
             self._call("rs_velocity_from_partials", det.ls_partials.data_ptr(), det.ntiles, det.F, k, c.velocity_bound,
-                       vel.data_ptr(), self.stream)
+                       det.overflow.data_ptr(), vel.data_ptr(), self.stream)
             return vel
         if c.irls_iters == 0:
             # sums per segment on all SMs, then the same per-frame reduction + solve as the fused path
@@ -316,7 +318,7 @@ class FramePipeline:
                        det.flags.data_ptr(), det.count.data_ptr(), t["grid_cs"].data_ptr() if use_grid else 0,
                        part.data_ptr(), det.seg_cap, det.ntiles, det.F, self.stream)
             self._call("rs_velocity_from_partials", part.data_ptr(), det.ntiles, det.F, k, c.velocity_bound,
-                       vel.data_ptr(), self.stream)
+                       det.overflow.data_ptr(), vel.data_ptr(), self.stream)
             return vel
         self._call(
             "rs_velocity_ls",
@@ -483,6 +485,23 @@ class FramePipeline:
                 enqueue_recheck(pending, None)
             main.wait_stream(side)
         return (vel, last[0], last[1]) if keep else vel
+
+    def status(self) -> Dict[str, int]:
+        """What the last process() call could not settle (synchronises): frames whose detection segments overflowed --
+        their velocity row reports success = 0 -- and flagged decisions the fp64 recheck left at their fp32 value (one
+        recheck pass settles 16 cells per segment / 256 per frame; process(keep=True) iterates until none is left).
+        Counters of the chunks that used the two workspace sets last."""
+        torch.cuda.synchronize(self.device)
+        out = {"overflow_frames": 0, "unresolved_detections": 0, "unresolved_angles": 0}
+        for tag in ("", "0", "1"):
+            ov = self._ws.get("det_overflow" + tag)
+            if ov is not None:
+                out["overflow_frames"] += int((ov[: self._ws.get("_nframes" + tag, 0)] != 0).sum().item())
+            for key, name in (("recheck_det_stats", "unresolved_detections"), ("recheck_ang_stats", "unresolved_angles")):
+                st = self._ws.get(key + tag)
+                if st is not None:
+                    out[name] += int(st[3].item())
+        return out
 
     def process_host(self, cube_host: torch.Tensor, chunk_frames: int = 32, vel_dev: Optional[torch.Tensor] = None,
                      vel_host: Optional[torch.Tensor] = None, copy_only: bool = False) -> torch.Tensor:

@@ -56,8 +56,9 @@ def test_reference_tests_import_this_repo(tmp_path):
         "from src.robust_angle_estimation import RobustAngleEstimator as R2\n"
         "from src.radar_signal.dechirp import SignalPreprocessor\n"
         "from src.algorithms.velocity_solver_improved import ImprovedVelocitySolver\n"
+        "from src.algorithms.advanced_velocity_optimization import AdvancedVelocityOptimizer\n"
         "print(RobustAngleEstimator.__module__, R2 is RobustAngleEstimator, SignalPreprocessor.__module__,\n"
-        "      ImprovedVelocitySolver.__module__)\n"
+        "      ImprovedVelocitySolver.__module__, AdvancedVelocityOptimizer.__module__)\n"
     )
     r = _run(code, tmp_path)
     assert r.returncode == 0, r.stderr[-2000:]
@@ -65,6 +66,7 @@ def test_reference_tests_import_this_repo(tmp_path):
     assert out[0] == "radar_slam_b200.compat.robust_angle_estimation" and out[1] == "True"
     assert out[2] == "radar_slam_b200.compat.dechirp"
     assert out[3] == "radar_slam_b200.compat.velocity_solver_improved"
+    assert out[4] == "radar_slam_b200.compat.advanced_velocity_optimization"
 
 
 def test_constructor_signatures_match_reference():
@@ -91,6 +93,26 @@ def test_constructor_signatures_match_reference():
                         (ref.velocity, velocity_solver, ["estimate_velocity_from_angles"])]:
         for fn in fns:
             assert list(inspect.signature(getattr(rm, fn)).parameters) == list(inspect.signature(getattr(mm, fn)).parameters)
+
+
+def test_advanced_optimizer_signatures_match_reference():
+    """src/algorithms/advanced_velocity_optimization.py keeps the reference's class, methods and defaults."""
+    import inspect
+    sys.path.insert(0, ROOT)
+    from oracle import ref_import
+    ref_import.load()
+    ref = ref_import._load(os.path.join(REF, "src/algorithms/advanced_velocity_optimization.py"), "_rsref_advanced_sig")
+    from radar_slam_b200.compat import advanced_velocity_optimization as mine
+    for name, fn in inspect.getmembers(ref.AdvancedVelocityOptimizer, predicate=inspect.isfunction):
+        if name.startswith("__") and name != "__init__":
+            continue
+        assert hasattr(mine.AdvancedVelocityOptimizer, name), name
+        rs, ms = inspect.signature(fn), inspect.signature(getattr(mine.AdvancedVelocityOptimizer, name))
+        assert list(rs.parameters) == list(ms.parameters), name
+        for k in rs.parameters:
+            assert rs.parameters[k].default == ms.parameters[k].default, (name, k)
+    assert list(inspect.signature(ref.optimize_velocity_advanced).parameters) == \
+        list(inspect.signature(mine.optimize_velocity_advanced).parameters)
 
 
 def test_real_time_shell_signatures_match_reference():
