@@ -42,7 +42,7 @@ WORKLOAD = "configs[1]: 1k-frame synthetic batch per GPU, 256 samples x 128 chir
 WORKLOAD4 = ("configs[4]: one 65536-frame synthetic sequence, 256 samples x 128 chirps x 16 channels, frame-sharded by contiguous "
              "block, MUSIC 1 deg grid, noise_power 0.01, threshold -20 dB, NCCL all-gather of the velocity rows")
 # kernels behind one C-ABI call (for gpu_launches): the 2-D transform is the persistent cluster kernel + the side kernel
-KERNELS_PER_CALL = {"rs_range_doppler_fft": 2, "rs_detect": 1, "rs_angles": 1, "rs_recheck_detections_f64": 1,
+KERNELS_PER_CALL = {"rs_range_doppler_fft": 2, "rs_range_doppler_detect": 4, "rs_detect": 1, "rs_angles": 1, "rs_recheck_detections_f64": 1,
                     "rs_recheck_angles_f64": 3, "rs_velocity_from_partials": 1, "rs_velocity_partials": 1, "rs_velocity_ls": 1,
                     "rs_range_fft": 1, "rs_doppler_fft": 1}
 
@@ -235,6 +235,10 @@ def stage_bytes(name, F, A, C, S, n_det):
     cells = F * A * C * S
     if name in ("rs_range_fft", "rs_doppler_fft", "rs_range_doppler_fft"):
         return 16 * cells                                   # read c64 + write c64 per cell (the fused 2-D kernel: cube in, RDS out)
+    if name == "rs_range_doppler_detect":
+        # cube in, RDS out; the detection rides on the plane in shared memory: its traffic is the hit masks (written by the
+        # FFT kernel, read by the compaction) and the lists (key + flag + leader per detection)
+        return 16 * cells + 2 * (cells // 8 + cells // 1024) + 9 * n_det
     if name == "rs_detect":
         return 8 * cells + 9 * n_det                        # read RDS once; key + power + flag per detection
     if name == "rs_angles":
@@ -265,17 +269,22 @@ def _max_over_ranks(x: float, world, dev) -> float:
     return float(t.item())
 
 
-def _time_steps(step, steps, warmup, world, dev):
+def _time_steps(step, steps, warmup, world, dev, finish=None):
     """W untimed warm-up steps, then exactly `steps` steps between barrier + synchronize on both sides; CUDA events on the
-    launching stream, max over ranks.  Returns total milliseconds."""
+    launching stream, max over ranks.  `finish` joins whatever the steps left on other streams (inside the timed region).
+    Returns total milliseconds."""
     import torch
     for _ in range(warmup):
         step()
+    if finish is not None:
+        finish()
     _barrier(world, dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
         step()
+    if finish is not None:
+        finish()
     e1.record()
     _barrier(world, dev)
     return _max_over_ranks(e0.elapsed_time(e1), world, dev)
@@ -329,13 +338,15 @@ def measure_configs4(args, world, rank, dev, steps, warmup):
     vel = gather.slot()
 
     def step():
+        # the steps are software pipelined: the fp64 recheck + solve of one launch set run on a side stream beside the FFT /
+        # angle kernels of the next one, the all-gather follows the last solve of the step on that stream
         for c0 in range(0, block, P):
             n = min(P, block - c0)
-            pipe.process(pool[:n], chunk_frames=args.chunk, vel_out=vel[c0:c0 + n])
-        gather.gather()
+            pipe.process(pool[:n], chunk_frames=args.chunk, vel_out=vel[c0:c0 + n], join=False,
+                         after_solve=gather.gather if c0 + P >= block else None)
 
     pipe.launches = 0
-    ms_total = _time_steps(step, steps, warmup, world, dev)
+    ms_total = _time_steps(step, steps, warmup, world, dev, finish=pipe.join)
     calls = pipe.launches // (steps + warmup)
     # ---- end to end on a bounded sample of the block (PCIe bound: a whole block would take seconds per step)
     n_e2e = min(block, args.e2e_frames4)
@@ -430,19 +441,21 @@ def measure_configs1(args, world, rank, dev, numa, detailed=True):
     vel = gather.slot()
 
     def step():
-        pipe.process(cube, chunk_frames=args.chunk, vel_out=vel)
-        gather.gather()                           # NCCL all_gather_into_tensor of the [F, 8] rows (no-op at N=1)
+        # Steps are software pipelined (FramePipeline.process(join=False)): the fp64 recheck + solve of step k run on a side
+        # stream beside the FFT / angle kernels of step k + 1 (two workspace sets); the NCCL all_gather_into_tensor of the
+        # [F, 8] rows (no-op at N=1) follows the solve on that stream.  The last step is joined inside the timed region.
+        pipe.process(cube, chunk_frames=args.chunk, vel_out=vel, join=False, after_solve=gather.gather)
 
     pipe.launches = 0
     pipe.call_counts = {}
-    ms_total = _time_steps(step, args.steps, args.warmup, world, dev)
+    ms_total = _time_steps(step, args.steps, args.warmup, world, dev, finish=pipe.join)
     launches = sum(KERNELS_PER_CALL.get(k, 1) * v for k, v in pipe.call_counts.items()) * args.steps // (args.steps + args.warmup)
 
     # ---- sustained: the same step for >= 1 s (thermally / power settled), reported next to the K-step figure
     sustained = None
     if detailed and args.sustain_s > 0:
         n_sus = max(args.steps, int(args.sustain_s * 1e3 / (ms_total / args.steps)) + 1)
-        ms_sus = _time_steps(step, n_sus, 0, world, dev)
+        ms_sus = _time_steps(step, n_sus, 0, world, dev, finish=pipe.join)
         sustained = {"steps": n_sus, "seconds": ms_sus / 1e3, "value": world * F * n_sus / (ms_sus / 1e3), "unit": "frames/s"}
 
     # ---- end to end through the public API with HOST buffers (pinned): H2D + kernels + all-gather + D2H in the timed region
@@ -543,8 +556,21 @@ def measure_configs1(args, world, rank, dev, numa, detailed=True):
                 "alg_bytes_per_launch": per_launch_bytes, "avg_launch_ms": dom["ms_per_step"] / dom["launches"],
                 "stages": stages}
     fft = [st for st in stages if st["kernel"] in ("rs_range_fft", "rs_doppler_fft", "rs_range_doppler_fft")]
-    if fft:
-        ms_fft = sum(st["ms_per_step"] for st in fft)
+    ms_fft = sum(st["ms_per_step"] for st in fft)
+    if not fft and (C, S) == (128, 256):
+        # the timed path runs the 2-D FFT with the detection fused into it (rs_range_doppler_detect); the transform alone
+        # (rs_range_doppler_fft: the same kernel without the detection) is timed here for the FFT-stage roofline
+        out = pipe._buf("rds0", (F, S, A, C), torch.complex64)
+        for _ in range(2):
+            pipe.range_doppler(cube, out=out)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        ev[0].record()
+        for _ in range(passes):
+            pipe.range_doppler(cube, out=out)
+        ev[1].record()
+        torch.cuda.synchronize(dev)
+        ms_fft = ev[0].elapsed_time(ev[1]) / passes
+    if ms_fft > 0:
         roofline["fft_stages"] = {
             "ms_per_step": ms_fft, "alg_bytes_per_step": 16 * F * A * C * S,
             "frac_hbm_2d": 16 * F * A * C * S / ms_fft / 1e6 / peak,
@@ -562,7 +588,18 @@ def measure_configs1(args, world, rank, dev, numa, detailed=True):
             "note": "per-cell MUSIC grid scan = [cells x lags] . [lags x grid pairs] on the tensor cores (mma.sync m16n8k16 + "
                     "m16n8k8, fp16 operands split hi + lo, fp32 accumulation); its argmax / runner-up tracking is ALU-issue "
                     "bound, not HBM bound"}
-    if dom["kernel"] == "rs_range_doppler_fft":
+    fd = next((st for st in stages if st["kernel"] == "rs_range_doppler_detect"), None)
+    if fd is not None:
+        # what the two-stage path (rs_range_doppler_fft + rs_detect) needs for the same result: 16 + 8 B/cell + the lists
+        two_stage = 24 * F * A * C * S + 9 * n_det_frame * F
+        fd["two_stage_alg_bytes_per_step"] = two_stage
+        fd["frac_hbm_of_two_stage_bytes"] = two_stage / fd["ms_per_step"] / 1e6 / peak
+    if dom["kernel"] == "rs_range_doppler_detect":
+        roofline["note"] = ("dominant stage is the fused 2-D FFT + detection (persistent warp-specialised 4-CTA clusters fed by TMA; "
+                            "the |X|^2 local-maximum test runs on the plane in distributed shared memory and leaves hit masks, a "
+                            "small kernel compacts them into the lists): the RDS is written once and not read by a detection "
+                            "pass; `achieved` counts cube in + RDS out + masks + lists")
+    elif dom["kernel"] == "rs_range_doppler_fft":
         roofline["note"] = ("dominant kernel is the fused 2-D FFT (persistent warp-specialised 4-CTA clusters fed by TMA + the side "
                             "kernel on the stranded SMs): HBM traffic at the algorithmic minimum (16 B/cell, plane held in "
                             "distributed shared memory between the passes)")

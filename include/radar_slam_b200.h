@@ -115,6 +115,28 @@ int rs_detect(const void* rds, const uint8_t* range_gate, float thr_power, float
               int32_t* det_count, int32_t* det_nlead, int32_t* det_overflow, int32_t* det_nnear, float* det_psum,
               int seg_cap, int F, int R, int D, int A, void* stream);
 
+/* (a1+a2+b) rs_range_doppler_fft + rs_detect in one call (dechirp.py:193-263).  For 256 x 128 planes with A % 8 == 0
+ *       the detection rides in the Doppler phase of the persistent 2-D FFT kernel: the (frame, antenna) plane is on chip
+ *       when the Doppler pass finishes, so |X|^2, the 3x3 local maximum, the threshold and the range gate are evaluated
+ *       there and only hit masks (4 KB per 256 KB plane) go to fused_ws; a small kernel turns the masks of an antenna
+ *       octet into exactly the segments / order / leaders / counters rs_detect writes.  The RDS is not read by a
+ *       detection pass (8 B per cell less HBM traffic).  Other shapes, or fused_ws == NULL, run the two stages one after
+ *       the other with identical results.
+ *       fused_ws   workspace of rs_fused_detect_ws_bytes(F, A) bytes (16-byte aligned), contents undefined on return
+ *       det_power  may be NULL on the fused path (the kernel keeps no |X|^2 and nothing on the path to the velocity reads
+ *                  it): rs_detection_power gathers the values on demand, or rs_angles writes them from the snapshots it
+ *                  holds anyway (det_power_out) */
+long long rs_fused_detect_ws_bytes(int F, int A);
+/*       det_power of every listed entry, gathered from the RDS the lists came from (bit-identical to rs_detect's values) */
+int rs_detection_power(const void* rds, const uint32_t* det_key, const uint32_t* det_lead, const int32_t* det_nlead,
+                       float* det_power, int seg_cap, int nseg_per_frame, int F, int R, int D, int A, void* stream);
+int rs_range_doppler_detect(const void* cube, const void* table, const void* twiddle_s, const void* twiddle_c,
+                            void* mid_ws, void* rds, void* fused_ws, int F, int A, int C_total, int chirp0, int C_used,
+                            int S, int dc_removal, const uint8_t* range_gate, float thr_power, float det_eps,
+                            uint32_t* det_key, float* det_power, uint8_t* det_flags, uint32_t* det_lead,
+                            int32_t* det_count, int32_t* det_nlead, int32_t* det_overflow, int32_t* det_nnear,
+                            float* det_psum, int seg_cap, void* stream);
+
 /* (c)   replaces AngleEstimator.process_targets (angle_estimation.py:253-309) for every detection:
  *       snapshot gather, (rank-1) MUSIC / beamforming scan over the azimuth grid with first-index
  *       argmax, or the ESPRIT closed form; also the inter-antenna phase the solver uses.
@@ -139,7 +161,10 @@ int rs_detect(const void* rds, const uint8_t* range_gate, float thr_power, float
  *                     a cell is flagged on many of them and all share one snapshot.  NULL: one evaluation per leader.
  *       tc_table      optional, bytes [tc_halves][cos, sin][KC][32 x 16 fp16]: the same tables as UMMA B operands (K-major,
  *                     no swizzle) for the tcgen05 / TMEM scan (radar_slam_b200/tables.py: scan_tc_table), tc_halves =
- *                     ceil(ceil(G/2)/32); used instead of the mma.sync scan when RS_ANGLES_TC=1 (measured variant). */
+ *                     ceil(ceil(G/2)/32); used instead of the mma.sync scan when RS_ANGLES_TC=1 (measured variant).
+ *       det_power_out optional float [F*nseg_per_frame*seg_cap]: |X|^2 of every entry (the det_power of rs_detect), for
+ *                     lists that came from rs_range_doppler_detect with det_power = NULL.  The scan holds the snapshot
+ *                     of every flagged cell in registers anyway, so the powers cost no memory traffic here. */
 #define RS_TIE_LIST_CAP 32
 int rs_angles(const void* rds, const float* scan_table, int scan_stride, const void* steer, const float* grid_deg, int G,
               int method, float tie_eps, double esprit_scale,
@@ -147,7 +172,8 @@ int rs_angles(const void* rds, const float* scan_table, int scan_stride, const v
               int32_t* det_aidx, float* det_adeg, float* det_phase,
               int seg_cap, int nseg_per_frame, int F, int R, int D, int A,
               const double* grid_cs, double* ls_partials, int grid_symmetric, int32_t* det_ntie, int32_t* det_tielist,
-              const float* mma_table, int mma_tiles, void* cell_ws, const void* tc_table, int tc_halves, void* stream);
+              const float* mma_table, int mma_tiles, void* cell_ws, const void* tc_table, int tc_halves,
+              float* det_power_out, void* stream);
 
 /* (d')  the velocity solve of rs_velocity_ls from the per-segment sums rs_angles already produced
  *       (no second pass over the detection lists); same output row layout.  det_overflow (int32 [F], may be NULL): frames

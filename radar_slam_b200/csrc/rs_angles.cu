@@ -42,7 +42,23 @@ struct AngleArgs {
     float* det_adeg;
     float* det_phase;
     int seg_cap, nseg_per_frame, R, D, A;
+    float* det_power;             // optional: |X|^2 of every entry (lists from rs_range_doppler_detect without det_power)
 };
+
+// |X|^2 of the k entries of a cell from its snapshot (the entries are the antennas that flagged the cell; their keys sit
+// in the sector the leader's key came from).  Same expression as the detection kernels: the values are bit-identical.
+template <int AP>
+__device__ __forceinline__ void emit_power(const AngleArgs& p, size_t o, int k, const float2 (&s)[AP]) {
+    if (p.det_power == nullptr) return;
+    for (int e = 0; e < k; ++e) {
+        const int a = (int)(p.det_key[o + e] >> 24);
+        float pw = 0.f;
+#pragma unroll
+        for (int m = 0; m < AP; ++m)
+            if (m == a) pw = fmaf(s[m].x, s[m].x, s[m].y * s[m].y);
+        p.det_power[o + e] = pw;
+    }
+}
 
 // write one cell's result to all of its detections (same snapshot on every antenna that flagged the cell)
 // returns how many of them are live (not RS_FLAG_DROPPED): the weight of the cell in the velocity sums
@@ -485,6 +501,7 @@ __global__ void __launch_bounds__(ANG_THREADS, MINB) angles_mma_kernel(AngleArgs
 #pragma unroll
                     for (int m = 0; m < AP; ++m) s[m] = (m < M) ? __ldg(cell + (size_t)m * p.D) : make_float2(0.f, 0.f);
                     yv = atan2f(s[1].y * s[0].x - s[1].x * s[0].y, s[1].x * s[0].x + s[1].y * s[0].y);
+                    emit_power<AP>(p, o, mult, s);
                 } else {
 #pragma unroll
                     for (int m = 0; m < AP; ++m) s[m] = make_float2(0.f, 0.f);
@@ -800,7 +817,10 @@ __global__ void __launch_bounds__(ANG_THREADS, 4) angles_tc5_kernel(AngleArgs p,
             float yv = 0.f;
             {
                 float rr0 = 0.f;
-                if (valid) yv = atan2f(s[1].y * s[0].x - s[1].x * s[0].y, s[1].x * s[0].x + s[1].y * s[0].y);
+                if (valid) {
+                    yv = atan2f(s[1].y * s[0].x - s[1].x * s[0].y, s[1].x * s[0].x + s[1].y * s[0].y);
+                    emit_power<AP>(p, o, mult, s);
+                }
 #pragma unroll
                 for (int m = 0; m < AP; ++m) rr0 = fmaf(s[m].x, s[m].x, fmaf(s[m].y, s[m].y, rr0));
                 const float inv = rr0 > 0.f ? 1.f / rr0 : 0.f;       // |R_k| <= R_0: the normalised lags lie in [-1, 1]
@@ -1194,6 +1214,25 @@ __global__ void spectra_f64_kernel(const double2* __restrict__ sig, const double
 
 }  // namespace
 
+// |X|^2 of every entry, gathered from the RDS, for the paths whose scan kernel does not write it on the way
+__global__ void __launch_bounds__(256) det_power_kernel(AngleArgs p) {
+    const int seg = blockIdx.x;
+    const int n = p.det_nlead[seg];
+    const int f = seg / p.nseg_per_frame;
+    const float2* frame = p.rds + (size_t)f * p.R * p.D * p.A;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint32_t ld = p.det_lead[(size_t)seg * p.seg_cap + i];
+        const size_t o = (size_t)seg * p.seg_cap + (ld & 0xFFFFu);
+        const int k = (int)(ld >> 16);
+        for (int e = 0; e < k; ++e) {
+            int a, r, d;
+            rs_split_key(p.det_key[o + e], a, r, d);
+            const float2 x = __ldg(frame + ((size_t)r * p.A + a) * p.D + d);
+            p.det_power[o + e] = fmaf(x.x, x.x, x.y * x.y);
+        }
+    }
+}
+
 extern "C" int rs_angles(const void* rds, const float* scan_table, int scan_stride, const void* steer,
                          const float* grid_deg, int G, int method, float tie_eps, double esprit_scale,
                          const uint32_t* det_key, const uint32_t* det_lead, const int32_t* det_nlead, uint8_t* det_flags,
@@ -1201,7 +1240,7 @@ extern "C" int rs_angles(const void* rds, const float* scan_table, int scan_stri
                          float* det_adeg, float* det_phase, int seg_cap, int nseg_per_frame, int F, int R, int D, int A,
                          const double* grid_cs, double* ls_partials, int grid_symmetric, int32_t* det_ntie,
                          int32_t* det_tielist, const float* mma_table, int mma_tiles, void* cell_ws, const void* tc_table,
-                         int tc_halves, void* stream) {
+                         int tc_halves, float* det_power_out, void* stream) {
     RS_CHECK_ARG(rds && det_key && det_lead && det_nlead && det_flags && det_aidx && det_adeg && det_phase,
                  "rs_angles: null pointer");
     RS_CHECK_ARG(ls_partials == nullptr || grid_cs != nullptr, "rs_angles: ls_partials needs grid_cs");
@@ -1213,7 +1252,7 @@ extern "C" int rs_angles(const void* rds, const float* scan_table, int scan_stri
     AngleArgs p{(const float2*)rds, scan_table, scan_stride, (const float2*)steer, grid_deg, G, method, tie_eps,
                 esprit_scale, det_key, det_lead, det_nlead, det_ntie, det_tielist, det_flags, det_aidx, det_adeg, det_phase, seg_cap,
                 nseg_per_frame,
-                R, D, A};
+                R, D, A, det_power_out};
     const long long blocks = (long long)F * nseg_per_frame;
     RS_CHECK_ARG(blocks < (1ll << 31), "rs_angles: too many segments");
     cudaStream_t st = (cudaStream_t)stream;
@@ -1276,8 +1315,17 @@ extern "C" int rs_angles(const void* rds, const float* scan_table, int scan_stri
             const char* mma_env = getenv("RS_ANGLES_MMA");  // 0: force the CUDA-core scan
             if (mma_table != nullptr && grid_symmetric && (ap == 8 || ap == 16) && !(mma_env && atoi(mma_env) == 0)) {
                 RS_CHECK_ARG(mma_tiles == ((G + 1) / 2 + 7) / 8, "rs_angles: mma_tiles must be ceil(ceil(G/2)/8)");
-                const size_t sm = ((size_t)mma_tiles * (ap / 8) * 192 + (size_t)(ANG_THREADS / 32) * 32 * (2 * ap + 8)) *
-                                  sizeof(float);
+                size_t sm = ((size_t)mma_tiles * (ap / 8) * 192 + (size_t)(ANG_THREADS / 32) * 32 * (2 * ap + 8)) *
+                            sizeof(float);
+                // RS_ANGLES_CTAS: resident CTAs per SM (by padding the shared-memory request).  Fewer than the 8 that fill the
+                // register file leave room for the CTAs of the fp64 recheck kernels, which FramePipeline.process runs on a
+                // second stream beside this scan
+                const char* cta_env = getenv("RS_ANGLES_CTAS");
+                const int ctas = cta_env ? atoi(cta_env) : 0;
+                if (ctas >= 1 && ctas < 8) {
+                    const size_t pad = (size_t)rs_smem_optin_limit() / (ctas + 1) + 1024;
+                    if (sm < pad) sm = pad;
+                }
                 if (sm <= (size_t)rs_smem_optin_limit()) {
                     // occupancy beats per-warp ILP here (measured): 64 registers / 8 CTAs per SM at A <= 8
                     if (ap == 8) {
@@ -1324,6 +1372,32 @@ extern "C" int rs_angles(const void* rds, const float* scan_table, int scan_stri
         }
     }
     RS_CHECK_LAUNCH("rs_angles");
+    if (det_power_out) {             // only the tensor-core scans write the powers on the way
+        det_power_kernel<<<(unsigned)blocks, 256, 0, st>>>(p);
+        RS_CHECK_LAUNCH("rs_angles(power)");
+    }
+    return RS_OK;
+}
+
+extern "C" int rs_detection_power(const void* rds, const uint32_t* det_key, const uint32_t* det_lead, const int32_t* det_nlead,
+                                  float* det_power, int seg_cap, int nseg_per_frame, int F, int R, int D, int A, void* stream) {
+    RS_CHECK_ARG(rds && det_key && det_lead && det_nlead && det_power, "rs_detection_power: null pointer");
+    RS_CHECK_ARG(F > 0 && R > 0 && D > 0 && A > 0 && seg_cap > 0 && nseg_per_frame > 0, "rs_detection_power: bad dims");
+    const long long blocks = (long long)F * nseg_per_frame;
+    RS_CHECK_ARG(blocks < (1ll << 31), "rs_detection_power: too many segments");
+    AngleArgs p{};
+    p.rds = (const float2*)rds;
+    p.det_key = det_key;
+    p.det_lead = det_lead;
+    p.det_nlead = det_nlead;
+    p.det_power = det_power;
+    p.seg_cap = seg_cap;
+    p.nseg_per_frame = nseg_per_frame;
+    p.R = R;
+    p.D = D;
+    p.A = A;
+    det_power_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p);
+    RS_CHECK_LAUNCH("rs_detection_power");
     return RS_OK;
 }
 

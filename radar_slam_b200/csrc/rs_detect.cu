@@ -15,7 +15,10 @@
 // angle and one inter-antenna phase.  The fast kernel therefore emits a cell's detections
 // contiguously and records one LEADER per cell -- det_lead = position | (multiplicity << 16) -- so
 // the angle stage evaluates every distinct cell once (-28 % work at 8 channels, -48 % at 16).
+#include <cmath>
+#include <cstdlib>
 #include "rs_common.cuh"
+#include "rs_detect_fused.cuh"
 
 namespace {
 
@@ -64,20 +67,6 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* warp_sums, int* 
     }
     __syncthreads();
     return warp_sums[wid] + inc - v;
-}
-
-// 0: not a detection; 1: detection; 3: detection whose margin to the best neighbour / threshold is inside
-// the fp32 guard band; 7: NOT a detection in fp32 but inside the band (a candidate the fp64 recheck may promote).
-__device__ __forceinline__ int classify(float c, float m, float thr, float eps) {
-    // cheap reject (91 % of the cells): more than 2 eps below the best neighbour or the threshold
-    const float cu = fmaf(c, 2.f * eps, c);
-    if (cu < m || cu <= thr) return 0;
-    const bool ge_m = c >= m, gt_t = c > thr;
-    const bool near_m = fabsf(c - m) <= eps * fmaxf(c, m);
-    const bool near_t = fabsf(c - thr) <= eps * fabsf(thr);
-    if (ge_m && gt_t) return (near_m || near_t) ? 3 : 1;
-    if ((ge_m || near_m) && (gt_t || near_t)) return 7;
-    return 0;
 }
 
 struct DetOut {
@@ -178,7 +167,7 @@ detect_kernel(const float2* __restrict__ rds, const uint8_t* __restrict__ gate, 
                     const int r = r0 + rr - 1;
                     if (r < R) {
                         const float m = fmaxf(fmaxf(h_prev, h_next), fmaxf(l1, rt1));
-                        const int cls = classify(c1, m, thr, eps);
+                        const int cls = rs_classify(c1, m, thr, eps);
                         if (cls && gate[r]) {
                             hit[q] |= 1u << (rr - 1);
                             ++my_count;
@@ -248,12 +237,80 @@ __device__ __forceinline__ int a8_off(int rr, int ddp, int quad) {          // f
     return rr * A8_W + ddp * A8_AC + ((quad ^ ((ddp >> 2) & 1)) << 2);
 }
 
+// Tail shared by detect_a8_kernel and compact_masks_kernel: per-thread masks (byte per row: antenna mask; rows rbase+1 ..
+// rbase+8 of the tile, Doppler column ddp) -> the tile's segment.  power_at(rr, j): |X|^2 of row rr (1-based), antenna j.
+template <class PowerAt>
+__device__ __forceinline__ void a8_emit(const uint32_t (&hit)[2], const uint32_t (&near)[2], const uint32_t (&cand)[2],
+                                        int my_near, float my_psum, const DetOut& out, int f, int r0, int d0, int a0,
+                                        int rbase, int ddp, PowerAt power_at) {
+    __shared__ int warp_sums[DET_THREADS / 32];
+    __shared__ int total_s;
+    const int tid = threadIdx.x;
+    // entries and leaders of this thread, scanned together (entries <= 2^14 per tile)
+    const int n_ent = __popc(hit[0]) + __popc(hit[1]);
+    int n_lead = 0;
+#pragma unroll
+    for (int i = 0; i < A8_HALF; ++i) n_lead += ((hit[i >> 2] >> ((i & 3) * 8)) & 0xFFu) != 0u;
+    const int packed = block_exclusive_scan(n_ent | (n_lead << 16), warp_sums, &total_s);
+    const int total = total_s & 0xFFFF, total_lead = total_s >> 16;
+    const size_t seg = (size_t)blockIdx.x;
+    int pos = packed & 0xFFFF, lpos = packed >> 16;
+    if (tid == 0) {
+        out.count[seg] = total < out.seg_cap ? total : out.seg_cap;
+        if (total > out.seg_cap) out.overflow[f] = 1;
+    }
+    {
+        __shared__ int near_s;
+        __shared__ float psum_s;
+        block_sums(my_near, my_psum, &near_s, &psum_s);
+        if (tid == 0) {
+            if (out.nnear) out.nnear[seg] = near_s;
+            if (out.psum) out.psum[seg] = psum_s;
+        }
+    }
+    // a leader is kept only if all of its cell's entries fit; because entries are emitted in order, the kept
+    // leaders are a prefix of the leader list -> nlead = number of leaders whose last entry fits
+    int kept = 0;
+#pragma unroll
+    for (int i = 0; i < A8_HALF; ++i) {
+        uint32_t m = (hit[i >> 2] >> ((i & 3) * 8)) & 0xFFu;
+        if (!m) continue;
+        const uint32_t nb = (near[i >> 2] >> ((i & 3) * 8)) & 0xFFu;
+        const uint32_t cb = (cand[i >> 2] >> ((i & 3) * 8)) & 0xFFu;
+        const int k = __popc(m);
+        const int rr = rbase + 1 + i;
+        if (pos + k <= out.seg_cap) {
+            out.lead[seg * out.seg_cap + lpos] = (uint32_t)pos | ((uint32_t)k << 16);
+            ++kept;
+        }
+        ++lpos;
+        while (m) {
+            const int j = __ffs(m) - 1;
+            m &= m - 1;
+            if (pos < out.seg_cap) {
+                const size_t o = seg * out.seg_cap + pos;
+                out.key[o] = rs_make_key(a0 + j, r0 + rr - 1, d0 + ddp - 1);
+                if (out.power) out.power[o] = power_at(rr, j);
+                out.flags[o] = ((cb >> j) & 1u) ? (RS_FLAG_NEARMAX | RS_FLAG_DROPPED) : ((nb >> j) & 1u) ? RS_FLAG_NEARMAX : 0;
+            }
+            ++pos;
+        }
+    }
+    // number of kept leaders: all of them unless the segment overflowed (then a block sum, uniform branch)
+    if (total <= out.seg_cap) {
+        if (tid == 0) out.nlead[seg] = total_lead;
+    } else {
+        __syncthreads();
+        block_exclusive_scan(kept, warp_sums, &total_s);
+        if (tid == 0) out.nlead[seg] = total_s;
+    }
+}
+
+
 __global__ void __launch_bounds__(DET_THREADS, 3)
 detect_a8_kernel(const float2* __restrict__ rds, const uint8_t* __restrict__ gate, float thr, float eps, DetOut out, int R,
                  int D, int A, Tiling tl) {
     extern __shared__ float pw[];   // [(TR+2)][W]
-    __shared__ int warp_sums[DET_THREADS / 32];
-    __shared__ int total_s;
 
     const int tile = blockIdx.x % tl.ntiles;
     const int f = blockIdx.x / tl.ntiles;
@@ -395,70 +452,63 @@ detect_a8_kernel(const float2* __restrict__ rds, const uint8_t* __restrict__ gat
             float m = fmaxf(fmaxf(at(rr - 1, ddp - 1), at(rr - 1, ddp)), at(rr - 1, ddp + 1));
             m = fmaxf(m, fmaxf(at(rr, ddp - 1), at(rr, ddp + 1)));
             m = fmaxf(m, fmaxf(fmaxf(at(rr + 1, ddp - 1), at(rr + 1, ddp)), at(rr + 1, ddp + 1)));
-            const int cls = classify(c, m, thr, eps);
+            const int cls = rs_classify(c, m, thr, eps);
             if (cls == 0) hit[w] &= ~(1u << b);
             if (cls & 2) { near[w] |= 1u << b; ++my_near; }
             if (cls & 4) cand[w] |= 1u << b;
         }
     }
-    // entries and leaders of this thread, scanned together (entries <= 2^14 per tile)
-    const int n_ent = __popc(hit[0]) + __popc(hit[1]);
-    int n_lead = 0;
+    a8_emit(hit, near, cand, my_near, my_psum, out, f, r0, d0, a0, rbase, ddp,
+            [&](int rr, int j) { return pw[a8_off(rr, ddp, j >> 2) + (j & 3)]; });
+}
+
+// ---------------------------------------------------------------------------------------------
+// Compaction of the hit masks the fused 2-D FFT kernel wrote (rs_detect_fused.cuh, rs_fft2d_ws.cu): the same segments,
+// order, leaders and counters as detect_a8_kernel, from 2 KB of mask words per tile instead of the tile's 144 KB of RDS.
+// Same thread <-> cell assignment as the walk above: thread = (Doppler bin, half of the 16 rows) = one row group of the
+// masks, all 8 antennas of the octet.  det_power (optional) is gathered from the RDS for the entries only.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t spread_nibbles(uint32_t v) {      // bit 4 i of the low 16 bits -> bit 8 i
+    return (v & 1u) | ((v & 0x10u) << 4) | ((v & 0x100u) << 8) | ((v & 0x1000u) << 12);
+}
+
+__global__ void __launch_bounds__(DET_THREADS)
+compact_masks_kernel(const float2* __restrict__ rds, FusedDetectMasks fd, DetOut out, int R, int D, int A, Tiling tl) {
+    const int tile = blockIdx.x % tl.ntiles;
+    const int f = blockIdx.x / tl.ntiles;
+    const int ia = tile % tl.nac;
+    const int ir = tile / tl.nac;                    // ntd == 1: a tile spans the Doppler axis
+    const int r0 = ir * A8_TR, d0 = 0, a0 = ia * A8_AC;
+    const int tid = threadIdx.x;
+    const int ddp = (tid & (A8_TD - 1)) + 1, rh = tid >> 7;
+    const int rbase = rh * A8_HALF;
+    const int d = ddp - 1, sh = d & 3;
+    uint32_t hit[2] = {0u, 0u}, near[2] = {0u, 0u}, cand[2] = {0u, 0u};
+    float my_psum = 0.f;
 #pragma unroll
-    for (int i = 0; i < A8_HALF; ++i) n_lead += ((hit[i >> 2] >> ((i & 3) * 8)) & 0xFFu) != 0u;
-    const int packed = block_exclusive_scan(n_ent | (n_lead << 16), warp_sums, &total_s);
-    const int total = total_s & 0xFFFF, total_lead = total_s >> 16;
-    const size_t seg = (size_t)blockIdx.x;
-    int pos = packed & 0xFFFF, lpos = packed >> 16;
-    if (tid == 0) {
-        out.count[seg] = total < out.seg_cap ? total : out.seg_cap;
-        if (total > out.seg_cap) out.overflow[f] = 1;
-    }
-    {
-        __shared__ int near_s;
-        __shared__ float psum_s;
-        block_sums(my_near, my_psum, &near_s, &psum_s);
-        if (tid == 0) {
-            if (out.nnear) out.nnear[seg] = near_s;
-            if (out.psum) out.psum[seg] = psum_s;
+    for (int j = 0; j < A8_AC; ++j) {
+        const size_t gi = ((size_t)f * A + a0 + j) * FD_GROUPS + 2 * ir + rh;
+        const uint32_t w = __ldg(fd.hit + gi * FD_WORDS + (d >> 2));
+        const uint32_t x = (w >> sh) & 0x11111111u;
+        hit[0] |= spread_nibbles(x & 0xFFFFu) << j;
+        hit[1] |= spread_nibbles(x >> 16) << j;
+        const float2 rec = __ldg(fd.rec + gi);
+        if (__float_as_int(rec.y)) {                 // warp-uniform: this row group has cells inside the guard band
+            const uint32_t xn = (__ldg(fd.near + gi * FD_WORDS + (d >> 2)) >> sh) & 0x11111111u;
+            const uint32_t xc = (__ldg(fd.cand + gi * FD_WORDS + (d >> 2)) >> sh) & 0x11111111u;
+            near[0] |= spread_nibbles(xn & 0xFFFFu) << j;
+            near[1] |= spread_nibbles(xn >> 16) << j;
+            cand[0] |= spread_nibbles(xc & 0xFFFFu) << j;
+            cand[1] |= spread_nibbles(xc >> 16) << j;
         }
+        if (d == 0) my_psum += rec.x;                // threads 0 and 128: the 16 row-group sums of the tile, fixed order
     }
-    // a leader is kept only if all of its cell's entries fit; because entries are emitted in order, the kept
-    // leaders are a prefix of the leader list -> nlead = number of leaders whose last entry fits
-    int kept = 0;
-#pragma unroll
-    for (int i = 0; i < A8_HALF; ++i) {
-        uint32_t m = (hit[i >> 2] >> ((i & 3) * 8)) & 0xFFu;
-        if (!m) continue;
-        const uint32_t nb = (near[i >> 2] >> ((i & 3) * 8)) & 0xFFu;
-        const uint32_t cb = (cand[i >> 2] >> ((i & 3) * 8)) & 0xFFu;
-        const int k = __popc(m);
-        const int rr = rbase + 1 + i;
-        if (pos + k <= out.seg_cap) {
-            out.lead[seg * out.seg_cap + lpos] = (uint32_t)pos | ((uint32_t)k << 16);
-            ++kept;
-        }
-        ++lpos;
-        while (m) {
-            const int j = __ffs(m) - 1;
-            m &= m - 1;
-            if (pos < out.seg_cap) {
-                const size_t o = seg * out.seg_cap + pos;
-                out.key[o] = rs_make_key(a0 + j, r0 + rr - 1, d0 + ddp - 1);
-                out.power[o] = pw[a8_off(rr, ddp, j >> 2) + (j & 3)];
-                out.flags[o] = ((cb >> j) & 1u) ? (RS_FLAG_NEARMAX | RS_FLAG_DROPPED) : ((nb >> j) & 1u) ? RS_FLAG_NEARMAX : 0;
-            }
-            ++pos;
-        }
-    }
-    // number of kept leaders: all of them unless the segment overflowed (then a block sum, uniform branch)
-    if (total <= out.seg_cap) {
-        if (tid == 0) out.nlead[seg] = total_lead;
-    } else {
-        __syncthreads();
-        block_exclusive_scan(kept, warp_sums, &total_s);
-        if (tid == 0) out.nlead[seg] = total_s;
-    }
+    const int my_near = __popc(near[0]) + __popc(near[1]);
+    const float2* frame = rds + (size_t)f * R * D * A;
+    a8_emit(hit, near, cand, my_near, my_psum, out, f, r0, d0, a0, rbase, ddp, [&](int rr, int j) {
+        const float2 x = __ldg(frame + ((size_t)(r0 + rr - 1) * A + a0 + j) * D + d);
+        return fmaf(x.x, x.x, x.y * x.y);
+    });
 }
 
 }  // namespace
@@ -473,6 +523,42 @@ extern "C" int rs_detect_tiling(int R, int D, int A, int* tile_r, int* tile_d, i
     return RS_OK;
 }
 
+// frames [f0, f0 + nf) of a batch through the stand-alone kernels (the overflow flags are cleared by the caller)
+static int launch_detect(const float2* rds, const uint8_t* gate, float thr, float eps, DetOut out, int f0, int nf, int R, int D,
+                         int A, cudaStream_t stream, const char* what) {
+    Tiling t = make_tiling(R, D, A);
+    const long long blocks = (long long)nf * t.ntiles;
+    RS_CHECK_ARG(blocks < (1ll << 31), "rs_detect: too many blocks");
+    if (nf <= 0) return RS_OK;
+    rds += (size_t)f0 * R * D * A;
+    const size_t s0 = (size_t)f0 * t.ntiles, e0 = s0 * out.seg_cap;
+    out.key += e0;
+    if (out.power) out.power += e0;
+    out.flags += e0;
+    out.lead += e0;
+    out.count += s0;
+    out.nlead += s0;
+    out.overflow += f0;
+    if (out.nnear) out.nnear += s0;
+    if (out.psum) out.psum += s0;
+    if (A % 8 == 0 && D % A8_TD == 0 && R % A8_TR == 0 && t.TD == A8_TD && t.AC == A8_AC && t.TR == A8_TR) {
+        const size_t smem = (size_t)(A8_TR + 2) * A8_W * sizeof(float);
+        cudaFuncSetAttribute(detect_a8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        detect_a8_kernel<<<(unsigned)blocks, DET_THREADS, smem, stream>>>(rds, gate, thr, eps, out, R, D, A, t);
+        RS_CHECK_LAUNCH(what);
+        return RS_OK;
+    }
+    const size_t smem = (size_t)(t.TR + 2) * (t.TD + 2) * t.AC * sizeof(float);
+    if (smem > (size_t)rs_smem_optin_limit()) {
+        rs_set_error("rs_detect: tile needs %zu B of shared memory", smem);
+        return RS_ECAPACITY;
+    }
+    cudaFuncSetAttribute(detect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    detect_kernel<<<(unsigned)blocks, DET_THREADS, smem, stream>>>(rds, gate, thr, eps, out, R, D, A, t);
+    RS_CHECK_LAUNCH(what);
+    return RS_OK;
+}
+
 extern "C" int rs_detect(const void* rds, const uint8_t* range_gate, float thr_power, float det_eps, uint32_t* det_key,
                          float* det_power, uint8_t* det_flags, uint32_t* det_lead, int32_t* det_count,
                          int32_t* det_nlead, int32_t* det_overflow, int32_t* det_nnear, float* det_psum, int seg_cap,
@@ -483,27 +569,88 @@ extern "C" int rs_detect(const void* rds, const uint8_t* range_gate, float thr_p
     RS_CHECK_ARG(F > 0 && R > 0 && D > 0 && A > 0 && R <= RS_MAX_RANGE_BINS && D <= RS_MAX_DOPPLER_BINS &&
                      A <= RS_MAX_ANTENNAS && seg_cap > 0 && seg_cap <= 65535,
                  "rs_detect: bad dims (seg_cap must be in 1..65535)");
-    Tiling t = make_tiling(R, D, A);
-    const long long blocks = (long long)F * t.ntiles;
-    RS_CHECK_ARG(blocks < (1ll << 31), "rs_detect: too many blocks");
     DetOut out{det_key, det_power, det_flags, det_lead, det_count, det_nlead, det_overflow, det_nnear, det_psum, seg_cap};
     cudaMemsetAsync(det_overflow, 0, sizeof(int32_t) * F, (cudaStream_t)stream);
-    if (A % 8 == 0 && D % A8_TD == 0 && R % A8_TR == 0 && t.TD == A8_TD && t.AC == A8_AC && t.TR == A8_TR) {
-        const size_t smem = (size_t)(A8_TR + 2) * A8_W * sizeof(float);
-        cudaFuncSetAttribute(detect_a8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        detect_a8_kernel<<<(unsigned)blocks, DET_THREADS, smem, (cudaStream_t)stream>>>(
-            (const float2*)rds, range_gate, thr_power, det_eps, out, R, D, A, t);
-        RS_CHECK_LAUNCH("rs_detect(a8)");
-        return RS_OK;
+    return launch_detect((const float2*)rds, range_gate, thr_power, det_eps, out, 0, F, R, D, A, (cudaStream_t)stream, "rs_detect");
+}
+
+// ---------------------------------------------------------------------------------------------
+// 2-D FFT + detection in one call (rows a3-a8): the detection rides in the Doppler phase of the persistent FFT kernel
+// ---------------------------------------------------------------------------------------------
+int rs_range_doppler_fft_impl(const void* cube, const void* table, const void* twiddle_s, const void* twiddle_c,
+                              void* mid_ws, void* rds, int F, int A, int C_total, int chirp0, int C_used, int S,
+                              int dc_removal, void* stream, FusedDetectReq* req);
+
+extern "C" long long rs_fused_detect_ws_bytes(int F, int A) {
+    return (F > 0 && A > 0) ? (long long)((size_t)F * A * FD_BYTES_PER_PLANE) : 0;
+}
+
+namespace {
+struct SideDetectCtx {
+    const float2* rds;
+    const uint8_t* gate;
+    float thr, eps;
+    DetOut out;
+    int R, D, A, rc;
+};
+void side_detect_hook(void* ctx_, int f0, int nf, cudaStream_t st) {
+    SideDetectCtx* c = (SideDetectCtx*)ctx_;
+    c->rc = launch_detect(c->rds, c->gate, c->thr, c->eps, c->out, f0, nf, c->R, c->D, c->A, st, "rs_range_doppler_detect(side)");
+}
+}  // namespace
+
+extern "C" int rs_range_doppler_detect(const void* cube, const void* table, const void* twiddle_s, const void* twiddle_c,
+                                       void* mid_ws, void* rds, void* fused_ws, int F, int A, int C_total, int chirp0,
+                                       int C_used, int S, int dc_removal, const uint8_t* range_gate, float thr_power,
+                                       float det_eps, uint32_t* det_key, float* det_power, uint8_t* det_flags,
+                                       uint32_t* det_lead, int32_t* det_count, int32_t* det_nlead, int32_t* det_overflow,
+                                       int32_t* det_nnear, float* det_psum, int seg_cap, void* stream) {
+    RS_CHECK_ARG(cube && table && twiddle_s && twiddle_c && rds && range_gate && det_key && det_flags && det_lead &&
+                     det_count && det_nlead && det_overflow,
+                 "rs_range_doppler_detect: null pointer");
+    RS_CHECK_ARG(F > 0 && A > 0 && A <= RS_MAX_ANTENNAS && S > 0 && S <= RS_MAX_RANGE_BINS && C_used > 0 &&
+                     C_used <= RS_MAX_DOPPLER_BINS && chirp0 >= 0 && chirp0 + C_used <= C_total && seg_cap > 0 && seg_cap <= 65535,
+                 "rs_range_doppler_detect: bad dims (seg_cap must be in 1..65535)");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int R = S, D = C_used;
+    DetOut out{det_key, det_power, det_flags, det_lead, det_count, det_nlead, det_overflow, det_nnear, det_psum, seg_cap};
+    cudaMemsetAsync(det_overflow, 0, sizeof(int32_t) * F, st);
+    const char* env = getenv("RS_FUSED_DETECT");           // 0: the two stages one after the other
+    Tiling t = make_tiling(R, D, A);
+    const bool fused = fused_ws && S == 256 && C_used == 128 && A % 8 == 0 && t.TD == A8_TD && t.AC == A8_AC && t.TR == A8_TR &&
+                       !(env && atoi(env) == 0);
+    if (!fused) {
+        RS_CHECK_ARG(det_power, "rs_range_doppler_detect: det_power is optional only on the fused path");
+        int rc = rs_range_doppler_fft_impl(cube, table, twiddle_s, twiddle_c, mid_ws, rds, F, A, C_total, chirp0, C_used, S,
+                                           dc_removal, stream, nullptr);
+        if (rc != RS_OK) return rc;
+        return launch_detect((const float2*)rds, range_gate, thr_power, det_eps, out, 0, F, R, D, A, st, "rs_range_doppler_detect");
     }
-    const size_t smem = (size_t)(t.TR + 2) * (t.TD + 2) * t.AC * sizeof(float);
-    if (smem > (size_t)rs_smem_optin_limit()) {
-        rs_set_error("rs_detect: tile needs %zu B of shared memory", smem);
-        return RS_ECAPACITY;
+    const size_t planes = (size_t)F * A;
+    uint32_t* words = (uint32_t*)fused_ws;
+    FusedDetectReq req;
+    req.masks.hit = words;
+    req.masks.near = words + planes * FD_GROUPS * FD_WORDS;
+    req.masks.cand = words + 2 * planes * FD_GROUPS * FD_WORDS;
+    req.masks.rec = (float2*)(words + 3 * planes * FD_GROUPS * FD_WORDS);
+    req.masks.gate = range_gate;
+    req.masks.thr = thr_power;
+    req.masks.thrn = nextafterf(thr_power, INFINITY);
+    req.masks.eps = det_eps;
+    SideDetectCtx ctx{(const float2*)rds, range_gate, thr_power, det_eps, out, R, D, A, RS_OK};
+    req.side_hook = side_detect_hook;
+    req.ctx = &ctx;
+    req.frames_masked = 0;
+    int rc = rs_range_doppler_fft_impl(cube, table, twiddle_s, twiddle_c, mid_ws, rds, F, A, C_total, chirp0, C_used, S,
+                                       dc_removal, stream, &req);
+    if (rc != RS_OK) return rc;
+    if (ctx.rc != RS_OK) return ctx.rc;
+    const int Fm = req.frames_masked;
+    if (Fm > 0) {
+        compact_masks_kernel<<<(unsigned)((long long)Fm * t.ntiles), DET_THREADS, 0, st>>>((const float2*)rds, req.masks, out, R, D, A, t);
+        RS_CHECK_LAUNCH("rs_range_doppler_detect(compact)");
     }
-    cudaFuncSetAttribute(detect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    detect_kernel<<<(unsigned)blocks, DET_THREADS, smem, (cudaStream_t)stream>>>(
-        (const float2*)rds, range_gate, thr_power, det_eps, out, R, D, A, t);
-    RS_CHECK_LAUNCH("rs_detect");
+    if (Fm == 0)          // the fused kernel was not available: the side hook did not run either
+        return launch_detect((const float2*)rds, range_gate, thr_power, det_eps, out, 0, F, R, D, A, st, "rs_range_doppler_detect");
     return RS_OK;
 }

@@ -16,6 +16,7 @@
 #include <cooperative_groups.h>
 #include <cstdlib>
 #include "rs_common.cuh"
+#include "rs_detect_fused.cuh"
 #include "rs_fft_pow2.cuh"
 
 namespace cg = cooperative_groups;
@@ -197,11 +198,14 @@ static ForkJoin* fork_join() {
 
 // K12 v2 (rs_fft2d_ws.cu): persistent warp-specialised cluster kernel fed by TMA.  1 = launched, 0 = not applicable here.
 int rs_fft2d_ws_launch(const void* cube, const void* table, const void* twiddle_s, const void* twiddle_c, void* rds, int F,
-                       int A, int C_total, int chirp0, int dc_removal, int store_tma, int variant, cudaStream_t stream);
+                       int A, int C_total, int chirp0, int dc_removal, int store_tma, int variant, const FusedDetectMasks* fd,
+                       cudaStream_t stream);
 
-extern "C" int rs_range_doppler_fft(const void* cube, const void* table, const void* twiddle_s, const void* twiddle_c,
-                                    void* mid_ws, void* rds, int F, int A, int C_total, int chirp0, int C_used, int S,
-                                    int dc_removal, void* stream) {
+// req != nullptr: rs_range_doppler_detect asks for the detection fused into the persistent kernel (rs_detect_fused.cuh)
+int rs_range_doppler_fft_impl(const void* cube, const void* table, const void* twiddle_s, const void* twiddle_c,
+                              void* mid_ws, void* rds, int F, int A, int C_total, int chirp0, int C_used, int S,
+                              int dc_removal, void* stream, FusedDetectReq* req) {
+    if (req) req->frames_masked = 0;
     RS_CHECK_ARG(cube && table && twiddle_s && twiddle_c && rds, "rs_range_doppler_fft: null pointer");
     RS_CHECK_ARG(F > 0 && A > 0 && A <= RS_MAX_ANTENNAS && S > 0 && C_used > 0 && chirp0 >= 0 && chirp0 + C_used <= C_total,
                  "rs_range_doppler_fft: bad dims");
@@ -219,6 +223,7 @@ extern "C" int rs_range_doppler_fft(const void* cube, const void* table, const v
             // strands two SMs).  Pairs of stranded SMs can still host 2-CTA clusters, so the last RS_K12_SIDE permille
             // (default 60) of the frames go to round 1's kernel at NC = 2 on a forked stream, joined before returning:
             // 0.98 -> 0.93 ms per 1000 frames (profiles/k12_side_probe.py; a 4-CTA-cluster side kernel gains nothing).
+            // With the fused detection the side frames also run the stand-alone detection kernel on the side stream.
             const char* sd = getenv("RS_K12_SIDE");
             int side = sd ? atoi(sd) : 60;
             int F_side = (F >= 64 && side > 0) ? (int)(((long long)F * side + 500) / 1000) : 0;
@@ -232,7 +237,9 @@ extern "C" int rs_range_doppler_fft(const void* cube, const void* table, const v
                 cudaStreamWaitEvent(fj->side, fj->fork, 0);
             }
             const int r = rs_fft2d_ws_launch(cube, table, twiddle_s, twiddle_c, rds, F_side ? F_main : F, A, C_total, chirp0,
-                                             dc_removal, st && st[0] == 't', vr ? atoi(vr) : -1, main_st);
+                                             dc_removal, st && st[0] == 't', vr ? atoi(vr) : -1, req ? &req->masks : nullptr,
+                                             main_st);
+            if (r == 1 && req) req->frames_masked = F_side ? F_main : F;
             if (r == 1 && F_side) {
                 using P = Fused<16, 16, 16, 8, 2, 512>;
                 auto kern = fft2d_cluster_kernel<16, 16, 16, 8, 2, 512, 1, true>;       // packed: bit-identical to the main kernel
@@ -243,6 +250,7 @@ extern "C" int rs_range_doppler_fft(const void* cube, const void* table, const v
                                                                               (const float2*)twiddle_c, rds_s, A, C_total, chirp0,
                                                                               dc_removal);
                 const cudaError_t e = cudaGetLastError();
+                if (req && req->side_hook) req->side_hook(req->ctx, F_main, F_side, fj->side);
                 cudaEventRecord(fj->join, fj->side);
                 cudaStreamWaitEvent(main_st, fj->join, 0);
                 if (e != cudaSuccess) {
@@ -286,4 +294,11 @@ extern "C" int rs_range_doppler_fft(const void* cube, const void* table, const v
     int rc = rs_range_fft(cube, table, twiddle_s, mid_ws, F, A, C_total, chirp0, C_used, S, dc_removal, stream);
     if (rc != RS_OK) return rc;
     return rs_doppler_fft(mid_ws, twiddle_c, rds, F, A, C_used, S, stream);
+}
+
+extern "C" int rs_range_doppler_fft(const void* cube, const void* table, const void* twiddle_s, const void* twiddle_c,
+                                    void* mid_ws, void* rds, int F, int A, int C_total, int chirp0, int C_used, int S,
+                                    int dc_removal, void* stream) {
+    return rs_range_doppler_fft_impl(cube, table, twiddle_s, twiddle_c, mid_ws, rds, F, A, C_total, chirp0, C_used, S,
+                                     dc_removal, stream, nullptr);
 }

@@ -26,7 +26,9 @@
 #include <cuda.h>
 #include <cstdlib>
 #include <mutex>
+#include <cmath>
 #include "rs_common.cuh"
+#include "rs_detect_fused.cuh"
 #include "rs_fft_pow2.cuh"
 
 namespace ws {
@@ -44,7 +46,8 @@ struct __align__(128) Smem {
     float2 M[2][ROWS * MP];             // this CTA's range bins x all chirps, double buffered over planes
     float2 tw1s[S];                     // range inter-pass twiddles w_S^{k1 n2}
     float2 tw1c[C];                     // Doppler inter-pass twiddles
-    unsigned long long full_ld[MAXSTAGE], empty_ld[MAXSTAGE], full_M[2], empty_M[2];
+    float halo[2][2][C];                // DETECT: |X|^2 of range rows -1 / ROWS (the neighbour CTAs' edge rows), per M buffer
+    unsigned long long full_ld[MAXSTAGE], empty_ld[MAXSTAGE], full_M[2], empty_M[2], halo_full[2];
 };
 
 __device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -105,6 +108,24 @@ __device__ __forceinline__ float2 lds2(uint32_t a) {
 __device__ __forceinline__ void sts2(uint32_t a, float2 v) {
     asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(v.x), "f"(v.y) : "memory");
 }
+__device__ __forceinline__ void st_async_f32(uint32_t addr, float v, uint32_t mbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f32 [%0], %1, [%2];"
+                 ::"r"(addr), "f"(v), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void sts1(uint32_t a, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory");
+}
+__device__ __forceinline__ float lds1(uint32_t a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float4 lds4(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
 __device__ __forceinline__ void st_cluster(uint32_t addr, float2 v) {
     asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(v.x), "f"(v.y) : "memory");
 }
@@ -129,10 +150,17 @@ constexpr unsigned long long EVICT_FIRST = 0x12F0000000000000ull;       // creat
 // XFER: how range bins reach their owner: 0 = st.shared::cluster + one release.cluster arrive per warp,
 //       1 = st.async completing bytes on the owner's transaction barrier (no fence anywhere).
 // PACKED: butterflies with f32x2 adds (FADD2).
-template <bool STORE_TMA, int XFER, bool PACKED, int RG, int CB>
+// DETECT: the Doppler group also runs the |X|^2 local-maximum / threshold test of dechirp.py:235-263 on the plane it
+//       holds and writes hit masks (rs_detect_fused.cuh) -- the RDS is not read again by a detection pass.  The powers of
+//       a finished Doppler row replace the row in M; the two edge rows of every CTA also go to the neighbour CTAs' halo
+//       rows with st.async (512 B each, completing on the neighbour's halo barrier); warp w then walks its own 8 rows:
+//       lane = 4 Doppler columns (left / right neighbours by shuffle), 3-row sliding window of horizontal maxima, the
+//       three-zone classification of rs_detect.cu with the threshold folded into the neighbour maximum.
+template <bool STORE_TMA, int XFER, bool PACKED, int RG, int CB, bool DETECT = false>
 __global__ void __cluster_dims__(NC, 1, 1) __launch_bounds__(THREADS, 1)
 fft2d_ws_kernel(const __grid_constant__ CUtensorMap map_cube, const float2* __restrict__ table, const float2* __restrict__ tw_s_g, const float2* __restrict__ tw_c_g,
-                float2* __restrict__ rds, int A, int C_total, int chirp0, int dc_removal, int nplanes) {
+                float2* __restrict__ rds, int A, int C_total, int chirp0, int dc_removal, int nplanes, const FusedDetectMasks fd) {
+    static_assert(!(DETECT && STORE_TMA), "the fused detection reuses the rows a bulk store would still be reading");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
     constexpr int NSTAGE = CPC / CB;
@@ -158,9 +186,12 @@ fft2d_ws_kernel(const __grid_constant__ CUtensorMap map_cube, const float2* __re
         for (int b = 0; b < 2; ++b) {
             mbar_init(&sm.full_M[b], XFER == 0 ? NC * (R_THREADS / 32) : 1);
             mbar_init(&sm.empty_M[b], NC * (D_THREADS / 32));
+            mbar_init(&sm.halo_full[b], 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (DETECT)
+        for (int i = tid; i < 4 * C; i += THREADS) (&sm.halo[0][0][0])[i] = -1.f;      // rows outside the plane never win
     __syncthreads();
     cluster_sync_all();                       // every CTA's barriers exist before the first remote arrive / store
 
@@ -275,12 +306,24 @@ fft2d_ws_kernel(const __grid_constant__ CUtensorMap map_cube, const float2* __re
 #pragma unroll
         for (int k1 = 0; k1 < 16; ++k1) twd[k1] = sm.tw1c[k1 * 8 + td];
         const int k1p = lane & 15;
+        // DETECT: where this warp's edge row goes (row 0 -> the upper halo of CTA q - 1, row ROWS - 1 -> the lower halo of
+        // CTA q + 1), the range gate of this thread's 8 rows as a mask over its 32 cells
+        const bool send_dn = DETECT && w == 0 && q > 0, send_up = DETECT && w == D_THREADS / 32 - 1 && q < NC - 1;
+        uint32_t halo_dst = 0, halo_bar = 0, gatew = 0;
+        if (DETECT) {
+            if (send_dn) { halo_dst = mapa(s32(&sm.halo[0][1][0]), q - 1); halo_bar = mapa(s32(&sm.halo_full[0]), q - 1); }
+            if (send_up) { halo_dst = mapa(s32(&sm.halo[0][0][0]), q + 1); halo_bar = mapa(s32(&sm.halo_full[0]), q + 1); }
+#pragma unroll
+            for (int rl = 0; rl < 8; ++rl) gatew |= fd.gate[q * ROWS + 8 * w + rl] ? (0xFu << (4 * rl)) : 0u;
+        }
+        const uint32_t halo_bytes = (uint32_t)(((q > 0) + (q < NC - 1)) * C * sizeof(float));
         int it = 0;
         for (int plane = cid; plane < nplanes; plane += ncl, ++it) {
             const int b = it & 1;
             const int f = plane / A, a = plane - f * A;
             float2* Mb = sm.M[b];
             if (XFER == 1 && w == 0 && lane == 0) mbar_expect_tx(&sm.full_M[b], ROWS * C * sizeof(float2));
+            if (DETECT && w == 1 && lane == 0) mbar_expect_tx(&sm.halo_full[b], halo_bytes);
             mbar_wait(&sm.full_M[b], (it >> 1) & 1);
             // pass 1, in place: radix 16 over chirps td + 8 j; V[k1][td] -> slot 8 k1 + (td ^ (k1 >> 1))
             const uint32_t Ma = s32(Mb);
@@ -301,7 +344,9 @@ fft2d_ws_kernel(const __grid_constant__ CUtensorMap map_cube, const float2* __re
             // pass 2: radix 8, Doppler fftshift
 #pragma unroll 1
             for (int i = 0; i < 4; ++i) {
-                const int row = 8 * w + 2 * i + (lane >> 4);
+                // DETECT: the last warp starts with the CTA's last row, so that both edge rows are under way first
+                const int ii = (DETECT && w == D_THREADS / 32 - 1) ? 3 - i : i;
+                const int row = 8 * w + 2 * ii + (lane >> 4);
                 const uint32_t rowa = Ma + (uint32_t)(row * MP * sizeof(float2));
                 const uint32_t ub = rowa + (uint32_t)((8 * k1p + (k1p >> 1)) * sizeof(float2));
                 float2 u[8];
@@ -323,9 +368,118 @@ fft2d_ws_kernel(const __grid_constant__ CUtensorMap map_cube, const float2* __re
                     __syncwarp();
                     if (k1p == 0) bulk_store_row(dst, rowa);
                 }
+                if (DETECT) {
+                    // |X|^2 in Doppler order replaces the row (its first 512 B); the CTA's edge rows also go to the neighbours
+                    float pw8[8];
+#pragma unroll
+                    for (int k2 = 0; k2 < 8; ++k2) pw8[k2] = fmaf(u[k2].x, u[k2].x, u[k2].y * u[k2].y);
+                    __syncwarp();                                       // both rows are read before they are rewritten
+#pragma unroll
+                    for (int k2 = 0; k2 < 8; ++k2)
+                        sts1(rowa + (uint32_t)((k1p + ((16 * k2 + C / 2) & (C - 1))) * sizeof(float)), pw8[k2]);
+                    if ((send_dn && row == 0) || (send_up && row == ROWS - 1)) {
+                        const uint32_t hd = halo_dst + (uint32_t)(b * 2 * C * sizeof(float)), hb = halo_bar + (uint32_t)(b * 8);
+#pragma unroll
+                        for (int k2 = 0; k2 < 8; ++k2)
+                            st_async_f32(hd + (uint32_t)((k1p + ((16 * k2 + C / 2) & (C - 1))) * sizeof(float)), pw8[k2], hb);
+                    }
+                }
             }
             if (STORE_TMA) {
                 if (k1p == 0) asm volatile("cp.async.bulk.commit_group;\n cp.async.bulk.wait_group.read 0;" ::: "memory");
+            }
+            if (DETECT) {
+                __syncwarp();                                           // this warp's 8 power rows are in place
+                auto rowaddr = [&](int rl) -> uint32_t {                // rl = -1 .. 8 relative to this warp's first row
+                    const int row = 8 * w + rl;
+                    if (row < 0) return s32(&sm.halo[b][0][0]);
+                    if (row >= ROWS) return s32(&sm.halo[b][1][0]);
+                    return Ma + (uint32_t)(row * MP * sizeof(float2));
+                };
+                // a row of 4 powers per lane with the edge columns of the neighbouring lanes: horizontal maxima
+                struct Row { float c[4], L, R, h[4]; };
+                auto load_row = [&](int rl) {
+                    Row r;
+                    const float4 v = lds4(rowaddr(rl) + (uint32_t)(lane * 16));
+                    r.c[0] = v.x; r.c[1] = v.y; r.c[2] = v.z; r.c[3] = v.w;
+                    r.L = __shfl_up_sync(0xffffffffu, v.w, 1);
+                    r.R = __shfl_down_sync(0xffffffffu, v.x, 1);
+                    if (lane == 0) r.L = -1.f;                          // Doppler bins -1 and C: outside the plane
+                    if (lane == 31) r.R = -1.f;
+                    r.h[0] = max3(r.L, v.x, v.y); r.h[1] = max3(v.x, v.y, v.z);
+                    r.h[2] = max3(v.y, v.z, v.w); r.h[3] = max3(v.z, v.w, r.R);
+                    return r;
+                };
+                const float band = 2.f * fd.eps;
+                uint32_t hitw = 0u, surew = 0u;
+                float psum = 0.f;
+                auto cells = [&](const Row& ra, const Row& rb, const Row& rc, const int rl) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float c = rb.c[j];
+                        const float left = j == 0 ? rb.L : rb.c[j - 1], right = j == 3 ? rb.R : rb.c[j + 1];
+                        // best neighbour, with "above the threshold" folded in: p > thr <=> p >= thrn
+                        const float m2 = max3(ra.h[j], rc.h[j], max3(left, right, fd.thrn));
+                        const float cu = fmaf(c, band, c), cl = fmaf(c, -band, c);
+                        psum += c;
+                        if (cu >= m2) hitw |= 1u << (4 * rl + j);       // surely or maybe a detection
+                        if (cl >= m2) surew |= 1u << (4 * rl + j);      // surely one
+                    }
+                };
+                {
+                    // rows 1 .. 6 need this warp's rows only: no waiting for anybody
+                    Row ra = load_row(0), rb = load_row(1);
+#pragma unroll
+                    for (int rl = 1; rl < 7; ++rl) {
+                        const Row rc = load_row(rl + 1);
+                        cells(ra, rb, rc, rl);
+                        ra = rb;
+                        rb = rc;
+                    }
+                }
+                // rows 0 and 7 also need the last / first row of the neighbouring warp (one 64-thread barrier per pair of
+                // warps) or of the neighbouring CTA (the halo rows)
+                if (w > 0) named_bar_sync(2 + w, 64);
+                if (w < D_THREADS / 32 - 1) named_bar_sync(3 + w, 64);
+                if (w == 0 || w == D_THREADS / 32 - 1) mbar_wait(&sm.halo_full[b], (it >> 1) & 1);
+                {
+                    const Row ra = load_row(-1), rb = load_row(0), rc = load_row(1);
+                    cells(ra, rb, rc, 0);
+                }
+                {
+                    const Row ra = load_row(6), rb = load_row(7), rc = load_row(8);
+                    cells(ra, rb, rc, 7);
+                }
+                hitw &= gatew;
+                uint32_t uncw = hitw & ~surew, nearw = 0u, candw = 0u;  // ~1e-5 of the cells: inside the 2 eps band
+                const bool anyunc = __any_sync(0xffffffffu, uncw != 0u);
+                if (anyunc) {
+                    while (uncw) {                                      // the exact rule on the nine powers, re-read from M
+                        const int bi = __ffs(uncw) - 1;
+                        uncw &= uncw - 1;
+                        const int rl = bi >> 2, d = 4 * lane + (bi & 3);
+                        auto at = [&](int r_, int d_) {
+                            return (d_ < 0 || d_ >= C) ? -1.f : lds1(rowaddr(r_) + (uint32_t)(d_ * sizeof(float)));
+                        };
+                        const float c = at(rl, d);
+                        float m = max3(at(rl - 1, d - 1), at(rl - 1, d), at(rl - 1, d + 1));
+                        m = fmaxf(m, fmaxf(at(rl, d - 1), at(rl, d + 1)));
+                        m = fmaxf(m, max3(at(rl + 1, d - 1), at(rl + 1, d), at(rl + 1, d + 1)));
+                        const int cls = rs_classify(c, m, fd.thr, fd.eps);
+                        if (cls == 0) hitw &= ~(1u << bi);
+                        if (cls & 2) nearw |= 1u << bi;
+                        if (cls & 4) candw |= 1u << bi;
+                    }
+                }
+#pragma unroll
+                for (int off = 16; off; off >>= 1) psum += __shfl_xor_sync(0xffffffffu, psum, off);
+                const size_t gi = (size_t)plane * FD_GROUPS + q * (ROWS / 8) + w;
+                fd.hit[gi * FD_WORDS + lane] = hitw;
+                if (anyunc) {
+                    fd.near[gi * FD_WORDS + lane] = nearw;
+                    fd.cand[gi * FD_WORDS + lane] = candw;
+                }
+                if (lane == 0) fd.rec[gi] = make_float2(psum, __int_as_float(anyunc ? 1 : 0));
             }
             __syncwarp();
             if (lane < NC) mbar_arrive_remote(mapa(s32(&sm.empty_M[b]), lane));
@@ -357,8 +511,10 @@ static EncodeTiledFn encode_fn() {
 }  // namespace ws
 
 // Returns 1 when the kernel was launched, 0 when this device / shape cannot take it (the caller falls back), < 0 on error.
+// fd != nullptr: the default variant with the fused detection (hit masks of every plane into fd's buffers).
 int rs_fft2d_ws_launch(const void* cube, const void* table, const void* twiddle_s, const void* twiddle_c, void* rds, int F,
-                       int A, int C_total, int chirp0, int dc_removal, int store_tma, int variant, cudaStream_t stream) {
+                       int A, int C_total, int chirp0, int dc_removal, int store_tma, int variant, const FusedDetectMasks* fd,
+                       cudaStream_t stream) {
     using namespace ws;
     EncodeTiledFn enc = encode_fn();
     if (!enc) return 0;
@@ -367,7 +523,8 @@ int rs_fft2d_ws_launch(const void* cube, const void* table, const void* twiddle_
     if (rows_in >= (1ll << 31) || (long long)F * S >= (1ll << 31)) return 0;
     if (sizeof(Smem) > (size_t)rs_smem_optin_limit()) return 0;
 
-    if (variant < 0 || variant >= NVARIANT) variant = 4;
+    if (variant < 0 || variant >= NVARIANT || fd) variant = 4;
+    if (fd) store_tma = 0;
     const int cb = variant == 4 ? 8 : 16;                  // chirps per stage = rows of the TMA box
     CUtensorMap map_cube;
     {
@@ -380,7 +537,8 @@ int rs_fft2d_ws_launch(const void* cube, const void* table, const void* twiddle_
                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return 0;
     }
-    typedef void (*Kern)(const CUtensorMap, const float2*, const float2*, const float2*, float2*, int, int, int, int, int);
+    typedef void (*Kern)(const CUtensorMap, const float2*, const float2*, const float2*, float2*, int, int, int, int, int,
+                         const FusedDetectMasks);
     // the measured variants: [bulk store][variant]: 0 = release-arrive hand-over, scalar, 1 subgroup (the first version),
     // 1 = st.async, scalar, 1 subgroup; 2 = st.async, packed, 1 subgroup; 3 = st.async, packed, 2 subgroups;
     // 4 = as 3 with 8-chirp stages: four ring slots, two per subgroup (a slot is refilled 3/4 of a plane ahead)
@@ -389,13 +547,13 @@ int rs_fft2d_ws_launch(const void* cube, const void* table, const void* twiddle_
          fft2d_ws_kernel<false, 1, true, 2, 16>, fft2d_ws_kernel<false, 1, true, 2, 8>},
         {fft2d_ws_kernel<true, 0, false, 1, 16>, fft2d_ws_kernel<true, 1, false, 1, 16>, fft2d_ws_kernel<true, 1, true, 1, 16>,
          fft2d_ws_kernel<true, 1, true, 2, 16>, fft2d_ws_kernel<true, 1, true, 2, 8>}};
-    Kern kern = kerns[store_tma ? 1 : 0][variant];
+    Kern kern = fd ? (Kern)fft2d_ws_kernel<false, 1, true, 2, 8, true> : kerns[store_tma ? 1 : 0][variant];
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)) != cudaSuccess) {
         cudaGetLastError();
         return 0;
     }
-    static int max_clusters[2][NVARIANT] = {{-1, -1, -1, -1, -1}, {-1, -1, -1, -1, -1}};
-    int& mc = max_clusters[store_tma ? 1 : 0][variant];
+    static int max_clusters[3][NVARIANT] = {{-1, -1, -1, -1, -1}, {-1, -1, -1, -1, -1}, {-1, -1, -1, -1, -1}};
+    int& mc = max_clusters[fd ? 2 : store_tma ? 1 : 0][variant];
     if (mc < 0) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(NC * 64);
@@ -416,7 +574,7 @@ int rs_fft2d_ws_launch(const void* cube, const void* table, const void* twiddle_
     if (ncl > nplanes) ncl = nplanes;
     kern<<<ncl * NC, THREADS, sizeof(Smem), stream>>>(map_cube, (const float2*)table, (const float2*)twiddle_s,
                                                        (const float2*)twiddle_c, (float2*)rds, A, C_total, chirp0, dc_removal,
-                                                       nplanes);
+                                                       nplanes, fd ? *fd : FusedDetectMasks{});
     if (cudaGetLastError() != cudaSuccess) return 0;
     return 1;
 }

@@ -94,6 +94,16 @@ class Detections:
     threshold_db: float = -20.0                    # the threshold rs_detect ran with (needed by the fp64 recheck)
     method: Optional[str] = None                   # the method rs_angles ran with
     tag: str = ""                                  # workspace set the buffers came from
+    power_pending: bool = False                    # range_doppler_detect(defer_power=True): `power` not written yet
+    power_fill: Optional[object] = None            # callable that writes `power` (gather from the RDS the lists came from)
+
+    def materialize_power(self) -> torch.Tensor:
+        """|X|^2 of every entry.  The fused FFT + detection kernel keeps no powers; nothing on the path to the velocity
+        reads them, so they are gathered from the RDS when somebody asks (or written by angles(write_power=True))."""
+        if self.power_pending:
+            self.power_fill()
+            self.power_pending = False
+        return self.power
 
     def valid_mask(self) -> torch.Tensor:
         n = self.F * self.ntiles
@@ -114,6 +124,7 @@ class Detections:
         order = torch.argsort(key)
         key = key[order]
         out = {"key": key.cpu().numpy().astype(np.uint32)}
+        self.materialize_power()
         for name in ("power", "flags", "aidx", "adeg", "phase"):
             out[name] = getattr(self, name)[sl][m][order].cpu().numpy()
         k = out["key"]
@@ -139,6 +150,8 @@ class FramePipeline:
         self.call_counts = None    # set to {} to count calls per entry point (bench.py: kernels launched)
         self.profile = None        # set to a list to collect (stage, start_event, end_event) per launch
         self.nvtx = os.environ.get("RS_NVTX") == "1"
+        self._chunk_no = 0         # chunks processed so far: picks the workspace set
+        self._pending = None       # chunk whose fp64 recheck + solve has not been enqueued on the side stream yet
 
     def _call(self, name: str, *args) -> None:
         fn = getattr(self.lib, name)
@@ -244,13 +257,8 @@ class FramePipeline:
         cap = self.seg_cap_override or max(32, (tr * td * min(A, 8) + 3) // 4)
         return cap, ntiles
 
-    def detect(self, rds: torch.Tensor, threshold_db: Optional[float] = None, min_range: Optional[float] = None,
-               max_range: Optional[float] = None, workspace=False) -> Detections:
-        assert rds.is_cuda and rds.dtype == torch.complex64 and rds.dim() == 4 and rds.is_contiguous()
-        F, R, A, D = rds.shape
+    def _alloc_detections(self, F: int, R: int, D: int, A: int, threshold_db: Optional[float], workspace) -> Detections:
         c = self.cfg
-        thr = tables.power_threshold(c.threshold_db if threshold_db is None else threshold_db)
-        gate = self._gate(R, c.min_range if min_range is None else min_range, c.max_range if max_range is None else max_range)
         cap, ntiles = self.seg_cap_for(R, D, A)
         n = F * ntiles * cap
         tag = workspace if isinstance(workspace, str) else ""      # "0" / "1": double-buffered workspaces
@@ -258,7 +266,7 @@ class FramePipeline:
             self._ws["_nframes" + tag] = F                          # status(): how much of the overflow buffer is current
         alloc = (lambda nm, shp, dt: self._buf(nm + tag, shp, dt)) if workspace else \
             (lambda nm, shp, dt: torch.empty(shp, dtype=dt, device=self.device))
-        det = Detections(
+        return Detections(
             key=alloc("det_key", (n,), torch.int32), power=alloc("det_power", (n,), torch.float32),
             flags=alloc("det_flags", (n,), torch.uint8), aidx=alloc("det_aidx", (n,), torch.int32),
             adeg=alloc("det_adeg", (n,), torch.float32), phase=alloc("det_phase", (n,), torch.float32),
@@ -269,14 +277,54 @@ class FramePipeline:
             nnear=alloc("det_nnear", (F * ntiles,), torch.int32), psum=alloc("det_psum", (F * ntiles,), torch.float32),
             ntie=alloc("det_ntie", (F * ntiles,), torch.int32),
             tielist=alloc("det_tielist", (F * ntiles * _lib.RS_TIE_LIST_CAP,), torch.int32))
+
+    def detect(self, rds: torch.Tensor, threshold_db: Optional[float] = None, min_range: Optional[float] = None,
+               max_range: Optional[float] = None, workspace=False) -> Detections:
+        assert rds.is_cuda and rds.dtype == torch.complex64 and rds.dim() == 4 and rds.is_contiguous()
+        F, R, A, D = rds.shape
+        c = self.cfg
+        thr = tables.power_threshold(c.threshold_db if threshold_db is None else threshold_db)
+        gate = self._gate(R, c.min_range if min_range is None else min_range, c.max_range if max_range is None else max_range)
+        det = self._alloc_detections(F, R, D, A, threshold_db, workspace)
         self._call("rs_detect", rds.data_ptr(), gate.data_ptr(), thr, c.det_eps, det.key.data_ptr(),
                    det.power.data_ptr(), det.flags.data_ptr(), det.lead.data_ptr(), det.count.data_ptr(),
                    det.nlead.data_ptr(), det.overflow.data_ptr(), det.nnear.data_ptr(), det.psum.data_ptr(),
-                   cap, F, R, D, A, self.stream)
+                   det.seg_cap, F, R, D, A, self.stream)
         return det
 
+    def range_doppler_detect(self, cube: torch.Tensor, out: Optional[torch.Tensor] = None,
+                             threshold_db: Optional[float] = None, min_range: Optional[float] = None,
+                             max_range: Optional[float] = None, workspace=False, defer_power: bool = False):
+        """range_doppler() + detect() as one call: on 256 x 128 planes the detection runs inside the 2-D FFT kernel on the
+        plane it holds on chip (rs_range_doppler_detect); other shapes run the two stages.  -> (rds, detections).
+        defer_power: do not write `power` here (the fused kernel keeps no |X|^2 and nothing on the path to the velocity
+        reads it): Detections.materialize_power() gathers it from the RDS on demand, angles(write_power=True) writes it
+        from the snapshots it holds in registers anyway."""
+        assert cube.is_cuda and cube.dtype == torch.complex64 and cube.dim() == 4 and cube.is_contiguous()
+        F, A, C, S = cube.shape
+        c = self.cfg
+        tab, tw_s, tw_c = self._fft_tables(S, C)[:3]
+        thr = tables.power_threshold(c.threshold_db if threshold_db is None else threshold_db)
+        gate = self._gate(S, c.min_range if min_range is None else min_range, c.max_range if max_range is None else max_range)
+        rds = out if out is not None else torch.empty((F, S, A, C), dtype=torch.complex64, device=self.device)
+        det = self._alloc_detections(F, S, C, A, threshold_db, workspace)
+        fused_ok = S == 256 and C == 128 and A % 8 == 0
+        det.power_pending = bool(defer_power and fused_ok)
+        mid = None if fused_ok else self._buf("mid", (F, S, A, C), torch.complex64)
+        fws = self._buf("fused_ws", (int(self.lib.rs_fused_detect_ws_bytes(F, A)),), torch.uint8) if fused_ok else None
+        self._call("rs_range_doppler_detect", cube.data_ptr(), tab.data_ptr(), tw_s.data_ptr(), tw_c.data_ptr(),
+                   _lib.ptr(mid), rds.data_ptr(), _lib.ptr(fws), F, A, C, 0, C, S, int(c.dc_removal), gate.data_ptr(), thr,
+                   c.det_eps, det.key.data_ptr(), 0 if det.power_pending else det.power.data_ptr(), det.flags.data_ptr(),
+                   det.lead.data_ptr(), det.count.data_ptr(), det.nlead.data_ptr(), det.overflow.data_ptr(),
+                   det.nnear.data_ptr(), det.psum.data_ptr(), det.seg_cap, self.stream)
+        if det.power_pending:
+            det.power_fill = lambda: self._call(
+                "rs_detection_power", rds.data_ptr(), det.key.data_ptr(), det.lead.data_ptr(), det.nlead.data_ptr(),
+                det.power.data_ptr(), det.seg_cap, det.ntiles, det.F, det.R, det.D, det.A, self.stream)
+        return rds, det
+
     def angles(self, rds: torch.Tensor, det: Detections, method: Optional[str] = None,
-               fuse_ls: bool = True) -> Detections:
+               fuse_ls: bool = True, write_power: bool = False) -> Detections:
         c = self.cfg
         method = method or c.method
         if method not in _lib.METHODS:
@@ -295,7 +343,10 @@ class FramePipeline:
             t["grid_cs"].data_ptr(), _lib.ptr(det.ls_partials), int(t["symmetric"]), det.ntie.data_ptr(), det.tielist.data_ptr(),
             _lib.ptr(t["mma"]), t["mma_tiles"],
             self._buf("cell_ws" + det.tag, (17 * det.F * det.R * det.D + 16,), torch.uint8).data_ptr() if det.A > 16 else 0,
-            _lib.ptr(t["tc"]), t["tc_halves"], self.stream)
+            _lib.ptr(t["tc"]), t["tc_halves"], det.power.data_ptr() if (write_power and det.power_pending) else 0,
+            self.stream)
+        if write_power:
+            det.power_pending = False
         return det
 
     def velocity(self, det: Detections, out: Optional[torch.Tensor] = None, lambda_c: Optional[float] = None,
@@ -421,9 +472,14 @@ class FramePipeline:
 
     # ------------------------------------------------------------------ whole path
     def process(self, cube: torch.Tensor, chunk_frames: int = 512, vel_out: Optional[torch.Tensor] = None,
-                keep: bool = False):
+                keep: bool = False, join: bool = True, after_solve=None):
         """Device-resident batch: returns vel float64 [F, 8] (and the last chunk's RDS / detections when
-        keep=True and the batch is a single chunk)."""
+        keep=True and the batch is a single chunk).
+        join=False: return without making the caller's stream wait for the side stream that runs the fp64 recheck and
+        the solve of the last chunk -- the next process() call then overlaps its FFT / angle kernels with them (the two
+        workspace sets alternate across calls).  `vel` and `cube` must not be touched before join().
+        after_solve: callable enqueued right behind the solve of the last chunk, on the stream that runs it (e.g. the
+        all-gather of the velocity rows), so that it needs no join either."""
         F = cube.shape[0]
         vel = vel_out if vel_out is not None else torch.empty((F, 8), dtype=torch.float64, device=self.device)
         last = None
@@ -437,54 +493,80 @@ class FramePipeline:
         side = self._ws["side_stream"]
         side_done = self._ws.setdefault("side_done", [None, None])
         overlap = self.cfg.recheck and not keep and os.environ.get("RS_NO_OVERLAP") != "1"
-        pending = None          # (lo, hi, rds, det, ready) of the chunk whose recheck has not been enqueued yet
+        fuse_detect = os.environ.get("RS_SPLIT_DETECT") != "1"      # 1: rs_range_doppler_fft and rs_detect as two calls
+        if not overlap and self._pending is not None:
+            self._enqueue_recheck(None)
 
-        def enqueue_recheck(job, after: Optional[torch.cuda.Event]):
-            jlo, jhi, jrds, jdet, jready, jslot = job
-            with torch.cuda.stream(side):
-                side.wait_event(jready)
-                if after is not None:
-                    side.wait_event(after)
-                self.recheck_detections(cube[jlo:jhi], jdet)
-                self.recheck_angles(cube[jlo:jhi], jrds, jdet)
-                self.velocity(jdet, out=vel[jlo:jhi])
-                done = torch.cuda.Event()
-                done.record(side)
-                side_done[jslot] = done
-
-        for ci, lo in enumerate(range(0, F, chunk_frames)):
+        for lo in range(0, F, chunk_frames):
             hi = min(F, lo + chunk_frames)
             n = hi - lo
             _, A, C, S = cube.shape
+            ci = self._chunk_no                                    # alternates across calls too (join=False)
+            self._chunk_no += 1
             tag = str(ci & 1)
-            if overlap and side_done[ci & 1] is not None:
+            if side_done[ci & 1] is not None:
                 main.wait_event(side_done[ci & 1])                 # workspace set free again
                 side_done[ci & 1] = None
-            rds = self.range_doppler(cube[lo:hi], out=None if keep else self._buf("rds" + tag, (n, S, A, C), torch.complex64))
-            det = self.detect(rds, workspace=False if keep else tag)
-            if overlap and pending is not None:
-                # the recheck of the previous chunk (HBM + fp64 bound) starts once this chunk's bandwidth-bound
-                # kernels are through, so that it runs beside this chunk's FP32-issue-bound angle scan
+            rds_out = None if keep else self._buf("rds" + tag, (n, S, A, C), torch.complex64)
+            if fuse_detect:
+                rds, det = self.range_doppler_detect(cube[lo:hi], out=rds_out, workspace=False if keep else tag,
+                                                     defer_power=True)
+            else:
+                rds = self.range_doppler(cube[lo:hi], out=rds_out)
+                det = self.detect(rds, workspace=False if keep else tag)
+            if overlap and self._pending is not None:       # RS_RECHECK_LATE=1 (see below)
                 after = torch.cuda.Event()
                 after.record(main)
-                enqueue_recheck(pending, after)
-                pending = None
+                self._enqueue_recheck(after)
             self.angles(rds, det)
             if overlap:
                 ready = torch.cuda.Event()
                 ready.record(main)
-                pending = (lo, hi, rds, det, ready, ci & 1)
+                self._pending = (cube[lo:hi], vel[lo:hi], rds, det, ready, ci & 1, after_solve if hi == F else None)
+                # The recheck + solve of this chunk go to the side stream right away: they run beside the NEXT chunk's 2-D
+                # FFT, whose persistent clusters leave 16 SMs to other work (3.33 ms per 1000-frame step against 3.44 with the
+                # recheck in line; profiles/overlap_probe.py).  Beside the angle scan instead (RS_RECHECK_LATE=1) nothing is
+                # gained: the scan needs all 8 of its CTAs per SM resident, and every CTA the recheck takes slows it by as
+                # much as the recheck gains (1.27 -> 1.97 ms while 0.73 ms of recheck runs, profiles/timeline_probe.py).
+                if os.environ.get("RS_RECHECK_LATE") != "1":
+                    self._enqueue_recheck(None)
             else:
                 if self.cfg.recheck:
                     self.recheck_detections(cube[lo:hi], det)
                     self.recheck_angles(cube[lo:hi], rds, det, exhaustive=keep)
                 self.velocity(det, out=vel[lo:hi])
+                if after_solve is not None and hi == F:
+                    after_solve()
             last = (rds, det)
-        if overlap:
-            if pending is not None:
-                enqueue_recheck(pending, None)
-            main.wait_stream(side)
+        if join:
+            self.join()
         return (vel, last[0], last[1]) if keep else vel
+
+    def _enqueue_recheck(self, after: Optional[torch.cuda.Event]) -> None:
+        """fp64 recheck + solve of the pending chunk on the side stream (after its angle scan, and after `after`)."""
+        jcube, jvel, jrds, jdet, jready, jslot, jafter = self._pending
+        self._pending = None
+        side = self._ws["side_stream"]
+        with torch.cuda.stream(side):
+            side.wait_event(jready)
+            if after is not None:
+                side.wait_event(after)
+            self.recheck_detections(jcube, jdet)
+            self.recheck_angles(jcube, jrds, jdet)
+            self.velocity(jdet, out=jvel)
+            if jafter is not None:
+                jafter()
+            done = torch.cuda.Event()
+            done.record(side)
+            self._ws["side_done"][jslot] = done
+
+    def join(self) -> None:
+        """Enqueue what process(join=False) left pending and make the current stream wait for the side stream."""
+        if self._pending is not None:
+            self._enqueue_recheck(None)
+        side = self._ws.get("side_stream")
+        if side is not None:
+            torch.cuda.current_stream(self.device).wait_stream(side)
 
     def status(self) -> Dict[str, int]:
         """What the last process() call could not settle (synchronises): frames whose detection segments overflowed --
