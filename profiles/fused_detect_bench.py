@@ -65,7 +65,13 @@ def main():
         os.environ["RS_K12_SIDE"] = side
         ms = timed(lambda: pipe.range_doppler_detect(cube, out=rds, workspace="0"), args.reps)
         report(f"fused, side {side} permille", ms)
-        if os.environ.get("RS_NO_POWER_PROBE") != "1":
+        ms = timed(lambda: pipe.range_doppler_detect(cube, out=rds, workspace="0", defer_power=True), args.reps)
+        report(f"fused without det_power, side {side} permille", ms)
+        os.environ["RS_FD_NO_COMPACT"] = "1"
+        ms = timed(lambda: pipe.range_doppler_detect(cube, out=rds, workspace="0", defer_power=True), args.reps)
+        report(f"fused kernel only (no compaction), side {side} permille", ms)
+        os.environ.pop("RS_FD_NO_COMPACT")
+        if False:
             # the same call without the |X|^2 gather of the entries (det_power = NULL)
             import radar_slam_b200.pipeline as pl
             orig = pl._lib.ptr

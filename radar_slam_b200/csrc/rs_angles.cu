@@ -453,7 +453,7 @@ __device__ __forceinline__ void track_max(Track& t, float hi, int pair) {
     t.idx = up ? pair : t.idx;
 }
 
-template <int AP, int MINB>
+template <int AP, int MINB, bool POWER = false>
 __global__ void __launch_bounds__(ANG_THREADS, MINB) angles_mma_kernel(AngleArgs p, const uint32_t* __restrict__ mma_table,
                                                                   int ntiles, const double* __restrict__ grid_cs,
                                                                   double* __restrict__ ls_partials) {
@@ -501,7 +501,7 @@ __global__ void __launch_bounds__(ANG_THREADS, MINB) angles_mma_kernel(AngleArgs
 #pragma unroll
                     for (int m = 0; m < AP; ++m) s[m] = (m < M) ? __ldg(cell + (size_t)m * p.D) : make_float2(0.f, 0.f);
                     yv = atan2f(s[1].y * s[0].x - s[1].x * s[0].y, s[1].x * s[0].x + s[1].y * s[0].y);
-                    emit_power<AP>(p, o, mult, s);
+                    if (POWER) emit_power<AP>(p, o, mult, s);      // own instantiation: the extra registers cost the plain scan 2 %
                 } else {
 #pragma unroll
                     for (int m = 0; m < AP; ++m) s[m] = make_float2(0.f, 0.f);
@@ -1328,15 +1328,20 @@ extern "C" int rs_angles(const void* rds, const float* scan_table, int scan_stri
                 }
                 if (sm <= (size_t)rs_smem_optin_limit()) {
                     // occupancy beats per-warp ILP here (measured): 64 registers / 8 CTAs per SM at A <= 8
+                    // (9 / 10 CTAs at 56 / 48 registers spill more than the extra warps hide: 1.49 / 1.64 ms against 1.26)
+#define LAUNCH_MMA(KERN)                                                                                       \
+    do {                                                                                                       \
+        cudaFuncSetAttribute(KERN, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);                     \
+        KERN<<<(unsigned)blocks, ANG_THREADS, sm, st>>>(p, (const uint32_t*)mma_table, mma_tiles, grid_cs, ls_partials); \
+    } while (0)
                     if (ap == 8) {
-                        cudaFuncSetAttribute(angles_mma_kernel<8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-                        angles_mma_kernel<8, 8><<<(unsigned)blocks, ANG_THREADS, sm, st>>>(p, (const uint32_t*)mma_table, mma_tiles, grid_cs,
-                                                                                        ls_partials);
+                        if (det_power_out) LAUNCH_MMA((angles_mma_kernel<8, 8, true>));
+                        else LAUNCH_MMA((angles_mma_kernel<8, 8>));
                     } else {
-                        cudaFuncSetAttribute(angles_mma_kernel<16, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-                        angles_mma_kernel<16, 5><<<(unsigned)blocks, ANG_THREADS, sm, st>>>(p, (const uint32_t*)mma_table, mma_tiles,
-                                                                                         grid_cs, ls_partials);
+                        if (det_power_out) LAUNCH_MMA((angles_mma_kernel<16, 5, true>));
+                        else LAUNCH_MMA((angles_mma_kernel<16, 5>));
                     }
+#undef LAUNCH_MMA
                     RS_CHECK_LAUNCH("rs_angles(mma)");
                     return RS_OK;
                 }

@@ -237,8 +237,8 @@ __device__ __forceinline__ int a8_off(int rr, int ddp, int quad) {          // f
     return rr * A8_W + ddp * A8_AC + ((quad ^ ((ddp >> 2) & 1)) << 2);
 }
 
-// Tail shared by detect_a8_kernel and compact_masks_kernel: per-thread masks (byte per row: antenna mask; rows rbase+1 ..
-// rbase+8 of the tile, Doppler column ddp) -> the tile's segment.  power_at(rr, j): |X|^2 of row rr (1-based), antenna j.
+// Tail of detect_a8_kernel: per-thread masks (byte per row: antenna mask; rows rbase+1 .. rbase+8 of the tile, Doppler
+// column ddp) -> the tile's segment.  power_at(rr, j): |X|^2 of row rr (1-based), antenna j.
 template <class PowerAt>
 __device__ __forceinline__ void a8_emit(const uint32_t (&hit)[2], const uint32_t (&near)[2], const uint32_t (&cand)[2],
                                         int my_near, float my_psum, const DetOut& out, int f, int r0, int d0, int a0,
@@ -466,49 +466,137 @@ detect_a8_kernel(const float2* __restrict__ rds, const uint8_t* __restrict__ gat
 // Compaction of the hit masks the fused 2-D FFT kernel wrote (rs_detect_fused.cuh, rs_fft2d_ws.cu): the same segments,
 // order, leaders and counters as detect_a8_kernel, from 2 KB of mask words per tile instead of the tile's 144 KB of RDS.
 // Same thread <-> cell assignment as the walk above: thread = (Doppler bin, half of the 16 rows) = one row group of the
-// masks, all 8 antennas of the octet.  det_power (optional) is gathered from the RDS for the entries only.
+// masks, all 8 antennas of the octet.  Byte (d & 3) of antenna j's word is the thread's 8-row column on that antenna; an
+// 8 x 8 bit transpose turns the eight columns into the 64-bit mask "byte i = antennas that flagged row i", whose set bits
+// in ascending order ARE the thread's entries in list order.  The list is assembled in shared memory and leaves as
+// coalesced rows (a thread's ~6 entries sit at consecutive positions: direct stores would touch 32 sectors per
+// instruction).  det_power (optional) is gathered from the RDS for the entries only.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t spread_nibbles(uint32_t v) {      // bit 4 i of the low 16 bits -> bit 8 i
-    return (v & 1u) | ((v & 0x10u) << 4) | ((v & 0x100u) << 8) | ((v & 0x1000u) << 12);
+constexpr int EMIT_STAGE = 2048;          // staged entries per tile (a tile of the benchmark scene holds ~1 500); the rest go direct
+
+__device__ __forceinline__ unsigned long long transpose8x8(unsigned long long x) {     // bit (8 r + c) <-> bit (8 c + r)
+    unsigned long long t;
+    t = (x ^ (x >> 7)) & 0x00AA00AA00AA00AAull;  x ^= t ^ (t << 7);
+    t = (x ^ (x >> 14)) & 0x0000CCCC0000CCCCull; x ^= t ^ (t << 14);
+    t = (x ^ (x >> 28)) & 0x00000000F0F0F0F0ull; x ^= t ^ (t << 28);
+    return x;
 }
 
 __global__ void __launch_bounds__(DET_THREADS)
 compact_masks_kernel(const float2* __restrict__ rds, FusedDetectMasks fd, DetOut out, int R, int D, int A, Tiling tl) {
+    __shared__ int warp_sums[DET_THREADS / 32];
+    __shared__ int total_s;
+    __shared__ uint32_t s_key[EMIT_STAGE], s_lead[EMIT_STAGE];
+    __shared__ __align__(16) uint8_t s_flags[EMIT_STAGE];
     const int tile = blockIdx.x % tl.ntiles;
     const int f = blockIdx.x / tl.ntiles;
     const int ia = tile % tl.nac;
     const int ir = tile / tl.nac;                    // ntd == 1: a tile spans the Doppler axis
-    const int r0 = ir * A8_TR, d0 = 0, a0 = ia * A8_AC;
+    const int a0 = ia * A8_AC;
     const int tid = threadIdx.x;
-    const int ddp = (tid & (A8_TD - 1)) + 1, rh = tid >> 7;
-    const int rbase = rh * A8_HALF;
-    const int d = ddp - 1, sh = d & 3;
-    uint32_t hit[2] = {0u, 0u}, near[2] = {0u, 0u}, cand[2] = {0u, 0u};
+    const int d = tid & (A8_TD - 1), rh = tid >> 7;
+    const int row0 = ir * A8_TR + rh * A8_HALF;      // first of this thread's 8 range bins
+    const int sh = 8 * (d & 3);
+    unsigned long long cols = 0ull, ncols = 0ull, ccols = 0ull;        // byte j: the 8-row column of antenna a0 + j
     float my_psum = 0.f;
+    bool any_near = false;
 #pragma unroll
     for (int j = 0; j < A8_AC; ++j) {
         const size_t gi = ((size_t)f * A + a0 + j) * FD_GROUPS + 2 * ir + rh;
         const uint32_t w = __ldg(fd.hit + gi * FD_WORDS + (d >> 2));
-        const uint32_t x = (w >> sh) & 0x11111111u;
-        hit[0] |= spread_nibbles(x & 0xFFFFu) << j;
-        hit[1] |= spread_nibbles(x >> 16) << j;
+        cols |= (unsigned long long)((w >> sh) & 0xFFu) << (8 * j);
         const float2 rec = __ldg(fd.rec + gi);
         if (__float_as_int(rec.y)) {                 // warp-uniform: this row group has cells inside the guard band
-            const uint32_t xn = (__ldg(fd.near + gi * FD_WORDS + (d >> 2)) >> sh) & 0x11111111u;
-            const uint32_t xc = (__ldg(fd.cand + gi * FD_WORDS + (d >> 2)) >> sh) & 0x11111111u;
-            near[0] |= spread_nibbles(xn & 0xFFFFu) << j;
-            near[1] |= spread_nibbles(xn >> 16) << j;
-            cand[0] |= spread_nibbles(xc & 0xFFFFu) << j;
-            cand[1] |= spread_nibbles(xc >> 16) << j;
+            any_near = true;
+            ncols |= (unsigned long long)((__ldg(fd.near + gi * FD_WORDS + (d >> 2)) >> sh) & 0xFFu) << (8 * j);
+            ccols |= (unsigned long long)((__ldg(fd.cand + gi * FD_WORDS + (d >> 2)) >> sh) & 0xFFu) << (8 * j);
         }
         if (d == 0) my_psum += rec.x;                // threads 0 and 128: the 16 row-group sums of the tile, fixed order
     }
-    const int my_near = __popc(near[0]) + __popc(near[1]);
+    const unsigned long long m64 = transpose8x8(cols);                 // byte i: antennas that flagged row row0 + i
+    unsigned long long n64 = 0ull, c64 = 0ull;
+    if (any_near) { n64 = transpose8x8(ncols); c64 = transpose8x8(ccols); }
+    // entries and leaders (= rows with a non-zero byte) of this thread, scanned together (entries <= 2^14 per tile)
+    unsigned long long nz = m64 | (m64 >> 4);
+    nz |= nz >> 2;
+    nz |= nz >> 1;
+    nz &= 0x0101010101010101ull;
+    const int packed = block_exclusive_scan(__popcll(m64) | (__popcll(nz) << 16), warp_sums, &total_s);
+    const int total = total_s & 0xFFFF, total_lead = total_s >> 16;
+    const size_t seg = (size_t)blockIdx.x;
+    int pos = packed & 0xFFFF, lpos = packed >> 16;
+    if (tid == 0) {
+        out.count[seg] = total < out.seg_cap ? total : out.seg_cap;
+        if (total > out.seg_cap) out.overflow[f] = 1;
+    }
+    {
+        __shared__ int near_s;
+        __shared__ float psum_s;
+        block_sums(__popcll(n64), my_psum, &near_s, &psum_s);
+        if (tid == 0) {
+            if (out.nnear) out.nnear[seg] = near_s;
+            if (out.psum) out.psum[seg] = psum_s;
+        }
+    }
     const float2* frame = rds + (size_t)f * R * D * A;
-    a8_emit(hit, near, cand, my_near, my_psum, out, f, r0, d0, a0, rbase, ddp, [&](int rr, int j) {
-        const float2 x = __ldg(frame + ((size_t)(r0 + rr - 1) * A + a0 + j) * D + d);
-        return fmaf(x.x, x.x, x.y * x.y);
-    });
+    uint32_t* gk = out.key + seg * out.seg_cap;
+    uint32_t* gl = out.lead + seg * out.seg_cap;
+    uint8_t* gf = out.flags + seg * out.seg_cap;
+    const uint32_t key0 = rs_make_key(a0, row0, d);
+    int kept = 0, last_row = -1;
+    unsigned long long m = m64;
+    while (m) {                                      // set bits in ascending order = rows ascending, antennas ascending
+        const int b = __ffsll((long long)m) - 1;
+        m &= m - 1;
+        const int i = b >> 3, j = b & 7;
+        if (i != last_row) {                         // first entry of a cell: its leader
+            last_row = i;
+            const int k = __popc((uint32_t)(m64 >> (8 * i)) & 0xFFu);
+            if (pos + k <= out.seg_cap) {            // a leader is kept only if all of its cell's entries fit
+                const uint32_t lv = (uint32_t)pos | ((uint32_t)k << 16);
+                if (lpos < EMIT_STAGE) s_lead[lpos] = lv;
+                else gl[lpos] = lv;
+                ++kept;
+            }
+            ++lpos;
+        }
+        if (pos < out.seg_cap) {
+            const uint32_t kv = key0 + ((uint32_t)j << 24) + ((uint32_t)i << 12);
+            const uint8_t fv = ((c64 >> b) & 1ull) ? (RS_FLAG_NEARMAX | RS_FLAG_DROPPED) : ((n64 >> b) & 1ull) ? RS_FLAG_NEARMAX : 0;
+            if (pos < EMIT_STAGE) {
+                s_key[pos] = kv;
+                s_flags[pos] = fv;
+            } else {
+                gk[pos] = kv;
+                gf[pos] = fv;
+            }
+            if (out.power) {
+                const float2 x = __ldg(frame + ((size_t)(row0 + i) * A + a0 + j) * D + d);
+                out.power[seg * out.seg_cap + pos] = fmaf(x.x, x.x, x.y * x.y);
+            }
+        }
+        ++pos;
+    }
+    __syncthreads();
+    {
+        const int n = min(min(total, out.seg_cap), EMIT_STAGE), nl = min(total_lead, EMIT_STAGE);
+        for (int i = tid; i < n; i += DET_THREADS) gk[i] = s_key[i];
+        for (int i = tid; i < nl; i += DET_THREADS) gl[i] = s_lead[i];      // slots beyond the kept leaders are never read
+        if (out.seg_cap % 4 == 0) {
+            for (int i = tid; i < (n + 3) / 4; i += DET_THREADS)            // the tail bytes of the last word lie beyond `count`
+                reinterpret_cast<uint32_t*>(gf)[i] = reinterpret_cast<const uint32_t*>(s_flags)[i];
+        } else {
+            for (int i = tid; i < n; i += DET_THREADS) gf[i] = s_flags[i];
+        }
+    }
+    // number of kept leaders: all of them unless the segment overflowed (then a block sum, uniform branch)
+    if (total <= out.seg_cap) {
+        if (tid == 0) out.nlead[seg] = total_lead;
+    } else {
+        __syncthreads();
+        block_exclusive_scan(kept, warp_sums, &total_s);
+        if (tid == 0) out.nlead[seg] = total_s;
+    }
 }
 
 }  // namespace
@@ -646,7 +734,8 @@ extern "C" int rs_range_doppler_detect(const void* cube, const void* table, cons
     if (rc != RS_OK) return rc;
     if (ctx.rc != RS_OK) return ctx.rc;
     const int Fm = req.frames_masked;
-    if (Fm > 0) {
+    const char* nc = getenv("RS_FD_NO_COMPACT");          // timing probe only: leave the lists unwritten
+    if (Fm > 0 && !(nc && atoi(nc) == 1)) {
         compact_masks_kernel<<<(unsigned)((long long)Fm * t.ntiles), DET_THREADS, 0, st>>>((const float2*)rds, req.masks, out, R, D, A, t);
         RS_CHECK_LAUNCH("rs_range_doppler_detect(compact)");
     }

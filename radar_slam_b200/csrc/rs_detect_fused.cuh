@@ -4,8 +4,9 @@
 //
 // The FFT kernel holds a whole (frame, antenna) plane on chip when the Doppler pass finishes, so the |X|^2 local-maximum
 // / threshold test runs there and the RDS is not read again: per plane it writes 32 row groups (8 range bins each) of
-//   hit   uint32 [32 lanes]   lane l covers Doppler bins 4 l .. 4 l + 3; bit 4 rl + j <=> cell (range 8 g + rl, Doppler 4 l + j)
-//                             is a detection or a near-miss candidate (the same set rs_detect's hit masks hold)
+//   hit   uint32 [32 lanes]   lane l covers Doppler bins 4 l .. 4 l + 3; bit 8 j + rl <=> cell (range 8 g + rl, Doppler 4 l + j)
+//                             is a detection or a near-miss candidate (the same set rs_detect's hit masks hold): byte j of
+//                             the word is the 8-row column of Doppler bin 4 l + j
 //   near / cand               the same layout for RS_FLAG_NEARMAX / near-miss candidates; written only for row groups whose
 //                             record says so (~1 % of them)
 //   rec   float2              x = sum of |X|^2 over the row group (noise level for the recheck bound), y = int: near / cand

@@ -314,7 +314,7 @@ fft2d_ws_kernel(const __grid_constant__ CUtensorMap map_cube, const float2* __re
             if (send_dn) { halo_dst = mapa(s32(&sm.halo[0][1][0]), q - 1); halo_bar = mapa(s32(&sm.halo_full[0]), q - 1); }
             if (send_up) { halo_dst = mapa(s32(&sm.halo[0][0][0]), q + 1); halo_bar = mapa(s32(&sm.halo_full[0]), q + 1); }
 #pragma unroll
-            for (int rl = 0; rl < 8; ++rl) gatew |= fd.gate[q * ROWS + 8 * w + rl] ? (0xFu << (4 * rl)) : 0u;
+            for (int rl = 0; rl < 8; ++rl) gatew |= fd.gate[q * ROWS + 8 * w + rl] ? (0x01010101u << rl) : 0u;
         }
         const uint32_t halo_bytes = (uint32_t)(((q > 0) + (q < NC - 1)) * C * sizeof(float));
         int it = 0;
@@ -422,8 +422,8 @@ fft2d_ws_kernel(const __grid_constant__ CUtensorMap map_cube, const float2* __re
                         const float m2 = max3(ra.h[j], rc.h[j], max3(left, right, fd.thrn));
                         const float cu = fmaf(c, band, c), cl = fmaf(c, -band, c);
                         psum += c;
-                        if (cu >= m2) hitw |= 1u << (4 * rl + j);       // surely or maybe a detection
-                        if (cl >= m2) surew |= 1u << (4 * rl + j);      // surely one
+                        if (cu >= m2) hitw |= 1u << (8 * j + rl);       // surely or maybe a detection
+                        if (cl >= m2) surew |= 1u << (8 * j + rl);      // surely one
                     }
                 };
                 {
@@ -457,7 +457,7 @@ fft2d_ws_kernel(const __grid_constant__ CUtensorMap map_cube, const float2* __re
                     while (uncw) {                                      // the exact rule on the nine powers, re-read from M
                         const int bi = __ffs(uncw) - 1;
                         uncw &= uncw - 1;
-                        const int rl = bi >> 2, d = 4 * lane + (bi & 3);
+                        const int rl = bi & 7, d = 4 * lane + (bi >> 3);
                         auto at = [&](int r_, int d_) {
                             return (d_ < 0 || d_ >= C) ? -1.f : lds1(rowaddr(r_) + (uint32_t)(d_ * sizeof(float)));
                         };
