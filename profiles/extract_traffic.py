@@ -8,10 +8,11 @@ import subprocess
 import sys
 
 STAGE = {"recheck_detect": "rs_recheck_detections_f64", "range_fft": "rs_range_fft",
-         "doppler_fft": "rs_doppler_fft", "detect_a8": "rs_detect", "detect_kernel": "rs_detect", "angles_": "rs_angles",
+         "doppler_fft": "rs_doppler_fft", "detect_kernel": "rs_detect", "angles_": "rs_angles",
          "velocity_from": "rs_velocity_from_partials"}
 RECHECK_PARTS = ("recheck_angles", "recheck_snapshots", "recheck_finish")
 K12_PARTS = ("fft2d_ws", "fft2d_cluster")        # one rs_range_doppler_fft call = persistent cluster kernel + side kernel
+FUSED_PARTS = ("compact_masks", "detect_a8")      # rs_range_doppler_detect = the two above (detection fused) + compaction + side frames' detect
 MULT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 
 
@@ -25,7 +26,7 @@ def main():
     acc, parts, k12 = {}, {}, {}
     for r in rows[2:]:
         b = num(r[rd]) * MULT[units[rd]] + num(r[wr]) * MULT[units[wr]]
-        hit12 = [k for k in K12_PARTS if k in r[ki]]
+        hit12 = [k for k in K12_PARTS + FUSED_PARTS if k in r[ki]]
         if hit12:
             k12.setdefault(hit12[0], []).append(b)
             continue
@@ -41,7 +42,12 @@ def main():
                 break
     per_frame = {k: sum(v) / len(v) / frames for k, v in acc.items()}
     if k12:
-        per_frame["rs_range_doppler_fft"] = sum(sum(v) / len(v) for v in k12.values()) / frames
+        fused = "compact_masks" in k12
+        if not fused and "detect_a8" in k12:
+            per_frame["rs_detect"] = sum(k12["detect_a8"]) / len(k12.pop("detect_a8")) / frames
+        per_frame["rs_range_doppler_detect" if fused else "rs_range_doppler_fft"] = sum(sum(v) / len(v) for v in k12.values()) / frames
+        if fused:
+            per_frame["parts_of_rs_range_doppler_detect"] = {k: sum(v) / len(v) / frames for k, v in k12.items()}
     if parts:
         per_frame["rs_recheck_angles_f64"] = sum(sum(v) / len(v) for v in parts.values()) / frames
     json.dump({"source": f"{d}/prof.ncu-rep (ncu --set full --clock-control none): dram__bytes_read.sum + dram__bytes_write.sum "
