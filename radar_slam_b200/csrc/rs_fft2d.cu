@@ -223,9 +223,13 @@ int rs_range_doppler_fft_impl(const void* cube, const void* table, const void* t
             // strands two SMs).  Pairs of stranded SMs can still host 2-CTA clusters, so the last RS_K12_SIDE permille
             // (default 60) of the frames go to round 1's kernel at NC = 2 on a forked stream, joined before returning:
             // 0.98 -> 0.93 ms per 1000 frames (profiles/k12_side_probe.py; a 4-CTA-cluster side kernel gains nothing).
-            // With the fused detection the side frames also run the stand-alone detection kernel on the side stream.
+            // With the fused detection (req) the side frames also run the stand-alone detection kernel on the side stream --
+            // but the default there is NO side kernel: that call is made by FramePipeline.process, which runs the fp64
+            // recheck of the previous launch set on a second stream at the same time, and the latency-bound recheck kernels
+            // make better use of the 16 stranded SMs than 6 % of the FFT does (3.15 against 3.27 ms per 1000-frame step,
+            // profiles/side_share_probe.sh).
             const char* sd = getenv("RS_K12_SIDE");
-            int side = sd ? atoi(sd) : 60;
+            int side = sd ? atoi(sd) : (req ? 0 : 60);
             int F_side = (F >= 64 && side > 0) ? (int)(((long long)F * side + 500) / 1000) : 0;
             if (F_side >= F) F_side = 0;
             const int F_main = F - F_side;

@@ -127,12 +127,22 @@ recheck_detect_kernel(CubeView v, double thr64, const uint32_t* __restrict__ det
     __shared__ int items[RC_MAX_ITEMS];
     __shared__ int wcnt[RC_WARPS];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    // which of the CTA's segments have anything to settle: all counters are fetched at once (one memory latency instead of
+    // one per segment -- almost every segment is clean, and a clean CTA used to walk eight dependent loads)
+    __shared__ unsigned todo_s;
+    if (threadIdx.x < 32) {
+        const int seg = blockIdx.x * RC_WARPS + lane;
+        bool work = false;
+        if (lane < RC_WARPS && seg < nseg_total) work = (det_nnear == nullptr || det_nnear[seg] != 0) && det_count[seg] != 0;
+        const unsigned m = __ballot_sync(0xffffffffu, work);
+        if (lane == 0) todo_s = m;
+    }
+    __syncthreads();
+    const unsigned todo_mask = todo_s;
     for (int sg = 0; sg < RC_WARPS; ++sg) {
+        if (!((todo_mask >> sg) & 1u)) continue;
         const int seg = blockIdx.x * RC_WARPS + sg;
-        if (seg >= nseg_total) break;
-        if (det_nnear != nullptr && det_nnear[seg] == 0) continue;
         const int n = det_count[seg];
-        if (n == 0) continue;
         const size_t base = (size_t)seg * seg_cap;
         // ordered list of the segment's undecided entries
         int total = 0;
@@ -397,6 +407,19 @@ struct StageAResult {
     int undecided, r, d, li;
 };
 
+// Everything the evaluation and the commit of one listed cell read from global memory, fetched by ONE thread per cell for
+// all cells of the CTA at once (A <= SA_AMAX): the chain leader -> key / old index / phase / flags -> snapshot is three
+// memory latencies for the whole CTA instead of eight per cell, which is what the kernel's time was (14 % issue, 16 %
+// occupancy: 0.22 ms per 1000 frames for 0.5 GFLOP).
+constexpr int SA_STAGE = 64;          // cells staged per round (a CTA of the benchmark scene lists ~14)
+constexpr int SA_AMAX = 16;
+struct StagedCell {
+    uint32_t pos;      // position of the cell's first entry in its segment
+    int k, r, d, old, w, li;
+    float y;
+    uint8_t fl[8];     // flags of its first 8 entries
+};
+
 __global__ void __launch_bounds__(RC_THREADS, 4)
 recheck_angles_kernel(CubeView v, AngleFix q, int32_t* __restrict__ work_idx, int32_t* __restrict__ work_cnt,
                       int32_t* __restrict__ frame_cnt, int4* __restrict__ frame_list, int32_t* __restrict__ stats) {
@@ -479,12 +502,84 @@ recheck_angles_kernel(CubeView v, AngleFix q, int32_t* __restrict__ work_idx, in
 
     // ---- phase 2: all listed cells of the CTA, round-robin over its warps
     const int total = off[RC_WARPS];
-    for (int t = wid; t < total; t += RC_WARPS) {
-        int w = 0;
-        while (t >= off[w + 1]) ++w;
-        evaluate(blockIdx.x * RC_WARPS + w, items[w][t - off[w]], ds_seg[w], res[t]);
+    if (A <= SA_AMAX) {
+        __shared__ StagedCell st[SA_STAGE];
+        for (int t0 = 0; t0 < total; t0 += SA_STAGE) {
+            const int nt = min(SA_STAGE, total - t0);
+            if ((int)threadIdx.x < nt) {                    // 2a: one thread per cell gathers what the cell needs
+                const int t = t0 + threadIdx.x;
+                int w = 0;
+                while (t >= off[w + 1]) ++w;
+                StagedCell& c = st[threadIdx.x];
+                c.w = w;
+                c.li = items[w][t - off[w]];
+                const int sg = blockIdx.x * RC_WARPS + w;
+                const size_t sbase = (size_t)sg * q.seg_cap;
+                const uint32_t ldj = q.det_lead[sbase + c.li];
+                c.pos = ldj & 0xFFFFu;
+                c.k = (int)(ldj >> 16);
+                const size_t o = sbase + c.pos;
+                int a;
+                rs_split_key(q.det_key[o], a, c.r, c.d);
+                c.old = q.det_aidx[o];
+                c.y = q.det_phase[o];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) c.fl[e] = e < c.k ? q.det_flags[o + e] : (uint8_t)0;
+                const float2* cell = q.rds + ((size_t)(sg / q.nseg) * q.R + c.r) * A * q.D + c.d;
+                double2* sn = smd + (size_t)threadIdx.x * A;
+                for (int m = 0; m < A; ++m) {
+                    const float2 x = cell[(size_t)m * q.D];
+                    sn[m] = make_double2((double)x.x, (double)x.y);
+                }
+            }
+            __syncthreads();
+            for (int j = wid; j < nt; j += RC_WARPS) {      // 2b: fp64 scans out of shared memory
+                const StagedCell& c = st[j];
+                const double2* sn = smd + (size_t)j * A;
+                double energy = 0;
+                for (int m = 0; m < A; ++m) energy += sn[m].x * sn[m].x + sn[m].y * sn[m].y;
+                // |dS|_2 <= fft_eps * rms * sqrt(A)  (noise-like part)  +  1.5e-7 |s|_2  (part that scales with the cell)
+                const ScanRes sr = scan_warp(q, sn, A, energy, ds_seg[c.w] + 1.5e-7 * sqrt(energy));
+                if (lane == 0) {
+                    StageAResult& out = res[t0 + j];
+                    for (int i = 0; i < 5; ++i) out.dl[i] = 0;
+                    out.undecided = sr.undecided ? 1 : 0;
+                    out.r = c.r; out.d = c.d; out.li = c.li;
+                    if (!sr.undecided) {                    // apply_angle() from the staged values
+                        const size_t o = (size_t)(blockIdx.x * RC_WARPS + c.w) * q.seg_cap + c.pos;
+                        const int idx = sr.idx;
+                        const float deg = q.grid_deg[idx];
+                        int live = 0;
+                        for (int e = 0; e < c.k; ++e) {
+                            const uint8_t fl = e < 8 ? c.fl[e] : q.det_flags[o + e];
+                            live += (fl & RS_FLAG_DROPPED) ? 0 : 1;
+                            q.det_flags[o + e] = fl | RS_FLAG_FIXED;
+                            q.det_aidx[o + e] = idx;
+                            q.det_adeg[o + e] = deg;
+                        }
+                        if (c.old != idx && live > 0) {
+                            const double wgt = (double)live, y = (double)c.y;
+                            const double c0 = q.grid_cs[2 * c.old], s0 = q.grid_cs[2 * c.old + 1];
+                            const double c1 = q.grid_cs[2 * idx], s1 = q.grid_cs[2 * idx + 1];
+                            out.dl[0] = wgt * (c1 * c1 - c0 * c0); out.dl[1] = wgt * (s1 * s1 - s0 * s0);
+                            out.dl[2] = wgt * (c1 * s1 - c0 * s0);
+                            out.dl[3] = wgt * y * (c1 - c0);       out.dl[4] = wgt * y * (s1 - s0);
+                        }
+                        atomicAdd(stats + 0, 1);
+                        if (c.old != idx) atomicAdd(stats + 1, 1);
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    } else {
+        for (int t = wid; t < total; t += RC_WARPS) {
+            int w = 0;
+            while (t >= off[w + 1]) ++w;
+            evaluate(blockIdx.x * RC_WARPS + w, items[w][t - off[w]], ds_seg[w], res[t]);
+        }
+        __syncthreads();
     }
-    __syncthreads();
 
     // ---- phase 3: commit this warp's segment in list order
     if (!seg_ok) return;
@@ -699,7 +794,7 @@ extern "C" int rs_recheck_angles_f64(const void* cube, const void* table128, con
                det_tielist, det_key, det_lead, det_nlead, det_flags, det_aidx, det_adeg, det_phase, ls_partials, seg_cap,
                nseg_per_frame, (int)nseg_total, S, C};
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t smem_a = (size_t)RC_WARPS * A * sizeof(double2);
+    const size_t smem_a = (size_t)(A <= SA_AMAX ? SA_STAGE : RC_WARPS) * A * sizeof(double2);
     const size_t smem_b1 = (size_t)(NB_MAX * C + RC_WARPS * NB_MAX) * sizeof(double2);
     if (smem_b1 > (size_t)rs_smem_optin_limit() || smem_a > (size_t)rs_smem_optin_limit()) {
         rs_set_error("rs_recheck_angles_f64: needs %zu B of shared memory", smem_b1 > smem_a ? smem_b1 : smem_a);
