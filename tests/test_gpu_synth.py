@@ -73,5 +73,56 @@ def test_simulator_class_matches_reference_interface():
     assert np.abs(frame - want[:, None, :]).max() <= 2e-7 * np.abs(want).max()
     td, ph = sim.compute_target_response(10.0, 0.2, 0.0, -5.0, 0.0)
     assert td == 2 * 10.0 / 3e8 and ph.shape == (4,)
-    with pytest.raises(NotImplementedError):
-        sim.process_sequence("x", "y")
+    with pytest.raises(FileNotFoundError):
+        sim.process_sequence("/nonexistent/sequence", "/tmp/rs_b200_unused_out")
+
+
+def test_process_sequence_file_interface(tmp_path, monkeypatch):
+    """simulate_raw.py:223-335: RadarScenes detections grouped by timestamp -> frame_NNNN.npy + synthesis_metadata.json.
+    h5py is replaced by a stand-in that serves a structured array (the container has no HDF5 library)."""
+    import json
+    import sys
+    import types
+    from radar_slam_b200.compat.simulate_raw import FMCWRadarSimulator
+    rng = np.random.RandomState(4)
+    n = 23
+    rec = np.zeros(n, dtype=[("timestamp", "i8"), ("range_sc", "f4"), ("azimuth_sc", "f4"), ("rcs", "f4"), ("vr", "f4"),
+                             ("x_cc", "f4"), ("y_cc", "f4")])
+    rec["timestamp"] = rng.choice([100, 250, 170, 900], size=n)           # unsorted: frames are the SORTED unique stamps
+    rec["range_sc"] = rng.uniform(5, 40, n)
+    rec["range_sc"][[3, 11]] = 0.0                                         # invalid scatterers are counted and skipped
+    rec["azimuth_sc"] = rng.uniform(-1, 1, n)
+    rec["rcs"] = rng.uniform(-10, 5, n)
+    rec["vr"] = rng.uniform(-3, 3, n)
+    seq = tmp_path / "sequence_1"
+    seq.mkdir()
+    (seq / "scenes.json").write_text("{}")
+    np.save(seq / "radar_data.h5.npy", rec)
+    (seq / "radar_data.h5").write_bytes(b"stand-in")
+
+    class FakeFile:
+        def __init__(self, path, mode="r"):
+            self.data = {"radar_data": np.load(str(path) + ".npy")}
+        def __enter__(self):
+            return self.data
+        def __exit__(self, *a):
+            return False
+    monkeypatch.setitem(sys.modules, "h5py", types.SimpleNamespace(File=FakeFile))
+    sim = FMCWRadarSimulator(chirp_duration=12.8e-6, num_chirps=4, num_antennas=4, noise_power=0.0)
+    out = tmp_path / "raw"
+    stats = sim.process_sequence(str(seq), str(out), max_frames=3, batch_frames=2)
+    stamps = np.unique(rec["timestamp"])[:3]
+    sel = np.isin(rec["timestamp"], stamps)
+    assert stats == {"total_frames": 3, "processed_frames": 3, "total_scatterers": int(sel.sum()),
+                     "valid_scatterers": int((rec["range_sc"][sel] > 0).sum())}
+    p = orc.RadarParams(chirp_duration=12.8e-6, num_chirps=4, num_antennas=4, noise_power=0.0)
+    for k, ts in enumerate(stamps):
+        rows = rec[rec["timestamp"] == ts]
+        table = np.stack([rows[c].astype(np.float64) for c in ("range_sc", "azimuth_sc", "rcs", "vr")], axis=1)
+        want = orc.scatterer_response(p, table)
+        got = np.load(out / f"frame_{k:04d}.npy")
+        assert got.shape == (4, 4, 128) and got.dtype == np.complex128
+        assert np.abs(got - want[:, None, :]).max() <= 2e-7 * max(np.abs(want).max(), 1e-30)
+    meta = json.loads((out / "synthesis_metadata.json").read_text())
+    assert meta["processing_stats"] == stats and meta["radar_params"]["num_chirps"] == 4
+    assert not (out / "frame_0003.npy").exists()
