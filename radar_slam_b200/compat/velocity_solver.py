@@ -45,6 +45,12 @@ class VelocitySolver:
         logger.info("Initialized velocity solver:")
         logger.info(f"  Wavelength: {self.lambda_c*1000:.2f} mm")
         logger.info(f"  Optimization method: {optimization_method}")
+        if optimization_method != 'differential_evolution':
+            # velocity_solver.py:255-262: any other method is an UNBOUNDED scipy.optimize.minimize from x0 = 0 (or the
+            # initial guess) with maxiter / tol; here every method gets the box-bounded least-squares minimiser DE converges to
+            logger.warning(f"optimization_method={optimization_method!r}: this path always returns the box-bounded least-squares "
+                           "solution (the reference's non-DE branch is an unbounded local minimisation; max_iterations, "
+                           "tolerance and initial_guess do not apply)")
 
     # ---- model helpers (vectorised restatements with the reference's signatures)
     def compute_phase_difference_model(self, target_positions: np.ndarray, target_angles: np.ndarray,
