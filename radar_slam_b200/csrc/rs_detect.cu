@@ -725,6 +725,7 @@ extern "C" int rs_range_doppler_detect(const void* cube, const void* table, cons
     req.masks.thr = thr_power;
     req.masks.thrn = nextafterf(thr_power, INFINITY);
     req.masks.eps = det_eps;
+    { const char* dbg = getenv("RS_FD_DBG"); req.masks.dbg = dbg ? atoi(dbg) : 0; }
     SideDetectCtx ctx{(const float2*)rds, range_gate, thr_power, det_eps, out, R, D, A, RS_OK};
     req.side_hook = side_detect_hook;
     req.ctx = &ctx;

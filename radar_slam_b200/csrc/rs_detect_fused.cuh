@@ -25,6 +25,7 @@ struct FusedDetectMasks {
     float thr;              // power threshold (strict)
     float thrn;             // nextafterf(thr, +inf):  p > thr  <=>  p >= thrn
     float eps;              // det_eps
+    int dbg;                // timing probes only (RS_FD_DBG): 1 skip the walk, 2 skip barriers / halo wait, 4 skip the power stores
 };
 
 // Request handed to the 2-D FFT dispatcher (rs_fft2d.cu) by rs_range_doppler_detect (rs_detect.cu): the mask buffers, and

@@ -374,9 +374,11 @@ fft2d_ws_kernel(const __grid_constant__ CUtensorMap map_cube, const float2* __re
 #pragma unroll
                     for (int k2 = 0; k2 < 8; ++k2) pw8[k2] = fmaf(u[k2].x, u[k2].x, u[k2].y * u[k2].y);
                     __syncwarp();                                       // both rows are read before they are rewritten
+                    if (!(fd.dbg & 4)) {
 #pragma unroll
                     for (int k2 = 0; k2 < 8; ++k2)
                         sts1(rowa + (uint32_t)((k1p + ((16 * k2 + C / 2) & (C - 1))) * sizeof(float)), pw8[k2]);
+                    }
                     if ((send_dn && row == 0) || (send_up && row == ROWS - 1)) {
                         const uint32_t hd = halo_dst + (uint32_t)(b * 2 * C * sizeof(float)), hb = halo_bar + (uint32_t)(b * 8);
 #pragma unroll
@@ -412,21 +414,37 @@ fft2d_ws_kernel(const __grid_constant__ CUtensorMap map_cube, const float2* __re
                 };
                 const float band = 2.f * fd.eps;
                 uint32_t hitw = 0u, surew = 0u;
-                float psum = 0.f;
+                float2 psum2 = make_float2(0.f, 0.f);
+                // bit <- (x >= m): one FSETP + one predicated LOP3 (the compiler's SEL + 3-input add form costs 2.5 per test)
+                auto set_if_ge = [](uint32_t& w, float x, float m, uint32_t bit) {
+                    asm("{\n .reg .pred p;\n setp.ge.f32 p, %1, %2;\n @p or.b32 %0, %0, %3;\n}" : "+r"(w) : "f"(x), "f"(m), "r"(bit));
+                };
                 auto cells = [&](const Row& ra, const Row& rb, const Row& rc, const int rl) {
+                    // the two scaled copies of the centre powers and the power sum in packed f32x2 arithmetic (FFMA2 / FADD2:
+                    // IEEE-identical to the scalar fmaf, half the instructions)
+                    float2 cu2[2], cl2[2];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const unsigned long long cc = pow2::pk2(rb.c[2 * h], rb.c[2 * h + 1]);
+                        unsigned long long u, l, ps = pow2::pk2(psum2.x, psum2.y);
+                        asm("fma.rn.f32x2 %0, %1, %2, %1;" : "=l"(u) : "l"(cc), "l"(pow2::pk2(band, band)));
+                        asm("fma.rn.f32x2 %0, %1, %2, %1;" : "=l"(l) : "l"(cc), "l"(pow2::pk2(-band, -band)));
+                        asm("add.rn.f32x2 %0, %0, %1;" : "+l"(ps) : "l"(cc));
+                        cu2[h] = pow2::up2(u);
+                        cl2[h] = pow2::up2(l);
+                        psum2 = pow2::up2(ps);
+                    }
+                    const float cu[4] = {cu2[0].x, cu2[0].y, cu2[1].x, cu2[1].y}, cl[4] = {cl2[0].x, cl2[0].y, cl2[1].x, cl2[1].y};
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const float c = rb.c[j];
                         const float left = j == 0 ? rb.L : rb.c[j - 1], right = j == 3 ? rb.R : rb.c[j + 1];
                         // best neighbour, with "above the threshold" folded in: p > thr <=> p >= thrn
                         const float m2 = max3(ra.h[j], rc.h[j], max3(left, right, fd.thrn));
-                        const float cu = fmaf(c, band, c), cl = fmaf(c, -band, c);
-                        psum += c;
-                        if (cu >= m2) hitw |= 1u << (8 * j + rl);       // surely or maybe a detection
-                        if (cl >= m2) surew |= 1u << (8 * j + rl);      // surely one
+                        set_if_ge(hitw, cu[j], m2, 1u << (8 * j + rl));      // surely or maybe a detection
+                        set_if_ge(surew, cl[j], m2, 1u << (8 * j + rl));     // surely one
                     }
                 };
-                {
+                if (!(fd.dbg & 1)) {
                     // rows 1 .. 6 need this warp's rows only: no waiting for anybody
                     Row ra = load_row(0), rb = load_row(1);
 #pragma unroll
@@ -439,14 +457,16 @@ fft2d_ws_kernel(const __grid_constant__ CUtensorMap map_cube, const float2* __re
                 }
                 // rows 0 and 7 also need the last / first row of the neighbouring warp (one 64-thread barrier per pair of
                 // warps) or of the neighbouring CTA (the halo rows)
+                if (!(fd.dbg & 2)) {
                 if (w > 0) named_bar_sync(2 + w, 64);
                 if (w < D_THREADS / 32 - 1) named_bar_sync(3 + w, 64);
                 if (w == 0 || w == D_THREADS / 32 - 1) mbar_wait(&sm.halo_full[b], (it >> 1) & 1);
-                {
+                }
+                if (!(fd.dbg & 1)) {
                     const Row ra = load_row(-1), rb = load_row(0), rc = load_row(1);
                     cells(ra, rb, rc, 0);
                 }
-                {
+                if (!(fd.dbg & 1)) {
                     const Row ra = load_row(6), rb = load_row(7), rc = load_row(8);
                     cells(ra, rb, rc, 7);
                 }
@@ -471,6 +491,7 @@ fft2d_ws_kernel(const __grid_constant__ CUtensorMap map_cube, const float2* __re
                         if (cls & 4) candw |= 1u << bi;
                     }
                 }
+                float psum = psum2.x + psum2.y;
 #pragma unroll
                 for (int off = 16; off; off >>= 1) psum += __shfl_xor_sync(0xffffffffu, psum, off);
                 const size_t gi = (size_t)plane * FD_GROUPS + q * (ROWS / 8) + w;
