@@ -400,9 +400,9 @@ fft2d_ws_kernel(const __grid_constant__ CUtensorMap map_cube, const float2* __re
                 };
                 // a row of 4 powers per lane with the edge columns of the neighbouring lanes: horizontal maxima
                 struct Row { float c[4], L, R, h[4]; };
-                auto load_row = [&](int rl) {
+                auto ld_row = [&](int rl) { return lds4(rowaddr(rl) + (uint32_t)(lane * 16)); };
+                auto fin_row = [&](const float4& v) {                   // neighbour columns by shuffle, horizontal maxima
                     Row r;
-                    const float4 v = lds4(rowaddr(rl) + (uint32_t)(lane * 16));
                     r.c[0] = v.x; r.c[1] = v.y; r.c[2] = v.z; r.c[3] = v.w;
                     r.L = __shfl_up_sync(0xffffffffu, v.w, 1);
                     r.R = __shfl_down_sync(0xffffffffu, v.x, 1);
@@ -444,12 +444,17 @@ fft2d_ws_kernel(const __grid_constant__ CUtensorMap map_cube, const float2* __re
                         set_if_ge(surew, cl[j], m2, 1u << (8 * j + rl));     // surely one
                     }
                 };
+                // The walk is latency, not issue: its LDS.128 -> shuffle -> FMNMX3 chains ran at 0.3 IPC.  All eight rows of the
+                // warp are requested at once, so the shared-memory latency is paid once and only the shuffles stay in the chains.
+                float4 v[8];
+#pragma unroll
+                for (int rl = 0; rl < 8; ++rl) v[rl] = ld_row(rl);
                 if (!(fd.dbg & 1)) {
                     // rows 1 .. 6 need this warp's rows only: no waiting for anybody
-                    Row ra = load_row(0), rb = load_row(1);
+                    Row ra = fin_row(v[0]), rb = fin_row(v[1]);
 #pragma unroll
                     for (int rl = 1; rl < 7; ++rl) {
-                        const Row rc = load_row(rl + 1);
+                        const Row rc = fin_row(v[rl + 1]);
                         cells(ra, rb, rc, rl);
                         ra = rb;
                         rb = rc;
@@ -463,12 +468,9 @@ fft2d_ws_kernel(const __grid_constant__ CUtensorMap map_cube, const float2* __re
                 if (w == 0 || w == D_THREADS / 32 - 1) mbar_wait(&sm.halo_full[b], (it >> 1) & 1);
                 }
                 if (!(fd.dbg & 1)) {
-                    const Row ra = load_row(-1), rb = load_row(0), rc = load_row(1);
-                    cells(ra, rb, rc, 0);
-                }
-                if (!(fd.dbg & 1)) {
-                    const Row ra = load_row(6), rb = load_row(7), rc = load_row(8);
-                    cells(ra, rb, rc, 7);
+                    const float4 vlo = ld_row(-1), vhi = ld_row(8);
+                    cells(fin_row(vlo), fin_row(v[0]), fin_row(v[1]), 0);
+                    cells(fin_row(v[6]), fin_row(v[7]), fin_row(vhi), 7);
                 }
                 hitw &= gatew;
                 uint32_t uncw = hitw & ~surew, nearw = 0u, candw = 0u;  // ~1e-5 of the cells: inside the 2 eps band
