@@ -71,27 +71,6 @@ def main():
         ms = timed(lambda: pipe.range_doppler_detect(cube, out=rds, workspace="0", defer_power=True), args.reps)
         report(f"fused kernel only (no compaction), side {side} permille", ms)
         os.environ.pop("RS_FD_NO_COMPACT")
-        if False:
-            # the same call without the |X|^2 gather of the entries (det_power = NULL)
-            import radar_slam_b200.pipeline as pl
-            orig = pl._lib.ptr
-            d = pipe._alloc_detections(F, 256, 128, A, None, "0")
-            real = d.power.data_ptr
-
-            class NoPower:
-                def data_ptr(self):
-                    return 0
-            pipe._ws["det_power0_saved"] = d.power
-            saved = pipe._alloc_detections
-
-            def alloc(*a, **k):
-                dd = saved(*a, **k)
-                dd.power = NoPower()
-                return dd
-            pipe._alloc_detections = alloc
-            ms2 = timed(lambda: pipe.range_doppler_detect(cube, out=rds, workspace="0"), args.reps)
-            pipe._alloc_detections = saved
-            report(f"fused without det_power, side {side} permille", ms2)
 
 
 if __name__ == "__main__":

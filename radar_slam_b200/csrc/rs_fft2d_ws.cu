@@ -23,6 +23,11 @@
 // are in flight all the time.  No __syncthreads and no barrier.cluster inside the plane loop: one 256-thread named
 // barrier per stage in the range group, __syncwarp in the Doppler group, mbarriers across CTAs.
 // HBM traffic stays at the algorithmic minimum, 8 B in + 8 B out per cell.
+// (The default variant streams 8-chirp stages through a four-slot ring, two independent range subgroups, and hands the
+// range bins over with st.async on a transaction mbarrier; the list above describes variant 0.  RS_K12_VARIANT.)
+//
+// DETECT (rs_range_doppler_detect): the Doppler group also runs the peak detection of dechirp.py:235-263 on the plane it
+// holds -- see the comment on the kernel template and rs_detect_fused.cuh -- so the RDS is never read by a detection pass.
 #include <cuda.h>
 #include <cstdlib>
 #include <mutex>
