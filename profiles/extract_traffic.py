@@ -23,8 +23,16 @@ def main():
     hdr, units = rows[0], rows[1]
     ki, rd, wr, gi = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("launch__grid_size")
     num = lambda x: float(x.replace(",", ""))
+    # the capture window may run past the benchmark step into smaller launch sets (the end-to-end chunks): per kernel keep
+    # only the launches that executed about as many instructions as the largest one
+    ii = hdr.index("smsp__inst_executed.sum")
+    biggest = {}
+    for r in rows[2:]:
+        biggest[r[ki]] = max(biggest.get(r[ki], 0.0), num(r[ii]))
     acc, parts, k12 = {}, {}, {}
     for r in rows[2:]:
+        if num(r[ii]) < 0.6 * biggest[r[ki]]:
+            continue
         b = num(r[rd]) * MULT[units[rd]] + num(r[wr]) * MULT[units[wr]]
         hit12 = [k for k in K12_PARTS + FUSED_PARTS if k in r[ki]]
         if hit12:

@@ -10,6 +10,6 @@ KREGEX='regex:fft2d_|range_fft|doppler_fft|detect_|compact_masks|angles_|velocit
 $CMD > $OUT/plain.log 2>&1 || { echo "plain run failed"; tail -20 $OUT/plain.log; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KREGEX" -s 50 -c 64 --csv \
     --log-file $OUT/launches.csv $CMD > $OUT/ncu_launches.log 2>&1
-ncu --set full --clock-control none --import-source on -k "$KREGEX" -s 50 -c 24 \
+ncu --set full --clock-control none --import-source on -k "$KREGEX" -s 50 -c 16 \
     -o $OUT/prof $CMD > $OUT/ncu_full.log 2>&1
 ls -la $OUT
