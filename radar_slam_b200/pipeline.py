@@ -524,10 +524,11 @@ class FramePipeline:
                 ready.record(main)
                 self._pending = (cube[lo:hi], vel[lo:hi], rds, det, ready, ci & 1, after_solve if hi == F else None)
                 # The recheck + solve of this chunk go to the side stream right away: they run beside the NEXT chunk's 2-D
-                # FFT, whose persistent clusters leave 16 SMs to other work (3.33 ms per 1000-frame step against 3.44 with the
-                # recheck in line; profiles/overlap_probe.py).  Beside the angle scan instead (RS_RECHECK_LATE=1) nothing is
-                # gained: the scan needs all 8 of its CTAs per SM resident, and every CTA the recheck takes slows it by as
-                # much as the recheck gains (1.27 -> 1.97 ms while 0.73 ms of recheck runs, profiles/timeline_probe.py).
+                # FFT, whose persistent clusters leave 16 SMs to other work (3.15 ms per 1000-frame step against 3.44 with the
+                # recheck in line; profiles/overlap_probe.py, profiles/side_share_probe.sh).  Beside the angle scan instead
+                # (RS_RECHECK_LATE=1) nothing is gained: the scan needs all 8 of its CTAs per SM resident, and every CTA the
+                # recheck takes slows it by as much as the recheck gains (1.27 -> 1.97 ms while 0.73 ms of recheck runs,
+                # profiles/timeline_probe.py).
                 if os.environ.get("RS_RECHECK_LATE") != "1":
                     self._enqueue_recheck(None)
             else:
