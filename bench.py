@@ -41,8 +41,9 @@ METRIC = "frames/s dechirp->range-Doppler->MUSIC->LS ego-velocity"
 WORKLOAD = "configs[1]: 1k-frame synthetic batch per GPU, 256 samples x 128 chirps x 8 channels, MUSIC 1 deg grid, noise_power 0.01, threshold -20 dB"
 WORKLOAD4 = ("configs[4]: one 65536-frame synthetic sequence, 256 samples x 128 chirps x 16 channels, frame-sharded by contiguous "
              "block, MUSIC 1 deg grid, noise_power 0.01, threshold -20 dB, NCCL all-gather of the velocity rows")
-# kernels behind one C-ABI call (for gpu_launches): the 2-D transform is the persistent cluster kernel + the side kernel
-KERNELS_PER_CALL = {"rs_range_doppler_fft": 2, "rs_range_doppler_detect": 4, "rs_detect": 1, "rs_angles": 1, "rs_recheck_detections_f64": 1,
+# kernels behind one C-ABI call (for gpu_launches): the 2-D transform alone is the persistent cluster kernel + the side
+# kernel; with the detection fused in it is the persistent kernel + the compaction kernel (no side kernels by default)
+KERNELS_PER_CALL = {"rs_range_doppler_fft": 2, "rs_range_doppler_detect": 2, "rs_detect": 1, "rs_angles": 1, "rs_recheck_detections_f64": 1,
                     "rs_recheck_angles_f64": 3, "rs_velocity_from_partials": 1, "rs_velocity_partials": 1, "rs_velocity_ls": 1,
                     "rs_range_fft": 1, "rs_doppler_fft": 1}
 
@@ -417,7 +418,7 @@ def run_gpu(args):
                                           f"all-gather of [F,8] velocity rows",
                            "host_binding": numa},
                 "roofline": c1["roofline"], "cpu_baseline": c1["cpu_baseline"], "e2e": c4["e2e"],
-                "gpu_launches": int(c4["stage_calls_per_step"] * args.steps * 10 / 6),   # 10 kernels behind the 6 stage calls
+                "gpu_launches": int(c4["stage_calls_per_step"] * args.steps * 8 / 5),    # 8 kernels behind the 5 stage calls
                 "configs1_weak": {k: c1[k] for k in ("value", "ms_per_step", "scaling", "e2e", "config")},
             }
         line["clocks"] = clocks
