@@ -164,7 +164,9 @@ int rs_range_doppler_detect(const void* cube, const void* table, const void* twi
  *                     ceil(ceil(G/2)/32); used instead of the mma.sync scan when RS_ANGLES_TC=1 (measured variant).
  *       det_power_out optional float [F*nseg_per_frame*seg_cap]: |X|^2 of every entry (the det_power of rs_detect), for
  *                     lists that came from rs_range_doppler_detect with det_power = NULL.  The scan holds the snapshot
- *                     of every flagged cell in registers anyway, so the powers cost no memory traffic here. */
+ *                     of every flagged cell in registers anyway, so the powers cost no memory traffic here.
+ *       det_nnear     optional int32 [F*nseg_per_frame], the counters rs_detect wrote: a segment without RS_FLAG_NEARMAX
+ *                     entries cannot hold an RS_FLAG_DROPPED one, so the scan skips reading the entries' flags there. */
 #define RS_TIE_LIST_CAP 32
 int rs_angles(const void* rds, const float* scan_table, int scan_stride, const void* steer, const float* grid_deg, int G,
               int method, float tie_eps, double esprit_scale,
@@ -173,7 +175,7 @@ int rs_angles(const void* rds, const float* scan_table, int scan_stride, const v
               int seg_cap, int nseg_per_frame, int F, int R, int D, int A,
               const double* grid_cs, double* ls_partials, int grid_symmetric, int32_t* det_ntie, int32_t* det_tielist,
               const float* mma_table, int mma_tiles, void* cell_ws, const void* tc_table, int tc_halves,
-              float* det_power_out, void* stream);
+              float* det_power_out, const int32_t* det_nnear, void* stream);
 
 /* (d')  the velocity solve of rs_velocity_ls from the per-segment sums rs_angles already produced
  *       (no second pass over the detection lists); same output row layout.  det_overflow (int32 [F], may be NULL): frames

@@ -43,6 +43,7 @@ struct AngleArgs {
     float* det_phase;
     int seg_cap, nseg_per_frame, R, D, A;
     float* det_power;             // optional: |X|^2 of every entry (lists from rs_range_doppler_detect without det_power)
+    const int32_t* det_nnear;     // optional: RS_FLAG_NEARMAX entries per segment (rs_detect): 0 = no entry can be DROPPED
 };
 
 // |X|^2 of the k entries of a cell from its snapshot (the entries are the antennas that flagged the cell; their keys sit
@@ -62,13 +63,25 @@ __device__ __forceinline__ void emit_power(const AngleArgs& p, size_t o, int k, 
 
 // write one cell's result to all of its detections (same snapshot on every antenna that flagged the cell)
 // returns how many of them are live (not RS_FLAG_DROPPED): the weight of the cell in the velocity sums
+// clean: the segment holds no RS_FLAG_NEARMAX entry (det_nnear == 0), hence no RS_FLAG_DROPPED one (only near-miss candidates
+// and the detection recheck, which touches NEARMAX entries only, carry / set that flag): every entry is live and the flags
+// need not be read -- one dependent global load per entry less in 99.98 % of the segments.
 template <bool BATCH = false>
 __device__ __forceinline__ int emit(const AngleArgs& p, int seg, int lead_i, size_t o, int k, int aidx, float adeg,
-                                    float phase, uint8_t extra_flags) {
+                                    float phase, uint8_t extra_flags, bool clean = false) {
     int live = 0;
     if ((extra_flags & (RS_FLAG_TIE | RS_FLAG_GUARD)) && p.det_ntie) {
         const int slot = atomicAdd(p.det_ntie + seg, 1);
         if (p.det_tielist && slot < RS_TIE_LIST_CAP) p.det_tielist[(size_t)seg * RS_TIE_LIST_CAP + slot] = lead_i;
+    }
+    if (clean) {
+        for (int e = 0; e < k; ++e) {
+            p.det_aidx[o + e] = aidx;
+            p.det_adeg[o + e] = adeg;
+            p.det_phase[o + e] = phase;
+            if (extra_flags) p.det_flags[o + e] = extra_flags;      // the entry's flags were 0
+        }
+        return k;
     }
     // BATCH (the tcgen05 kernel: few resident warps, registers to spare): the flags of up to eight entries are fetched
     // together -- one latency instead of k; longer groups finish in the loop below
@@ -466,6 +479,7 @@ __global__ void __launch_bounds__(ANG_THREADS, MINB) angles_mma_kernel(AngleArgs
     __shared__ double red[ANG_THREADS / 32][8];
     const int seg = blockIdx.x;
     const int n = p.det_nlead[seg];
+    const bool seg_clean = p.det_nnear != nullptr && p.det_nnear[seg] == 0;
     double acc_ls[7] = {0, 0, 0, 0, 0, 0, 0};
     if (n > 0) {
         for (int i = threadIdx.x; i < ntiles * KS * 32; i += blockDim.x) {
@@ -632,7 +646,7 @@ __global__ void __launch_bounds__(ANG_THREADS, MINB) angles_mma_kernel(AngleArgs
                     const float full = (float)M;
                     if (full - pnorm <= 1e-4f * full) flags |= RS_FLAG_GUARD;
                 }
-                const int live = emit(p, seg, i, o, mult, bi, p.grid_deg[bi], yv, flags);
+                const int live = emit(p, seg, i, o, mult, bi, p.grid_deg[bi], yv, flags, seg_clean);
                 if (ls_partials != nullptr) {
                     const double c = grid_cs[2 * bi], sn = grid_cs[2 * bi + 1], y = (double)yv, w = (double)live;
                     acc_ls[0] += w * c * c; acc_ls[1] += w * sn * sn; acc_ls[2] += w * c * sn;
@@ -739,6 +753,7 @@ __global__ void __launch_bounds__(ANG_THREADS, 4) angles_tc5_kernel(AngleArgs p,
     __shared__ double red[ANG_THREADS / 32][8];
     const int seg = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int n = p.det_nlead[seg];
+    const bool seg_clean = p.det_nnear != nullptr && p.det_nnear[seg] == 0;
     double acc_ls[7] = {0, 0, 0, 0, 0, 0, 0};
     if (n > 0) {
         if (wid == 0) {
@@ -944,7 +959,7 @@ __global__ void __launch_bounds__(ANG_THREADS, 4) angles_tc5_kernel(AngleArgs p,
                     const float full = (float)M;
                     if (full - pnorm <= 1e-4f * full) flags |= RS_FLAG_GUARD;
                 }
-                const int live = emit<true>(p, seg, i, o, mult, bi, p.grid_deg[bi], yv, flags);
+                const int live = emit<true>(p, seg, i, o, mult, bi, p.grid_deg[bi], yv, flags, seg_clean);
                 if (ls_partials != nullptr) {
                     const double c = grid_cs[2 * bi], sn = grid_cs[2 * bi + 1], y = (double)yv, w = (double)live;
                     acc_ls[0] += w * c * c; acc_ls[1] += w * sn * sn; acc_ls[2] += w * c * sn;
@@ -1240,7 +1255,7 @@ extern "C" int rs_angles(const void* rds, const float* scan_table, int scan_stri
                          float* det_adeg, float* det_phase, int seg_cap, int nseg_per_frame, int F, int R, int D, int A,
                          const double* grid_cs, double* ls_partials, int grid_symmetric, int32_t* det_ntie,
                          int32_t* det_tielist, const float* mma_table, int mma_tiles, void* cell_ws, const void* tc_table,
-                         int tc_halves, float* det_power_out, void* stream) {
+                         int tc_halves, float* det_power_out, const int32_t* det_nnear, void* stream) {
     RS_CHECK_ARG(rds && det_key && det_lead && det_nlead && det_flags && det_aidx && det_adeg && det_phase,
                  "rs_angles: null pointer");
     RS_CHECK_ARG(ls_partials == nullptr || grid_cs != nullptr, "rs_angles: ls_partials needs grid_cs");
@@ -1252,7 +1267,7 @@ extern "C" int rs_angles(const void* rds, const float* scan_table, int scan_stri
     AngleArgs p{(const float2*)rds, scan_table, scan_stride, (const float2*)steer, grid_deg, G, method, tie_eps,
                 esprit_scale, det_key, det_lead, det_nlead, det_ntie, det_tielist, det_flags, det_aidx, det_adeg, det_phase, seg_cap,
                 nseg_per_frame,
-                R, D, A, det_power_out};
+                R, D, A, det_power_out, det_nnear};
     const long long blocks = (long long)F * nseg_per_frame;
     RS_CHECK_ARG(blocks < (1ll << 31), "rs_angles: too many segments");
     cudaStream_t st = (cudaStream_t)stream;

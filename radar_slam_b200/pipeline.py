@@ -344,7 +344,7 @@ class FramePipeline:
             _lib.ptr(t["mma"]), t["mma_tiles"],
             self._buf("cell_ws" + det.tag, (17 * det.F * det.R * det.D + 16,), torch.uint8).data_ptr() if det.A > 16 else 0,
             _lib.ptr(t["tc"]), t["tc_halves"], det.power.data_ptr() if (write_power and det.power_pending) else 0,
-            self.stream)
+            _lib.ptr(det.nnear), self.stream)
         if write_power:
             det.power_pending = False
         return det
