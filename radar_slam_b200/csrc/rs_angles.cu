@@ -736,51 +736,62 @@ __device__ __forceinline__ void ld8(uint32_t taddr, float (&v)[8]) {
 template <int AP>
 __global__ void __launch_bounds__(ANG_THREADS, 4) angles_tc5_kernel(AngleArgs p, const uint4* __restrict__ tc_table, int njobs,
                                                                  const double* __restrict__ grid_cs,
-                                                                 double* __restrict__ ls_partials) {
+                                                                 double* __restrict__ ls_partials, int nsegs) {
     using namespace tc5;
-    constexpr int K = AP;                              // lag slots per part (AP - 1 lags + one zero)
+    constexpr int K = AP;                              // lag slots per part (AP - 1 lags + one constant)
     constexpr int KC = AP == 8 ? 2 : 3;                // 16-wide K chunks per matrix: AP 8: [hi|lo][hi|0]; AP 16: [hi][lo][hi]
     constexpr int B_CHUNK = NPH * 32;                  // bytes of one [32 x 16] fp16 chunk
     constexpr int A_CHUNK = 128 * 32;                  // bytes of one [128 x 16] fp16 chunk
     constexpr int A_CHUNKS = 2;                        // stored A chunks per matrix (AP 16 re-uses [hi] for the third)
-    constexpr int LSTRIDE = K + 1;
+    constexpr int LSTRIDE = K + 4;                     // fp32 rows read as float4: stride 12 / 20 words is conflict free
     extern __shared__ __align__(128) unsigned char smraw[];
     unsigned char* Bt = smraw;                                                   // [njobs][E, O][KC][B_CHUNK]
     unsigned char* At = Bt + (size_t)njobs * 2 * KC * B_CHUNK;                   // [E, O][A_CHUNKS][A_CHUNK]
     float* Lx = reinterpret_cast<float*>(At + 2 * A_CHUNKS * A_CHUNK);           // [128][LSTRIDE] odd lags / R_0 (fp32)
+    float* St = Lx + 128 * LSTRIDE;                                              // [pairs][LSTRIDE] sin(k phi_pair), fp32
     __shared__ unsigned long long mbar[2];
     __shared__ uint32_t tmem_base_s;
     __shared__ double red[ANG_THREADS / 32][8];
-    const int seg = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int M = p.A, G = p.G;
+    const int half = G / 2, odd = G & 1, last_pair = (G + 1) / 2 - 1;
+    // Persistent: a CTA allocates its TMEM columns, initialises its barriers and stages the tables ONCE and then walks the
+    // segments blockIdx.x, blockIdx.x + gridDim.x, ... (a segment is ~9 tiles: the set-up was 13 % of the stall samples).
+    if (wid == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(&tmem_base_s)), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(&mbar[0])) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(&mbar[1])) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    {
+        const int n16 = njobs * 2 * KC * B_CHUNK / 16;
+        uint4* dst = reinterpret_cast<uint4*>(Bt);
+        for (int i = tid; i < n16; i += ANG_THREADS) dst[i] = __ldg(tc_table + i);
+        // the fp32 sin rows of the scan table: the sign of the winner's odd part is re-evaluated from them after the scan
+        for (int i = tid; i < (last_pair + 1) * LSTRIDE; i += ANG_THREADS) {
+            const int pr = i / LSTRIDE, k = i - pr * LSTRIDE;
+            St[i] = k < AP - 1 ? __ldg(p.scan_table + (size_t)pr * p.scan_stride + 2 * k + 1) : 0.f;
+        }
+#pragma unroll
+        for (int k = AP - 1; k < LSTRIDE; ++k) Lx[tid * LSTRIDE + k] = 0.f;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_s;
+    const uint32_t trow = tmem_base + ((uint32_t)(wid * 32) << 16);          // this warp's 32 TMEM lanes
+    uint32_t phase[2] = {0u, 0u};
+    for (int seg = blockIdx.x; seg < nsegs; seg += gridDim.x) {
     const int n = p.det_nlead[seg];
     const bool seg_clean = p.det_nnear != nullptr && p.det_nnear[seg] == 0;
     double acc_ls[7] = {0, 0, 0, 0, 0, 0, 0};
     if (n > 0) {
-        if (wid == 0) {
-            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(&tmem_base_s)), "n"(TMEM_COLS) : "memory");
-            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-        }
-        if (tid == 0) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(&mbar[0])) : "memory");
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(&mbar[1])) : "memory");
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
-        {
-            const int n16 = njobs * 2 * KC * B_CHUNK / 16;
-            uint4* dst = reinterpret_cast<uint4*>(Bt);
-            for (int i = tid; i < n16; i += ANG_THREADS) dst[i] = __ldg(tc_table + i);
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t tmem_base = tmem_base_s;
-        const uint32_t trow = tmem_base + ((uint32_t)(wid * 32) << 16);          // this warp's 32 TMEM lanes
-        uint32_t phase[2] = {0u, 0u};
         const int f = seg / p.nseg_per_frame;
         const float2* frame = p.rds + (size_t)f * p.R * p.D * p.A;
-        const int M = p.A, G = p.G;
-        const int half = G / 2, odd = G & 1, last_pair = (G + 1) / 2 - 1;
         const float NEG = -3.0e38f;
         // this thread's row of a chunk: (tid / 8) * 256 + (tid % 8) * 16, k 0..7 at +0, k 8..15 at +128
         const uint32_t arow = (uint32_t)((tid >> 3) * 256 + (tid & 7) * 16);
@@ -854,7 +865,7 @@ __global__ void __launch_bounds__(ANG_THREADS, 4) angles_tc5_kernel(AngleArgs p,
                     lo_[k - 1] = xi * inv;
                     row[k - 1] = xi * inv;                            // the odd lags are needed again after the scan
                 }
-                le[K - 1] = 0.f;
+                le[K - 1] = 1.f;     // constant-one slot: the table holds 0 there for grid pairs, -16384 for the padding columns
                 lo_[K - 1] = 0.f;
                 // fp16 hi / lo split, packed along K, into this thread's rows of the E and O operands
 #pragma unroll
@@ -892,7 +903,18 @@ __global__ void __launch_bounds__(ANG_THREADS, 4) angles_tc5_kernel(AngleArgs p,
             // the next tile's snapshot is requested now and consumed after this tile's scan: its latency hides under the tracking
             snapshot(base + ANG_THREADS + tid, key1);
             ld2 = lead_of(base + 2 * ANG_THREADS + tid);
-            Track tr[4] = {Track{NEG, NEG, 0}, Track{NEG, NEG, 0}, Track{NEG, NEG, 0}, Track{NEG, NEG, 0}};
+            // Two-level tracking.  The scan is bound by instruction issue, and a (best, runner-up, index) tracker costs 6
+            // operations per grid pair.  Here a group of 8 pair maxima is reduced to its maximum with four 3-input maxima
+            // and only THAT enters the tracker (best / runner-up over the group maxima, 5 operations per group); the group
+            // that raises the best leaves its eight values in a stash (8 predicated moves).  After the scan the winner's
+            // index inside its group and the runner-up inside the group come from the stash, once per cell: every value
+            // outside the winning group is bounded by its own group maximum, so
+            //     runner-up = max(second largest group maximum, second largest value of the winning group)
+            // exactly as the flat tracker computes it.  ~3.1 instead of ~9 instructions per pair and cell.
+            // Columns beyond the last grid pair need no mask: the table puts -TC_PAD on the constant-one K slot there.
+            float g_best = NEG, g_second = NEG;
+            int g_idx = 0, g_run = 0;
+            float stash[8] = {NEG, NEG, NEG, NEG, NEG, NEG, NEG, NEG};
             for (int jb = 0; jb < njobs; ++jb) {
                 const int b = jb & 1;
                 {
@@ -907,8 +929,7 @@ __global__ void __launch_bounds__(ANG_THREADS, 4) angles_tc5_kernel(AngleArgs p,
                 }
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t tb = trow + (uint32_t)(b * 2 * NPH);
-                // TMEM reads (64 B / clk / SM) are the scarce resource of this kernel: groups of 8 pairs, the loads of group
-                // g + 1 in flight while group g is tracked
+                // TMEM reads (64 B / clk / SM): groups of 8 pairs, the loads of group g + 1 in flight while group g is reduced
                 float e[2][8], od[2][8];
                 ld8(tb, e[0]);
                 ld8(tb + (uint32_t)NPH, od[0]);
@@ -919,13 +940,18 @@ __global__ void __launch_bounds__(ANG_THREADS, 4) angles_tc5_kernel(AngleArgs p,
                         ld8(tb + (uint32_t)(8 * (g + 1)), e[(g + 1) & 1]);
                         ld8(tb + (uint32_t)(NPH + 8 * (g + 1)), od[(g + 1) & 1]);
                     }
-                    const int pb = jb * NPH + 8 * g;
+                    float v[8];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        float hi = e[g & 1][j] + fabsf(od[g & 1][j]);
-                        if (pb + j > last_pair) hi = NEG;
-                        track_max(tr[j & 3], hi, pb + j);
-                    }
+                    for (int j = 0; j < 8; ++j) v[j] = e[g & 1][j] + fabsf(od[g & 1][j]);
+                    const float gm = fmaxf(fmaxf(fmaxf(v[0], v[1]), v[2]),
+                                           fmaxf(fmaxf(fmaxf(v[3], v[4]), v[5]), fmaxf(v[6], v[7])));
+                    const bool up = gm > g_best;                         // strict: the earliest group keeps exact ties
+                    g_second = fmaxf(g_second, fminf(g_best, gm));
+                    g_best = fmaxf(g_best, gm);
+                    g_idx = up ? g_run : g_idx;
+                    ++g_run;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) stash[j] = up ? v[j] : stash[j];
                 }
                 if (jb + 2 < njobs) {
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -933,22 +959,25 @@ __global__ void __launch_bounds__(ANG_THREADS, 4) angles_tc5_kernel(AngleArgs p,
                     if (tid == 0) issue_job(jb + 2);
                 }
             }
-            // the four interleaved trackers of this cell
-            auto merge = [](Track& k, const Track& t) {
-                k.second = fmaxf(fmaxf(k.second, t.second), fminf(k.best, t.best));
-                if (t.best > k.best || (t.best == k.best && t.idx < k.idx)) { k.best = t.best; k.idx = t.idx; }
-            };
-            merge(tr[0], tr[1]);
-            merge(tr[2], tr[3]);
-            merge(tr[0], tr[2]);
-            float my_best = tr[0].best, my_second = tr[0].second;
-            const int my_pair = tr[0].idx;
+            // inside the winning group: first index holding the maximum, and the largest of the other seven
+            int in_idx = 7;
+#pragma unroll
+            for (int j = 6; j >= 0; --j) in_idx = (stash[j] == g_best) ? j : in_idx;
+            float in_second = NEG;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) in_second = fmaxf(in_second, j == in_idx ? NEG : stash[j]);
+            float my_best = g_best, my_second = fmaxf(g_second, in_second);
+            const int my_pair = 8 * g_idx + in_idx;
             if (valid) {
                 // which side of the pair won: sign of the odd part, re-evaluated with the fp32 table
-                const float* trow_t = p.scan_table + (size_t)my_pair * p.scan_stride;
+                const float4* st4 = reinterpret_cast<const float4*>(St + my_pair * LSTRIDE);
+                const float4* rw4 = reinterpret_cast<const float4*>(row);
                 float od = 0.f;
 #pragma unroll
-                for (int k = 1; k < AP; ++k) od = fmaf(row[k - 1], __ldg(trow_t + 2 * (k - 1) + 1), od);
+                for (int q = 0; q < AP / 4; ++q) {                      // slot AP - 1 is zero in both rows
+                    const float4 x = rw4[q], t = st4[q];
+                    od = fmaf(x.x, t.x, od); od = fmaf(x.y, t.y, od); od = fmaf(x.z, t.z, od); od = fmaf(x.w, t.w, od);
+                }
                 const bool middle = odd && my_pair == half;             // the middle angle has no partner
                 const int bi = middle ? half : (od >= 0.f ? my_pair : G - 1 - my_pair);
                 if (!middle) my_second = fmaxf(my_second, my_best - 2.f * fabsf(od));   // the losing side of the winning pair
@@ -970,26 +999,29 @@ __global__ void __launch_bounds__(ANG_THREADS, 4) angles_tc5_kernel(AngleArgs p,
             ld1 = ld2;
             key1 = key_of(base + 2 * ANG_THREADS + tid, ld1);
         }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    if (ls_partials != nullptr) {
+#pragma unroll
+        for (int q = 0; q < 7; ++q) {
+#pragma unroll
+            for (int off = 16; off; off >>= 1) acc_ls[q] += __shfl_xor_sync(0xffffffffu, acc_ls[q], off);
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int q = 0; q < 7; ++q) red[wid][q] = acc_ls[q];
+        }
         __syncthreads();
-        if (wid == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+        if (tid < 7) {
+            double t = 0;
+            for (int w = 0; w < ANG_THREADS / 32; ++w) t += red[w][tid];
+            ls_partials[(size_t)seg * 8 + tid] = t;
+        }
+        __syncthreads();                                             // red is reused by the next segment
     }
-    if (ls_partials == nullptr) return;
-#pragma unroll
-    for (int q = 0; q < 7; ++q) {
-#pragma unroll
-        for (int off = 16; off; off >>= 1) acc_ls[q] += __shfl_xor_sync(0xffffffffu, acc_ls[q], off);
-    }
-    if (lane == 0) {
-#pragma unroll
-        for (int q = 0; q < 7; ++q) red[wid][q] = acc_ls[q];
-    }
+    }   // segments
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (threadIdx.x < 7) {
-        double t = 0;
-        for (int w = 0; w < ANG_THREADS / 32; ++w) t += red[w][threadIdx.x];
-        ls_partials[(size_t)seg * 8 + threadIdx.x] = t;
-    }
+    if (wid == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
 }
 
 // ---- any A (used for A > 16): one warp evaluates one cell, lanes over antennas / grid points, snapshot in smem ----
@@ -1311,17 +1343,22 @@ extern "C" int rs_angles(const void* rds, const float* scan_table, int scan_stri
             if (tc_table != nullptr && tc_halves > 0 && grid_symmetric && (ap == 8 || ap == 16) && use_tc) {
                 RS_CHECK_ARG(tc_halves == ((G + 1) / 2 + tc5::NPH - 1) / tc5::NPH, "rs_angles: tc_halves must be ceil(ceil(G/2)/32)");
                 const int kc = ap == 8 ? 2 : 3;
-                size_t sm = (size_t)tc_halves * 2 * kc * tc5::NPH * 32 + 2 * 2 * 128 * 32 + (size_t)128 * (ap + 1) * sizeof(float);
+                size_t sm = (size_t)tc_halves * 2 * kc * tc5::NPH * 32 + 2 * 2 * 128 * 32 +
+                            (size_t)(128 + (G + 1) / 2) * (ap + 4) * sizeof(float);
                 // at most four CTAs (4 x 128 TMEM columns) may be resident on an SM: pad the request so that a fifth never fits
                 const size_t floor4 = (size_t)rs_smem_optin_limit() / 5 + 1024;
                 if (sm < floor4) sm = floor4;
                 if (sm <= (size_t)rs_smem_optin_limit()) {
+                    // persistent: as many CTAs as fit (4 per SM by TMEM columns, fewer when the tables of a fine grid are large)
+                    const size_t per_sm = (size_t)rs_smem_optin_limit() / (sm + 1024);
+                    const long long resident = (long long)rs_sm_count() * (long long)(per_sm < 4 ? (per_sm < 1 ? 1 : per_sm) : 4);
+                    const unsigned tc_grid = (unsigned)(blocks < resident ? blocks : resident);
                     if (ap == 8) {
                         cudaFuncSetAttribute(angles_tc5_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-                        angles_tc5_kernel<8><<<(unsigned)blocks, ANG_THREADS, sm, st>>>(p, (const uint4*)tc_table, tc_halves, grid_cs, ls_partials);
+                        angles_tc5_kernel<8><<<tc_grid, ANG_THREADS, sm, st>>>(p, (const uint4*)tc_table, tc_halves, grid_cs, ls_partials, (int)blocks);
                     } else {
                         cudaFuncSetAttribute(angles_tc5_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-                        angles_tc5_kernel<16><<<(unsigned)blocks, ANG_THREADS, sm, st>>>(p, (const uint4*)tc_table, tc_halves, grid_cs, ls_partials);
+                        angles_tc5_kernel<16><<<tc_grid, ANG_THREADS, sm, st>>>(p, (const uint4*)tc_table, tc_halves, grid_cs, ls_partials, (int)blocks);
                     }
                     RS_CHECK_LAUNCH("rs_angles(tcgen05)");
                     return RS_OK;

@@ -124,7 +124,9 @@ def scan_tc_table(scan: np.ndarray, G: int, A: int, pairs_per_half: int = 32) ->
     (n // 8) * 256 + (k // 8) * 128 + (n % 8) * 16 + (k % 8) * 2.  K packing of the hi / lo split (x = hi + lo, both fp16):
         A <= 8 : chunk 0 = [hi(8) | hi(8)] (against A = [a_hi | a_lo]), chunk 1 = [lo(8) | 0] (against [a_hi | 0])
         A <= 16: chunk 0 = hi(16) (against a_hi), chunk 1 = hi(16) (against a_lo), chunk 2 = lo(16) (against a_hi)
-    K-slot j holds lag j + 1; the last slot is zero.  Returns (uint8 bytes, number of halves)."""
+    K-slot j holds lag j + 1; the last slot multiplies a constant one in the A operand: 0 for the grid pairs and -16384 in
+    the cos table for the padding columns of the last job, so that the scan needs no mask there.
+    Returns (uint8 bytes, number of halves)."""
     ap = padded_antennas(A)
     assert ap in (8, 16)
     npairs = (G + 1) // 2
@@ -134,6 +136,7 @@ def scan_tc_table(scan: np.ndarray, G: int, A: int, pairs_per_half: int = 32) ->
     for k in range(ap - 1):
         T[0, k, :npairs] = scan[:npairs, 2 * k]
         T[1, k, :npairs] = scan[:npairs, 2 * k + 1]
+    T[0, ap - 1, npairs:] = -16384.0
     hi, lo = f16_split(T)
     out = np.zeros((nh, 2, kc, pairs_per_half * 16), dtype=np.float16)
     n = np.arange(pairs_per_half)
