@@ -722,6 +722,11 @@ __device__ __forceinline__ void ld16(uint32_t taddr, float (&v)[16]) {
     for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
 }
 
+__device__ __forceinline__ unsigned long long pk2f(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
 __device__ __forceinline__ void ld8(uint32_t taddr, float (&v)[8]) {
     uint32_t r[8];
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -749,6 +754,8 @@ __global__ void __launch_bounds__(ANG_THREADS, 4) angles_tc5_kernel(AngleArgs p,
     unsigned char* At = Bt + (size_t)njobs * 2 * KC * B_CHUNK;                   // [E, O][A_CHUNKS][A_CHUNK]
     float* Lx = reinterpret_cast<float*>(At + 2 * A_CHUNKS * A_CHUNK);           // [128][LSTRIDE] odd lags / R_0 (fp32)
     float* St = Lx + 128 * LSTRIDE;                                              // [pairs][LSTRIDE] sin(k phi_pair), fp32
+    double2* Gc = reinterpret_cast<double2*>(St + (((p.G + 1) / 2) * LSTRIDE + 3) / 4 * 4);   // [G] cos / sin of the grid angle
+    float* Gd = reinterpret_cast<float*>(Gc + p.G);                              // [G] grid angle in degrees
     __shared__ unsigned long long mbar[2];
     __shared__ uint32_t tmem_base_s;
     __shared__ double red[ANG_THREADS / 32][8];
@@ -777,6 +784,10 @@ __global__ void __launch_bounds__(ANG_THREADS, 4) angles_tc5_kernel(AngleArgs p,
         }
 #pragma unroll
         for (int k = AP - 1; k < LSTRIDE; ++k) Lx[tid * LSTRIDE + k] = 0.f;
+        for (int i = tid; i < G; i += ANG_THREADS) {
+            Gc[i] = grid_cs != nullptr ? make_double2(grid_cs[2 * i], grid_cs[2 * i + 1]) : make_double2(0.0, 0.0);
+            Gd[i] = p.grid_deg[i];
+        }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -831,8 +842,10 @@ __global__ void __launch_bounds__(ANG_THREADS, 4) angles_tc5_kernel(AngleArgs p,
                 for (int m = 0; m < AP; ++m) s[m] = make_float2(0.f, 0.f);
             }
         };
-        uint32_t ld = lead_of(tid), ld1 = lead_of(ANG_THREADS + tid), ld2 = 1u << 16;
-        uint32_t key1 = 0u;
+        // (the key of tile t + 2 is requested at the START of tile t's scan, from a leader that arrived a tile earlier: a
+        // load issued at the end of the iteration made the first scoreboard wait of the next one a full L2 latency)
+        uint32_t ld = lead_of(tid), ld1 = lead_of(ANG_THREADS + tid), ld2 = lead_of(2 * ANG_THREADS + tid), ld3 = 1u << 16;
+        uint32_t key1 = 0u, key2 = 0u;
         snapshot(tid, key_of(tid, ld));
         key1 = key_of(ANG_THREADS + tid, ld1);
         for (int base = 0; base < n; base += ANG_THREADS) {
@@ -851,16 +864,19 @@ __global__ void __launch_bounds__(ANG_THREADS, 4) angles_tc5_kernel(AngleArgs p,
                 for (int m = 0; m < AP; ++m) rr0 = fmaf(s[m].x, s[m].x, fmaf(s[m].y, s[m].y, rr0));
                 const float inv = rr0 > 0.f ? 1.f / rr0 : 0.f;       // |R_k| <= R_0: the normalised lags lie in [-1, 1]
                 float le[K], lo_[K];
+                // lags in packed f32x2 arithmetic: (xr, xi) += s[m+k] * (s[m].x, s[m].x), then += (s[m+k].y, -s[m+k].x) *
+                // (s[m].y, s[m].y) -- per component the same fused multiply-adds in the same order as the scalar form (the
+                // half swap, the sign and the broadcast are operand modifiers of FFMA2): half the instructions
 #pragma unroll
                 for (int k = 1; k < AP; ++k) {
-                    float xr = 0.f, xi = 0.f;
+                    unsigned long long acc = tc5::pk2f(0.f, 0.f);
 #pragma unroll
                     for (int m = 0; m + k < AP; ++m) {
-                        xr = fmaf(s[m + k].x, s[m].x, xr);
-                        xr = fmaf(s[m + k].y, s[m].y, xr);
-                        xi = fmaf(s[m + k].y, s[m].x, xi);
-                        xi = fmaf(-s[m + k].x, s[m].y, xi);
+                        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(tc5::pk2f(s[m + k].x, s[m + k].y)), "l"(tc5::pk2f(s[m].x, s[m].x)));
+                        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(tc5::pk2f(s[m + k].y, -s[m + k].x)), "l"(tc5::pk2f(s[m].y, s[m].y)));
                     }
+                    float xr, xi;
+                    asm("mov.b64 {%0, %1}, %2;" : "=f"(xr), "=f"(xi) : "l"(acc));
                     le[k - 1] = xr * inv;
                     lo_[k - 1] = xi * inv;
                     row[k - 1] = xi * inv;                            // the odd lags are needed again after the scan
@@ -902,7 +918,8 @@ __global__ void __launch_bounds__(ANG_THREADS, 4) angles_tc5_kernel(AngleArgs p,
             }
             // the next tile's snapshot is requested now and consumed after this tile's scan: its latency hides under the tracking
             snapshot(base + ANG_THREADS + tid, key1);
-            ld2 = lead_of(base + 2 * ANG_THREADS + tid);
+            key2 = key_of(base + 2 * ANG_THREADS + tid, ld2);
+            ld3 = lead_of(base + 3 * ANG_THREADS + tid);
             // Two-level tracking.  The scan is bound by instruction issue, and a (best, runner-up, index) tracker costs 6
             // operations per grid pair.  Here a group of 8 pair maxima is reduced to its maximum with four 3-input maxima
             // and only THAT enters the tracker (best / runner-up over the group maxima, 5 operations per group); the group
@@ -988,16 +1005,18 @@ __global__ void __launch_bounds__(ANG_THREADS, 4) angles_tc5_kernel(AngleArgs p,
                     const float full = (float)M;
                     if (full - pnorm <= 1e-4f * full) flags |= RS_FLAG_GUARD;
                 }
-                const int live = emit<true>(p, seg, i, o, mult, bi, p.grid_deg[bi], yv, flags, seg_clean);
+                const int live = emit<true>(p, seg, i, o, mult, bi, Gd[bi], yv, flags, seg_clean);
                 if (ls_partials != nullptr) {
-                    const double c = grid_cs[2 * bi], sn = grid_cs[2 * bi + 1], y = (double)yv, w = (double)live;
+                    const double2 cs = Gc[bi];
+                    const double c = cs.x, sn = cs.y, y = (double)yv, w = (double)live;
                     acc_ls[0] += w * c * c; acc_ls[1] += w * sn * sn; acc_ls[2] += w * c * sn;
                     acc_ls[3] += w * y * c; acc_ls[4] += w * y * sn; acc_ls[5] += w * y * y; acc_ls[6] += w;
                 }
             }
             ld = ld1;
             ld1 = ld2;
-            key1 = key_of(base + 2 * ANG_THREADS + tid, ld1);
+            ld2 = ld3;
+            key1 = key2;
         }
     }
     if (ls_partials != nullptr) {
@@ -1335,16 +1354,16 @@ extern "C" int rs_angles(const void* rds, const float* scan_table, int scan_stri
             angles_scan_kernel<AP, ND, false><<<(unsigned)blocks, ANG_THREADS, smem, st>>>(p, grid_cs, ls_partials);     \
         }                                                                                                                \
     } while (0)
-            // RS_ANGLES_TC: 1 / 0 force the tcgen05 / TMEM scan on / off.  Default: on for 9..16 antennas, where it beats the
-            // mma.sync scan (1.46 vs 1.67 ms per 300 frames of 256 x 128 x 16), off for 5..8 (1.56 vs 1.27 ms per 1000 frames of
-            // 256 x 128 x 8: there the TMEM read-out of 2 x 91 fp32 accumulators per cell at 64 B/clk/SM is what bounds it)
+            // RS_ANGLES_TC: 1 / 0 force the tcgen05 / TMEM scan on / off.  Default: on.  With the two-level tracking, the
+            // persistent CTAs and the packed lag arithmetic it beats the mma.sync scan at both widths: 1.12 vs 1.56 ms per
+            // 300 frames of 256 x 128 x 16, 1.04 vs 1.26 ms per 1000 frames of 256 x 128 x 8 (profiles/angles_bench.py)
             const char* tc_env = getenv("RS_ANGLES_TC");
-            const bool use_tc = tc_env ? atoi(tc_env) == 1 : ap == 16;
+            const bool use_tc = tc_env ? atoi(tc_env) == 1 : true;
             if (tc_table != nullptr && tc_halves > 0 && grid_symmetric && (ap == 8 || ap == 16) && use_tc) {
                 RS_CHECK_ARG(tc_halves == ((G + 1) / 2 + tc5::NPH - 1) / tc5::NPH, "rs_angles: tc_halves must be ceil(ceil(G/2)/32)");
                 const int kc = ap == 8 ? 2 : 3;
                 size_t sm = (size_t)tc_halves * 2 * kc * tc5::NPH * 32 + 2 * 2 * 128 * 32 +
-                            (size_t)(128 + (G + 1) / 2) * (ap + 4) * sizeof(float);
+                            (size_t)(128 + (G + 1) / 2) * (ap + 4) * sizeof(float) + 16 + (size_t)G * 20;
                 // at most four CTAs (4 x 128 TMEM columns) may be resident on an SM: pad the request so that a fifth never fits
                 const size_t floor4 = (size_t)rs_smem_optin_limit() / 5 + 1024;
                 if (sm < floor4) sm = floor4;
