@@ -159,15 +159,19 @@ int rs_range_doppler_detect(const void* cube, const void* table, const void* twi
  *       cell_ws       optional workspace of 17 * F*R*D bytes (16-byte aligned) for A > 16: every distinct cell of a frame is
  *                     evaluated once (mark / evaluate / scatter) instead of once per detection -- with many antennas
  *                     a cell is flagged on many of them and all share one snapshot.  NULL: one evaluation per leader.
+ *                     A == 16 with the tcgen05 scan: RS_ANGLES_WS_BYTES of scratch (16-byte aligned); the two antenna-octet
+ *                     segments of a tile are then scanned as a pair and a cell flagged on both octets is evaluated once
+ *                     (RS_ANGLES_DEDUP=0 turns it off).  NULL: every segment on its own.
  *       tc_table      optional, bytes [tc_halves][cos, sin][KC][32 x 16 fp16]: the same tables as UMMA B operands (K-major,
  *                     no swizzle) for the tcgen05 / TMEM scan (radar_slam_b200/tables.py: scan_tc_table), tc_halves =
- *                     ceil(ceil(G/2)/32); used instead of the mma.sync scan when RS_ANGLES_TC=1 (measured variant).
+ *                     ceil(ceil(G/2)/32); the default scan for 5..16 antennas on a symmetric grid (RS_ANGLES_TC=0: mma.sync).
  *       det_power_out optional float [F*nseg_per_frame*seg_cap]: |X|^2 of every entry (the det_power of rs_detect), for
  *                     lists that came from rs_range_doppler_detect with det_power = NULL.  The scan holds the snapshot
  *                     of every flagged cell in registers anyway, so the powers cost no memory traffic here.
  *       det_nnear     optional int32 [F*nseg_per_frame], the counters rs_detect wrote: a segment without RS_FLAG_NEARMAX
  *                     entries cannot hold an RS_FLAG_DROPPED one, so the scan skips reading the entries' flags there. */
 #define RS_TIE_LIST_CAP 32
+#define RS_ANGLES_WS_BYTES (32 << 20)
 int rs_angles(const void* rds, const float* scan_table, int scan_stride, const void* steer, const float* grid_deg, int G,
               int method, float tie_eps, double esprit_scale,
               const uint32_t* det_key, const uint32_t* det_lead, const int32_t* det_nlead, uint8_t* det_flags,

@@ -14,6 +14,7 @@ from . import build as _build
 RS_METHOD_MUSIC, RS_METHOD_BEAMFORMING, RS_METHOD_ESPRIT = 0, 1, 2
 RS_RECHECK_FRAME_CAP = 256
 RS_TIE_LIST_CAP = 32
+RS_ANGLES_WS_BYTES = 32 << 20
 RS_FLAG_TIE, RS_FLAG_NEARMAX, RS_FLAG_GUARD, RS_FLAG_FIXED, RS_FLAG_DROPPED, RS_FLAG_DETFIXED = 1, 2, 4, 8, 16, 32
 METHODS = {"music": RS_METHOD_MUSIC, "beamforming": RS_METHOD_BEAMFORMING, "esprit": RS_METHOD_ESPRIT}
 

@@ -694,6 +694,8 @@ __global__ void __launch_bounds__(ANG_THREADS, MINB) angles_mma_kernel(AngleArgs
 namespace tc5 {
 
 constexpr int NPH = 32;                    // grid pairs per job (UMMA N); two jobs in flight in 2 x 64 TMEM columns
+constexpr int PAIR_CELLS = 2048;           // pair mode: cells of a detection tile (16 range x 128 Doppler bins)
+constexpr int PAIR_WS_BYTES = PAIR_CELLS * (8 + 2);              // per CTA: result table + queue of cell indices
 constexpr int TMEM_COLS = 128;
 
 __device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -738,10 +740,11 @@ __device__ __forceinline__ void ld8(uint32_t taddr, float (&v)[8]) {
 
 }  // namespace tc5
 
-template <int AP>
+template <int AP, bool PAIR>
 __global__ void __launch_bounds__(ANG_THREADS, 4) angles_tc5_kernel(AngleArgs p, const uint4* __restrict__ tc_table, int njobs,
                                                                  const double* __restrict__ grid_cs,
-                                                                 double* __restrict__ ls_partials, int nsegs) {
+                                                                 double* __restrict__ ls_partials, int nsegs,
+                                                                 unsigned char* __restrict__ ws, int pair_tr, int pair_td) {
     using namespace tc5;
     constexpr int K = AP;                              // lag slots per part (AP - 1 lags + one constant)
     constexpr int KC = AP == 8 ? 2 : 3;                // 16-wide K chunks per matrix: AP 8: [hi|lo][hi|0]; AP 16: [hi][lo][hi]
@@ -759,6 +762,8 @@ __global__ void __launch_bounds__(ANG_THREADS, 4) angles_tc5_kernel(AngleArgs p,
     __shared__ unsigned long long mbar[2];
     __shared__ uint32_t tmem_base_s;
     __shared__ double red[ANG_THREADS / 32][8];
+    __shared__ uint32_t cellmap[PAIR_CELLS / 32];      // pair mode: cells of the tile flagged on either antenna octet
+    __shared__ int wsum[ANG_THREADS / 32];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int M = p.A, G = p.G;
     const int half = G / 2, odd = G & 1, last_pair = (G + 1) / 2 - 1;
@@ -796,8 +801,83 @@ __global__ void __launch_bounds__(ANG_THREADS, 4) angles_tc5_kernel(AngleArgs p,
     const uint32_t tmem_base = tmem_base_s;
     const uint32_t trow = tmem_base + ((uint32_t)(wid * 32) << 16);          // this warp's 32 TMEM lanes
     uint32_t phase[2] = {0u, 0u};
-    for (int seg = blockIdx.x; seg < nsegs; seg += gridDim.x) {
-    const int n = p.det_nlead[seg];
+    // PAIR (16 antennas, scratch in ws): the detection tiles are per antenna OCTET, so a cell flagged on both octets of
+    // its (range, Doppler) tile leads a group in two segments -- 26 % of all leaders at the benchmark density -- with the
+    // same 16-channel snapshot in both.  A unit is then the segment PAIR of one tile:
+    //   mark      both leader lists set the bit of their cells in a 2048-bit map (shared memory);
+    //   enumerate the set bits, in cell order, become the queue of the tile loop (ordered compaction);
+    //   scan      every distinct cell once; (grid index, TIE / GUARD bits, phase) go to a table indexed by the cell
+    //             (per-CTA scratch in global memory, 20 KB that stay in L2);
+    //   scatter   every leader of both segments copies its cell's row to its group (emit) and adds to the segment's
+    //             velocity sums, thread t taking the leaders [t c, t c + c): fixed order, fixed sums.
+    // (A first version scanned segment 0, then the cells of segment 1 not seen yet: fewer instructions but 2x the DRAM
+    // traffic and 13 % slower -- by the time the second pass gathered its cells the tile had left L2.)
+    uint2* wres = reinterpret_cast<uint2*>(ws + (size_t)blockIdx.x * PAIR_WS_BYTES);       // [cells] result table
+    unsigned short* wqc = reinterpret_cast<unsigned short*>(wres + PAIR_CELLS);            // [cells] queue of cell indices
+    const int pair_dmask = pair_td - 1, pair_dshift = 31 - __clz(pair_td);
+    const int nunits = PAIR ? nsegs / 2 : nsegs;
+    // leaders [t c, t c + c) of a segment through fn(index, leader word, key): words, then keys, requested together
+    auto for_leaders = [&](int sg, auto fn) {
+        const int nl = p.det_nlead[sg];
+        const size_t sb = (size_t)sg * p.seg_cap;
+        const int c = (nl + ANG_THREADS - 1) / ANG_THREADS, i0 = tid * c;
+#pragma unroll 1
+        for (int j0 = 0; j0 < c; j0 += 4) {
+            uint32_t lv[4], kv[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) lv[j] = (j0 + j < c && i0 + j0 + j < nl) ? __ldg(p.det_lead + sb + i0 + j0 + j) : 0u;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) kv[j] = (j0 + j < c && i0 + j0 + j < nl) ? __ldg(p.det_key + sb + (lv[j] & 0xFFFFu)) : 0u;
+#pragma unroll 1
+            for (int j = 0; j < 4; ++j) {                            // rolled: fn may inline the (large) emit
+                const uint32_t l = j == 0 ? lv[0] : j == 1 ? lv[1] : j == 2 ? lv[2] : lv[3];
+                const uint32_t ky = j == 0 ? kv[0] : j == 1 ? kv[1] : j == 2 ? kv[2] : kv[3];
+                if (j0 + j < c && i0 + j0 + j < nl) fn(i0 + j0 + j, l, ky);
+            }
+        }
+    };
+    auto cell_of = [&](uint32_t key) -> int {
+        int a_, r_, d_;
+        rs_split_key(key, a_, r_, d_);
+        return ((r_ & (pair_tr - 1)) << pair_dshift) | (d_ & pair_dmask);
+    };
+    for (int unit = blockIdx.x; unit < nunits; unit += gridDim.x) {
+    const int seg = PAIR ? 2 * unit : unit;
+    int n = 0, tile_r0 = 0, tile_d0 = 0;
+    if constexpr (PAIR) {
+        const int tile = (seg % p.nseg_per_frame) >> 1, ntd = p.D / pair_td;
+        tile_r0 = (tile / ntd) * pair_tr;
+        tile_d0 = (tile % ntd) * pair_td;
+        if (tid < PAIR_CELLS / 32) cellmap[tid] = 0u;
+        __syncthreads();
+        for (int sg = seg; sg < seg + 2; ++sg)
+            for_leaders(sg, [&](int, uint32_t, uint32_t key) {
+                const int cell = cell_of(key);
+                atomicOr(&cellmap[cell >> 5], 1u << (cell & 31));
+            });
+        __syncthreads();
+        // thread t enumerates bits [16 t, 16 t + 16)
+        const uint32_t bits = (cellmap[tid >> 1] >> (16 * (tid & 1))) & 0xFFFFu;
+        const int mine = __popc(bits);
+        int inc = mine;
+#pragma unroll
+        for (int o_ = 1; o_ < 32; o_ <<= 1) {
+            const int t_ = __shfl_up_sync(0xffffffffu, inc, o_);
+            if (lane >= o_) inc += t_;
+        }
+        if (lane == 31) wsum[wid] = inc;
+        __syncthreads();
+        int off = inc - mine;
+#pragma unroll
+        for (int w = 0; w < ANG_THREADS / 32; ++w) {
+            if (w < wid) off += wsum[w];
+            n += wsum[w];
+        }
+        for (uint32_t b = bits; b; b &= b - 1) __stcg(wqc + off++, (unsigned short)(16 * tid + __ffs(b) - 1));
+        __syncthreads();                                             // the queue is complete
+    } else {
+        n = p.det_nlead[seg];
+    }
     const bool seg_clean = p.det_nnear != nullptr && p.det_nnear[seg] == 0;
     double acc_ls[7] = {0, 0, 0, 0, 0, 0, 0};
     if (n > 0) {
@@ -828,8 +908,15 @@ __global__ void __launch_bounds__(ANG_THREADS, 4) angles_tc5_kernel(AngleArgs p,
         // leader of tile t + 2; its key is requested after the scan.
         float2 s[AP];
         const size_t segbase = (size_t)seg * p.seg_cap;
-        auto lead_of = [&](int i) -> uint32_t { return i < n ? p.det_lead[segbase + i] : (1u << 16); };
-        auto key_of = [&](int i, uint32_t l) -> uint32_t { return i < n ? p.det_key[segbase + (l & 0xFFFFu)] : 0u; };
+        // PAIR: slot i is the i-th queued cell; its "leader word" is the cell index, its "key" the (range, Doppler) key
+        auto lead_of = [&](int i) -> uint32_t {
+            if constexpr (PAIR) return i < n ? (uint32_t)__ldcg(wqc + i) : 0u;
+            else return i < n ? p.det_lead[segbase + i] : (1u << 16);
+        };
+        auto key_of = [&](int i, uint32_t l) -> uint32_t {
+            if constexpr (PAIR) return ((uint32_t)(tile_r0 + (int)(l >> pair_dshift)) << 12) | (uint32_t)(tile_d0 + (int)(l & pair_dmask));
+            else return i < n ? p.det_key[segbase + (l & 0xFFFFu)] : 0u;
+        };
         auto snapshot = [&](int i, uint32_t key) {
             if (i < n) {
                 int a, r, d;
@@ -858,7 +945,7 @@ __global__ void __launch_bounds__(ANG_THREADS, 4) angles_tc5_kernel(AngleArgs p,
                 float rr0 = 0.f;
                 if (valid) {
                     yv = atan2f(s[1].y * s[0].x - s[1].x * s[0].y, s[1].x * s[0].x + s[1].y * s[0].y);
-                    emit_power<AP>(p, o, mult, s);
+                    if constexpr (!PAIR) emit_power<AP>(p, o, mult, s);
                 }
 #pragma unroll
                 for (int m = 0; m < AP; ++m) rr0 = fmaf(s[m].x, s[m].x, fmaf(s[m].y, s[m].y, rr0));
@@ -1005,12 +1092,16 @@ __global__ void __launch_bounds__(ANG_THREADS, 4) angles_tc5_kernel(AngleArgs p,
                     const float full = (float)M;
                     if (full - pnorm <= 1e-4f * full) flags |= RS_FLAG_GUARD;
                 }
-                const int live = emit<true>(p, seg, i, o, mult, bi, Gd[bi], yv, flags, seg_clean);
-                if (ls_partials != nullptr) {
-                    const double2 cs = Gc[bi];
-                    const double c = cs.x, sn = cs.y, y = (double)yv, w = (double)live;
-                    acc_ls[0] += w * c * c; acc_ls[1] += w * sn * sn; acc_ls[2] += w * c * sn;
-                    acc_ls[3] += w * y * c; acc_ls[4] += w * y * sn; acc_ls[5] += w * y * y; acc_ls[6] += w;
+                if constexpr (PAIR) {
+                    __stcg(wres + (ld & 0xFFFFu), make_uint2((uint32_t)bi | ((uint32_t)flags << 16), __float_as_uint(yv)));
+                } else {
+                    const int live = emit<true>(p, seg, i, o, mult, bi, Gd[bi], yv, flags, seg_clean);
+                    if (ls_partials != nullptr) {
+                        const double2 cs = Gc[bi];
+                        const double c = cs.x, sn = cs.y, y = (double)yv, w = (double)live;
+                        acc_ls[0] += w * c * c; acc_ls[1] += w * sn * sn; acc_ls[2] += w * c * sn;
+                        acc_ls[3] += w * y * c; acc_ls[4] += w * y * sn; acc_ls[5] += w * y * y; acc_ls[6] += w;
+                    }
                 }
             }
             ld = ld1;
@@ -1019,7 +1110,7 @@ __global__ void __launch_bounds__(ANG_THREADS, 4) angles_tc5_kernel(AngleArgs p,
             key1 = key2;
         }
     }
-    if (ls_partials != nullptr) {
+    auto reduce_sums = [&](int sg) {
 #pragma unroll
         for (int q = 0; q < 7; ++q) {
 #pragma unroll
@@ -1033,11 +1124,36 @@ __global__ void __launch_bounds__(ANG_THREADS, 4) angles_tc5_kernel(AngleArgs p,
         if (tid < 7) {
             double t = 0;
             for (int w = 0; w < ANG_THREADS / 32; ++w) t += red[w][tid];
-            ls_partials[(size_t)seg * 8 + tid] = t;
+            ls_partials[(size_t)sg * 8 + tid] = t;
         }
-        __syncthreads();                                             // red is reused by the next segment
+        __syncthreads();                                             // red is reused
+    };
+    if constexpr (PAIR) {
+        __syncthreads();                                             // the table is complete
+        for (int sg = seg; sg < seg + 2; ++sg) {
+            const bool clean = p.det_nnear != nullptr && p.det_nnear[sg] == 0;
+            const size_t sb = (size_t)sg * p.seg_cap;
+#pragma unroll
+            for (int q = 0; q < 7; ++q) acc_ls[q] = 0.0;
+            for_leaders(sg, [&](int i, uint32_t l, uint32_t key) {
+                const uint2 rv = __ldcg(wres + cell_of(key));
+                const int bi = (int)(rv.x & 0xFFFFu);
+                const float yv = __uint_as_float(rv.y);
+                const int live = emit<true>(p, sg, i, sb + (l & 0xFFFFu), (int)(l >> 16), bi, Gd[bi], yv, (uint8_t)(rv.x >> 16), clean);
+                if (ls_partials != nullptr) {
+                    const double2 cs = Gc[bi];
+                    const double c = cs.x, sn = cs.y, y = (double)yv, w = (double)live;
+                    acc_ls[0] += w * c * c; acc_ls[1] += w * sn * sn; acc_ls[2] += w * c * sn;
+                    acc_ls[3] += w * y * c; acc_ls[4] += w * y * sn; acc_ls[5] += w * y * y; acc_ls[6] += w;
+                }
+            });
+            if (ls_partials != nullptr) reduce_sums(sg);
+        }
+        __syncthreads();                                             // table, queue and bit map are free again
+    } else {
+        if (ls_partials != nullptr) reduce_sums(seg);
     }
-    }   // segments
+    }   // units
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (wid == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
@@ -1370,15 +1486,35 @@ extern "C" int rs_angles(const void* rds, const float* scan_table, int scan_stri
                 if (sm <= (size_t)rs_smem_optin_limit()) {
                     // persistent: as many CTAs as fit (4 per SM by TMEM columns, fewer when the tables of a fine grid are large)
                     const size_t per_sm = (size_t)rs_smem_optin_limit() / (sm + 1024);
-                    const long long resident = (long long)rs_sm_count() * (long long)(per_sm < 4 ? (per_sm < 1 ? 1 : per_sm) : 4);
-                    const unsigned tc_grid = (unsigned)(blocks < resident ? blocks : resident);
-                    if (ap == 8) {
-                        cudaFuncSetAttribute(angles_tc5_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-                        angles_tc5_kernel<8><<<tc_grid, ANG_THREADS, sm, st>>>(p, (const uint4*)tc_table, tc_halves, grid_cs, ls_partials, (int)blocks);
-                    } else {
-                        cudaFuncSetAttribute(angles_tc5_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-                        angles_tc5_kernel<16><<<tc_grid, ANG_THREADS, sm, st>>>(p, (const uint4*)tc_table, tc_halves, grid_cs, ls_partials, (int)blocks);
+                    long long resident = (long long)rs_sm_count() * (long long)(per_sm < 4 ? (per_sm < 1 ? 1 : per_sm) : 4);
+                    // pair mode (see the kernel): 16 antennas in two octet segments per tile, scratch in cell_ws
+                    unsigned char* ws = nullptr;
+                    int rmask = 1, dshift = 1;                                   // tile rows / Doppler bins
+                    const char* dd_env = getenv("RS_ANGLES_DEDUP");
+                    if (A == 16 && cell_ws != nullptr && det_power_out == nullptr && !(dd_env && atoi(dd_env) == 0)) {
+                        int tr = 0, td = 0, nt = 0;
+                        rs_detect_tiling(R, D, A, &tr, &td, &nt);
+                        const bool pow2 = tr > 0 && td > 0 && (tr & (tr - 1)) == 0 && (td & (td - 1)) == 0;
+                        if (pow2 && nt == nseg_per_frame && (nt & 1) == 0 && tr * td <= tc5::PAIR_CELLS && D % td == 0 && R % tr == 0) {
+                            ws = (unsigned char*)cell_ws;
+                            rmask = tr;
+                            dshift = td;
+                            const long long cap = RS_ANGLES_WS_BYTES / tc5::PAIR_WS_BYTES;
+                            if (resident > cap) resident = cap;
+                        }
                     }
+                    const long long units = ws ? blocks / 2 : blocks;
+                    const unsigned tc_grid = (unsigned)(units < resident ? units : resident);
+#define LAUNCH_TC5(AP_, PAIR_)                                                                                          \
+    do {                                                                                                                \
+        cudaFuncSetAttribute(angles_tc5_kernel<AP_, PAIR_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);      \
+        angles_tc5_kernel<AP_, PAIR_><<<tc_grid, ANG_THREADS, sm, st>>>(p, (const uint4*)tc_table, tc_halves, grid_cs,  \
+                                                                        ls_partials, (int)blocks, ws, rmask, dshift);   \
+    } while (0)
+                    if (ap == 8) LAUNCH_TC5(8, false);
+                    else if (ws != nullptr) LAUNCH_TC5(16, true);
+                    else LAUNCH_TC5(16, false);
+#undef LAUNCH_TC5
                     RS_CHECK_LAUNCH("rs_angles(tcgen05)");
                     return RS_OK;
                 }

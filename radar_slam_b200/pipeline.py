@@ -342,7 +342,8 @@ class FramePipeline:
             det.seg_cap, det.ntiles, det.F, det.R, det.D, det.A,
             t["grid_cs"].data_ptr(), _lib.ptr(det.ls_partials), int(t["symmetric"]), det.ntie.data_ptr(), det.tielist.data_ptr(),
             _lib.ptr(t["mma"]), t["mma_tiles"],
-            self._buf("cell_ws" + det.tag, (17 * det.F * det.R * det.D + 16,), torch.uint8).data_ptr() if det.A > 16 else 0,
+            self._buf("cell_ws" + det.tag, (17 * det.F * det.R * det.D + 16,), torch.uint8).data_ptr() if det.A > 16 else
+            (self._buf("pair_ws" + det.tag, (_lib.RS_ANGLES_WS_BYTES,), torch.uint8).data_ptr() if det.A == 16 else 0),
             _lib.ptr(t["tc"]), t["tc_halves"], det.power.data_ptr() if (write_power and det.power_pending) else 0,
             _lib.ptr(det.nnear), self.stream)
         if write_power:
