@@ -53,3 +53,37 @@ def test_tcgen05_scan_matches_oracle_and_mma(monkeypatch, A, method, res):
     for f in range(2):
         assert np.array_equal(tc[f]["aidx"], mma[f]["aidx"])
     assert np.abs(v_tc[:, :2] - v_mma[:, :2]).max() < 1e-9
+
+
+def test_pair_mode_equals_per_segment_scan(monkeypatch):
+    """16 channels: scanning the two antenna-octet segments of a tile as a pair (every distinct cell once, RS_ANGLES_DEDUP
+    default) writes exactly what the per-segment scan writes -- the snapshot of a cell is the same on both octets."""
+    from radar_slam_b200 import RadarConfig, FramePipeline
+    A = 16
+    p = orc.RadarParams(chirp_duration=25.6e-6, num_chirps=128, num_antennas=A)
+    scene = np.array([(8.0, 0.0, -10.0, 0.0), (12.0, 0.5, -8.0, 0.0), (25.0, -0.7, 0.0, 0.0)])
+    np.random.seed(77)
+    cube = torch.from_numpy(np.stack([orc.synthesize_frame(p, scene) for _ in range(3)]).astype(np.complex64)).cuda()
+    out = {}
+    for dd in ("1", "0"):
+        monkeypatch.setenv("RS_ANGLES_TC", "1")
+        monkeypatch.setenv("RS_ANGLES_DEDUP", dd)
+        cfg = RadarConfig(chirp_duration=25.6e-6, num_chirps=128, num_antennas=A, recheck=False)
+        pipe = FramePipeline(cfg)
+        rds = pipe.range_doppler(cube)
+        det = pipe.angles(rds, pipe.detect(rds))
+        torch.cuda.synchronize()
+        n = det.F * det.ntiles * det.seg_cap
+        m = det.valid_mask().reshape(-1)
+        out[dd] = dict(aidx=det.aidx[:n][m].cpu().numpy(), flags=det.flags[:n][m].cpu().numpy(),
+                       adeg=det.adeg[:n][m].cpu().numpy(), phase=det.phase[:n][m].cpu().numpy(),
+                       ntie=det.ntie.cpu().numpy().copy(), part=det.ls_partials.cpu().numpy().copy(),
+                       tie=[np.sort(t[:c]) for t, c in zip(det.tielist.cpu().numpy().reshape(-1, 32),
+                                                           np.minimum(det.ntie.cpu().numpy(), 32))])
+    a, b = out["1"], out["0"]
+    assert a["aidx"].size > 50000
+    for k in ("aidx", "flags", "adeg", "phase", "ntie"):
+        assert np.array_equal(a[k], b[k]), k
+    assert all(np.array_equal(x, y) for x, y in zip(a["tie"], b["tie"]))
+    # the seven velocity sums of every segment (slot 8 is padding): same terms, another summation order
+    assert np.allclose(a["part"][:, :7], b["part"][:, :7], rtol=1e-12, atol=1e-9)
