@@ -215,3 +215,30 @@ def test_plateau_overflow_is_reported_and_recoverable():
     assert int(det2.overflow.sum()) == 0
     pk = orc.extract_peaks(rds_ref.astype(np.complex128), p, threshold_db=-20.0)
     assert np.array_equal(det2.frame(0)["key"], _keys(pk)) and len(pk["antenna"]) > 8 * 50 * 32
+
+
+@pytest.mark.parametrize("S,C,A,res", [(128, 64, 16, 1.0),      # pair mode on 16 x 64 tiles
+                                       (256, 256, 16, 1.0),     # pair mode, two Doppler tiles per range row
+                                       (120, 32, 16, 2.0),      # range bins not a multiple of the tile: per-segment scan
+                                       (256, 128, 16, 0.5),     # 361 grid points: six jobs per tile
+                                       (128, 64, 12, 1.0),      # padded to 16 channels, no pair mode
+                                       (128, 64, 7, 1.0)])      # padded to 8 channels
+def test_tcgen05_scan_geometries(S, C, A, res):
+    """The persistent tcgen05 scan (and its 16-channel pair mode) on dense noise lists at shapes that move its tile / queue
+    / job geometry: every disagreement with the oracle's fp64 argmax is flagged, velocity within the contract."""
+    p = orc.RadarParams(chirp_duration=S / 10e6, num_chirps=C, num_antennas=A)
+    np.random.seed(S + C + A)
+    cube = orc.synthesize_frame(p, SCENE[:3]).astype(np.complex64)
+    pipe, vel, rds, det, ref, pk = _run(p, cube, -20.0, "music", res=res)
+    d = _check_rds_and_keys(rds, det, ref, pk)
+    assert len(d["key"]) > 2000
+    grid = orc.azimuth_grid((-90, 90), res)
+    steer = orc.steering_matrix(grid, p.antenna_positions, p.lambda_c)
+    pos = np.searchsorted(d["key"], _keys(pk))
+    ok = (pos < len(d["key"])) & (d["key"][np.minimum(pos, len(d["key"]) - 1)] == _keys(pk))
+    sigs = orc.spatial_signatures(ref, pk["range_bin"][ok], pk["doppler_bin"][ok])
+    idx = np.argmax(orc.beamforming_spectra(sigs, steer), axis=1)
+    bad = d["aidx"][pos[ok]] != idx
+    assert np.all(d["flags"][pos[ok]][bad] & 5) and bad.mean() < 5e-3
+    sol = orc.solve_velocity(pk["range_m"][ok], np.radians(grid[idx]), sigs, p.lambda_c, 0.1)
+    assert np.abs(vel[0, :2].cpu().numpy() - sol["velocity"][:2]).max() < 1e-3
