@@ -1304,6 +1304,108 @@ __global__ void __launch_bounds__(ANG_THREADS) eval_cells_kernel(AngleArgs p, co
     }
 }
 
+// ESPRIT on the marked cells (large_cell's closed form, re-arranged after an ncu capture of eval_cells_kernel at
+// 512 x 256 x 192: 1055 warp instructions per cell, 64 % issue, the L1 pipe at 81 %):
+//  * asin(atan2()) in fp64 and atan2f() ran on all 32 lanes for the one value lane 0 keeps (~400 of the 1055
+//    instructions): here a warp works through a batch of 32 cells, lane j captures the sums of cell j, and the
+//    transcendental functions run once per batch, a lane per cell;
+//  * lane l owns the PER consecutive antennas [l PER, l PER + PER): the neighbours x_{m+1}, u_{m+1} of both sums are
+//    registers, except across the block edge (one shuffle each) -- no shared memory, so the whole unified array stays L1
+//    for the strided gathers (a first version with fp64 staging in shared memory left 7 KB of L1 and ran 2.3x slower);
+//  * w_m = v0 x_{m+1} + v1 x_{m+2} of the second sum is u_{m+1} of its first factor: u is computed once per antenna --
+//    14 instead of 32 fp64 operations per antenna.
+// The four warps of a CTA take the four cells of a 32-byte sector (4 Doppler bins of an antenna row) at the same time.
+template <int PER>
+__global__ void __launch_bounds__(ANG_THREADS) eval_cells_esprit_kernel(AngleArgs p, const uint8_t* __restrict__ mark,
+                                                                         CellResult* __restrict__ cells, long long ncells) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    constexpr int NW = ANG_THREADS / 32;
+    const int M = p.A, m0 = lane * PER;
+    const long long per_frame = (long long)p.R * p.D;
+    for (long long g0 = (long long)blockIdx.x * 32 * NW; g0 < ncells; g0 += (long long)gridDim.x * 32 * NW) {
+        // cell i of this warp's batch: g0 + NW i + wid
+        double cap_nr = 0, cap_ni = 0;
+        float2 c0 = make_float2(0.f, 0.f), c1 = make_float2(0.f, 0.f);
+        const long long mine = g0 + (long long)NW * lane + wid;
+        const uint32_t marked = __ballot_sync(0xffffffffu, mine < ncells && mark[mine] != 0);
+        for (uint32_t todo = marked; todo; todo &= todo - 1) {
+            const int j = __ffs(todo) - 1;
+            const long long c = g0 + (long long)NW * j + wid;
+            const long long f = c / per_frame;
+            const long long rd = c - f * per_frame;
+            const int r = (int)(rd / p.D), d = (int)(rd - (long long)r * p.D);
+            const float2* cell = p.rds + ((size_t)f * p.R + r) * M * p.D + d;
+            float2 s[PER];
+#pragma unroll
+            for (int k = 0; k < PER; ++k) s[k] = m0 + k < M ? __ldg(cell + (size_t)(m0 + k) * p.D) : make_float2(0.f, 0.f);
+            float2 sn;                                           // x of the next lane's first antenna
+            sn.x = __shfl_down_sync(0xffffffffu, s[0].x, 1);
+            sn.y = __shfl_down_sync(0xffffffffu, s[0].y, 1);
+            double alpha = 0, gamma = 0, br = 0, bi = 0;
+#pragma unroll
+            for (int k = 0; k < PER; ++k) {
+                if (m0 + k < M - 1) {
+                    const float2 xf = s[k], yf = k + 1 < PER ? s[k + 1] : sn;
+                    const double xx = xf.x, xy = xf.y, yx = yf.x, yy = yf.y;
+                    alpha += xx * xx + xy * xy; gamma += yx * yx + yy * yy;
+                    br += xx * yx + xy * yy;    bi += xx * yy - xy * yx;
+                }
+            }
+#pragma unroll
+            for (int off = 16; off; off >>= 1) {
+                alpha += __shfl_xor_sync(0xffffffffu, alpha, off); gamma += __shfl_xor_sync(0xffffffffu, gamma, off);
+                br += __shfl_xor_sync(0xffffffffu, br, off);       bi += __shfl_xor_sync(0xffffffffu, bi, off);
+            }
+            const double half = 0.5 * (alpha - gamma);
+            const double lam = 0.5 * (alpha + gamma) + sqrt(half * half + br * br + bi * bi);
+            double v0r, v0i, v1r, v1i;
+            const double na = br * br + bi * bi + (lam - alpha) * (lam - alpha);
+            const double nb2 = (lam - gamma) * (lam - gamma) + br * br + bi * bi;
+            if (na >= nb2) { v0r = br; v0i = bi; v1r = lam - alpha; v1i = 0; }
+            else           { v0r = lam - gamma; v0i = 0; v1r = br; v1i = -bi; }
+            double2 u[PER];
+#pragma unroll
+            for (int k = 0; k < PER; ++k) {
+                const float2 xf = s[k], yf = k + 1 < PER ? s[k + 1] : sn;
+                const double x0x = xf.x, x0y = xf.y, x1x = yf.x, x1y = yf.y;
+                u[k] = make_double2(v0r * x0x - v0i * x0y + v1r * x1x - v1i * x1y,
+                                    v0r * x0y + v0i * x0x + v1r * x1y + v1i * x1x);
+            }
+            double2 un;                                          // u of the next lane's first antenna
+            un.x = __shfl_down_sync(0xffffffffu, u[0].x, 1);
+            un.y = __shfl_down_sync(0xffffffffu, u[0].y, 1);
+            double nr = 0, ni = 0;
+#pragma unroll
+            for (int k = 0; k < PER; ++k) {
+                if (m0 + k < M - 2) {
+                    const double2 a = u[k], w = k + 1 < PER ? u[k + 1] : un;
+                    nr += a.x * w.x + a.y * w.y;
+                    ni += a.x * w.y - a.y * w.x;
+                }
+            }
+#pragma unroll
+            for (int off = 16; off; off >>= 1) {
+                nr += __shfl_xor_sync(0xffffffffu, nr, off);
+                ni += __shfl_xor_sync(0xffffffffu, ni, off);
+            }
+            // antennas 0 and 1 (the inter-antenna phase) sit on lane 0 (PER >= 2)
+            const float a0x = __shfl_sync(0xffffffffu, s[0].x, 0), a0y = __shfl_sync(0xffffffffu, s[0].y, 0);
+            const float a1x = __shfl_sync(0xffffffffu, s[1].x, 0), a1y = __shfl_sync(0xffffffffu, s[1].y, 0);
+            if (lane == j) {
+                cap_nr = nr; cap_ni = ni;
+                c0 = make_float2(a0x, a0y);
+                c1 = make_float2(a1x, a1y);
+            }
+        }
+        if ((marked >> lane) & 1u) {
+            CellResult out{-1, 0.f, 0.f, 0u};
+            out.phase = atan2f(c1.y * c0.x - c1.x * c0.y, c1.x * c0.x + c1.y * c0.y);
+            out.adeg = (float)(asin(atan2(cap_ni, cap_nr) * p.esprit_scale) * (180.0 / 3.14159265358979323846));
+            cells[mine] = out;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) scatter_cells_kernel(AngleArgs p, const CellResult* __restrict__ cells) {
     const int seg = blockIdx.x;
     const int n = p.det_nlead[seg];
@@ -1577,7 +1679,17 @@ extern "C" int rs_angles(const void* rds, const float* scan_table, int scan_stri
             mark_cells_kernel<<<(unsigned)blocks, 256, 0, st>>>(p, mark);
             const long long want = (ncells + ANG_THREADS / 32 - 1) / (ANG_THREADS / 32);
             const long long cap = (long long)rs_sm_count() * 64;
-            eval_cells_kernel<<<(unsigned)(want < cap ? want : cap), ANG_THREADS, smem, st>>>(p, mark, cells, ncells);
+            if (method == RS_METHOD_ESPRIT && A <= 256 && !getenv("RS_ESPRIT_LEGACY")) {
+                const long long want32 = (ncells + 32 * (ANG_THREADS / 32) - 1) / (32 * (ANG_THREADS / 32));
+                const unsigned eg = (unsigned)(want32 < cap ? want32 : cap);
+                const int per = (A + 31) / 32;
+                if (per <= 2) eval_cells_esprit_kernel<2><<<eg, ANG_THREADS, 0, st>>>(p, mark, cells, ncells);
+                else if (per <= 4) eval_cells_esprit_kernel<4><<<eg, ANG_THREADS, 0, st>>>(p, mark, cells, ncells);
+                else if (per <= 6) eval_cells_esprit_kernel<6><<<eg, ANG_THREADS, 0, st>>>(p, mark, cells, ncells);
+                else eval_cells_esprit_kernel<8><<<eg, ANG_THREADS, 0, st>>>(p, mark, cells, ncells);
+            } else {
+                eval_cells_kernel<<<(unsigned)(want < cap ? want : cap), ANG_THREADS, smem, st>>>(p, mark, cells, ncells);
+            }
             scatter_cells_kernel<<<(unsigned)blocks, 256, 0, st>>>(p, cells);
         } else {
             angles_large_kernel<<<(unsigned)blocks, ANG_THREADS, smem, st>>>(p);
