@@ -222,7 +222,9 @@ def test_plateau_overflow_is_reported_and_recoverable():
                                        (120, 32, 16, 2.0),      # range bins not a multiple of the tile: per-segment scan
                                        (256, 128, 16, 0.5),     # 361 grid points: six jobs per tile
                                        (128, 64, 12, 1.0),      # padded to 16 channels, no pair mode
-                                       (128, 64, 7, 1.0)])      # padded to 8 channels
+                                       (128, 64, 7, 1.0),       # padded to 8 channels
+                                       (128, 64, 8, 5.0),       # 37 grid points: a single job per tile
+                                       (128, 64, 16, 0.25)])    # 721 grid points: twelve jobs, one CTA per SM
 def test_tcgen05_scan_geometries(S, C, A, res):
     """The persistent tcgen05 scan (and its 16-channel pair mode) on dense noise lists at shapes that move its tile / queue
     / job geometry: every disagreement with the oracle's fp64 argmax is flagged, velocity within the contract."""
