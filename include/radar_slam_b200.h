@@ -165,6 +165,9 @@ int rs_range_doppler_detect(const void* cube, const void* table, const void* twi
  *       tc_table      optional, bytes [tc_halves][cos, sin][KC][32 x 16 fp16]: the same tables as UMMA B operands (K-major,
  *                     no swizzle) for the tcgen05 / TMEM scan (radar_slam_b200/tables.py: scan_tc_table), tc_halves =
  *                     ceil(ceil(G/2)/32); the default scan for 5..16 antennas on a symmetric grid (RS_ANGLES_TC=0: mma.sync).
+ *                     A > 16 (MUSIC / beamforming, D a multiple of 128, cell_ws given): the B operands of the steering GEMM
+ *                     [tc_halves][ceil(A/8)][hi, lo][192 x 16 fp16] (tables.py: steer_tc_table), tc_halves = ceil(G/96):
+ *                     the grid scan runs as a dense contraction on the tensor cores (RS_MUSIC_TC=0: CUDA-core scan).
  *       det_power_out optional float [F*nseg_per_frame*seg_cap]: |X|^2 of every entry (the det_power of rs_detect), for
  *                     lists that came from rs_range_doppler_detect with det_power = NULL.  The scan holds the snapshot
  *                     of every flagged cell in registers anyway, so the powers cost no memory traffic here.

@@ -1023,11 +1023,15 @@ __global__ void __launch_bounds__(ANG_THREADS, 4) angles_tc5_kernel(AngleArgs p,
                 const int b = jb & 1;
                 {
                     uint32_t ok = 0;
-                    const long long t0 = clock64();
-                    while (!ok) {
-                        asm volatile("{\n .reg .pred q;\n mbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\n selp.u32 %0, 1, 0, q;\n}"
-                                     : "=r"(ok) : "r"(s32(&mbar[b])), "r"(phase[b]) : "memory");
-                        if (!ok && clock64() - t0 > 4000000000ll) __trap();
+                    asm volatile("{\n .reg .pred q;\n mbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\n selp.u32 %0, 1, 0, q;\n}"
+                                 : "=r"(ok) : "r"(s32(&mbar[b])), "r"(phase[b]) : "memory");
+                    if (!ok) {                                           // the clock (a hang becomes a trap) only on the slow path
+                        const long long t0 = clock64();
+                        while (!ok) {
+                            asm volatile("{\n .reg .pred q;\n mbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\n selp.u32 %0, 1, 0, q;\n}"
+                                         : "=r"(ok) : "r"(s32(&mbar[b])), "r"(phase[b]) : "memory");
+                            if (!ok && clock64() - t0 > 4000000000ll) __trap();
+                        }
                     }
                     phase[b] ^= 1u;
                 }
@@ -1406,6 +1410,197 @@ __global__ void __launch_bounds__(ANG_THREADS) eval_cells_esprit_kernel(AngleArg
     }
 }
 
+// ---- A > 16, MUSIC / beamforming: the steering scan as a dense contraction on the 5th-generation tensor cores ----------
+// With many antennas y_g = a_g^H s over the whole grid IS a GEMM: [cells x 2A] . [2A x 2G] (real form; at A = 192, G = 181
+// it is 384 x 362 per cell, 35 k complex multiply-adds, against 1.4 k for the 8-channel lag scan).  One CTA = 128 threads =
+// 128 consecutive Doppler cells of one range row = the 128 TMEM lanes of a UMMA tile, so the snapshot gathers are perfectly
+// coalesced (thread t reads antenna m of cell d0 + t: 1 KB rows).  Per tile:
+//   pre-pass   |s|^2 of every cell -> scale 1 / |s| (the fp16 operands need a per-cell scale: a strong target is 10^4 x the noise)
+//   per N-half (96 grid points = 192 accumulator columns: Re y, Im y interleaved), per chunk of 8 antennas:
+//     every thread splits its scaled [Re s (8) | Im s (8)] into fp16 hi / lo and writes its row of the two A operands
+//     (K-major, no swizzle), the CTA copies the chunk's [192 x 16] hi / lo B operands (radar_slam_b200/tables.py:
+//     steer_tc_table, L2 resident), one thread issues three tcgen05.mma 128 x 192 x 16 (hi.hi + lo.hi + hi.lo, fp32
+//     accumulation in TMEM) and commits to the stage's mbarrier; two stages, so the tensor core works on chunk c while
+//     the threads prepare chunk c + 1 (the next chunk's snapshot loads are in flight across the barrier);
+//   epilogue  tcgen05.ld: every thread owns the whole accumulator row of its cell: P_g = Re^2 + Im^2, two-level argmax /
+//     runner-up tracking as in angles_tc5_kernel (groups of 8 grid points), carried over the halves.
+// Every cell of the tile is evaluated (at these channel counts every cell carries detections); results go to the
+// CellResult table the scatter kernel reads.  The TIE band is at least 2e-5: 1152 products per output in fp32.
+namespace tc5 {
+constexpr int SG_N = 192;                                                  // accumulator columns per N-half
+constexpr uint32_t IDESC_SG = (1u << 4) | ((uint32_t)(SG_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+__device__ __forceinline__ void umma_sg(uint32_t tmem_d, unsigned long long da, unsigned long long db, uint32_t accumulate) {
+    asm volatile(
+        "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(IDESC_SG), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_trap(unsigned long long* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    asm volatile("{\n .reg .pred q;\n mbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\n selp.u32 %0, 1, 0, q;\n}"
+                 : "=r"(ok) : "r"(s32(bar)), "r"(parity) : "memory");
+    if (!ok) {
+        const long long t0 = clock64();
+        while (!ok) {
+            asm volatile("{\n .reg .pred q;\n mbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\n selp.u32 %0, 1, 0, q;\n}"
+                         : "=r"(ok) : "r"(s32(bar)), "r"(parity) : "memory");
+            if (!ok && clock64() - t0 > 4000000000ll) __trap();
+        }
+    }
+}
+}  // namespace tc5
+
+__global__ void __launch_bounds__(ANG_THREADS, 2) music_tc_kernel(AngleArgs p, const uint4* __restrict__ btab, int nhalves,
+                                                               int nchunks, CellResult* __restrict__ cells, long long ntiles) {
+    using namespace tc5;
+    constexpr int A_BYTES = 128 * 32, B_BYTES = SG_N * 32, STAGE = 2 * A_BYTES + 2 * B_BYTES, SG_TMEM = 256;
+    extern __shared__ __align__(128) unsigned char sgsm[];                   // [2 stages][A_hi, A_lo, B_hi, B_lo]
+    __shared__ unsigned long long mbar[2];
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, wid = tid >> 5;
+    const int M = p.A, G = p.G;
+    if (wid == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(&tmem_base_s)), "n"(SG_TMEM) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(&mbar[0])) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(&mbar[1])) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_s;
+    const uint32_t trow = tmem_base + ((uint32_t)(wid * 32) << 16);
+    uint32_t phase[2] = {0u, 0u};
+    const uint32_t arow = (uint32_t)((tid >> 3) * 256 + (tid & 7) * 16);
+    const uint32_t sm_base = s32(sgsm);
+    const float NEG = -3.0e38f;
+    const float tie_eps = fmaxf(p.tie_eps, 2e-5f);
+    const int tiles_d = p.D / 128;
+    for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const long long fr = t / tiles_d;                                    // f * R + r
+        const int d = (int)(t - fr * tiles_d) * 128 + tid;
+        const float2* cell = p.rds + (size_t)fr * M * p.D + d;
+        // pre-pass: energy of the cell (and the two antennas of the inter-antenna phase)
+        float e = 0.f;
+        float2 s0 = make_float2(0.f, 0.f), s1 = make_float2(0.f, 0.f);
+        for (int m0 = 0; m0 < M; m0 += 8) {
+            float2 x[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[j] = m0 + j < M ? __ldg(cell + (size_t)(m0 + j) * p.D) : make_float2(0.f, 0.f);
+            if (m0 == 0) { s0 = x[0]; s1 = x[1]; }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) e = fmaf(x[j].x, x[j].x, fmaf(x[j].y, x[j].y, e));
+        }
+        const float scale = e > 0.f ? 1.f / sqrtf(e) : 0.f;
+        auto load_chunk = [&](int c, float2 (&x)[8]) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[j] = 8 * c + j < M ? __ldg(cell + (size_t)(8 * c + j) * p.D) : make_float2(0.f, 0.f);
+        };
+        float g_best = NEG, g_second = NEG;
+        int g_idx = 0, g_run = 0;
+        float stash[8] = {NEG, NEG, NEG, NEG, NEG, NEG, NEG, NEG};
+        float2 nx[8];
+        load_chunk(0, nx);
+        for (int h = 0; h < nhalves; ++h) {
+            for (int c = 0; c < nchunks; ++c) {
+                const int st = c & 1;
+                if (c >= 2) {                                                // the MMAs that read this stage two chunks ago
+                    mbar_wait_trap(&mbar[st], phase[st]);
+                    phase[st] ^= 1u;
+                }
+                unsigned char* sa = sgsm + (size_t)st * STAGE;
+                {
+                    uint32_t rh[4], rl[4], ih[4], il[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        split_f16x2(nx[2 * j].x * scale, nx[2 * j + 1].x * scale, rh[j], rl[j]);
+                        split_f16x2(nx[2 * j].y * scale, nx[2 * j + 1].y * scale, ih[j], il[j]);
+                    }
+                    *reinterpret_cast<uint4*>(sa + arow) = make_uint4(rh[0], rh[1], rh[2], rh[3]);
+                    *reinterpret_cast<uint4*>(sa + arow + 128) = make_uint4(ih[0], ih[1], ih[2], ih[3]);
+                    *reinterpret_cast<uint4*>(sa + A_BYTES + arow) = make_uint4(rl[0], rl[1], rl[2], rl[3]);
+                    *reinterpret_cast<uint4*>(sa + A_BYTES + arow + 128) = make_uint4(il[0], il[1], il[2], il[3]);
+                }
+                {
+                    const uint4* src = btab + (size_t)(h * nchunks + c) * (2 * B_BYTES / 16);
+                    uint4* dst = reinterpret_cast<uint4*>(sa + 2 * A_BYTES);
+#pragma unroll
+                    for (int i = 0; i < 2 * B_BYTES / 16 / ANG_THREADS; ++i) dst[tid + i * ANG_THREADS] = __ldg(src + tid + i * ANG_THREADS);
+                }
+                // the next chunk's snapshot (of the next half when this one ends) is requested before the barrier
+                if (c + 1 < nchunks) load_chunk(c + 1, nx);
+                else if (h + 1 < nhalves) load_chunk(0, nx);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncthreads();
+                if (tid == 0) {
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a_hi = sm_base + (uint32_t)(st * STAGE), a_lo = a_hi + A_BYTES;
+                    const uint32_t b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
+                    umma_sg(tmem_base, smem_desc(a_hi), smem_desc(b_hi), c > 0 ? 1u : 0u);
+                    umma_sg(tmem_base, smem_desc(a_lo), smem_desc(b_hi), 1u);
+                    umma_sg(tmem_base, smem_desc(a_hi), smem_desc(b_lo), 1u);
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(&mbar[st])) : "memory");
+                }
+            }
+            // the last two chunks' commits (in issue order): all MMAs of this half are done
+            if (nchunks >= 2) {
+                const int st = (nchunks - 2) & 1;
+                mbar_wait_trap(&mbar[st], phase[st]);
+                phase[st] ^= 1u;
+            }
+            {
+                const int st = (nchunks - 1) & 1;
+                mbar_wait_trap(&mbar[st], phase[st]);
+                phase[st] ^= 1u;
+            }
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            // epilogue: 12 groups of 8 grid points (16 columns), the next group's read in flight
+            float acc[2][16];
+            ld16(trow, acc[0]);
+#pragma unroll
+            for (int g = 0; g < SG_N / 16; ++g) {
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (g + 1 < SG_N / 16) ld16(trow + (uint32_t)(16 * (g + 1)), acc[(g + 1) & 1]);
+                float v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = fmaf(acc[g & 1][2 * j], acc[g & 1][2 * j], acc[g & 1][2 * j + 1] * acc[g & 1][2 * j + 1]);
+                const float gm = fmaxf(fmaxf(fmaxf(v[0], v[1]), v[2]), fmaxf(fmaxf(fmaxf(v[3], v[4]), v[5]), fmaxf(v[6], v[7])));
+                const bool up = gm > g_best;
+                g_second = fmaxf(g_second, fminf(g_best, gm));
+                g_best = fmaxf(g_best, gm);
+                g_idx = up ? g_run : g_idx;
+                ++g_run;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) stash[j] = up ? v[j] : stash[j];
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");   // the next half's first MMA comes after a barrier
+        }
+        int in_idx = 7;
+#pragma unroll
+        for (int j = 6; j >= 0; --j) in_idx = (stash[j] == g_best) ? j : in_idx;
+        float in_second = NEG;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) in_second = fmaxf(in_second, j == in_idx ? NEG : stash[j]);
+        const float best = g_best, second = fmaxf(g_second, in_second);
+        int bi = 8 * g_idx + in_idx;
+        bi = bi < G ? bi : G - 1;
+        CellResult out{bi, p.grid_deg[bi], 0.f, 0u};
+        out.phase = atan2f(s1.y * s0.x - s1.x * s0.y, s1.x * s0.x + s1.y * s0.y);
+        if ((best - second) <= tie_eps * best) out.flags |= RS_FLAG_TIE;
+        if (p.method == RS_METHOD_MUSIC) {
+            const float full = (float)M * (e * scale * scale);
+            if (full - best <= 1e-4f * full) out.flags |= RS_FLAG_GUARD;
+        }
+        cells[(size_t)fr * p.D + d] = out;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (wid == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(SG_TMEM) : "memory");
+}
+
 __global__ void __launch_bounds__(256) scatter_cells_kernel(AngleArgs p, const CellResult* __restrict__ cells) {
     const int seg = blockIdx.x;
     const int n = p.det_nlead[seg];
@@ -1679,7 +1874,18 @@ extern "C" int rs_angles(const void* rds, const float* scan_table, int scan_stri
             mark_cells_kernel<<<(unsigned)blocks, 256, 0, st>>>(p, mark);
             const long long want = (ncells + ANG_THREADS / 32 - 1) / (ANG_THREADS / 32);
             const long long cap = (long long)rs_sm_count() * 64;
-            if (method == RS_METHOD_ESPRIT && A <= 256 && !getenv("RS_ESPRIT_LEGACY")) {
+            const char* mtc_env = getenv("RS_MUSIC_TC");
+            const int sg_halves = (G + 95) / 96;
+            if (method != RS_METHOD_ESPRIT && tc_table != nullptr && tc_halves == sg_halves && D % 128 == 0 &&
+                !(mtc_env && atoi(mtc_env) == 0)) {
+                // steering GEMM on the tensor cores: every cell of the batch, 128-cell tiles, two CTAs (2 x 256 TMEM columns) per SM
+                const long long ntiles = ncells / 128;
+                const size_t smem_sg = 2 * (2 * 128 * 32 + 2 * (size_t)tc5::SG_N * 32);
+                const long long resident = 2ll * rs_sm_count();
+                cudaFuncSetAttribute(music_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sg);
+                music_tc_kernel<<<(unsigned)(ntiles < resident ? ntiles : resident), ANG_THREADS, smem_sg, st>>>(
+                    p, (const uint4*)tc_table, sg_halves, (A + 7) / 8, cells, ntiles);
+            } else if (method == RS_METHOD_ESPRIT && A <= 256 && !getenv("RS_ESPRIT_LEGACY")) {
                 const long long want32 = (ncells + 32 * (ANG_THREADS / 32) - 1) / (32 * (ANG_THREADS / 32));
                 const unsigned eg = (unsigned)(want32 < cap ? want32 : cap);
                 const int per = (A + 31) / 32;

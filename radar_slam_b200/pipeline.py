@@ -200,6 +200,8 @@ class FramePipeline:
             symmetric = bool(np.array_equal(grid[::-1], -grid))
             mma, mma_tiles = (tables.scan_mma_table(scan, len(grid), A) if symmetric and 4 < A <= 16 else (None, 0))
             tc, tc_halves = (tables.scan_tc_table(scan, len(grid), A) if symmetric and 4 < A <= 16 else (None, 0))
+            if A > 16:                      # steering GEMM on the tensor cores (MUSIC / beamforming scan at many channels)
+                tc, tc_halves = tables.steer_tc_table(steer)
             self._tab[key] = {
                 "grid": grid, "G": len(grid), "stride": stride,
                 "scan": self._dev(scan), "grid_f32": self._dev(grid.astype(np.float32)),

@@ -155,6 +155,42 @@ def scan_tc_table(scan: np.ndarray, G: int, A: int, pairs_per_half: int = 32) ->
     return out.reshape(-1).view(np.uint8), nh
 
 
+STEER_TC_POINTS = 96          # grid points per N-half of the steering GEMM (192 accumulator columns: Re, Im interleaved)
+
+
+def steer_tc_table(steer: np.ndarray) -> Tuple[np.ndarray, int]:
+    """B operands of the tcgen05 steering GEMM (csrc/rs_angles.cu, music_tc_kernel; A > 16).
+    y_g = a_g^H s is a real contraction over K = 2 A: the A operand row of a cell is, per chunk of 8 antennas, the 16 K slots
+    [Re s (8) | Im s (8)]; column 2 j of an N-half is Re y_g, column 2 j + 1 is Im y_g of grid point g = 96 h + j:
+        Re y_g = sum_m  Re a_m Re s_m + Im a_m Im s_m        Im y_g = sum_m  Re a_m Im s_m - Im a_m Re s_m.
+    Layout: [halves][chunks][hi, lo][192 columns x 16 slots] fp16, every [192 x 16] block in the canonical K-major
+    no-swizzle UMMA layout (element (n, k) at (n // 8) * 256 + (k // 8) * 128 + (n % 8) * 16 + (k % 8) * 2 bytes);
+    x = hi + lo as in scan_tc_table.  steer is the c128 [A][G] table of `steering`; grid points and antennas beyond the
+    table are zero columns / slots.  Returns (uint8 bytes, number of halves)."""
+    A, G = steer.shape
+    nh = (G + STEER_TC_POINTS - 1) // STEER_TC_POINTS
+    nc = (A + 7) // 8
+    st = np.zeros((nc * 8, nh * STEER_TC_POINTS), dtype=np.complex128)
+    st[:A, :G] = steer
+    N = 2 * STEER_TC_POINTS
+    T = np.zeros((nh, nc, N, 16), dtype=np.float32)                          # [half][chunk][column][slot]
+    for h in range(nh):
+        blk = st[:, h * STEER_TC_POINTS:(h + 1) * STEER_TC_POINTS].reshape(nc, 8, STEER_TC_POINTS)   # [chunk][m][j]
+        re, im = blk.real.transpose(0, 2, 1), blk.imag.transpose(0, 2, 1)    # [chunk][j][m]
+        T[h, :, 0::2, 0:8] = re
+        T[h, :, 0::2, 8:16] = im
+        T[h, :, 1::2, 0:8] = -im
+        T[h, :, 1::2, 8:16] = re
+    hi, lo = f16_split(T)
+    n = np.arange(N)[:, None]
+    k = np.arange(16)[None, :]
+    off = ((n // 8) * 128 + (k // 8) * 64 + (n % 8) * 8 + (k % 8)).reshape(-1)   # in fp16 elements
+    out = np.zeros((nh, nc, 2, N * 16), dtype=np.float16)
+    out[:, :, 0, off] = hi.reshape(nh, nc, -1)
+    out[:, :, 1, off] = lo.reshape(nh, nc, -1)
+    return out.reshape(-1).view(np.uint8), nh
+
+
 def grid_cos_sin(grid_deg: np.ndarray) -> np.ndarray:
     """(cos, sin) of np.radians(grid) -- what velocity_solver.py:94-97 evaluates per target. f64 [G][2]."""
     az = np.radians(grid_deg)

@@ -87,3 +87,42 @@ def test_pair_mode_equals_per_segment_scan(monkeypatch):
     assert all(np.array_equal(x, y) for x, y in zip(a["tie"], b["tie"]))
     # the seven velocity sums of every segment (slot 8 is padding): same terms, another summation order
     assert np.allclose(a["part"][:, :7], b["part"][:, :7], rtol=1e-12, atol=1e-9)
+
+
+@pytest.mark.parametrize("A,method,res", [(192, "music", 1.0), (40, "beamforming", 0.5), (17, "music", 2.0)])
+def test_steering_gemm_on_tensor_cores(monkeypatch, A, method, res):
+    """A > 16: the grid scan as a dense [cells x 2A] . [2A x 2G] contraction on tcgen05 (music_tc_kernel) against the
+    oracle's fp64 argmax (every disagreement flagged) and against the CUDA-core scan it replaces (RS_MUSIC_TC=0)."""
+    from radar_slam_b200 import RadarConfig, FramePipeline
+    S, C = 64, 128
+    p = orc.RadarParams(chirp_duration=S / 10e6, num_chirps=C, num_antennas=A)
+    scene = np.array([(3.0, 0.3, 10.0, 0.0), (6.0, -0.6, 0.0, 0.0)])
+    np.random.seed(900 + A)
+    cube = np.stack([orc.synthesize_frame(p, scene) for _ in range(2)]).astype(np.complex64)
+    grid = orc.azimuth_grid((-90, 90), res)
+    steer = orc.steering_matrix(grid, p.antenna_positions, p.lambda_c)
+    runs = {}
+    for tc in ("1", "0"):
+        monkeypatch.setenv("RS_MUSIC_TC", tc)
+        cfg = RadarConfig(chirp_duration=S / 10e6, num_chirps=C, num_antennas=A, search_resolution=res, method=method,
+                          recheck=False)
+        pipe = FramePipeline(cfg)
+        vel, rds, det = pipe.process(torch.from_numpy(cube).cuda(), keep=True)
+        torch.cuda.synchronize()
+        runs[tc] = [det.frame(f) for f in range(2)]
+    for f in range(2):
+        ref = orc.range_doppler_spectrum(cube[f].astype(np.complex128), p)
+        got, old = runs["1"][f], runs["0"][f]
+        assert np.array_equal(got["key"], old["key"]) and len(got["key"]) > 5000
+        sub = np.arange(0, len(got["key"]), max(1, len(got["key"]) // 4000))
+        sigs = orc.spatial_signatures(ref, got["range_bin"][sub], got["doppler_bin"][sub])
+        idx, _ = orc.argmax_angles(orc.beamforming_spectra(sigs, steer) if method == "beamforming"
+                                   else orc.music_spectra(sigs, steer), grid)
+        for r in (got, old):
+            bad = r["aidx"][sub] != idx
+            assert np.all(r["flags"][sub][bad] & 5), "unflagged angle mismatch"
+            assert bad.mean() < 0.03
+        diff = got["aidx"] != old["aidx"]
+        assert np.all((got["flags"][diff] | old["flags"][diff]) & 5)
+        assert np.allclose(got["phase"], old["phase"])
+        assert np.mean((got["flags"] & 1) != 0) < 0.05            # the wider TIE band still flags few cells
