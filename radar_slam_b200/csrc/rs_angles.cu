@@ -1452,8 +1452,9 @@ __device__ __forceinline__ void mbar_wait_trap(unsigned long long* bar, uint32_t
 __global__ void __launch_bounds__(ANG_THREADS, 2) music_tc_kernel(AngleArgs p, const uint4* __restrict__ btab, int nhalves,
                                                                int nchunks, CellResult* __restrict__ cells, long long ntiles) {
     using namespace tc5;
-    constexpr int A_BYTES = 128 * 32, B_BYTES = SG_N * 32, STAGE = 2 * A_BYTES + 2 * B_BYTES, SG_TMEM = 256;
-    extern __shared__ __align__(128) unsigned char sgsm[];                   // [2 stages][A_hi, A_lo, B_hi, B_lo]
+    constexpr int A_BYTES = 128 * 32, B_BYTES = SG_N * 32, A_STAGE = 2 * A_BYTES, B_STAGE = 2 * B_BYTES, SG_TMEM = 256;
+    constexpr int B_STAGES = 4;
+    extern __shared__ __align__(128) unsigned char sgsm[];                   // [2][A_hi, A_lo] then [4][B_hi, B_lo]
     __shared__ unsigned long long mbar[2];
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, wid = tid >> 5;
@@ -1485,13 +1486,13 @@ __global__ void __launch_bounds__(ANG_THREADS, 2) music_tc_kernel(AngleArgs p, c
         // pre-pass: energy of the cell (and the two antennas of the inter-antenna phase)
         float e = 0.f;
         float2 s0 = make_float2(0.f, 0.f), s1 = make_float2(0.f, 0.f);
-        for (int m0 = 0; m0 < M; m0 += 8) {
-            float2 x[8];
+        for (int m0 = 0; m0 < M; m0 += 32) {                                 // 32 rows in flight per thread
+            float2 x[32];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) x[j] = m0 + j < M ? __ldg(cell + (size_t)(m0 + j) * p.D) : make_float2(0.f, 0.f);
+            for (int j = 0; j < 32; ++j) x[j] = m0 + j < M ? __ldg(cell + (size_t)(m0 + j) * p.D) : make_float2(0.f, 0.f);
             if (m0 == 0) { s0 = x[0]; s1 = x[1]; }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) e = fmaf(x[j].x, x[j].x, fmaf(x[j].y, x[j].y, e));
+            for (int j = 0; j < 32; ++j) e = fmaf(x[j].x, x[j].x, fmaf(x[j].y, x[j].y, e));
         }
         const float scale = e > 0.f ? 1.f / sqrtf(e) : 0.f;
         auto load_chunk = [&](int c, float2 (&x)[8]) {
@@ -1501,16 +1502,33 @@ __global__ void __launch_bounds__(ANG_THREADS, 2) music_tc_kernel(AngleArgs p, c
         float g_best = NEG, g_second = NEG;
         int g_idx = 0, g_run = 0;
         float stash[8] = {NEG, NEG, NEG, NEG, NEG, NEG, NEG, NEG};
-        float2 nx[8];
+        // B operands: a four-stage ring filled with cp.async two chunks ahead (stage (q + 2) & 3 was last read by the MMAs
+        // of chunk q - 2, whose commit this thread has waited for by then); snapshot rows two chunks ahead in registers
+        const int nseq = nhalves * nchunks;
+        auto fetch_b = [&](int q) {
+            if (q < nseq) {
+                const uint4* src = btab + (size_t)q * (B_STAGE / 16);
+                const uint32_t dst = sm_base + (uint32_t)(2 * A_STAGE + (q & (B_STAGES - 1)) * B_STAGE);
+#pragma unroll
+                for (int i = 0; i < B_STAGE / 16 / ANG_THREADS; ++i)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)((tid + i * ANG_THREADS) * 16)),
+                                 "l"(src + tid + i * ANG_THREADS) : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        fetch_b(0);
+        fetch_b(1);
+        float2 nx[8], nx2[8];
         load_chunk(0, nx);
+        load_chunk(nchunks > 1 ? 1 : 0, nx2);
         for (int h = 0; h < nhalves; ++h) {
             for (int c = 0; c < nchunks; ++c) {
-                const int st = c & 1;
+                const int st = c & 1, q = h * nchunks + c;
                 if (c >= 2) {                                                // the MMAs that read this stage two chunks ago
                     mbar_wait_trap(&mbar[st], phase[st]);
                     phase[st] ^= 1u;
                 }
-                unsigned char* sa = sgsm + (size_t)st * STAGE;
+                unsigned char* sa = sgsm + (size_t)st * A_STAGE;
                 {
                     uint32_t rh[4], rl[4], ih[4], il[4];
 #pragma unroll
@@ -1523,27 +1541,23 @@ __global__ void __launch_bounds__(ANG_THREADS, 2) music_tc_kernel(AngleArgs p, c
                     *reinterpret_cast<uint4*>(sa + A_BYTES + arow) = make_uint4(rl[0], rl[1], rl[2], rl[3]);
                     *reinterpret_cast<uint4*>(sa + A_BYTES + arow + 128) = make_uint4(il[0], il[1], il[2], il[3]);
                 }
-                {
-                    const uint4* src = btab + (size_t)(h * nchunks + c) * (2 * B_BYTES / 16);
-                    uint4* dst = reinterpret_cast<uint4*>(sa + 2 * A_BYTES);
 #pragma unroll
-                    for (int i = 0; i < 2 * B_BYTES / 16 / ANG_THREADS; ++i) dst[tid + i * ANG_THREADS] = __ldg(src + tid + i * ANG_THREADS);
-                }
-                // the next chunk's snapshot (of the next half when this one ends) is requested before the barrier
-                if (c + 1 < nchunks) load_chunk(c + 1, nx);
-                else if (h + 1 < nhalves) load_chunk(0, nx);
+                for (int j = 0; j < 8; ++j) nx[j] = nx2[j];
+                if (q + 2 < nseq) load_chunk((q + 2) % nchunks, nx2);        // rows of chunk q + 2 (the next half's when this one ends)
+                asm volatile("cp.async.wait_group 1;" ::: "memory");         // this thread's part of B(q) has landed
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncthreads();
                 if (tid == 0) {
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t a_hi = sm_base + (uint32_t)(st * STAGE), a_lo = a_hi + A_BYTES;
-                    const uint32_t b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
+                    const uint32_t a_hi = sm_base + (uint32_t)(st * A_STAGE), a_lo = a_hi + A_BYTES;
+                    const uint32_t b_hi = sm_base + (uint32_t)(2 * A_STAGE + (q & (B_STAGES - 1)) * B_STAGE), b_lo = b_hi + B_BYTES;
                     umma_sg(tmem_base, smem_desc(a_hi), smem_desc(b_hi), c > 0 ? 1u : 0u);
                     umma_sg(tmem_base, smem_desc(a_lo), smem_desc(b_hi), 1u);
                     umma_sg(tmem_base, smem_desc(a_hi), smem_desc(b_lo), 1u);
                     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(&mbar[st])) : "memory");
                 }
+                fetch_b(q + 2);
             }
             // the last two chunks' commits (in issue order): all MMAs of this half are done
             if (nchunks >= 2) {
@@ -1880,7 +1894,7 @@ extern "C" int rs_angles(const void* rds, const float* scan_table, int scan_stri
                 !(mtc_env && atoi(mtc_env) == 0)) {
                 // steering GEMM on the tensor cores: every cell of the batch, 128-cell tiles, two CTAs (2 x 256 TMEM columns) per SM
                 const long long ntiles = ncells / 128;
-                const size_t smem_sg = 2 * (2 * 128 * 32 + 2 * (size_t)tc5::SG_N * 32);
+                const size_t smem_sg = 2 * (2 * 128 * 32) + 4 * (2 * (size_t)tc5::SG_N * 32);
                 const long long resident = 2ll * rs_sm_count();
                 cudaFuncSetAttribute(music_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sg);
                 music_tc_kernel<<<(unsigned)(ntiles < resident ? ntiles : resident), ANG_THREADS, smem_sg, st>>>(
