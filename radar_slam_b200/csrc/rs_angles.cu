@@ -1479,6 +1479,11 @@ __global__ void __launch_bounds__(ANG_THREADS, 2) music_tc_kernel(AngleArgs p, c
     const float NEG = -3.0e38f;
     const float tie_eps = fmaxf(p.tie_eps, 2e-5f);
     const int tiles_d = p.D / 128;
+    const bool exact = (M & 7) == 0;
+    const size_t row8 = (size_t)8 * p.D * sizeof(float2);
+    uint32_t roff[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) roff[j] = (uint32_t)(j * p.D * (int)sizeof(float2));
     for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const long long fr = t / tiles_d;                                    // f * R + r
         const int d = (int)(t - fr * tiles_d) * 128 + tid;
@@ -1495,9 +1500,17 @@ __global__ void __launch_bounds__(ANG_THREADS, 2) music_tc_kernel(AngleArgs p, c
             for (int j = 0; j < 32; ++j) e = fmaf(x[j].x, x[j].x, fmaf(x[j].y, x[j].y, e));
         }
         const float scale = e > 0.f ? 1.f / sqrtf(e) : 0.f;
+        // rows 8 c .. 8 c + 7 of this thread's cell: one base pointer per chunk, the eight row offsets are kernel constants
         auto load_chunk = [&](int c, float2 (&x)[8]) {
+            const char* base = reinterpret_cast<const char*>(cell) + (size_t)c * row8;
+            if (exact) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) x[j] = 8 * c + j < M ? __ldg(cell + (size_t)(8 * c + j) * p.D) : make_float2(0.f, 0.f);
+                for (int j = 0; j < 8; ++j) x[j] = __ldg(reinterpret_cast<const float2*>(base + roff[j]));
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    x[j] = 8 * c + j < M ? __ldg(reinterpret_cast<const float2*>(base + roff[j])) : make_float2(0.f, 0.f);
+            }
         };
         float g_best = NEG, g_second = NEG;
         int g_idx = 0, g_run = 0;
@@ -1543,7 +1556,7 @@ __global__ void __launch_bounds__(ANG_THREADS, 2) music_tc_kernel(AngleArgs p, c
                 }
 #pragma unroll
                 for (int j = 0; j < 8; ++j) nx[j] = nx2[j];
-                if (q + 2 < nseq) load_chunk((q + 2) % nchunks, nx2);        // rows of chunk q + 2 (the next half's when this one ends)
+                if (q + 2 < nseq) load_chunk(c + 2 < nchunks ? c + 2 : c + 2 - nchunks, nx2);   // chunk q + 2 (wraps into the next half)
                 asm volatile("cp.async.wait_group 1;" ::: "memory");         // this thread's part of B(q) has landed
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
