@@ -8,7 +8,9 @@ ego-velocity) over one batch of synthetic frames.
 
   N = 1 (headline)   BASELINE.json configs[1]: 1k frames of 256 samples x 128 chirps x 8 channels, MUSIC on a 1 degree
                      grid, reference-default noise and threshold, the 1.95 GiB cube resident in HBM (>> L2).
-                     The same line carries `configs4_n1`: the N > 1 workload measured on this one GPU.
+                     The same line carries `configs4_n1`: the N > 1 workload measured on this one GPU, and
+                     `configs2_n1` / `configs3_n1`: BASELINE configs[2] (512 x 256 x 192, ESPRIT) and the configs[3] style
+                     scene (threshold 31 dB, 3 Huber iterations) on this GPU.
   N > 1              BASELINE.json configs[4]: ONE 65 536-frame sequence of 256 x 128 x 16 cubes, STRONG-scaled: rank r
                      owns the contiguous frame block frame_block(r, N, 65536), walks it in chunks through a resident pool
                      of synthetic frames (inputs resident in HBM when the timed region starts; pool >> L2), the solve
@@ -397,6 +399,23 @@ def run_gpu(args):
         steps4 = args.steps if wl == "configs4" else max(2, min(args.steps, 3))
         c4 = measure_configs4(args, world, rank, dev, steps4, args.warmup if wl == "configs4" else 3)
     c1 = measure_configs1(args, world, rank, dev, numa, detailed=(wl == "configs1"))
+    # N = 1, default arguments: BASELINE configs[2] and configs[3] ride along as side objects (same code path, their
+    # own shapes; a failure there is reported in the object and never costs the headline line)
+    side = {}
+    if world == 1 and args.workload == "auto" and not args.no_side_configs and workload_name(args) == WORKLOAD:
+        import argparse
+        import gc
+        for key, over in (("configs2_n1", dict(samples=512, chirps=256, antennas=192, method="esprit", frames=8, chunk=8,
+                                                 e2e_frames=8, host_chunk=4, steps=max(3, min(args.steps, 5)))),
+                          ("configs3_n1", dict(threshold_db=31.0, irls=3, steps=max(3, min(args.steps, 5))))):
+            gc.collect()
+            torch.cuda.empty_cache()
+            try:
+                a2 = argparse.Namespace(**{**vars(args), **over})
+                r2 = measure_configs1(a2, world, rank, dev, numa, detailed=False)
+                side[key] = {k: r2[k] for k in ("value", "unit", "ms_per_step", "steps", "scaling", "e2e", "config", "gpu_launches")}
+            except Exception as exc:                              # noqa: BLE001 -- reported, not raised
+                side[key] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
     clocks = sampler.stop() if rank == 0 else None
 
     if rank == 0:
@@ -404,6 +423,7 @@ def run_gpu(args):
             line = c1
             if c4 is not None:
                 line["configs4_n1" if world == 1 else "configs4"] = c4
+            line.update(side)
         else:
             line = {
                 "metric": METRIC, "value": c4["value"], "unit": "frames/s", "n_gpus": world, "steps": args.steps,
@@ -660,6 +680,7 @@ def main():
     ap.add_argument("--pool-frames", type=int, default=512, help="configs[4]: resident synthetic frames per GPU (2 GiB at 512)")
     ap.add_argument("--e2e-frames4", type=int, default=1024, help="configs[4]: frames per GPU of the end-to-end sample")
     ap.add_argument("--no-configs4", action="store_true", help="N = 1: skip the configs[4] side measurement")
+    ap.add_argument("--no-side-configs", action="store_true", help="N = 1: skip the configs[2] / configs[3] side measurements")
     ap.add_argument("--sustain-s", type=float, default=1.0, help="length of the sustained run (0: off)")
     ap.add_argument("--profile-passes", type=int, default=5, help="passes averaged for the per-stage times")
     ap.add_argument("--ref-procs", type=int, default=0)
