@@ -1308,105 +1308,70 @@ __global__ void __launch_bounds__(ANG_THREADS) eval_cells_kernel(AngleArgs p, co
     }
 }
 
-// ESPRIT on the marked cells (large_cell's closed form, re-arranged after an ncu capture of eval_cells_kernel at
-// 512 x 256 x 192: 1055 warp instructions per cell, 64 % issue, the L1 pipe at 81 %):
-//  * asin(atan2()) in fp64 and atan2f() ran on all 32 lanes for the one value lane 0 keeps (~400 of the 1055
-//    instructions): here a warp works through a batch of 32 cells, lane j captures the sums of cell j, and the
-//    transcendental functions run once per batch, a lane per cell;
-//  * lane l owns the PER consecutive antennas [l PER, l PER + PER): the neighbours x_{m+1}, u_{m+1} of both sums are
-//    registers, except across the block edge (one shuffle each) -- no shared memory, so the whole unified array stays L1
-//    for the strided gathers (a first version with fp64 staging in shared memory left 7 KB of L1 and ran 2.3x slower);
-//  * w_m = v0 x_{m+1} + v1 x_{m+2} of the second sum is u_{m+1} of its first factor: u is computed once per antenna --
-//    14 instead of 32 fp64 operations per antenna.
-// The four warps of a CTA take the four cells of a 32-byte sector (4 Doppler bins of an antenna row) at the same time.
-template <int PER>
+// ESPRIT on the marked cells as ONE streaming pass, a thread per cell (large_cell's closed form, re-arranged after an ncu
+// capture of the warp-per-cell eval_cells_kernel at 512 x 256 x 192: 1055 warp instructions per cell -- cross-lane
+// reductions, the eigen-solve and fp64 asin(atan2()) replicated on 32 lanes -- the L1 pipe at 81 % from one 32-byte
+// sector per 8-byte element).  The closed form needs only three lag sums of the snapshot:
+//     T0 = sum |x_m|^2,   L1 = sum_{m < M-1} conj(x_m) x_{m+1},   L2 = sum_{m < M-2} conj(x_m) x_{m+2}
+//   alpha = T0 - |x_{M-1}|^2, gamma = T0 - |x_0|^2, b = L1                      (the 2 x 2 Hermitian problem, :195-221)
+//   n = sum_{m < M-2} conj(u_m) u_{m+1},  u_m = v0 x_m + v1 x_{m+1}
+//     = |v0|^2 (L1 - conj(x_{M-2}) x_{M-1}) + conj(v0) v1 L2 + conj(v1) v0 (T0 - |x_0|^2 - |x_{M-1}|^2) + |v1|^2 (L1 - conj(x_0) x_1)
+// so thread t of a CTA walks the antennas of cell c0 + t once (consecutive cells are consecutive Doppler bins: every
+// load instruction of a warp is one contiguous 256-byte run), accumulates the three sums in fp64 and finishes the cell
+// on its own: no shuffles, no shared memory, the snapshot read exactly once -- HBM bound.
 __global__ void __launch_bounds__(ANG_THREADS) eval_cells_esprit_kernel(AngleArgs p, const uint8_t* __restrict__ mark,
                                                                          CellResult* __restrict__ cells, long long ncells) {
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    constexpr int NW = ANG_THREADS / 32;
-    const int M = p.A, m0 = lane * PER;
+    const int M = p.A;
     const long long per_frame = (long long)p.R * p.D;
-    for (long long g0 = (long long)blockIdx.x * 32 * NW; g0 < ncells; g0 += (long long)gridDim.x * 32 * NW) {
-        // cell i of this warp's batch: g0 + NW i + wid
-        double cap_nr = 0, cap_ni = 0;
-        float2 c0 = make_float2(0.f, 0.f), c1 = make_float2(0.f, 0.f);
-        const long long mine = g0 + (long long)NW * lane + wid;
-        const uint32_t marked = __ballot_sync(0xffffffffu, mine < ncells && mark[mine] != 0);
-        for (uint32_t todo = marked; todo; todo &= todo - 1) {
-            const int j = __ffs(todo) - 1;
-            const long long c = g0 + (long long)NW * j + wid;
-            const long long f = c / per_frame;
-            const long long rd = c - f * per_frame;
-            const int r = (int)(rd / p.D), d = (int)(rd - (long long)r * p.D);
-            const float2* cell = p.rds + ((size_t)f * p.R + r) * M * p.D + d;
-            float2 s[PER];
+    for (long long c = (long long)blockIdx.x * ANG_THREADS + threadIdx.x; c < ncells; c += (long long)gridDim.x * ANG_THREADS) {
+        if (!mark[c]) continue;
+        const long long f = c / per_frame;
+        const long long rd = c - f * per_frame;
+        const int r = (int)(rd / p.D), d = (int)(rd - (long long)r * p.D);
+        const float2* cell = p.rds + ((size_t)f * p.R + r) * M * p.D + d;
+        double t0 = 0, l1r = 0, l1i = 0, l2r = 0, l2i = 0;
+        double p1x = 0, p1y = 0, p2x = 0, p2y = 0;              // x_{m-1}, x_{m-2}
+        double x0x = 0, x0y = 0, x1x = 0, x1y = 0;              // x_0, x_1
+        float2 f0 = make_float2(0.f, 0.f), f1 = make_float2(0.f, 0.f);
+        for (int m0 = 0; m0 < M; m0 += 8) {
+            float2 xs[8];
 #pragma unroll
-            for (int k = 0; k < PER; ++k) s[k] = m0 + k < M ? __ldg(cell + (size_t)(m0 + k) * p.D) : make_float2(0.f, 0.f);
-            float2 sn;                                           // x of the next lane's first antenna
-            sn.x = __shfl_down_sync(0xffffffffu, s[0].x, 1);
-            sn.y = __shfl_down_sync(0xffffffffu, s[0].y, 1);
-            double alpha = 0, gamma = 0, br = 0, bi = 0;
+            for (int j = 0; j < 8; ++j) xs[j] = m0 + j < M ? __ldg(cell + (size_t)(m0 + j) * p.D) : make_float2(0.f, 0.f);
+            if (m0 == 0) { f0 = xs[0]; f1 = xs[1]; x0x = xs[0].x; x0y = xs[0].y; x1x = xs[1].x; x1y = xs[1].y; }
 #pragma unroll
-            for (int k = 0; k < PER; ++k) {
-                if (m0 + k < M - 1) {
-                    const float2 xf = s[k], yf = k + 1 < PER ? s[k + 1] : sn;
-                    const double xx = xf.x, xy = xf.y, yx = yf.x, yy = yf.y;
-                    alpha += xx * xx + xy * xy; gamma += yx * yx + yy * yy;
-                    br += xx * yx + xy * yy;    bi += xx * yy - xy * yx;
+            for (int j = 0; j < 8; ++j) {
+                if (m0 + j < M) {
+                    const double xx = xs[j].x, xy = xs[j].y;
+                    t0 += xx * xx + xy * xy;
+                    l1r += p1x * xx + p1y * xy;  l1i += p1x * xy - p1y * xx;        // conj(x_{m-1}) x_m  (zero for m = 0)
+                    l2r += p2x * xx + p2y * xy;  l2i += p2x * xy - p2y * xx;        // conj(x_{m-2}) x_m
+                    p2x = p1x; p2y = p1y; p1x = xx; p1y = xy;
                 }
             }
-#pragma unroll
-            for (int off = 16; off; off >>= 1) {
-                alpha += __shfl_xor_sync(0xffffffffu, alpha, off); gamma += __shfl_xor_sync(0xffffffffu, gamma, off);
-                br += __shfl_xor_sync(0xffffffffu, br, off);       bi += __shfl_xor_sync(0xffffffffu, bi, off);
-            }
-            const double half = 0.5 * (alpha - gamma);
-            const double lam = 0.5 * (alpha + gamma) + sqrt(half * half + br * br + bi * bi);
-            double v0r, v0i, v1r, v1i;
-            const double na = br * br + bi * bi + (lam - alpha) * (lam - alpha);
-            const double nb2 = (lam - gamma) * (lam - gamma) + br * br + bi * bi;
-            if (na >= nb2) { v0r = br; v0i = bi; v1r = lam - alpha; v1i = 0; }
-            else           { v0r = lam - gamma; v0i = 0; v1r = br; v1i = -bi; }
-            double2 u[PER];
-#pragma unroll
-            for (int k = 0; k < PER; ++k) {
-                const float2 xf = s[k], yf = k + 1 < PER ? s[k + 1] : sn;
-                const double x0x = xf.x, x0y = xf.y, x1x = yf.x, x1y = yf.y;
-                u[k] = make_double2(v0r * x0x - v0i * x0y + v1r * x1x - v1i * x1y,
-                                    v0r * x0y + v0i * x0x + v1r * x1y + v1i * x1x);
-            }
-            double2 un;                                          // u of the next lane's first antenna
-            un.x = __shfl_down_sync(0xffffffffu, u[0].x, 1);
-            un.y = __shfl_down_sync(0xffffffffu, u[0].y, 1);
-            double nr = 0, ni = 0;
-#pragma unroll
-            for (int k = 0; k < PER; ++k) {
-                if (m0 + k < M - 2) {
-                    const double2 a = u[k], w = k + 1 < PER ? u[k + 1] : un;
-                    nr += a.x * w.x + a.y * w.y;
-                    ni += a.x * w.y - a.y * w.x;
-                }
-            }
-#pragma unroll
-            for (int off = 16; off; off >>= 1) {
-                nr += __shfl_xor_sync(0xffffffffu, nr, off);
-                ni += __shfl_xor_sync(0xffffffffu, ni, off);
-            }
-            // antennas 0 and 1 (the inter-antenna phase) sit on lane 0 (PER >= 2)
-            const float a0x = __shfl_sync(0xffffffffu, s[0].x, 0), a0y = __shfl_sync(0xffffffffu, s[0].y, 0);
-            const float a1x = __shfl_sync(0xffffffffu, s[1].x, 0), a1y = __shfl_sync(0xffffffffu, s[1].y, 0);
-            if (lane == j) {
-                cap_nr = nr; cap_ni = ni;
-                c0 = make_float2(a0x, a0y);
-                c1 = make_float2(a1x, a1y);
-            }
         }
-        if ((marked >> lane) & 1u) {
-            CellResult out{-1, 0.f, 0.f, 0u};
-            out.phase = atan2f(c1.y * c0.x - c1.x * c0.y, c1.x * c0.x + c1.y * c0.y);
-            out.adeg = (float)(asin(atan2(cap_ni, cap_nr) * p.esprit_scale) * (180.0 / 3.14159265358979323846));
-            cells[mine] = out;
-        }
+        // after the loop p1 = x_{M-1}, p2 = x_{M-2}
+        const double e0 = x0x * x0x + x0y * x0y, eL = p1x * p1x + p1y * p1y;
+        const double alpha = t0 - eL, gamma = t0 - e0, br = l1r, bi = l1i;
+        const double half = 0.5 * (alpha - gamma);
+        const double lam = 0.5 * (alpha + gamma) + sqrt(half * half + br * br + bi * bi);
+        double v0r, v0i, v1r, v1i;
+        const double na = br * br + bi * bi + (lam - alpha) * (lam - alpha);
+        const double nb = (lam - gamma) * (lam - gamma) + br * br + bi * bi;
+        if (na >= nb) { v0r = br; v0i = bi; v1r = lam - alpha; v1i = 0; }
+        else          { v0r = lam - gamma; v0i = 0; v1r = br; v1i = -bi; }
+        // the four data sums of n
+        const double sar = l1r - (p2x * p1x + p2y * p1y), sai = l1i - (p2x * p1y - p2y * p1x);   // L1 - conj(x_{M-2}) x_{M-1}
+        const double sbr = l1r - (x0x * x1x + x0y * x1y), sbi = l1i - (x0x * x1y - x0y * x1x);   // L1 - conj(x_0) x_1
+        const double e1 = t0 - e0 - eL;
+        const double a00 = v0r * v0r + v0i * v0i, a11 = v1r * v1r + v1i * v1i;
+        const double cr = v0r * v1r + v0i * v1i, ci = v0r * v1i - v0i * v1r;                     // conj(v0) v1
+        // n = a00 Sa + (conj(v0) v1) L2 + conj(conj(v0) v1) e1 + a11 Sb
+        const double nr = a00 * sar + (cr * l2r - ci * l2i) + cr * e1 + a11 * sbr;
+        const double ni = a00 * sai + (cr * l2i + ci * l2r) - ci * e1 + a11 * sbi;
+        CellResult out{-1, 0.f, 0.f, 0u};
+        out.phase = atan2f(f1.y * f0.x - f1.x * f0.y, f1.x * f0.x + f1.y * f0.y);
+        out.adeg = (float)(asin(atan2(ni, nr) * p.esprit_scale) * (180.0 / 3.14159265358979323846));
+        cells[c] = out;
     }
 }
 
@@ -1912,14 +1877,9 @@ extern "C" int rs_angles(const void* rds, const float* scan_table, int scan_stri
                 cudaFuncSetAttribute(music_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sg);
                 music_tc_kernel<<<(unsigned)(ntiles < resident ? ntiles : resident), ANG_THREADS, smem_sg, st>>>(
                     p, (const uint4*)tc_table, sg_halves, (A + 7) / 8, cells, ntiles);
-            } else if (method == RS_METHOD_ESPRIT && A <= 256 && !getenv("RS_ESPRIT_LEGACY")) {
-                const long long want32 = (ncells + 32 * (ANG_THREADS / 32) - 1) / (32 * (ANG_THREADS / 32));
-                const unsigned eg = (unsigned)(want32 < cap ? want32 : cap);
-                const int per = (A + 31) / 32;
-                if (per <= 2) eval_cells_esprit_kernel<2><<<eg, ANG_THREADS, 0, st>>>(p, mark, cells, ncells);
-                else if (per <= 4) eval_cells_esprit_kernel<4><<<eg, ANG_THREADS, 0, st>>>(p, mark, cells, ncells);
-                else if (per <= 6) eval_cells_esprit_kernel<6><<<eg, ANG_THREADS, 0, st>>>(p, mark, cells, ncells);
-                else eval_cells_esprit_kernel<8><<<eg, ANG_THREADS, 0, st>>>(p, mark, cells, ncells);
+            } else if (method == RS_METHOD_ESPRIT && A >= 3 && !getenv("RS_ESPRIT_LEGACY")) {
+                const long long wantc = (ncells + ANG_THREADS - 1) / ANG_THREADS;
+                eval_cells_esprit_kernel<<<(unsigned)(wantc < cap ? wantc : cap), ANG_THREADS, 0, st>>>(p, mark, cells, ncells);
             } else {
                 eval_cells_kernel<<<(unsigned)(want < cap ? want : cap), ANG_THREADS, smem, st>>>(p, mark, cells, ncells);
             }
