@@ -137,13 +137,30 @@ velocity_partials_kernel(const int32_t* __restrict__ det_aidx, const float* __re
     const size_t seg = blockIdx.x;
     const int n = det_count[seg];
     Sums s{};
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    // Thread t takes the contiguous entries [t per, t per + per): the entries of a cell are contiguous and share their
+    // angle, so off the grid (ESPRIT: an fp64 sincos per angle) the previous entry's (cos, sin) is reused while the angle
+    // repeats -- one sincos per cell and thread instead of one per detection (17 detections per cell at 192 channels:
+    // 0.24 -> 0.1 ms per 8 frames of 512 x 256 x 192).
+    const int per = (n + (int)blockDim.x - 1) / (int)blockDim.x;
+    const int i0 = (int)threadIdx.x * per, i1 = min(n, i0 + per);
+    float last = 0.f;
+    bool have = false;
+    double c = 1.0, sn = 0.0;
+    for (int i = i0; i < i1; ++i) {
         const size_t o = seg * seg_cap + i;
         if (det_flags[o] & RS_FLAG_DROPPED) continue;
-        double c, sn;
         const int ai = det_aidx[o];
-        if (grid_cs != nullptr && ai >= 0) { c = grid_cs[2 * ai]; sn = grid_cs[2 * ai + 1]; }
-        else { sincos((double)det_adeg[o] * (3.14159265358979323846 / 180.0), &sn, &c); }
+        if (grid_cs != nullptr && ai >= 0) {
+            c = grid_cs[2 * ai]; sn = grid_cs[2 * ai + 1];
+            have = false;
+        } else {
+            const float a = det_adeg[o];
+            if (!have || a != last) {
+                sincos((double)a * (3.14159265358979323846 / 180.0), &sn, &c);
+                last = a;
+                have = true;
+            }
+        }
         const double y = (double)det_phase[o];
         s.cc += c * c; s.ss += sn * sn; s.cs += c * sn;
         s.yc += y * c; s.ys += y * sn; s.yy += y * y; s.n += 1.0;
