@@ -816,23 +816,39 @@ __global__ void __launch_bounds__(ANG_THREADS, 4) angles_tc5_kernel(AngleArgs p,
     unsigned short* wqc = reinterpret_cast<unsigned short*>(wres + PAIR_CELLS);            // [cells] queue of cell indices
     const int pair_dmask = pair_td - 1, pair_dshift = 31 - __clz(pair_td);
     const int nunits = PAIR ? nsegs / 2 : nsegs;
-    // leaders [t c, t c + c) of a segment through fn(index, leader word, key): words, then keys, requested together
-    auto for_leaders = [&](int sg, auto fn) {
+    // leaders [t c, t c + c) of a segment through fn(index, leader word, key, row): four at a time, their words, then
+    // their keys, then (WITH_ROW) their rows of the result table requested together -- three load latencies per four
+    // leaders; fn itself runs in a rolled loop (it may inline the large emit)
+    auto for_leaders = [&](int sg, auto with_row, auto fn) {
+        constexpr bool WITH_ROW = decltype(with_row)::value;
         const int nl = p.det_nlead[sg];
         const size_t sb = (size_t)sg * p.seg_cap;
         const int c = (nl + ANG_THREADS - 1) / ANG_THREADS, i0 = tid * c;
 #pragma unroll 1
         for (int j0 = 0; j0 < c; j0 += 4) {
             uint32_t lv[4], kv[4];
+            uint2 rv[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) lv[j] = (j0 + j < c && i0 + j0 + j < nl) ? __ldg(p.det_lead + sb + i0 + j0 + j) : 0u;
 #pragma unroll
             for (int j = 0; j < 4; ++j) kv[j] = (j0 + j < c && i0 + j0 + j < nl) ? __ldg(p.det_key + sb + (lv[j] & 0xFFFFu)) : 0u;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                rv[j] = make_uint2(0u, 0u);
+                if (WITH_ROW && j0 + j < c && i0 + j0 + j < nl) {
+                    int a_, r_, d_;
+                    rs_split_key(kv[j], a_, r_, d_);
+                    rv[j] = __ldcg(wres + (((r_ & (pair_tr - 1)) << pair_dshift) | (d_ & pair_dmask)));
+                }
+            }
 #pragma unroll 1
-            for (int j = 0; j < 4; ++j) {                            // rolled: fn may inline the (large) emit
-                const uint32_t l = j == 0 ? lv[0] : j == 1 ? lv[1] : j == 2 ? lv[2] : lv[3];
-                const uint32_t ky = j == 0 ? kv[0] : j == 1 ? kv[1] : j == 2 ? kv[2] : kv[3];
-                if (j0 + j < c && i0 + j0 + j < nl) fn(i0 + j0 + j, l, ky);
+            for (int j = 0; j < 4; ++j) {
+                uint32_t l = lv[0], ky = kv[0];
+                uint2 row = rv[0];
+#pragma unroll
+                for (int q = 1; q < 4; ++q)
+                    if (j == q) { l = lv[q]; ky = kv[q]; row = rv[q]; }
+                if (j0 + j < c && i0 + j0 + j < nl) fn(i0 + j0 + j, l, ky, row);
             }
         }
     };
@@ -851,7 +867,7 @@ __global__ void __launch_bounds__(ANG_THREADS, 4) angles_tc5_kernel(AngleArgs p,
         if (tid < PAIR_CELLS / 32) cellmap[tid] = 0u;
         __syncthreads();
         for (int sg = seg; sg < seg + 2; ++sg)
-            for_leaders(sg, [&](int, uint32_t, uint32_t key) {
+            for_leaders(sg, std::false_type{}, [&](int, uint32_t, uint32_t key, uint2) {
                 const int cell = cell_of(key);
                 atomicOr(&cellmap[cell >> 5], 1u << (cell & 31));
             });
@@ -1139,8 +1155,7 @@ __global__ void __launch_bounds__(ANG_THREADS, 4) angles_tc5_kernel(AngleArgs p,
             const size_t sb = (size_t)sg * p.seg_cap;
 #pragma unroll
             for (int q = 0; q < 7; ++q) acc_ls[q] = 0.0;
-            for_leaders(sg, [&](int i, uint32_t l, uint32_t key) {
-                const uint2 rv = __ldcg(wres + cell_of(key));
+            for_leaders(sg, std::true_type{}, [&](int i, uint32_t l, uint32_t, uint2 rv) {
                 const int bi = (int)(rv.x & 0xFFFFu);
                 const float yv = __uint_as_float(rv.y);
                 const int live = emit<true>(p, sg, i, sb + (l & 0xFFFFu), (int)(l >> 16), bi, Gd[bi], yv, (uint8_t)(rv.x >> 16), clean);
