@@ -606,15 +606,34 @@ def measure_configs1(args, world, rank, dev, numa, detailed=True):
         flops = cells * (G * 2 * (ap - 1) + 8 * ap * ap)
         roofline["angle_scan"] = {
             "distinct_cells_per_step": cells, "scan_tflops_fp32_equivalent": flops / ang["ms_per_step"] / 1e9,
-            "note": "per-cell MUSIC grid scan = [cells x lags] . [lags x grid pairs] on the tensor cores (mma.sync m16n8k16 + "
-                    "m16n8k8, fp16 operands split hi + lo, fp32 accumulation); its argmax / runner-up tracking is ALU-issue "
-                    "bound, not HBM bound"}
+            "note": "per-cell MUSIC grid scan = [cells x lags] . [lags x grid pairs] on the 5th-generation tensor cores "
+                    "(tcgen05.mma 128x32x16 into TMEM, fp16 operands split hi + lo, fp32 accumulation, persistent CTAs); its "
+                    "two-level argmax / runner-up tracking is instruction-issue bound, not HBM bound"}
     fd = next((st for st in stages if st["kernel"] == "rs_range_doppler_detect"), None)
     if fd is not None:
         # what the two-stage path (rs_range_doppler_fft + rs_detect) needs for the same result: 16 + 8 B/cell + the lists
         two_stage = 24 * F * A * C * S + 9 * n_det_frame * F
         fd["two_stage_alg_bytes_per_step"] = two_stage
         fd["frac_hbm_of_two_stage_bytes"] = two_stage / fd["ms_per_step"] / 1e6 / peak
+        if (C, S) == (128, 256) and A % 8 == 0:
+            # the stage is two kernels (persistent FFT + detection kernel, then the mask compaction): the first one alone,
+            # the compaction left out (RS_FD_NO_COMPACT), against cube in + RDS out + the masks it writes
+            out = pipe._buf("rds0", (F, S, A, C), torch.complex64)
+            os.environ["RS_FD_NO_COMPACT"] = "1"
+            try:
+                for _ in range(2):
+                    pipe.range_doppler_detect(cube, out=out, workspace="0", defer_power=True)
+                ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+                ev[0].record()
+                for _ in range(passes):
+                    pipe.range_doppler_detect(cube, out=out, workspace="0", defer_power=True)
+                ev[1].record()
+                torch.cuda.synchronize(dev)
+                ms_k = ev[0].elapsed_time(ev[1]) / passes
+                kb = (16 + 0.27) * F * A * C * S
+                fd["fft_detect_kernel_alone"] = {"ms_per_step": ms_k, "alg_bytes_per_step": kb, "frac_hbm": kb / ms_k / 1e6 / peak}
+            finally:
+                os.environ.pop("RS_FD_NO_COMPACT", None)
     if dom["kernel"] == "rs_range_doppler_detect":
         roofline["note"] = ("dominant stage is the fused 2-D FFT + detection (persistent warp-specialised 4-CTA clusters fed by TMA; "
                             "the |X|^2 local-maximum test runs on the plane in distributed shared memory and leaves hit masks, a "
