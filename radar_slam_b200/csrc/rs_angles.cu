@@ -675,13 +675,14 @@ __global__ void __launch_bounds__(ANG_THREADS, MINB) angles_mma_kernel(AngleArgs
 }
 
 // ---------------------------------------------------------------------------------------------
-// tcgen05 scan (RS_ANGLES_TC=1): the same contraction on the 5th-generation tensor cores.
+// tcgen05 scan (the default for 5..16 antennas on a symmetric grid; RS_ANGLES_TC=0 selects the mma.sync kernel above): the
+// same contraction on the 5th-generation tensor cores.
 //
 // One CTA = 128 threads = 128 cells = the 128 TMEM lanes of a UMMA tile.  Every thread gathers its cell's snapshot,
 // forms the normalised lags and writes its ROW of the A operand ([Re R_k] for the even part, [Im R_k] for the odd
 // part, fp16 hi / lo split packed along K exactly as in the mma.sync kernel) into shared memory in the canonical
 // K-major no-swizzle UMMA layout (8 x 16-byte core matrices).  One elected thread issues
-//     tcgen05.mma.cta_group::1.kind::f16   D[128 x 48] (+)= A[128 x 16] . B[16 x 48]
+//     tcgen05.mma.cta_group::1.kind::f16   D[128 x 32] (+)= A[128 x 16] . B[16 x 32]
 // per 16-wide K chunk for the cos table (E) and the sin table (O) of one "job" of 32 grid pairs into one of two 64-column TMEM
 // buffers, commits to that buffer's mbarrier, and after the wait each thread reads ITS OWN cell's 32 + 32 accumulators with
 // tcgen05.ld.32x32b -- a whole row per thread, so the pair maximum E + |O| is tracked without any cross-lane merge
@@ -689,7 +690,8 @@ __global__ void __launch_bounds__(ANG_THREADS, MINB) angles_mma_kernel(AngleArgs
 // flight: the tensor core fills one buffer while the threads track the other, and the next tile's snapshot loads are
 // issued before the tracking starts, so their latency is hidden too.  The B operand (cos / sin tables, split hi / lo,
 // already in UMMA layout) is built on the host (tables.scan_tc_table).
-// 128 TMEM columns per CTA: four CTAs per SM keep 16 warps resident for the ALU-bound tracking.
+// 128 TMEM columns per CTA: four persistent CTAs per SM keep 16 warps resident; they walk the segments (or, with 16
+// antennas, the segment pairs of a tile: PAIR below).  The tracking is two-level (group maxima + stash, see the tile loop).
 // ---------------------------------------------------------------------------------------------
 namespace tc5 {
 
